@@ -1,0 +1,120 @@
+/* ptb200.h -- C-ABI of the B200-native Point Teacher hot path (libptb200.so, sm_100a).
+ *
+ * Conventions: every entry point returns 0 on success or a negative PT_ERR_* code and never throws;
+ * pt_last_error() returns the thread-local message.  All pointers are DEVICE pointers unless the
+ * parameter name ends in _host.  The caller owns all memory (outputs pre-allocated), kernels are
+ * enqueued on `stream` (a cudaStream_t passed as void*), there are no internal syncs and no global
+ * state, so calls are re-entrant per stream and CUDA-graph capturable.
+ *
+ * Each function names the reference interface it replaces (paths relative to /root/reference).
+ */
+#ifndef PTB200_H_
+#define PTB200_H_
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PT_OK 0
+#define PT_ERR_ARG (-1)
+#define PT_ERR_CUDA (-2)
+#define PT_ERR_UNSUPPORTED (-3)
+#define PT_ERR_DRIVER (-4)
+
+const char* pt_last_error(void);
+int pt_abi_version(void);
+const char* pt_build_arch(void);
+
+/* ---- bag construction ----------------------------------------------------------------------
+ * fine_proposals_from_cfg + bbox2roi:
+ *   HBB_TOD/mmdet/models/detectors/syn_images_generator_v2.py:262-324, core/bbox/transforms.py:58-78.
+ * in_rois [G,5] (img,x1,y1,x2,y2) -> out_rois [G*U,5], valid [G*U] (iof with the image > 0.7),
+ * U = n_ratios^2 * (1 + 4*n_shake); order GT-major, ratio_w outer, ratio_h inner, shake minor.
+ * ratios_host / shake_host are HOST arrays.  img_wh [B,2] = (w,h) per image. */
+int pt_bag_gen(const float* in_rois, long long G, const float* img_wh, int B, const float* ratios_host,
+               int n_ratios, const float* shake_host, int n_shake, float min_scale, float* out_rois,
+               unsigned char* valid, void* stream);
+
+/* gen_negative_proposals' weight test (syn_images_generator_v2.py:254-255):
+ * weight[n] = all(IoU(neg n, base bags of the same image) < 0.3).  bag_rois sorted by image,
+ * bag_offsets [B+1] int32. */
+int pt_neg_weight(const float* neg_rois, int n_neg, const float* bag_rois, const int* bag_offsets, int B,
+                  unsigned char* weight, void* stream);
+
+/* bbox_overlaps (HBB_TOD/mmdet/core/bbox/iou_calculators/iou2d_calculator.py:74-260):
+ * mode 0 iou / 1 iof / 2 giou; a [M,4] row stride lda floats, b [N,4] stride ldb; out (M,N) or,
+ * aligned, (M,). */
+int pt_bbox_overlaps(const float* a, int lda, const float* b, int ldb, long long M, long long N, int mode,
+                     int aligned, float eps, float* out, void* stream);
+
+/* ---- RoIAlign --------------------------------------------------------------------------------
+ * mmcv.ops.RoIAlign / RoIAlignRotated forward as built by
+ *   HBB_TOD/mmdet/models/roi_heads/roi_extractors/base_roi_extractor.py:50-59 and called from
+ *   single_level_roi_extractor.py:56-114 / OBB_TOD/.../rotate_single_level_roi_extractor.py:90-167.
+ * pt_nchw_to_nhwc: [B,C,H,W] fp32 -> [B,H,W,C] fp32 or bf16 (done once per step).
+ * pt_roi_align_forward: feat NHWC; rois [K,5] or rotated [K,6] (img,cx,cy,w,h,theta rad).
+ *   out_mode 0: bf16 [K, ld_out], column (ph*7+pw)*C + c (the FC1 operand layout)
+ *   out_mode 1: fp32 [K,C,7,7] (the extractor's public layout)
+ *   out_mode 2: bf16 [K, ld_out] = [hi | lo | hi] segments of 49*C (fp32-emulation operand) */
+int pt_nchw_to_nhwc(const float* in, void* out, int B, int C, int H, int W, int out_bf16, void* stream);
+int pt_roi_align_forward(const void* feat, int feat_bf16, const float* rois, void* out, long long ld_out,
+                         int out_mode, int K, int B, int C, int H, int W, int pooled, float spatial_scale,
+                         int sampling_ratio, int aligned, int rotated, int clockwise, const int* roi_level,
+                         int level, void* stream);
+/* multi-level FPN helpers (single_level_roi_extractor.py:35-54, base_roi_extractor.py:61-83):
+ * levels[k] = clamp(floor(log2(sqrt(w*h)/finest_scale + 1e-6)), 0, L-1); pt_roi_align_forward then skips
+ * RoIs whose roi_level != level (roi_level may be NULL: single level). */
+int pt_map_roi_levels(const float* rois, int K, int rotated, float finest_scale, int num_levels, int* levels,
+                      void* stream);
+int pt_roi_rescale(const float* rois, int K, int rotated, float factor_h, float factor_w, float* out, void* stream);
+
+/* ---- bag-feature FC (tcgen05 / TMA bf16 GEMM) --------------------------------------------------
+ * nn.Linear (+ReLU) of shared_fcs_reg / shared_fcs_bag,
+ *   HBB_TOD/mmdet/models/dense_heads/fcos_head_p2b_ts.py:1205-1206, 1246-1247, 1271-1272.
+ * C[M,N] = act(A[M,K] * B[N,K]^T + bias); A, B bf16 row-major (K contiguous); C bf16 or fp32.
+ * N % 256 == 0, K % 64 == 0.  workspace: pt_fc_gemm_workspace_bytes(), ZERO-filled once by the
+ * caller (the kernel leaves it zeroed); may be NULL (no split-K tail balancing). */
+long long pt_fc_gemm_workspace_bytes(int num_sms);
+int pt_fc_gemm_bf16(const void* A, long long lda, const void* B, long long ldb, const float* bias, void* C,
+                    long long ldc, int M, int N, int K, int relu, int out_f32, void* workspace,
+                    long long workspace_bytes, int num_sms, int allow_split, void* stream);
+
+/* weight preparation for the GEMM (FC1 column permutation c*49+bin -> bin*C+c, bf16 cast;
+ * x3: [hi | hi | lo] K segments for the fp32-emulation mode) */
+int pt_prep_fc1_weight(const float* w, void* out_bf16, int N, int C, int bins, long long ld, int x3, void* stream);
+int pt_cast_weight_bf16(const float* w, void* out_bf16, int N, int K, long long ld, int x3, void* stream);
+
+/* ---- MIL head tails ------------------------------------------------------------------------------
+ * pt_reg_decode: fc_reg + DeltaXYWHBBoxCoder.decode + DN_DIoULoss partial sums + IoU logs
+ *   (fcos_head_p2b_ts.py:1207-1223; core/bbox/coder/delta_xywh_bbox_coder.py:144-270;
+ *    models/losses/iou_loss.py:398-466).  sums: float[8], zeroed by the caller per stage.
+ * pt_cls_ins_heads: fc_cls / fc_ins (fcos_head_p2b_ts.py:1249, :1273).
+ * pt_score_select: mil_bag_training's positive term + mil_bag_selection(_single)
+ *   (fcos_head_p2b_ts.py:1092-1180); top-k replays ATen's CPU tie rule.
+ *   pseudo / merged_pts / sums may be NULL (no beta blend / no centres / no loss accumulation).
+ * pt_neg_loss: negative-bag term (:1169-1179).  pt_finalize_losses -> out[5] =
+ *   {scale_bbox*loss_mil_bbox, scale_bags*loss_mil_bags, coarse_bags_iou, refine_bags_iou, num_sample};
+ *   the scales are the detector's alpha (fcos_p2b_teacher_student.py:460-461). */
+int pt_reg_decode(const void* H, int h_f32, long long ldh, int D, const float* Wreg, const float* breg,
+                  const float* bag_rois, const unsigned char* valid, const float* ref_boxes,
+                  const float* real_boxes, int U, int K, float max_w, float max_h, float wh_ratio_clip,
+                  float hyper, float eps, float* out_rois, float* out_deltas, float* iou_target, float* sums,
+                  void* stream);
+int pt_cls_ins_heads(const void* H, int h_f32, long long ldh, int D, const float* Wcls, const float* bcls,
+                     const float* Wins, const float* bins, int C, int M, float* cls, float* ins, void* stream);
+int pt_score_select(const float* cls, const float* ins, const unsigned char* valid, const float* bag_rois,
+                    const long long* labels, const float* pseudo, const float* img_wh, int B, int G, int U1,
+                    int U2, int C, int topk, float beta, float* merged, float* merged_pts, int* sel_idx,
+                    float* sel_score, float* sums, void* stream);
+int pt_neg_loss(const float* neg_cls, const unsigned char* weight, int n, int C, float* sums, void* stream);
+int pt_finalize_losses(const float* sums, int K, int has_neg, float scale_bbox, float scale_bags, float* out,
+                       void* stream);
+/* fp32 [M,N] -> bf16 [M,3N] = [hi | lo | hi]: activation operand of the fp32-emulation (bf16x3) GEMM */
+int pt_split_bf16x3(const float* in, void* out_bf16, long long M, int N, void* stream);
+/* mean aligned IoU of n pairs: the coarse_bboxes_iou / stage{s}_refine_bboxes_iou logs of
+ * HBB_TOD/mmdet/models/detectors/fcos_p2b_teacher_student.py:436-438, :457-459 */
+int pt_aligned_iou_mean(const float* a, int lda, const float* b, int ldb, int n, float* out, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PTB200_H_ */

@@ -33,5 +33,11 @@ def load():
     if _LIB is None:
         build()
         _LIB = ctypes.CDLL(_SO)
-        _LIB.oracle_single_iou_rotated.restype = ctypes.c_float
+        vp, i, l, f = ctypes.c_void_p, ctypes.c_int, ctypes.c_long, ctypes.c_float
+        _LIB.oracle_single_iou_rotated.restype = f
+        _LIB.oracle_single_iou_rotated.argtypes = [vp, vp, i]
+        _LIB.oracle_box_iou_rotated.argtypes = [vp, vp, vp, l, l, i, i]
+        _LIB.oracle_nms_rotated.argtypes = [vp, vp, vp, l, f]
+        _LIB.oracle_roi_align.argtypes = [vp, vp, vp, i, i, i, i, l, i, f, i, i]
+        _LIB.oracle_roi_align_rotated.argtypes = [vp, vp, vp, i, i, i, i, l, i, f, i, i, i]
     return _LIB

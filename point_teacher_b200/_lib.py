@@ -1,0 +1,76 @@
+"""ctypes binding of the C-ABI library (include/ptb200.h).  There is NO fallback: if the
+library is missing or a call fails the error is raised immediately."""
+import ctypes
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+SO_PATH = os.path.join(_HERE, "_C", "libptb200.so")
+
+c_void_p, c_int, c_ll, c_float = ctypes.c_void_p, ctypes.c_int, ctypes.c_longlong, ctypes.c_float
+c_fp = ctypes.POINTER(ctypes.c_float)
+
+# name -> (restype, argtypes); must list every symbol include/ptb200.h declares
+SIGNATURES = {
+    "pt_last_error": (ctypes.c_char_p, []),
+    "pt_abi_version": (c_int, []),
+    "pt_build_arch": (ctypes.c_char_p, []),
+    "pt_bag_gen": (c_int, [c_void_p, c_ll, c_void_p, c_int, c_fp, c_int, c_fp, c_int, c_float, c_void_p,
+                           c_void_p, c_void_p]),
+    "pt_neg_weight": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_int, c_void_p, c_void_p]),
+    "pt_bbox_overlaps": (c_int, [c_void_p, c_int, c_void_p, c_int, c_ll, c_ll, c_int, c_int, c_float, c_void_p,
+                                 c_void_p]),
+    "pt_nchw_to_nhwc": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p]),
+    "pt_roi_align_forward": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_ll, c_int, c_int, c_int, c_int, c_int,
+                                     c_int, c_int, c_float, c_int, c_int, c_int, c_int, c_void_p, c_int, c_void_p]),
+    "pt_map_roi_levels": (c_int, [c_void_p, c_int, c_int, c_float, c_int, c_void_p, c_void_p]),
+    "pt_roi_rescale": (c_int, [c_void_p, c_int, c_int, c_float, c_float, c_void_p, c_void_p]),
+    "pt_fc_gemm_workspace_bytes": (c_ll, [c_int]),
+    "pt_fc_gemm_bf16": (c_int, [c_void_p, c_ll, c_void_p, c_ll, c_void_p, c_void_p, c_ll, c_int, c_int, c_int,
+                                c_int, c_int, c_void_p, c_ll, c_int, c_int, c_void_p]),
+    "pt_prep_fc1_weight": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_ll, c_int, c_void_p]),
+    "pt_cast_weight_bf16": (c_int, [c_void_p, c_void_p, c_int, c_int, c_ll, c_int, c_void_p]),
+    "pt_reg_decode": (c_int, [c_void_p, c_int, c_ll, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+                              c_void_p, c_int, c_int, c_float, c_float, c_float, c_float, c_float, c_void_p,
+                              c_void_p, c_void_p, c_void_p, c_void_p]),
+    "pt_cls_ins_heads": (c_int, [c_void_p, c_int, c_ll, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int,
+                                 c_void_p, c_void_p, c_void_p]),
+    "pt_score_select": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int,
+                                c_int, c_int, c_int, c_int, c_float, c_void_p, c_void_p, c_void_p, c_void_p,
+                                c_void_p, c_void_p]),
+    "pt_neg_loss": (c_int, [c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p]),
+    "pt_finalize_losses": (c_int, [c_void_p, c_int, c_int, c_float, c_float, c_void_p, c_void_p]),
+    "pt_split_bf16x3": (c_int, [c_void_p, c_void_p, c_ll, c_int, c_void_p]),
+    "pt_aligned_iou_mean": (c_int, [c_void_p, c_int, c_void_p, c_int, c_int, c_void_p, c_void_p]),
+}
+
+_LIB = None
+
+
+class PTB200Error(RuntimeError):
+    pass
+
+
+def load():
+    """Load libptb200.so; raises if it has not been built (python -m point_teacher_b200.build)."""
+    global _LIB
+    if _LIB is not None:
+        return _LIB
+    if not os.path.exists(SO_PATH):
+        raise PTB200Error(
+            f"{SO_PATH} is missing: build it with `python -m point_teacher_b200.build` "
+            "(nvcc, sm_100a).  There is no CPU / PyTorch fallback for this path.")
+    lib = ctypes.CDLL(SO_PATH)
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(lib, name)  # AttributeError if the .so does not export a declared symbol
+        fn.restype = res
+        fn.argtypes = args
+    _LIB = lib
+    return lib
+
+
+def call(name, *args):
+    lib = load()
+    rc = getattr(lib, name)(*args)
+    if rc != 0:
+        raise PTB200Error(f"{name} failed (code {rc}): {lib.pt_last_error().decode()}")
+    return rc

@@ -1,0 +1,394 @@
+// RoIAlign / RoIAlignRotated forward for sm_100a: NHWC gathers, one warp per (RoI, output row).
+//
+// Replaces mmcv.ops.RoIAlign(output_size=7, sampling_ratio=0, pool_mode='avg', aligned=True) and
+// mmcv.ops.RoIAlignRotated(output_size=7, sampling_ratio=2, aligned=True, clockwise=True) as reached through
+//   HBB_TOD/mmdet/models/roi_heads/roi_extractors/base_roi_extractor.py:50-59 (layer construction)
+//   HBB_TOD/mmdet/models/roi_heads/roi_extractors/single_level_roi_extractor.py:56-114
+//   OBB_TOD/mmrotate/models/roi_heads/roi_extractors/rotate_single_level_roi_extractor.py:90-167
+//
+// Access pattern: the feature map is transposed once per step to NHWC so that the 256 channels of one pixel
+// are one contiguous 1 KB (fp32) / 512 B (bf16) line; a lane owns 8 consecutive channels (16/32-byte vector
+// loads, 16-byte bf16 stores).  For the horizontal op a warp sweeps one output row left to right, keeps the
+// two current feature columns (already interpolated in y) in registers and only loads a new column when the
+// sample crosses a pixel boundary -- tiny objects (2x2 feature pixels) touch ~3 columns for 7 bins.
+// Sample coordinates use non-contracted fp32 arithmetic in the reference's operation order so the adaptive
+// grid size and the border rule are decided identically.
+#include "common.cuh"
+
+namespace ptb {
+
+constexpr int P7 = 7;
+
+// --------------------------------------------------------------------------------- NCHW -> NHWC
+template <typename TOut>
+__global__ void nchw_to_nhwc_kernel(const float* __restrict__ in, TOut* __restrict__ out, int C, int HW) {
+  __shared__ float tile[32][33];
+  const int b = blockIdx.z;
+  const int c0 = blockIdx.y * 32, p0 = blockIdx.x * 32;
+  const float* src = in + (size_t)b * C * HW;
+  TOut* dst = out + (size_t)b * C * HW;
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    int c = c0 + i, p = p0 + threadIdx.x;
+    tile[i][threadIdx.x] = (c < C && p < HW) ? src[(size_t)c * HW + p] : 0.f;
+  }
+  __syncthreads();
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    int p = p0 + i, c = c0 + threadIdx.x;
+    if (c < C && p < HW) dst[(size_t)p * C + c] = (TOut)tile[threadIdx.x][i];
+  }
+}
+
+// --------------------------------------------------------------------------------- helpers
+struct F8 { float v[8]; };
+
+__device__ __forceinline__ F8 load8(const float* p) {
+  F8 r;
+  float4 a = __ldg(reinterpret_cast<const float4*>(p)), b = __ldg(reinterpret_cast<const float4*>(p) + 1);
+  r.v[0] = a.x; r.v[1] = a.y; r.v[2] = a.z; r.v[3] = a.w; r.v[4] = b.x; r.v[5] = b.y; r.v[6] = b.z; r.v[7] = b.w;
+  return r;
+}
+__device__ __forceinline__ F8 load8(const __nv_bfloat16* p) {
+  F8 r;
+  uint4 u = __ldg(reinterpret_cast<const uint4*>(p));
+  const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+  for (int i = 0; i < 4; i++) {
+    r.v[2 * i] = __uint_as_float(w[i] << 16);
+    r.v[2 * i + 1] = __uint_as_float(w[i] & 0xffff0000u);
+  }
+  return r;
+}
+
+// one axis of the Detectron2 bilinear rule; returns false when the sample is outside [-1, size]
+__device__ __forceinline__ bool axis_setup(float v, int size, int& lo, int& hi, float& l, float& h) {
+  if (v < -1.0f || v > (float)size) return false;
+  if (v <= 0.f) v = 0.f;
+  lo = (int)v;
+  if (lo >= size - 1) { hi = lo = size - 1; v = (float)lo; } else hi = lo + 1;
+  l = fsub(v, (float)lo);
+  h = fsub(1.0f, l);
+  return true;
+}
+
+enum { OUT_BF16_BINMAJOR = 0, OUT_F32_NCHW = 1, OUT_BF16X3_BINMAJOR = 2 };
+
+template <int MODE>
+__device__ __forceinline__ void store_bins(void* out, long long ld_out, int roi, int ph, int C, int c0,
+                                           const float (&acc)[P7][8], float inv_count, float* stage) {
+  if (MODE == OUT_F32_NCHW) {
+    // transposed staging: element (c, bin) at bin*(C+1) + (c%8)*(C/8) + c/8 (conflict-free both ways for C=256)
+#pragma unroll
+    for (int pw = 0; pw < P7; pw++) {
+      const int bin = ph * P7 + pw;
+#pragma unroll
+      for (int j = 0; j < 8; j++) {
+        const int c = c0 + j;
+        stage[bin * (C + 1) + (c & 7) * (C >> 3) + (c >> 3)] = acc[pw][j] * inv_count;
+      }
+    }
+  } else {
+    __nv_bfloat16* row = reinterpret_cast<__nv_bfloat16*>(out) + (size_t)roi * ld_out;
+    const int seg = P7 * P7 * C;
+#pragma unroll
+    for (int pw = 0; pw < P7; pw++) {
+      float v[8];
+#pragma unroll
+      for (int j = 0; j < 8; j++) v[j] = acc[pw][j] * inv_count;
+      const size_t o = (size_t)(ph * P7 + pw) * C + c0;
+      uint4 hi = make_uint4(pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]), pack_bf16(v[4], v[5]), pack_bf16(v[6], v[7]));
+      *reinterpret_cast<uint4*>(row + o) = hi;
+      if (MODE == OUT_BF16X3_BINMAJOR) {
+        // fp32 emulation operand [hi | lo | hi]: A*W ~= hi*Whi + lo*Whi + hi*Wlo
+        float l[8];
+#pragma unroll
+        for (int j = 0; j < 8; j++) l[j] = v[j] - __bfloat162float(__float2bfloat16_rn(v[j]));
+        uint4 lo = make_uint4(pack_bf16(l[0], l[1]), pack_bf16(l[2], l[3]), pack_bf16(l[4], l[5]), pack_bf16(l[6], l[7]));
+        *reinterpret_cast<uint4*>(row + seg + o) = lo;
+        *reinterpret_cast<uint4*>(row + 2 * seg + o) = hi;
+      }
+    }
+  }
+}
+
+template <int MODE>
+__device__ __forceinline__ void flush_stage(float* out, int roi, int C, const float* stage) {
+  // coalesced write of one RoI's (C, 7, 7) block from the transposed smem staging
+  const int n = C * P7 * P7;
+  float* dst = out + (size_t)roi * n;
+  for (int o = threadIdx.x * 4; o < n; o += blockDim.x * 4) {
+    float v[4];
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+      const int c = (o + i) / (P7 * P7), bin = (o + i) - c * (P7 * P7);
+      v[i] = stage[bin * (C + 1) + (c & 7) * (C >> 3) + (c >> 3)];
+    }
+    *reinterpret_cast<float4*>(dst + o) = make_float4(v[0], v[1], v[2], v[3]);
+  }
+}
+
+// --------------------------------------------------------------------------------- horizontal RoIAlign
+template <typename TIn, int MODE>
+__global__ void __launch_bounds__(P7 * 32, 2)
+roi_align_fwd_kernel(const TIn* __restrict__ feat, const float* __restrict__ rois, void* __restrict__ out,
+                     long long ld_out, int K, int B, int C, int H, int W, float scale, int sampling_ratio,
+                     int aligned, const int* __restrict__ roi_level, int level) {
+  extern __shared__ float stage[];
+  const int ph = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const float off = aligned ? 0.5f : 0.f;
+  for (int roi = blockIdx.x; roi < K; roi += gridDim.x) {
+    if (roi_level != nullptr && roi_level[roi] != level) continue;  // multi-level FPN: other level's RoI
+    const float* r = rois + (size_t)roi * 5;
+    const int b = (int)__ldg(r);
+    const float x1 = fsub(fmul(__ldg(r + 1), scale), off), y1 = fsub(fmul(__ldg(r + 2), scale), off);
+    const float x2 = fsub(fmul(__ldg(r + 3), scale), off), y2 = fsub(fmul(__ldg(r + 4), scale), off);
+    float rw = fsub(x2, x1), rh = fsub(y2, y1);
+    if (!aligned) { rw = fmaxf(rw, 1.f); rh = fmaxf(rh, 1.f); }
+    const float bh = fdiv(rh, (float)P7), bw = fdiv(rw, (float)P7);
+    const int gh = sampling_ratio > 0 ? sampling_ratio : (int)ceilf(bh);
+    const int gw = sampling_ratio > 0 ? sampling_ratio : (int)ceilf(bw);
+    const int cnt = gh * gw > 1 ? gh * gw : 1;
+    const float inv_count = 1.0f / (float)cnt;
+    const bool b_ok = b >= 0 && b < B;
+    const TIn* fb = feat + (size_t)(b_ok ? b : 0) * H * W * C;
+    const float ybase = fadd(y1, fmul((float)ph, bh));
+
+    for (int c0 = lane * 8; c0 < C; c0 += 256) {
+      float acc[P7][8];
+#pragma unroll
+      for (int pw = 0; pw < P7; pw++)
+#pragma unroll
+        for (int j = 0; j < 8; j++) acc[pw][j] = 0.f;
+
+      for (int iy = 0; iy < gh && b_ok; iy++) {
+        const float y = fadd(ybase, fdiv(fmul((float)iy + .5f, bh), (float)gh));
+        int yl, yh; float ly, hy;
+        if (!axis_setup(y, H, yl, yh, ly, hy)) continue;
+        const TIn* row_lo = fb + (size_t)yl * W * C + c0;
+        const TIn* row_hi = fb + (size_t)yh * W * C + c0;
+        int i0 = -1, i1 = -1;   // cached feature columns (already blended in y)
+        float t0[8], t1[8];
+#pragma unroll
+        for (int pw = 0; pw < P7; pw++) {
+          const float xb = fadd(x1, fmul((float)pw, bw));
+          for (int ix = 0; ix < gw; ix++) {
+            const float x = fadd(xb, fdiv(fmul((float)ix + .5f, bw), (float)gw));
+            int xl, xh; float lx, hx;
+            if (!axis_setup(x, W, xl, xh, lx, hx)) continue;
+            if (xl != i0) {
+              if (xl == i1) {
+#pragma unroll
+                for (int j = 0; j < 8; j++) t0[j] = t1[j];
+              } else {
+                F8 a = load8(row_lo + (size_t)xl * C), c = load8(row_hi + (size_t)xl * C);
+#pragma unroll
+                for (int j = 0; j < 8; j++) t0[j] = hy * a.v[j] + ly * c.v[j];
+              }
+              i0 = xl;
+            }
+            if (xh != i1) {
+              if (xh == i0) {
+#pragma unroll
+                for (int j = 0; j < 8; j++) t1[j] = t0[j];
+              } else {
+                F8 a = load8(row_lo + (size_t)xh * C), c = load8(row_hi + (size_t)xh * C);
+#pragma unroll
+                for (int j = 0; j < 8; j++) t1[j] = hy * a.v[j] + ly * c.v[j];
+              }
+              i1 = xh;
+            }
+#pragma unroll
+            for (int j = 0; j < 8; j++) acc[pw][j] += hx * t0[j] + lx * t1[j];
+          }
+        }
+      }
+      store_bins<MODE>(out, ld_out, roi, ph, C, c0, acc, inv_count, stage);
+    }
+    if (MODE == OUT_F32_NCHW) {
+      __syncthreads();
+      flush_stage<MODE>(reinterpret_cast<float*>(out), roi, C, stage);
+      __syncthreads();
+    }
+  }
+}
+
+// --------------------------------------------------------------------------------- rotated RoIAlign
+template <typename TIn, int MODE>
+__global__ void __launch_bounds__(P7 * 32, 2)
+roi_align_rotated_fwd_kernel(const TIn* __restrict__ feat, const float* __restrict__ rois, void* __restrict__ out,
+                             long long ld_out, int K, int B, int C, int H, int W, float scale,
+                             int sampling_ratio, int aligned, int clockwise,
+                             const int* __restrict__ roi_level, int level) {
+  extern __shared__ float stage[];
+  const int ph = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const float off = aligned ? 0.5f : 0.f;
+  for (int roi = blockIdx.x; roi < K; roi += gridDim.x) {
+    if (roi_level != nullptr && roi_level[roi] != level) continue;
+    const float* r = rois + (size_t)roi * 6;
+    const int b = (int)__ldg(r);
+    const float cx = fsub(fmul(__ldg(r + 1), scale), off), cy = fsub(fmul(__ldg(r + 2), scale), off);
+    float rw = fmul(__ldg(r + 3), scale), rh = fmul(__ldg(r + 4), scale);
+    float theta = __ldg(r + 5);
+    if (clockwise) theta = -theta;
+    if (!aligned) { rw = fmaxf(rw, 1.f); rh = fmaxf(rh, 1.f); }
+    const float bh = fdiv(rh, (float)P7), bw = fdiv(rw, (float)P7);
+    const int gh = sampling_ratio > 0 ? sampling_ratio : (int)ceilf(bh);
+    const int gw = sampling_ratio > 0 ? sampling_ratio : (int)ceilf(bw);
+    const float sh = fdiv(-rh, 2.0f), sw = fdiv(-rw, 2.0f);
+    const float ct = cosf(theta), st = sinf(theta);
+    const int cnt = gh * gw > 1 ? gh * gw : 1;
+    const float inv_count = 1.0f / (float)cnt;
+    const bool b_ok = b >= 0 && b < B;
+    const TIn* fb = feat + (size_t)(b_ok ? b : 0) * H * W * C;
+
+    for (int c0 = lane * 8; c0 < C; c0 += 256) {
+      float acc[P7][8];
+#pragma unroll
+      for (int pw = 0; pw < P7; pw++)
+#pragma unroll
+        for (int j = 0; j < 8; j++) acc[pw][j] = 0.f;
+      for (int iy = 0; iy < gh && b_ok; iy++) {
+        const float yy = fadd(fadd(sh, fmul((float)ph, bh)), fdiv(fmul((float)iy + .5f, bh), (float)gh));
+#pragma unroll
+        for (int pw = 0; pw < P7; pw++) {
+          const float xb = fadd(sw, fmul((float)pw, bw));
+          for (int ix = 0; ix < gw; ix++) {
+            const float xx = fadd(xb, fdiv(fmul((float)ix + .5f, bw), (float)gw));
+            const float y = fadd(fsub(fmul(yy, ct), fmul(xx, st)), cy);
+            const float x = fadd(fadd(fmul(yy, st), fmul(xx, ct)), cx);
+            int yl, yh, xl, xh; float ly, hy, lx, hx;
+            if (y < -1.0f || y > (float)H || x < -1.0f || x > (float)W) continue;
+            axis_setup(y, H, yl, yh, ly, hy);
+            axis_setup(x, W, xl, xh, lx, hx);
+            const float w1 = hy * hx, w2 = hy * lx, w3 = ly * hx, w4 = ly * lx;
+            F8 f1 = load8(fb + ((size_t)yl * W + xl) * C + c0), f2 = load8(fb + ((size_t)yl * W + xh) * C + c0);
+            F8 f3 = load8(fb + ((size_t)yh * W + xl) * C + c0), f4 = load8(fb + ((size_t)yh * W + xh) * C + c0);
+#pragma unroll
+            for (int j = 0; j < 8; j++) acc[pw][j] += w1 * f1.v[j] + w2 * f2.v[j] + w3 * f3.v[j] + w4 * f4.v[j];
+          }
+        }
+      }
+      store_bins<MODE>(out, ld_out, roi, ph, C, c0, acc, inv_count, stage);
+    }
+    if (MODE == OUT_F32_NCHW) {
+      __syncthreads();
+      flush_stage<MODE>(reinterpret_cast<float*>(out), roi, C, stage);
+      __syncthreads();
+    }
+  }
+}
+
+// FPN level of each RoI: clamp(floor(log2(sqrt(w*h)/finest + 1e-6)), 0, L-1)
+// (single_level_roi_extractor.py:35-54; rotated: sqrt(w*h) of columns 3,4, rotate_single_level_roi_extractor.py:84)
+__global__ void map_roi_levels_kernel(const float* __restrict__ rois, int K, int rotated, float finest, int L,
+                                      int* __restrict__ lvl) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= K) return;
+  const float* r = rois + (size_t)i * (rotated ? 6 : 5);
+  const float area = rotated ? fmul(r[3], r[4]) : fmul(fsub(r[3], r[1]), fsub(r[4], r[2]));
+  const float scale = sqrtf(area);
+  float t = floorf(log2f(fadd(fdiv(scale, finest), 1e-6f)));
+  t = fminf(fmaxf(t, 0.f), (float)(L - 1));   // NaN (negative area) clamps like torch: stays NaN -> long cast
+  lvl[i] = (t == t) ? (int)t : 0;
+}
+
+// roi_rescale (base_roi_extractor.py:61-83; rotated: rotate_single_level_roi_extractor.py:150-167)
+__global__ void roi_rescale_kernel(const float* __restrict__ rois, int K, int rotated, float fh, float fw,
+                                   float* __restrict__ out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= K) return;
+  if (rotated) {
+    const float* r = rois + (size_t)i * 6; float* o = out + (size_t)i * 6;
+    o[0] = r[0]; o[1] = r[1]; o[2] = r[2]; o[3] = fmul(fw, r[3]); o[4] = fmul(fh, r[4]); o[5] = r[5];
+  } else {
+    const float* r = rois + (size_t)i * 5; float* o = out + (size_t)i * 5;
+    const float cx = fmul(fadd(r[1], r[3]), 0.5f), cy = fmul(fadd(r[2], r[4]), 0.5f);
+    const float nw = fmul(fsub(r[3], r[1]), fw), nh = fmul(fsub(r[4], r[2]), fh);
+    o[0] = r[0]; o[1] = fsub(cx, fmul(nw, 0.5f)); o[2] = fsub(cy, fmul(nh, 0.5f));
+    o[3] = fadd(cx, fmul(nw, 0.5f)); o[4] = fadd(cy, fmul(nh, 0.5f));
+  }
+}
+
+template <typename TIn, int MODE>
+static int launch_fwd(bool rotated, const void* feat, const float* rois, void* out, long long ld_out, int K, int B,
+                      int C, int H, int W, float scale, int sampling_ratio, int aligned, int clockwise,
+                      const int* roi_level, int level, cudaStream_t stream) {
+  size_t smem = MODE == OUT_F32_NCHW ? (size_t)P7 * P7 * (C + 1) * sizeof(float) : 0;
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  int grid = K < sms * 8 ? K : sms * 8;
+  if (rotated) {
+    auto kern = roi_align_rotated_fwd_kernel<TIn, MODE>;
+    if (smem > 48 * 1024) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    kern<<<grid, P7 * 32, smem, stream>>>(reinterpret_cast<const TIn*>(feat), rois, out, ld_out, K, B, C, H, W,
+                                           scale, sampling_ratio, aligned, clockwise, roi_level, level);
+  } else {
+    auto kern = roi_align_fwd_kernel<TIn, MODE>;
+    if (smem > 48 * 1024) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    kern<<<grid, P7 * 32, smem, stream>>>(reinterpret_cast<const TIn*>(feat), rois, out, ld_out, K, B, C, H, W,
+                                           scale, sampling_ratio, aligned, roi_level, level);
+  }
+  return check_launch(rotated ? "roi_align_rotated_fwd_kernel" : "roi_align_fwd_kernel");
+}
+
+}  // namespace ptb
+
+using namespace ptb;
+
+extern "C" int pt_nchw_to_nhwc(const float* in, void* out, int B, int C, int H, int W, int out_bf16, void* stream) {
+  if (B <= 0 || C <= 0 || H <= 0 || W <= 0) return PT_OK;
+  const int HW = H * W;
+  dim3 grid((HW + 31) / 32, (C + 31) / 32, B), block(32, 8);
+  if (out_bf16)
+    nchw_to_nhwc_kernel<__nv_bfloat16><<<grid, block, 0, (cudaStream_t)stream>>>(in, (__nv_bfloat16*)out, C, HW);
+  else
+    nchw_to_nhwc_kernel<float><<<grid, block, 0, (cudaStream_t)stream>>>(in, (float*)out, C, HW);
+  return check_launch("nchw_to_nhwc_kernel");
+}
+
+// feat: NHWC [B,H,W,C] fp32 (feat_bf16=0) or bf16 (=1).  rois: [K,5] (b,x1,y1,x2,y2) or, rotated, [K,6]
+// (b,cx,cy,w,h,theta).  out_mode 0: bf16 [K, ld_out] with k = (ph*7+pw)*C + c;  1: fp32 [K,C,7,7];
+// 2: bf16 [K, ld_out] three segments [hi | lo | hi] of 49*C each.
+extern "C" int pt_roi_align_forward(const void* feat, int feat_bf16, const float* rois, void* out, long long ld_out,
+                                    int out_mode, int K, int B, int C, int H, int W, int pooled, float spatial_scale,
+                                    int sampling_ratio, int aligned, int rotated, int clockwise,
+                                    const int* roi_level, int level, void* stream) {
+  if (K <= 0) return PT_OK;
+  if (pooled != P7) { set_error("pt_roi_align_forward: only output_size=7 is built (got %d)", pooled); return PT_ERR_UNSUPPORTED; }
+  if (C % 8 != 0) { set_error("pt_roi_align_forward: C must be a multiple of 8 (got %d)", C); return PT_ERR_ARG; }
+  if (out_mode == OUT_F32_NCHW && C % 8 != 0) return PT_ERR_ARG;
+  if (out_mode != OUT_F32_NCHW) {
+    const long long need = (out_mode == OUT_BF16X3_BINMAJOR ? 3LL : 1LL) * P7 * P7 * C;
+    if (ld_out < need || (ld_out % 8) != 0) { set_error("pt_roi_align_forward: ld_out %lld too small / unaligned", ld_out); return PT_ERR_ARG; }
+  }
+  cudaStream_t s = (cudaStream_t)stream;
+  const bool rot = rotated != 0;
+#define PT_DISPATCH(T, M) return launch_fwd<T, M>(rot, feat, rois, out, ld_out, K, B, C, H, W, spatial_scale, sampling_ratio, aligned, clockwise, roi_level, level, s)
+  if (feat_bf16) {
+    if (out_mode == OUT_BF16_BINMAJOR) PT_DISPATCH(__nv_bfloat16, OUT_BF16_BINMAJOR);
+    if (out_mode == OUT_F32_NCHW) PT_DISPATCH(__nv_bfloat16, OUT_F32_NCHW);
+    if (out_mode == OUT_BF16X3_BINMAJOR) PT_DISPATCH(__nv_bfloat16, OUT_BF16X3_BINMAJOR);
+  } else {
+    if (out_mode == OUT_BF16_BINMAJOR) PT_DISPATCH(float, OUT_BF16_BINMAJOR);
+    if (out_mode == OUT_F32_NCHW) PT_DISPATCH(float, OUT_F32_NCHW);
+    if (out_mode == OUT_BF16X3_BINMAJOR) PT_DISPATCH(float, OUT_BF16X3_BINMAJOR);
+  }
+#undef PT_DISPATCH
+  set_error("pt_roi_align_forward: bad out_mode %d", out_mode);
+  return PT_ERR_ARG;
+}
+
+extern "C" int pt_map_roi_levels(const float* rois, int K, int rotated, float finest_scale, int num_levels,
+                                 int* levels, void* stream) {
+  if (K <= 0) return PT_OK;
+  map_roi_levels_kernel<<<(K + 255) / 256, 256, 0, (cudaStream_t)stream>>>(rois, K, rotated, finest_scale,
+                                                                           num_levels, levels);
+  return check_launch("map_roi_levels_kernel");
+}
+
+extern "C" int pt_roi_rescale(const float* rois, int K, int rotated, float factor_h, float factor_w, float* out,
+                              void* stream) {
+  if (K <= 0) return PT_OK;
+  roi_rescale_kernel<<<(K + 255) / 256, 256, 0, (cudaStream_t)stream>>>(rois, K, rotated, factor_h, factor_w, out);
+  return check_launch("roi_rescale_kernel");
+}

@@ -1,0 +1,277 @@
+"""Tensor-level wrappers over the C-ABI (include/ptb200.h).  PyTorch is used for device memory
+and streams only; every computation below is a hand-written sm_100a kernel.  Shape / dtype /
+device violations raise ``ValueError`` before anything is launched; a missing or failing
+library raises ``PTB200Error`` -- there is no CPU or eager fallback."""
+import ctypes
+
+import torch
+
+from . import _lib
+
+_f32, _bf16, _u8, _i32, _i64 = torch.float32, torch.bfloat16, torch.uint8, torch.int32, torch.int64
+
+
+def _stream():
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _chk(t, name, dtype=None, dim=None, last=None):
+    if not isinstance(t, torch.Tensor):
+        raise ValueError(f"{name}: expected a tensor")
+    if not t.is_cuda:
+        raise ValueError(f"{name}: expected a CUDA tensor (this path has no CPU fallback)")
+    if dtype is not None and t.dtype != dtype:
+        raise ValueError(f"{name}: expected dtype {dtype}, got {t.dtype}")
+    if dim is not None and t.dim() != dim:
+        raise ValueError(f"{name}: expected {dim} dims, got shape {tuple(t.shape)}")
+    if last is not None and t.shape[-1] != last:
+        raise ValueError(f"{name}: expected last dim {last}, got shape {tuple(t.shape)}")
+    if not t.is_contiguous():
+        raise ValueError(f"{name}: expected a contiguous tensor")
+    return t
+
+
+def _p(t):
+    return ctypes.c_void_p(t.data_ptr()) if t is not None else ctypes.c_void_p(0)
+
+
+def _farr(vals):
+    vals = [float(v) for v in vals]
+    return (ctypes.c_float * max(len(vals), 1))(*vals), len(vals)
+
+
+def num_sms():
+    return torch.cuda.get_device_properties(torch.cuda.current_device()).multi_processor_count
+
+
+# ------------------------------------------------------------------------------ bags
+def bag_gen(in_rois, img_wh, base_ratios, shake_ratio, min_scale):
+    """in_rois (G,5) -> (rois (G*U,5), valid (G*U,) uint8)."""
+    _chk(in_rois, "in_rois", _f32, 2, 5)
+    _chk(img_wh, "img_wh", _f32, 2, 2)
+    ratios, nr = _farr(base_ratios)
+    shake, ns = _farr(shake_ratio or [])
+    U = nr * nr * (1 + 4 * ns)
+    G = in_rois.shape[0]
+    out = torch.empty((G * U, 5), dtype=_f32, device=in_rois.device)
+    valid = torch.empty((G * U,), dtype=_u8, device=in_rois.device)
+    _lib.call("pt_bag_gen", _p(in_rois), G, _p(img_wh), img_wh.shape[0], ratios, nr, shake, ns, float(min_scale),
+              _p(out), _p(valid), _stream())
+    return out, valid
+
+
+def neg_weight(neg_rois, bag_rois, bag_offsets):
+    _chk(neg_rois, "neg_rois", _f32, 2, 5)
+    _chk(bag_rois, "bag_rois", _f32, 2, 5)
+    _chk(bag_offsets, "bag_offsets", _i32, 1)
+    w = torch.empty((neg_rois.shape[0],), dtype=_u8, device=neg_rois.device)
+    _lib.call("pt_neg_weight", _p(neg_rois), neg_rois.shape[0], _p(bag_rois), _p(bag_offsets),
+              bag_offsets.shape[0] - 1, _p(w), _stream())
+    return w
+
+
+_MODES = {"iou": 0, "iof": 1, "giou": 2}
+
+
+def bbox_overlaps(b1, b2, mode="iou", is_aligned=False, eps=1e-6):
+    if mode not in _MODES:
+        raise ValueError(f"Unsupported mode {mode}")
+    _chk(b1, "bboxes1", _f32, 2)
+    _chk(b2, "bboxes2", _f32, 2)
+    M, N = b1.shape[0], b2.shape[0]
+    if is_aligned and M != N:
+        raise ValueError("is_aligned requires the same number of boxes")
+    out = torch.empty((M,) if is_aligned else (M, N), dtype=_f32, device=b1.device)
+    if M * N == 0:
+        return out
+    if b1.shape[1] < 4 or b2.shape[1] < 4:
+        raise ValueError("boxes must have at least 4 columns")
+    _lib.call("pt_bbox_overlaps", _p(b1), b1.shape[1], _p(b2), b2.shape[1], M, N, _MODES[mode], int(is_aligned),
+              float(eps), _p(out), _stream())
+    return out
+
+
+# ------------------------------------------------------------------------------ RoIAlign
+def nchw_to_nhwc(x, out_dtype=_f32):
+    _chk(x, "feat", _f32, 4)
+    B, C, H, W = x.shape
+    out = torch.empty((B, H, W, C), dtype=out_dtype, device=x.device)
+    _lib.call("pt_nchw_to_nhwc", _p(x), _p(out), B, C, H, W, int(out_dtype == _bf16), _stream())
+    return out
+
+
+OUT_BF16_BINMAJOR, OUT_F32_NCHW, OUT_BF16X3_BINMAJOR = 0, 1, 2
+
+
+def roi_align_forward(feat_nhwc, rois, out_mode, spatial_scale, sampling_ratio=0, aligned=True, rotated=False,
+                      clockwise=True, pooled=7, out=None, rows=None, roi_level=None, level=0):
+    """feat_nhwc (B,H,W,C) fp32|bf16; rois (K,5) or rotated (K,6).  ``out``/``rows`` let the caller
+    hand in a (row-padded) GEMM operand buffer."""
+    if feat_nhwc.dtype not in (_f32, _bf16):
+        raise ValueError("feat must be fp32 or bf16")
+    _chk(feat_nhwc, "feat_nhwc", None, 4)
+    _chk(rois, "rois", _f32, 2, 6 if rotated else 5)
+    B, H, W, C = feat_nhwc.shape
+    K = rois.shape[0]
+    kcols = pooled * pooled * C
+    if out is None:
+        if out_mode == OUT_F32_NCHW:
+            out = torch.empty((K, C, pooled, pooled), dtype=_f32, device=rois.device)
+        else:
+            out = torch.empty((rows or K, kcols * (3 if out_mode == OUT_BF16X3_BINMAJOR else 1)), dtype=_bf16,
+                              device=rois.device)
+    ld = out.shape[1] if out_mode != OUT_F32_NCHW else 0
+    _lib.call("pt_roi_align_forward", _p(feat_nhwc), int(feat_nhwc.dtype == _bf16), _p(rois), _p(out), ld, out_mode,
+              K, B, C, H, W, pooled, float(spatial_scale), int(sampling_ratio), int(aligned), int(rotated),
+              int(clockwise), _p(roi_level), int(level), _stream())
+    return out
+
+
+def map_roi_levels(rois, num_levels, finest_scale=56, rotated=False):
+    _chk(rois, "rois", _f32, 2, 6 if rotated else 5)
+    lv = torch.empty((rois.shape[0],), dtype=_i32, device=rois.device)
+    _lib.call("pt_map_roi_levels", _p(rois), rois.shape[0], int(rotated), float(finest_scale), int(num_levels),
+              _p(lv), _stream())
+    return lv
+
+
+def roi_rescale(rois, factor, rotated=False):
+    _chk(rois, "rois", _f32, 2, 6 if rotated else 5)
+    fh, fw = (factor, factor) if not isinstance(factor, (tuple, list)) else factor
+    out = torch.empty_like(rois)
+    _lib.call("pt_roi_rescale", _p(rois), rois.shape[0], int(rotated), float(fh), float(fw), _p(out), _stream())
+    return out
+
+
+# ------------------------------------------------------------------------------ FC GEMM
+_WS = {}
+
+
+def gemm_workspace(device):
+    key = (device.index if device.index is not None else torch.cuda.current_device())
+    if key not in _WS:
+        n = _lib.load().pt_fc_gemm_workspace_bytes(num_sms())
+        _WS[key] = torch.zeros((n,), dtype=_u8, device=device)  # zeroed once; the kernel leaves it zeroed
+    return _WS[key]
+
+
+def fc_gemm(A, B, bias=None, relu=False, out_dtype=_bf16, M=None, out=None, allow_split=True):
+    """C[M,N] = act(A[M,K] @ B[N,K]^T + bias) on tcgen05 tensor cores; A, B bf16."""
+    _chk(A, "A", _bf16, 2)
+    _chk(B, "B", _bf16, 2)
+    if A.shape[1] != B.shape[1]:
+        raise ValueError(f"K mismatch: A {tuple(A.shape)} vs B {tuple(B.shape)}")
+    M = A.shape[0] if M is None else M
+    N, K = B.shape
+    if bias is not None:
+        _chk(bias, "bias", _f32, 1)
+        if bias.shape[0] != N:
+            raise ValueError("bias length must equal N")
+    if out is None:
+        out = torch.empty((A.shape[0], N), dtype=out_dtype, device=A.device)
+    ws = gemm_workspace(A.device)
+    _lib.call("pt_fc_gemm_bf16", _p(A), A.shape[1], _p(B), B.shape[1], _p(bias), _p(out), out.shape[1], M, N, K,
+              int(relu), int(out.dtype == _f32), _p(ws), ws.numel(), num_sms(), int(allow_split), _stream())
+    return out
+
+
+def prep_fc1_weight(w, C, bins=49, x3=False):
+    _chk(w, "fc1 weight", _f32, 2)
+    N, K = w.shape
+    if K != C * bins:
+        raise ValueError(f"fc1 weight has {K} inputs, expected {C}*{bins}")
+    out = torch.empty((N, K * (3 if x3 else 1)), dtype=_bf16, device=w.device)
+    _lib.call("pt_prep_fc1_weight", _p(w), _p(out), N, C, bins, out.shape[1], int(x3), _stream())
+    return out
+
+
+def cast_weight(w, x3=False):
+    _chk(w, "weight", _f32, 2)
+    N, K = w.shape
+    out = torch.empty((N, K * (3 if x3 else 1)), dtype=_bf16, device=w.device)
+    _lib.call("pt_cast_weight_bf16", _p(w), _p(out), N, K, out.shape[1], int(x3), _stream())
+    return out
+
+
+# ------------------------------------------------------------------------------ head tails
+def reg_decode(H, Wreg, breg, bag_rois, valid, ref_boxes, real_boxes, U, max_wh, sums, K=None, hyper=0.2,
+               eps=1e-6, wh_ratio_clip=16 / 1000, want_deltas=False, out_rois=None):
+    if H.dtype not in (_f32, _bf16):
+        raise ValueError("hidden must be fp32 or bf16")
+    _chk(H, "hidden", None, 2)
+    _chk(Wreg, "fc_reg.weight", _f32, 2)
+    _chk(bag_rois, "bag_rois", _f32, 2, 5)
+    K = bag_rois.shape[0] if K is None else K
+    dev = H.device
+    if out_rois is None:
+        out_rois = torch.empty((K, 5), dtype=_f32, device=dev)
+    else:
+        _chk(out_rois, "out_rois", _f32, 2, 5)
+        if out_rois.shape[0] < K:
+            raise ValueError("out_rois has fewer rows than K")
+    deltas = torch.empty((K, 4), dtype=_f32, device=dev) if want_deltas else None
+    iou_t = torch.empty((K,), dtype=_f32, device=dev)
+    _lib.call("pt_reg_decode", _p(H), int(H.dtype == _f32), H.shape[1], Wreg.shape[1], _p(Wreg), _p(breg),
+              _p(bag_rois), _p(valid), _p(ref_boxes), _p(real_boxes), U, K, float(max_wh[0]), float(max_wh[1]),
+              float(wh_ratio_clip), float(hyper), float(eps), _p(out_rois), _p(deltas), _p(iou_t), _p(sums),
+              _stream())
+    return out_rois, deltas, iou_t
+
+
+def cls_ins_heads(H, Wcls, bcls, Wins, bins, M=None):
+    _chk(H, "hidden", None, 2)
+    M = H.shape[0] if M is None else M
+    C = Wcls.shape[0]
+    cls = torch.empty((M, C), dtype=_f32, device=H.device)
+    ins = torch.empty((M, C), dtype=_f32, device=H.device)
+    _lib.call("pt_cls_ins_heads", _p(H), int(H.dtype == _f32), H.shape[1], Wcls.shape[1], _p(Wcls), _p(bcls),
+              _p(Wins), _p(bins), C, M, _p(cls), _p(ins), _stream())
+    return cls, ins
+
+
+def score_select(cls, ins, valid, bag_rois, labels, pseudo, img_wh, G, U1, U2, topk, beta, sums):
+    """Returns (merged (G,4), merged centres (G,2), selected idx (G,topk) int32, scores (G,topk))."""
+    _chk(cls, "cls", _f32, 2)
+    _chk(ins, "ins", _f32, 2)
+    _chk(labels, "labels", _i64, 1)
+    if pseudo is not None:
+        _chk(pseudo, "pseudo_boxes", _f32, 2, 4)
+    C = cls.shape[1]
+    dev = cls.device
+    merged = torch.empty((G, 4), dtype=_f32, device=dev)
+    pts = torch.empty((G, 2), dtype=_f32, device=dev)
+    idx = torch.empty((G, topk), dtype=_i32, device=dev)
+    sc = torch.empty((G, topk), dtype=_f32, device=dev)
+    _lib.call("pt_score_select", _p(cls), _p(ins), _p(valid), _p(bag_rois), _p(labels), _p(pseudo), _p(img_wh),
+              img_wh.shape[0], G, U1, U2, C, topk, float(beta), _p(merged), _p(pts), _p(idx), _p(sc), _p(sums),
+              _stream())
+    return merged, pts, idx, sc
+
+
+def neg_loss(neg_cls, weight, sums, n=None):
+    n = neg_cls.shape[0] if n is None else n
+    _lib.call("pt_neg_loss", _p(neg_cls), _p(weight), n, neg_cls.shape[1], _p(sums), _stream())
+
+
+def finalize_losses(sums, K, has_neg, scale_bbox=1.0, scale_bags=1.0):
+    out = torch.empty((5,), dtype=_f32, device=sums.device)
+    _lib.call("pt_finalize_losses", _p(sums), K, int(has_neg), float(scale_bbox), float(scale_bags), _p(out),
+              _stream())
+    return out
+
+
+def split_bf16x3(x):
+    _chk(x, "x", _f32, 2)
+    out = torch.empty((x.shape[0], 3 * x.shape[1]), dtype=_bf16, device=x.device)
+    _lib.call("pt_split_bf16x3", _p(x), _p(out), x.shape[0], x.shape[1], _stream())
+    return out
+
+
+def aligned_iou_mean(a, b):
+    _chk(a, "a", _f32, 2)
+    _chk(b, "b", _f32, 2)
+    if a.shape[0] != b.shape[0]:
+        raise ValueError("aligned IoU needs the same number of boxes")
+    out = torch.empty((1,), dtype=_f32, device=a.device)
+    _lib.call("pt_aligned_iou_mean", _p(a), a.shape[1], _p(b), b.shape[1], a.shape[0], _p(out), _stream())
+    return out[0]

@@ -1,0 +1,215 @@
+"""Kernel-level parity (B200): every CUDA kernel against the CPU oracle on the same seeded inputs.
+Bit-exact for geometry / validity / indices; 1e-3 relative (fp32) or 2e-2 (bf16) for features."""
+import math
+import os
+
+import pytest
+import torch
+
+from oracle import hbb, rotated
+from point_teacher_b200 import synth
+
+pytestmark = pytest.mark.gpu
+
+
+def _rel(a, b):
+    a, b = a.double().cpu(), b.double().cpu()
+    return ((a - b).abs().max() / b.abs().max().clamp_min(1e-12)).item()
+
+
+# ------------------------------------------------------------------------------ bags (bit-exact)
+@pytest.mark.parametrize("cfg_i,seed", [(0, 0), (1, 1)])
+def test_bag_gen_bit_exact(cuda, cfg_i, seed):
+    from point_teacher_b200 import proposals
+    d = synth.hbb_batch(seed=seed, gt_range=(40, 90))
+    for cfg in (synth.HBB_FINE_CFG[cfg_i], synth.HBB_EXT_CFG[cfg_i]):
+        ref_p, ref_v = hbb.fine_proposals(d["pseudo_boxes"], cfg, d["img_metas"])
+        got_p, got_v = proposals.fine_proposals_from_cfg([b.to(cuda) for b in d["pseudo_boxes"]], cfg, d["img_metas"])
+        for rp, rv, gp, gv in zip(ref_p, ref_v, got_p, got_v):
+            assert torch.equal(gp.cpu(), rp)
+            assert torch.equal(gv.cpu(), rv)
+
+
+def test_bag_gen_edge_boxes_and_validity(cuda):
+    from point_teacher_b200 import proposals
+    metas = [dict(img_shape=(800, 800, 3))]
+    boxes = [torch.tensor([[-30., -30., 10., 10.], [780., 790., 900., 830.], [5., 5., 5., 5.], [0., 0., 800., 800.],
+                           [100., 100., 3000., 3000.], [400., 400., 401., 403.]])]
+    cfg = synth.HBB_EXT_CFG[1]
+    rp, rv = hbb.fine_proposals(boxes, cfg, metas)
+    gp, gv = proposals.fine_proposals_from_cfg([boxes[0].to(cuda)], cfg, metas)
+    assert torch.equal(gp[0].cpu(), rp[0]) and torch.equal(gv[0].cpu(), rv[0])
+    assert 0 < int(rv[0].sum()) < rv[0].numel()
+
+
+def test_mil_gen_proposals_replication_and_neg_weights(cuda):
+    from point_teacher_b200 import proposals
+    d = synth.hbb_batch(seed=2, gt_range=(30, 60))
+    cfg = synth.HBB_FINE_CFG[0]
+    to = lambda l: [t.to(cuda) for t in l]  # noqa: E731
+    rp, rv, rr, rl = hbb.mil_gen_proposals(d["pseudo_points"], d["pseudo_boxes"], cfg, d["gt_boxes"], d["img_metas"])
+    gp, gv, gr, gl = proposals.MIL_gen_proposals_from_cfg(to(d["pseudo_points"]), to(d["pseudo_boxes"]), cfg,
+                                                          to(d["gt_boxes"]), d["img_metas"])
+    for a, b in zip(rr + rl, gr + gl):
+        assert torch.equal(b.cpu(), a)
+    rn, rw = hbb.gen_negative_proposals(d["pseudo_points"], cfg, rp, d["img_metas"], injected=d["neg_boxes"][0])
+    gn, gw = proposals.gen_negative_proposals(to(d["pseudo_points"]), cfg, gp, d["img_metas"],
+                                              neg_boxes=to(d["neg_boxes"][0]))
+    for a, b in zip(rw, gw):
+        assert torch.equal(b.cpu(), a)
+    assert 0 < int(torch.cat(rw).sum()) < torch.cat(rw).numel()
+
+
+def test_bbox_overlaps_bit_exact_and_golden(cuda, golden_dir):
+    from point_teacher_b200 import ops
+    g = torch.load(os.path.join(golden_dir, "bbox_overlaps.pt"))
+    gen = torch.Generator().manual_seed(7)
+    a = synth.make_boxes(gen, 37, (800, 800))
+    b = synth.jitter_boxes(gen, synth.make_boxes(gen, 53, (800, 800)))
+    a2 = synth.jitter_boxes(torch.Generator().manual_seed(8), a)
+    for mode in ("iou", "iof", "giou"):
+        assert torch.equal(ops.bbox_overlaps(a.to(cuda), b.to(cuda), mode).cpu(), g[mode])
+        assert torch.equal(ops.bbox_overlaps(a.to(cuda), a2.to(cuda), mode, True).cpu(), g[mode + "_aligned"])
+    assert ops.bbox_overlaps(a.to(cuda), b[:0].to(cuda)).shape == (37, 0)
+    kat1 = torch.tensor([[0., 0, 10, 10], [10, 10, 20, 20], [32, 32, 38, 42]], device=cuda)
+    kat2 = torch.tensor([[0., 0, 10, 20], [0, 10, 10, 19], [10, 10, 20, 20]], device=cuda)
+    assert torch.allclose(ops.bbox_overlaps(kat1, kat2, "giou", True).cpu(),
+                          torch.tensor([0.5, -0.05, -0.8214]), atol=1e-4)
+
+
+# ------------------------------------------------------------------------------ RoIAlign
+def _roi_inputs(seed, n, hw=(320, 320), C=256, B=2):
+    g = torch.Generator().manual_seed(seed)
+    x = torch.randn(B, C, hw[0] // 8, hw[1] // 8, generator=g)
+    boxes = synth.make_boxes(g, n, hw, median=14, hi=120)
+    boxes[:4] += torch.tensor([-30., -30., -30., -30.])
+    boxes[4:8] += torch.tensor([300., 290., 310., 300.])
+    boxes[8] = torch.tensor([50., 60., 40., 50.])            # negative width/height -> zeros
+    boxes[9] = torch.tensor([100., 100., 100., 100.])        # degenerate
+    boxes[10] = torch.tensor([0., 0., 320., 320.])           # whole image: 6x6 sampling grid
+    rois = torch.cat([torch.randint(0, B, (n, 1), generator=g).float(), boxes], 1)
+    return x, rois
+
+
+def test_roi_align_fp32_nchw_vs_torchvision_semantics(cuda):
+    from point_teacher_b200.roi_extractors import SingleRoIExtractor
+    x, rois = _roi_inputs(11, 300)
+    ext = SingleRoIExtractor(dict(type="RoIAlign", output_size=7), 256, [8]).to(cuda)
+    got = ext((x.to(cuda),), rois.to(cuda))
+    ref = hbb.single_roi_extract((x,), rois, [8])
+    assert got.shape == ref.shape == (300, 256, 7, 7)
+    assert _rel(got, ref) < 1e-3
+    assert (got.cpu() - ref).abs().max() < 2e-5 * 8
+    assert torch.count_nonzero(got[8]) == 0
+    # empty RoIs -> zeros (0, C, 7, 7), like single_level_roi_extractor.py:75-77
+    assert ext((x.to(cuda),), rois[:0].to(cuda)).shape == (0, 256, 7, 7)
+
+
+def test_roi_align_sampling_ratio2_and_small_channel_count(cuda):
+    from point_teacher_b200 import ops
+    x, rois = _roi_inputs(12, 64, C=16)
+    feat = ops.nchw_to_nhwc(x.to(cuda))
+    assert torch.equal(feat.cpu(), x.permute(0, 2, 3, 1).contiguous())
+    got = ops.roi_align_forward(feat, rois.to(cuda), ops.OUT_F32_NCHW, 0.125, sampling_ratio=2)
+    ref = rotated.roi_align(x, rois, 7, 0.125, 2, True)
+    assert _rel(got, ref) < 1e-3
+
+
+def test_roi_align_bf16_operand_layout(cuda):
+    from point_teacher_b200 import ops
+    x, rois = _roi_inputs(13, 200)
+    feat = ops.nchw_to_nhwc(x.to(cuda))
+    ref = hbb.single_roi_extract((x,), rois, [8])                       # (K, C, 7, 7)
+    ref_binmajor = ref.permute(0, 2, 3, 1).reshape(200, -1)             # k' = (ph*7+pw)*C + c
+    got = ops.roi_align_forward(feat, rois.to(cuda), ops.OUT_BF16_BINMAJOR, 0.125).float().cpu()
+    assert (got - ref_binmajor).abs().max() <= 2e-2 * ref_binmajor.abs().max()
+    x3 = ops.roi_align_forward(feat, rois.to(cuda), ops.OUT_BF16X3_BINMAJOR, 0.125).float().cpu()
+    hi, lo, hi2 = x3[:, :12544], x3[:, 12544:25088], x3[:, 25088:]
+    assert torch.equal(hi, hi2)
+    assert _rel(hi + lo, ref_binmajor) < 1e-3
+    # bf16 feature map input (2e-2 class)
+    featb = ops.nchw_to_nhwc(x.to(cuda), torch.bfloat16)
+    gotb = ops.roi_align_forward(featb, rois.to(cuda), ops.OUT_BF16_BINMAJOR, 0.125).float().cpu()
+    assert (gotb - ref_binmajor).abs().max() <= 2e-2 * ref_binmajor.abs().max()
+
+
+def test_roi_align_rotated_vs_oracle(cuda):
+    from point_teacher_b200.roi_extractors import RotatedSingleRoIExtractor
+    g = torch.Generator().manual_seed(14)
+    x = torch.randn(2, 256, 64, 64, generator=g)
+    boxes = synth.make_boxes(g, 150, (512, 512), median=20, hi=100)
+    c = hbb.xyxy_to_cxcywh(boxes)
+    th = torch.rand(150, 1, generator=g) * math.pi - math.pi / 2
+    rois = torch.cat([torch.randint(0, 2, (150, 1), generator=g).float(), c, th], 1)
+    rois[:3, 1:3] = torch.tensor([[2., 2.], [510., 5.], [256., 511.]])     # straddling the border
+    ext = RotatedSingleRoIExtractor(dict(type="RoIAlignRotated", out_size=7, sample_num=2, clockwise=True), 256,
+                                    [8]).to(cuda)
+    got = ext((x.to(cuda),), rois.to(cuda))
+    ref = rotated.roi_align_rotated(x, rois, 7, 0.125, 2, True, True)
+    assert _rel(got, ref) < 1e-3
+
+
+def test_multi_level_extractor_matches_oracle(cuda):
+    from point_teacher_b200.roi_extractors import SingleRoIExtractor
+    g = torch.Generator().manual_seed(15)
+    feats = [torch.randn(2, 256, 64 >> i, 64 >> i, generator=g) for i in range(3)]
+    boxes = synth.make_boxes(g, 120, (512, 512), median=90, sigma=1.0, lo=8, hi=500)
+    rois = torch.cat([torch.randint(0, 2, (120, 1), generator=g).float(), boxes], 1)
+    lv = hbb.map_roi_levels(rois, 3)
+    assert len(set(lv.tolist())) == 3
+    ext = SingleRoIExtractor(dict(type="RoIAlign", output_size=7), 256, [8, 16, 32]).to(cuda)
+    assert torch.equal(ext.map_roi_levels(rois.to(cuda), 3).cpu(), lv)
+    got = ext(tuple(f.to(cuda) for f in feats), rois.to(cuda))
+    ref = hbb.single_roi_extract(tuple(feats), rois, [8, 16, 32])
+    assert _rel(got, ref) < 1e-3
+    got2 = ext(tuple(f.to(cuda) for f in feats), rois.to(cuda), roi_scale_factor=1.3)
+    ref2 = hbb.single_roi_extract(tuple(feats), rois, [8, 16, 32], roi_scale_factor=1.3)
+    assert _rel(got2, ref2) < 1e-3
+
+
+# ------------------------------------------------------------------------------ tcgen05 GEMM
+@pytest.mark.parametrize("M,N,K,relu,f32,split", [
+    (128, 256, 64, False, True, False), (300, 256, 128, True, False, False), (1000, 1024, 1024, True, False, True),
+    (5400, 1024, 12544, True, False, True), (5400, 1024, 12544, True, False, False),
+    (4736, 1024, 1024, False, True, True), (77, 512, 3072, True, True, True)])
+def test_fc_gemm_vs_fp32_reference(cuda, M, N, K, relu, f32, split):
+    from point_teacher_b200 import ops
+    g = torch.Generator().manual_seed(M + N + K)
+    A = (torch.randn(M, K, generator=g)).to(torch.bfloat16)
+    B = (torch.randn(N, K, generator=g) * 0.05).to(torch.bfloat16)
+    bias = torch.randn(N, generator=g)
+    ref = A.float().to(cuda) @ B.float().to(cuda).t() + bias.to(cuda)     # fp32 reference of the same op
+    if relu:
+        ref = ref.relu()
+    for _ in range(2):   # second call checks the self-re-zeroing split-K workspace
+        out = ops.fc_gemm(A.to(cuda), B.to(cuda), bias.to(cuda), relu=relu,
+                          out_dtype=torch.float32 if f32 else torch.bfloat16, allow_split=split)
+        tol = 1e-3 if f32 else 2e-2                      # fp32 out: accumulation-order noise only
+        err = (out.float() - ref).abs().max().item()
+        assert err <= tol * ref.abs().max().item(), (err, ref.abs().max().item())
+    assert torch.count_nonzero(ops.gemm_workspace(cuda)) == 0
+
+
+def test_fc_gemm_rejects_bad_shapes(cuda):
+    from point_teacher_b200 import ops
+    from point_teacher_b200._lib import PTB200Error
+    A = torch.zeros(8, 64, dtype=torch.bfloat16, device=cuda)
+    with pytest.raises(PTB200Error):
+        ops.fc_gemm(A, torch.zeros(100, 64, dtype=torch.bfloat16, device=cuda))
+    with pytest.raises(ValueError):
+        ops.fc_gemm(A, torch.zeros(256, 128, dtype=torch.bfloat16, device=cuda))
+
+
+def test_weight_prep_layouts(cuda):
+    from point_teacher_b200 import ops
+    g = torch.Generator().manual_seed(21)
+    w = torch.randn(256, 256 * 49, generator=g) * 0.01
+    p = ops.prep_fc1_weight(w.to(cuda), 256).float().cpu()
+    ref = w.view(256, 256, 49).permute(0, 2, 1).reshape(256, -1)
+    assert torch.equal(p, ref.to(torch.bfloat16).float())
+    p3 = ops.prep_fc1_weight(w.to(cuda), 256, x3=True).float().cpu()
+    K = 12544
+    assert torch.equal(p3[:, :K], p3[:, K:2 * K])
+    assert _rel(p3[:, :K] + p3[:, 2 * K:], ref) < 1e-4
+    c3 = ops.cast_weight(w[:, :1024].contiguous().to(cuda), x3=True).float().cpu()
+    assert _rel(c3[:, :1024] + c3[:, 2048:], w[:, :1024]) < 1e-4

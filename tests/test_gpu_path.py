@@ -1,0 +1,161 @@
+"""End-to-end parity of the phase-2 MIL refinement path on a B200 against the CPU oracle (run live
+on the same seeded inputs) and against the golden vectors produced by the reference's own files."""
+import os
+
+import pytest
+import torch
+
+from oracle import hbb
+from point_teacher_b200 import synth
+
+pytestmark = pytest.mark.gpu
+
+SMALL = dict(batch=2, img_hw=(256, 256), gt_range=(6, 10), n_neg=20)
+
+
+def _make_head(cuda, P, stages, topk, precision):
+    from point_teacher_b200.mil_head import MILHead
+    head = MILHead(num_classes=P.num_classes, num_stages=stages, top_k=topk, precision=precision).to(cuda)
+    missing, unexpected = head.load_state_dict({k: v for k, v in P.state_dict().items()}, strict=False)
+    assert not unexpected
+    assert all(m.split(".")[0] in ("shared_fcs", "shared_fcs_refine", "fc_iou") for m in missing), missing
+    return head
+
+
+def _run_cuda(cuda, d, P, stages, topk, precision, alpha=(1.0, 1.0), cap=100):
+    from point_teacher_b200.refine import phase2_refine
+    head = _make_head(cuda, P, stages, topk, precision)
+    to = lambda l: [t.to(cuda) for t in l]  # noqa: E731
+    negs = [to(n) for n in d["neg_boxes"]]
+    with torch.no_grad():
+        out = phase2_refine(head, (d["feat"].to(cuda),), d["img_metas"], to(d["pseudo_boxes"]),
+                            to(d["pseudo_points"]), to(d["pseudo_labels"]), to(d["gt_boxes"]), synth.HBB_FINE_CFG,
+                            synth.HBB_EXT_CFG, num_stages=stages, num_training_burninstep2=cap, alpha=alpha,
+                            neg_boxes=negs)
+    torch.cuda.synchronize()
+    return out, head
+
+
+def _run_oracle(d, P, stages, topk, alpha=(1.0, 1.0), cap=100):
+    with torch.no_grad():
+        return hbb.phase2_refine(P, (d["feat"],), [d["stride"]], d["img_metas"], d["pseudo_boxes"],
+                                 d["pseudo_points"], d["pseudo_labels"], d["gt_boxes"], synth.HBB_FINE_CFG,
+                                 synth.HBB_EXT_CFG, num_stages=stages, cap=cap, alpha=alpha, topk=topk,
+                                 injected_negs=d["neg_boxes"])
+
+
+def _rel(a, b):
+    a, b = a.double().cpu(), b.double().cpu()
+    return ((a - b).abs().max() / b.abs().max().clamp_min(1e-12)).item()
+
+
+@pytest.mark.parametrize("precision,tol", [("fp32", 1e-3), ("bf16", 2e-2)])
+@pytest.mark.parametrize("seed,stages,topk", [(0, 1, 1), (1, 2, 3)])
+def test_phase2_refine_vs_oracle(cuda, precision, tol, seed, stages, topk):
+    d = synth.hbb_batch(seed=seed, num_stages=stages, **SMALL)
+    P = hbb.MilHeadParams(num_stages=stages, seed=seed)
+    ob, op, ol, aux = _run_oracle(d, P, stages, topk, alpha=(0.01, 0.25))
+    (gb, gp, gl), head = _run_cuda(cuda, d, P, stages, topk, precision, alpha=(0.01, 0.25))
+    R = head.last_results
+    ref = aux[-1]
+    # scores of the last stage
+    assert _rel(R["cls_score"], ref["cls_score"]) < tol
+    assert _rel(R["ins_score"], ref["ins_score"]) < tol
+    assert _rel(R["neg_cls_score"], ref["neg_cls_score"]) < tol
+    assert _rel(torch.cat(R["extensive_bags"]), torch.cat(ref["extensive_bags"])) < tol
+    for k in ol:
+        assert abs(float(gl[k]) - float(ol[k])) <= tol * max(abs(float(ol[k])), 1e-3), (k, float(gl[k]), float(ol[k]))
+    for i in range(len(ob)):
+        assert _rel(gb[i], ob[i]) < tol
+        assert _rel(gp[i], op[i]) < tol
+    if precision == "fp32":
+        agree = (R["_b200"]["sel_idx"].cpu().long() == ref["selected_idx"]).float().mean().item()
+        assert agree >= 0.999, agree
+
+
+@pytest.mark.parametrize("tag", ["s1_top1", "s2_top3"])
+def test_phase2_against_reference_golden(cuda, golden_dir, tag):
+    g = torch.load(os.path.join(golden_dir, f"hbb_phase2_{tag}.pt"))
+    d = synth.hbb_batch(seed=g["seed"], num_stages=g["stages"], **g["small"])
+    P = hbb.MilHeadParams(num_stages=g["stages"], seed=g["seed"])
+    (gb, gp, gl), head = _run_cuda(cuda, d, P, g["stages"], g["topk"], "fp32")
+    last = g["per_stage"][-1]
+    R = head.last_results
+    assert torch.equal(R["_b200"]["coarse"][:, 1:5].cpu(), last["ext_bags"])            # bag geometry: bit-exact
+    assert torch.equal(R["_b200"]["evalid"].bool().cpu().reshape(-1, 1), last["ext_valid"])
+    assert _rel(torch.cat(R["extensive_bags"]), last["refined_bags"]) < 1e-3
+    assert _rel(R["cls_score"], last["cls_score"]) < 1e-3
+    assert _rel(R["ins_score"], last["ins_score"]) < 1e-3
+    s = g["stages"] - 1
+    assert abs(float(gl[f"stage{s}_loss_mil_bbox"]) - float(last["loss_mil_bbox"])) < 1e-3 * float(last["loss_mil_bbox"])
+    assert abs(float(gl[f"stage{s}_loss_mil_bags"]) - float(last["loss_mil_bags"])) < 1e-3 * float(last["loss_mil_bags"])
+    merged = torch.cat([b[:100] for b in gb])
+    assert _rel(merged, last["merged"]) < 1e-3
+
+
+@pytest.mark.parametrize("U1,U2,topk,levels", [(1, 25, 1, 0), (1, 25, 3, 4), (1, 64, 1, 3), (1, 125, 3, 0), (2, 25, 1, 5)])
+def test_score_select_index_agreement_on_identical_scores(cuda, U1, U2, topk, levels):
+    """Feed the SAME scores to the oracle and the kernel: selected instances must agree >= 99.9 %
+    (tie-heavy inputs with few distinct score levels exercise the ATen CPU top-k tie rule)."""
+    from point_teacher_b200 import ops
+    g = torch.Generator().manual_seed(U2 * 7 + topk)
+    G, C = 400, 8
+    cls = torch.randn(G, U1, U2, C, generator=g)
+    ins = torch.randn(G, U1, U2, C, generator=g)
+    if levels:
+        cls = torch.round(cls * levels / 3) * 3 / levels
+        ins = torch.round(ins * levels / 3) * 3 / levels
+    valid = torch.rand(G * U1 * U2, generator=g) > 0.1
+    valid[:U1 * U2] = False                                    # an all-invalid bag: all-zero scores, pure tie
+    labels = torch.randint(0, C, (G,), generator=g)
+    bags = synth.make_boxes(g, G * U1 * U2, (800, 800))
+    pseudo = synth.make_boxes(g, G, (800, 800))
+    metas = [dict(img_shape=(800, 800, 3))]
+    R = dict(cls_score=cls, ins_score=ins, extensive_bags_valid=[valid.reshape(-1, 1)], extensive_bags=[bags])
+    hbb_head_topk = topk
+    merged, idx, sc = hbb.mil_bag_selection(R, metas, [pseudo], [labels], topk=hbb_head_topk, beta=0.25)
+    rois = torch.cat([torch.zeros(bags.shape[0], 1), bags], 1)
+    sums = torch.zeros(8, device=cuda)
+    m2, pts, idx2, sc2 = ops.score_select(cls.reshape(-1, C).contiguous().to(cuda), ins.reshape(-1, C).contiguous().to(cuda),
+                                          valid.to(torch.uint8).to(cuda), rois.to(cuda), labels.to(cuda),
+                                          pseudo.to(cuda), torch.tensor([[800., 800.]], device=cuda), G, U1, U2, topk,
+                                          0.25, sums)
+    agree = (idx2.cpu().long() == idx).float().mean().item()
+    assert agree >= 0.999, agree
+    assert _rel(m2, merged[0]) < 1e-3
+    assert _rel(sc2, sc) < 1e-3
+    # bag loss on the same scores
+    R["neg_cls_score"] = None
+    loss = hbb.mil_bag_training(R, [labels], None)
+    out = ops.finalize_losses(sums, G * U1 * U2, False).cpu()
+    assert abs(float(out[1]) - float(loss)) < 1e-3 * float(loss)
+
+
+def test_stress_bag_64_full_size_properties(cuda):
+    """Config #4 shape (bag of 64, many GTs) at a size the oracle cannot finish quickly: size-independent
+    properties -- bag geometry idempotence under ratio 1.0, merged boxes inside the image, beta-blend
+    bounds, valid selected indices, finite losses."""
+    from point_teacher_b200.refine import phase2_refine
+    d = synth.hbb_batch(seed=5, gt_range=(700, 700))
+    P = hbb.MilHeadParams(num_stages=1, seed=5)
+    head = _make_head(cuda, P, 1, 1, "bf16")
+    to = lambda l: [t.to(cuda) for t in l]  # noqa: E731
+    ext = synth.stress_ext_cfg(8)
+    with torch.no_grad():
+        gb, gp, gl = phase2_refine(head, (d["feat"].to(cuda),), d["img_metas"], to(d["pseudo_boxes"]),
+                                   to(d["pseudo_points"]), to(d["pseudo_labels"]), to(d["gt_boxes"]),
+                                   synth.HBB_FINE_CFG, ext, num_stages=1, num_training_burninstep2=700,
+                                   neg_boxes=[to(d["neg_boxes"][0])])
+    b = head.last_results["_b200"]
+    assert b["U2"] == 64 and b["K"] == 1400 * 64
+    idx = b["sel_idx"].cpu()
+    assert int(idx.min()) >= 0 and int(idx.max()) < 64
+    m = torch.cat(gb).cpu()
+    assert torch.isfinite(m).all() and (m[:, 0::2] >= -1e-3).all() and (m[:, 0::2] <= 800 + 1e-3).all()
+    for k, v in gl.items():
+        assert torch.isfinite(v).all(), k
+    # with base_ratios [1.0] the base bags are the pseudo boxes themselves (clamp(min_scale=0) only)
+    from point_teacher_b200.proposals import fine_proposals_from_cfg
+    props, _ = fine_proposals_from_cfg(to(d["pseudo_boxes"]), synth.HBB_FINE_CFG[0], d["img_metas"])
+    c = hbb.xyxy_to_cxcywh(d["pseudo_boxes"][0])
+    assert torch.equal(props[0].cpu(), hbb.cxcywh_to_xyxy(c))

@@ -1,0 +1,139 @@
+"""CPU tests that pin the oracle: the reference's own known answers, the committed golden
+vectors generated from the reference's files (oracle/make_golden.py), and cross-checks of the
+C restatements of the un-vendored mmcv kernels."""
+import math
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import hbb, rotated
+from point_teacher_b200 import synth
+
+
+def test_giou_known_answer_from_reference_tests():
+    # HBB_TOD/tests/test_metrics/test_box_overlap.py:86-99
+    b1 = torch.FloatTensor([[0, 0, 10, 10], [10, 10, 20, 20], [32, 32, 38, 42]])
+    b2 = torch.FloatTensor([[0, 0, 10, 20], [0, 10, 10, 19], [10, 10, 20, 20]])
+    g = hbb.bbox_overlaps(b1, b2, "giou", is_aligned=True)
+    assert torch.allclose(g, torch.tensor([0.5000, -0.0500, -0.8214]), atol=1e-4)
+
+
+def test_delta2bbox_docstring_example():
+    # HBB_TOD/mmdet/core/bbox/coder/delta_xywh_bbox_coder.py delta2bbox docstring
+    rois = torch.Tensor([[0., 0., 1., 1.], [0., 0., 1., 1.], [0., 0., 1., 1.], [5., 5., 5., 5.]])
+    deltas = torch.Tensor([[0., 0., 0., 0.], [1., 1., 1., 1.], [0., 0., 2., -1.], [0.7, -1.9, -0.5, 0.3]])
+    out = hbb.delta2bbox(rois, deltas, max_shape=(32, 32, 3))
+    exp = torch.tensor([[0.0000, 0.0000, 1.0000, 1.0000], [0.1409, 0.1409, 2.8591, 2.8591],
+                        [0.0000, 0.3161, 4.1945, 0.6839], [5.0000, 5.0000, 5.0000, 5.0000]])
+    assert torch.allclose(out, exp, atol=1e-4)
+
+
+def test_bbox_overlaps_golden(golden_dir):
+    g = torch.load(os.path.join(golden_dir, "bbox_overlaps.pt"))
+    gen = torch.Generator().manual_seed(7)
+    a = synth.make_boxes(gen, 37, (800, 800))
+    b = synth.jitter_boxes(gen, synth.make_boxes(gen, 53, (800, 800)))
+    a2 = synth.jitter_boxes(torch.Generator().manual_seed(8), a)
+    for mode in ("iou", "iof", "giou"):
+        assert torch.equal(hbb.bbox_overlaps(a, b, mode), g[mode])
+        assert torch.equal(hbb.bbox_overlaps(a, a2, mode, True), g[mode + "_aligned"])
+
+
+def _replay_golden(path):
+    """Re-run the oracle on the regenerated inputs and compare with the reference's outputs."""
+    g = torch.load(path)
+    d = synth.hbb_batch(seed=g["seed"], num_stages=g["stages"], **g["small"])
+    P = hbb.MilHeadParams(num_stages=g["stages"], seed=g["seed"])
+    with torch.no_grad():
+        _, _, losses, aux = hbb.phase2_refine(P, (d["feat"],), [d["stride"]], d["img_metas"], d["pseudo_boxes"],
+                                              d["pseudo_points"], d["pseudo_labels"], d["gt_boxes"],
+                                              synth.HBB_FINE_CFG, synth.HBB_EXT_CFG, num_stages=g["stages"],
+                                              alpha=(1.0, 1.0), topk=g["topk"], injected_negs=d["neg_boxes"])
+    return g, losses, aux
+
+
+@pytest.mark.parametrize("tag", ["s1_top1", "s2_top3"])
+def test_oracle_reproduces_reference_golden(golden_dir, tag):
+    g, losses, aux = _replay_golden(os.path.join(golden_dir, f"hbb_phase2_{tag}.pt"))
+    for s, (ref, R) in enumerate(zip(g["per_stage"], aux)):
+        assert torch.equal(torch.cat(R["coarse_extensive_bags"]), ref["ext_bags"])       # bag geometry: bit-exact
+        assert torch.equal(torch.cat(R["extensive_bags_valid"]), ref["ext_valid"])
+        assert torch.equal(torch.cat(R["extensive_bags"]), ref["refined_bags"])
+        assert torch.equal(R["cls_score"], ref["cls_score"])
+        assert torch.equal(R["ins_score"], ref["ins_score"])
+        assert torch.equal(R["neg_cls_score"], ref["neg_cls_score"])
+        assert torch.allclose(losses[f"stage{s}_loss_mil_bbox"], ref["loss_mil_bbox"], rtol=1e-6)
+        assert torch.allclose(losses[f"stage{s}_loss_mil_bags"], ref["loss_mil_bags"], rtol=1e-6)
+        assert torch.allclose(R["coarse_bags_iou"], ref["coarse_bags_iou"], rtol=1e-6)
+
+
+def test_c_roi_align_matches_torchvision():
+    import torchvision
+    g = torch.Generator().manual_seed(3)
+    x = torch.randn(2, 16, 40, 40, generator=g)
+    boxes = synth.make_boxes(g, 60, (320, 320), median=30, hi=200)
+    boxes[:5] += torch.tensor([-40., -40., -40., -40.])      # partly outside the image
+    boxes[5:8] += torch.tensor([300., 300., 300., 300.])
+    rois = torch.cat([torch.randint(0, 2, (60, 1), generator=g).float(), boxes], 1)
+    for sr in (0, 2):
+        ref = torchvision.ops.roi_align(x, rois, (7, 7), 0.125, sr, True)
+        out = rotated.roi_align(x, rois, 7, 0.125, sr, True)
+        assert torch.allclose(out, ref, atol=2e-5), (out - ref).abs().max()
+
+
+def test_rotated_roi_align_theta0_equals_horizontal():
+    g = torch.Generator().manual_seed(4)
+    x = torch.randn(2, 8, 32, 32, generator=g)
+    boxes = synth.make_boxes(g, 40, (256, 256), median=24, hi=120)
+    b = torch.randint(0, 2, (40, 1), generator=g).float()
+    rois5 = torch.cat([b, boxes], 1)
+    c = hbb.xyxy_to_cxcywh(boxes)
+    rois6 = torch.cat([b, c, torch.zeros(40, 1)], 1)
+    ref = rotated.roi_align(x, rois5, 7, 0.125, 2, True)
+    out = rotated.roi_align_rotated(x, rois6, 7, 0.125, 2, True, True)
+    assert torch.allclose(out, ref, atol=2e-5)
+
+
+def test_rotated_roi_align_orientation_kat():
+    # square RoI, theta=+pi/2, clockwise=True == theta=0 transposed and flipped
+    g = torch.Generator().manual_seed(5)
+    x = torch.randn(1, 4, 32, 32, generator=g)
+    r0 = torch.tensor([[0., 128., 120., 64., 64., 0.]])
+    r90 = torch.tensor([[0., 128., 120., 64., 64., math.pi / 2]])
+    a = rotated.roi_align_rotated(x, r0, 7, 0.125, 2, True, True)
+    b = rotated.roi_align_rotated(x, r90, 7, 0.125, 2, True, True)
+    assert torch.allclose(b, a.transpose(2, 3).flip(2), atol=1e-5)
+
+
+def test_rotated_iou_theta0_equals_axis_aligned_and_cv2():
+    import cv2
+    g = torch.Generator().manual_seed(6)
+    a = synth.make_boxes(g, 50, (400, 400), median=40, hi=150)
+    b = synth.jitter_boxes(g, a, ctr_sigma=10)
+    a5 = torch.cat([hbb.xyxy_to_cxcywh(a), torch.zeros(50, 1)], 1)
+    b5 = torch.cat([hbb.xyxy_to_cxcywh(b), torch.zeros(50, 1)], 1)
+    assert torch.allclose(rotated.box_iou_rotated(a5, b5), hbb.bbox_overlaps(a, b), atol=1e-4)
+    # random angles against OpenCV's polygon intersection (Appendix A.7)
+    a5[:, 4] = torch.rand(50, generator=g) * math.pi - math.pi / 2
+    b5[:, 4] = torch.rand(50, generator=g) * math.pi - math.pi / 2
+    got = rotated.box_iou_rotated(a5, b5, aligned=True)
+    for i in range(50):
+        ra = ((float(a5[i, 0]), float(a5[i, 1])), (float(a5[i, 2]), float(a5[i, 3])), math.degrees(float(a5[i, 4])))
+        rb = ((float(b5[i, 0]), float(b5[i, 1])), (float(b5[i, 2]), float(b5[i, 3])), math.degrees(float(b5[i, 4])))
+        ret, pts = cv2.rotatedRectangleIntersection(ra, rb)
+        inter = cv2.contourArea(cv2.convexHull(pts)) if ret != 0 and pts is not None else 0.0
+        union = float(a5[i, 2] * a5[i, 3] + b5[i, 2] * b5[i, 3]) - inter
+        assert abs(float(got[i]) - inter / union) < 2e-3
+    ident = rotated.box_iou_rotated(a5, a5, aligned=True)
+    assert torch.allclose(ident, torch.ones(50), atol=1e-4)
+
+
+def test_rotated_nms_keeps_descending_score_order():
+    dets = torch.tensor([[50., 50., 20., 20., 0.], [52., 50., 20., 20., 0.1], [150., 150., 20., 10., 0.7],
+                         [50., 51., 20., 20., 0.]])
+    scores = torch.tensor([0.9, 0.8, 0.5, 0.95])
+    out, keep = rotated.nms_rotated(dets, scores, 0.05)
+    assert keep.tolist() == [3, 2]
+    assert out.shape == (2, 6)
