@@ -52,9 +52,12 @@ def test_mil_gen_proposals_replication_and_neg_weights(cuda):
                                                           to(d["gt_boxes"]), d["img_metas"])
     for a, b in zip(rr + rl, gr + gl):
         assert torch.equal(b.cpu(), a)
-    rn, rw = hbb.gen_negative_proposals(d["pseudo_points"], cfg, rp, d["img_metas"], injected=d["neg_boxes"][0])
-    gn, gw = proposals.gen_negative_proposals(to(d["pseudo_points"]), cfg, gp, d["img_metas"],
-                                              neg_boxes=to(d["neg_boxes"][0]))
+    negs = [n.clone() for n in d["neg_boxes"][0]]
+    for i in range(len(negs)):                       # make a third of the negatives collide with base bags
+        k = min(negs[i].shape[0] // 3, rp[i].shape[0])
+        negs[i][:k] = rp[i][:k] + torch.tensor([1.5, -1.0, 2.0, 0.5])
+    rn, rw = hbb.gen_negative_proposals(d["pseudo_points"], cfg, rp, d["img_metas"], injected=negs)
+    gn, gw = proposals.gen_negative_proposals(to(d["pseudo_points"]), cfg, gp, d["img_metas"], neg_boxes=to(negs))
     for a, b in zip(rw, gw):
         assert torch.equal(b.cpu(), a)
     assert 0 < int(torch.cat(rw).sum()) < torch.cat(rw).numel()

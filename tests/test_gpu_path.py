@@ -81,8 +81,20 @@ def test_phase2_against_reference_golden(cuda, golden_dir, tag):
     (gb, gp, gl), head = _run_cuda(cuda, d, P, g["stages"], g["topk"], "fp32")
     last = g["per_stage"][-1]
     R = head.last_results
-    assert torch.equal(R["_b200"]["coarse"][:, 1:5].cpu(), last["ext_bags"])            # bag geometry: bit-exact
-    assert torch.equal(R["_b200"]["evalid"].bool().cpu().reshape(-1, 1), last["ext_valid"])
+    if g["stages"] == 1:      # later stages start from GPU-refined boxes, so only stage 0 sees identical inputs
+        assert torch.equal(R["_b200"]["coarse"][:, 1:5].cpu(), last["ext_bags"])        # bag geometry: bit-exact
+        assert torch.equal(R["_b200"]["evalid"].bool().cpu().reshape(-1, 1), last["ext_valid"])
+    else:
+        assert _rel(R["_b200"]["coarse"][:, 1:5], last["ext_bags"]) < 1e-3
+    # every stage's bag generation, bit-exact from the reference's own stage inputs
+    from point_teacher_b200 import ops
+    for s_i, st in enumerate(g["per_stage"]):
+        cfg = synth.HBB_EXT_CFG[s_i]
+        rois = torch.cat([torch.zeros(st["base_bags"].shape[0], 1), st["base_bags"]], 1).to(cuda)
+        wh = torch.tensor([[256., 256.]], device=cuda)
+        eb, ev = ops.bag_gen(rois, wh, cfg["base_ratios"], cfg["shake_ratio"], cfg["min_scale"])
+        assert torch.equal(eb[:, 1:5].cpu(), st["ext_bags"])
+        assert torch.equal(ev.bool().cpu().reshape(-1, 1), st["ext_valid"])
     assert _rel(torch.cat(R["extensive_bags"]), last["refined_bags"]) < 1e-3
     assert _rel(R["cls_score"], last["cls_score"]) < 1e-3
     assert _rel(R["ins_score"], last["ins_score"]) < 1e-3
@@ -103,8 +115,13 @@ def test_score_select_index_agreement_on_identical_scores(cuda, U1, U2, topk, le
     cls = torch.randn(G, U1, U2, C, generator=g)
     ins = torch.randn(G, U1, U2, C, generator=g)
     if levels:
-        cls = torch.round(cls * levels / 3) * 3 / levels
-        ins = torch.round(ins * levels / 3) * 3 / levels
+        # exact ties: every bag holds only `levels` distinct (cls, ins) rows, replicated at random positions
+        # (quantising the logits instead would create *mathematical* ties, sigma(c)e^i == sigma(-c)e^(i+c),
+        # that CPU and GPU rounding break differently -- not a property of the tie rule)
+        pick = torch.randint(0, levels, (G, U1, U2), generator=g)
+        idx4 = pick[..., None].expand(G, U1, U2, C)
+        cls = torch.gather(cls, 2, idx4)
+        ins = torch.gather(ins, 2, idx4)
     valid = torch.rand(G * U1 * U2, generator=g) > 0.1
     valid[:U1 * U2] = False                                    # an all-invalid bag: all-zero scores, pure tie
     labels = torch.randint(0, C, (G,), generator=g)
@@ -151,7 +168,9 @@ def test_stress_bag_64_full_size_properties(cuda):
     idx = b["sel_idx"].cpu()
     assert int(idx.min()) >= 0 and int(idx.max()) < 64
     m = torch.cat(gb).cpu()
-    assert torch.isfinite(m).all() and (m[:, 0::2] >= -1e-3).all() and (m[:, 0::2] <= 800 + 1e-3).all()
+    pseudo = torch.cat([b[:700] for b in d["pseudo_boxes"]])
+    raw = (m - 0.25 * pseudo) / 0.75                       # undo the beta blend: the clamped weighted box
+    assert torch.isfinite(m).all() and (raw >= -1e-2).all() and (raw <= 800 + 1e-2).all()
     for k, v in gl.items():
         assert torch.isfinite(v).all(), k
     # with base_ratios [1.0] the base bags are the pseudo boxes themselves (clamp(min_scale=0) only)

@@ -4,7 +4,7 @@ mkdir -p gpurun_out
 nvidia-smi --query-gpu=name,memory.total,clocks.max.sm --format=csv > gpurun_out/gpu.txt 2>&1
 for f in tests/test_gpu_kernels.py tests/test_gpu_path.py; do
   echo "=== $f" >> gpurun_out/bringup.log
-  timeout 600 python -m pytest $f -m gpu -q -x --no-header -p no:cacheprovider "$@" >> gpurun_out/bringup.log 2>&1
+  timeout 600 python -m pytest $f -m gpu -q --no-header --tb=short -p no:cacheprovider "$@" >> gpurun_out/bringup.log 2>&1
   echo "exit $?" >> gpurun_out/bringup.log
 done
-tail -n 60 gpurun_out/bringup.log
+grep -vE '^E    (\+|   )' gpurun_out/bringup.log | tail -n 120
