@@ -34,6 +34,10 @@ int pt_bag_gen(const float* in_rois, long long G, const float* img_wh, int B, co
                int n_ratios, const float* shake_host, int n_shake, float min_scale, float* out_rois,
                unsigned char* valid, void* stream);
 
+/* bbox2roi / rbbox2roi (HBB_TOD/mmdet/core/bbox/transforms.py:58-78, OBB_TOD/mmrotate/core/bbox/transforms.py:73-92):
+ * boxes [n, ldb] + img_idx [n] int32 -> out_rois [n, box_dim+1] = (img, box...). */
+int pt_make_rois(const float* boxes, int ldb, const int* img_idx, int n, int box_dim, float* out_rois, void* stream);
+
 /* gen_negative_proposals' weight test (syn_images_generator_v2.py:254-255):
  * weight[n] = all(IoU(neg n, base bags of the same image) < 0.3).  bag_rois sorted by image,
  * bag_offsets [B+1] int32. */

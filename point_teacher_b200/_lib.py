@@ -16,6 +16,7 @@ SIGNATURES = {
     "pt_build_arch": (ctypes.c_char_p, []),
     "pt_bag_gen": (c_int, [c_void_p, c_ll, c_void_p, c_int, c_fp, c_int, c_fp, c_int, c_float, c_void_p,
                            c_void_p, c_void_p]),
+    "pt_make_rois": (c_int, [c_void_p, c_int, c_void_p, c_int, c_int, c_void_p, c_void_p]),
     "pt_neg_weight": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_int, c_void_p, c_void_p]),
     "pt_bbox_overlaps": (c_int, [c_void_p, c_int, c_void_p, c_int, c_ll, c_ll, c_int, c_int, c_float, c_void_p,
                                  c_void_p]),
@@ -68,9 +69,15 @@ def load():
     return lib
 
 
+LAUNCHES = {"count": 0}   # kernels enqueued through the C-ABI (every launching entry point = one kernel)
+_NO_KERNEL = {"pt_last_error", "pt_abi_version", "pt_build_arch", "pt_fc_gemm_workspace_bytes"}
+
+
 def call(name, *args):
     lib = load()
     rc = getattr(lib, name)(*args)
+    if name not in _NO_KERNEL:
+        LAUNCHES["count"] += 1
     if rc != 0:
         raise PTB200Error(f"{name} failed (code {rc}): {lib.pt_last_error().decode()}")
     return rc

@@ -200,3 +200,23 @@ extern "C" int pt_bbox_overlaps(const float* a, int lda, const float* b, int ldb
                                                                                eps, out);
   return check_launch("bbox_overlaps_kernel");
 }
+
+namespace ptb {
+// boxes [n, ldb>=4(+1 angle)] + per-box image index -> RoIs [n, 5|6] (bbox2roi / rbbox2roi without host loops)
+__global__ void make_rois_kernel(const float* __restrict__ boxes, int ldb, const int* __restrict__ img, int n,
+                                 int nbox, float* __restrict__ out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  float* o = out + (size_t)i * (nbox + 1);
+  o[0] = (float)img[i];
+  for (int j = 0; j < nbox; j++) o[1 + j] = boxes[(size_t)i * ldb + j];
+}
+}  // namespace ptb
+
+extern "C" int pt_make_rois(const float* boxes, int ldb, const int* img_idx, int n, int box_dim, float* out_rois,
+                            void* stream) {
+  if (n <= 0) return PT_OK;
+  if (box_dim != 4 && box_dim != 5) { ptb::set_error("pt_make_rois: box_dim must be 4 or 5"); return PT_ERR_ARG; }
+  ptb::make_rois_kernel<<<(n + 255) / 256, 256, 0, (cudaStream_t)stream>>>(boxes, ldb, img_idx, n, box_dim, out_rois);
+  return ptb::check_launch("make_rois_kernel");
+}

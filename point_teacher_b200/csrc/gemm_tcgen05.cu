@@ -220,7 +220,10 @@ fc_gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
           tmem_ld_32x32(taddr + ch * 32, r);
           tmem_ld_wait();
 #pragma unroll
-          for (int j = 0; j < 32; j++) atomicAdd(wrow + ch * 32 + j, __uint_as_float(r[j]));
+          for (int j = 0; j < 8; j++)   // fire-and-forget 16-byte reductions at L2 (REDG.F32x4)
+            asm volatile("red.relaxed.gpu.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(wrow + ch * 32 + 4 * j),
+                         "r"(r[4 * j]), "r"(r[4 * j + 1]), "r"(r[4 * j + 2]), "r"(r[4 * j + 3])
+                         : "memory");
         }
         tc_fence_before();
         __syncwarp();
@@ -340,7 +343,8 @@ extern "C" int pt_fc_gemm_bf16(const void* A, long long lda, const void* B, long
   if (allow_split && tail > 0 && workspace != nullptr) {
     int S = grid / tail;
     const int kb_total = K / BK;
-    if (S > kb_total) S = kb_total;
+    // every split must keep >= 8 k-blocks of MMA work, otherwise the fp32 reduction costs more than it saves
+    if (S > kb_total / 8) S = kb_total / 8;
     const long long need = (long long)tail * BM * BN * 4 + (long long)tail * 4;
     if (S >= 2 && need <= workspace_bytes) {
       p.split = S;

@@ -20,20 +20,29 @@ namespace ptb {
 // x3: three K segments [hi | hi | lo] pairing with the activation's [hi | lo | hi].
 __global__ void prep_fc1_weight_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ out, int C, int bins,
                                        long long ld, int x3) {
-  extern __shared__ float srow[];
-  const int n = blockIdx.x, K = C * bins;
+  extern __shared__ float srow[];   // transposed staging [bin][C+1] (the +1 keeps both phases conflict-free)
+  const int n = blockIdx.x, K = C * bins, S = C + 1;
   const float* src = w + (size_t)n * K;
-  for (int i = threadIdx.x; i < K; i += blockDim.x) srow[i] = src[i];
+  for (int i = threadIdx.x; i < K; i += blockDim.x) {     // coalesced read, k = c*bins + bin
+    const int c = i / bins, bin = i - c * bins;
+    srow[bin * S + c] = src[i];
+  }
   __syncthreads();
   __nv_bfloat16* dst = out + (size_t)n * ld;
-  for (int kp = threadIdx.x; kp < K; kp += blockDim.x) {
+  for (int kp = threadIdx.x * 8; kp < K; kp += blockDim.x * 8) {   // 16-byte stores, k' = bin*C + c
     const int bin = kp / C, c = kp - bin * C;
-    const float v = srow[c * bins + bin];
-    const __nv_bfloat16 hi = __float2bfloat16_rn(v);
-    dst[kp] = hi;
+    float v[8], l[8];
+#pragma unroll
+    for (int j = 0; j < 8; j++) {
+      v[j] = srow[bin * S + c + j];
+      l[j] = v[j] - __bfloat162float(__float2bfloat16_rn(v[j]));
+    }
+    const uint4 hi = make_uint4(pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]), pack_bf16(v[4], v[5]), pack_bf16(v[6], v[7]));
+    *reinterpret_cast<uint4*>(dst + kp) = hi;
     if (x3) {
-      dst[K + kp] = hi;
-      dst[2 * K + kp] = __float2bfloat16_rn(v - __bfloat162float(hi));
+      *reinterpret_cast<uint4*>(dst + K + kp) = hi;
+      *reinterpret_cast<uint4*>(dst + 2 * K + kp) =
+          make_uint4(pack_bf16(l[0], l[1]), pack_bf16(l[2], l[3]), pack_bf16(l[4], l[5]), pack_bf16(l[6], l[7]));
     }
   }
 }
@@ -72,25 +81,42 @@ template <> struct RowLoader<float> {
   }
 };
 
-// out[o] = sum_k h[k] * Wsm[o*D + k]; all lanes return the reduced values.  NOUT <= 24.
+// out[r][o] = sum_k h_r[k] * Wsm[o*D + k] for ROWS consecutive rows: every weight vector fetched from shared
+// memory is reused by ROWS rows (the small-N heads are shared-memory-bandwidth bound otherwise).  All lanes
+// return the reduced values.  nrows <= ROWS rows are valid.
+constexpr int HEAD_ROWS = 4;
 template <typename TH, int NOUT>
-__device__ __forceinline__ void row_dot(const TH* __restrict__ h, const float* __restrict__ wsm, int D, int lane,
-                                        float (&out)[NOUT]) {
+__device__ __forceinline__ void rows_dot(const TH* __restrict__ h, long long ldh, int nrows,
+                                         const float* __restrict__ wsm, int D, int lane,
+                                         float (&out)[HEAD_ROWS][NOUT]) {
 #pragma unroll
-  for (int o = 0; o < NOUT; o++) out[o] = 0.f;
+  for (int r = 0; r < HEAD_ROWS; r++)
+#pragma unroll
+    for (int o = 0; o < NOUT; o++) out[r][o] = 0.f;
   for (int k0 = lane * 8; k0 < D; k0 += 256) {
-    float v[8];
-    RowLoader<TH>::load(h + k0, v);
+    float v[HEAD_ROWS][8];
+#pragma unroll
+    for (int r = 0; r < HEAD_ROWS; r++) {
+      if (r < nrows) RowLoader<TH>::load(h + (size_t)r * ldh + k0, v[r]);
+      else {
+#pragma unroll
+        for (int j = 0; j < 8; j++) v[r][j] = 0.f;
+      }
+    }
 #pragma unroll
     for (int o = 0; o < NOUT; o++) {
       const float4* wp = reinterpret_cast<const float4*>(wsm + (size_t)o * D + k0);
       const float4 w0 = wp[0], w1 = wp[1];
-      out[o] += v[0] * w0.x + v[1] * w0.y + v[2] * w0.z + v[3] * w0.w + v[4] * w1.x + v[5] * w1.y + v[6] * w1.z +
-                v[7] * w1.w;
+#pragma unroll
+      for (int r = 0; r < HEAD_ROWS; r++)
+        out[r][o] += v[r][0] * w0.x + v[r][1] * w0.y + v[r][2] * w0.z + v[r][3] * w0.w + v[r][4] * w1.x +
+                     v[r][5] * w1.y + v[r][6] * w1.z + v[r][7] * w1.w;
     }
   }
 #pragma unroll
-  for (int o = 0; o < NOUT; o++) out[o] = warp_sum(out[o]);
+  for (int r = 0; r < HEAD_ROWS; r++)
+#pragma unroll
+    for (int o = 0; o < NOUT; o++) out[r][o] = warp_sum(out[r][o]);
 }
 
 __device__ __forceinline__ float aligned_iou(const float* a, const float* b) {
@@ -149,10 +175,17 @@ __global__ void reg_decode_kernel(const TH* __restrict__ H, long long ldh, int D
   float* red = wsm + 4 * D;
   const int lane = threadIdx.x & 31, nw = blockDim.x >> 5;
   float part[5] = {0.f, 0.f, 0.f, 0.f, 0.f};
-  for (int k = blockIdx.x * nw + (threadIdx.x >> 5); k < K; k += gridDim.x * nw) {
-    float d[4];
-    row_dot<TH, 4>(H + (size_t)k * ldh, wsm, D, lane, d);
-    if (lane == 0) {
+  for (int kb = (blockIdx.x * nw + (threadIdx.x >> 5)) * HEAD_ROWS; kb < K; kb += gridDim.x * nw * HEAD_ROWS) {
+    float dd[HEAD_ROWS][4];
+    const int nrows = K - kb < HEAD_ROWS ? K - kb : HEAD_ROWS;
+    rows_dot<TH, 4>(H + (size_t)kb * ldh, ldh, nrows, wsm, D, lane, dd);
+    float d[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+    for (int r = 0; r < HEAD_ROWS; r++)
+#pragma unroll
+      for (int j = 0; j < 4; j++) d[j] = (lane == r) ? dd[r][j] : d[j];
+    const int k = kb + lane;          // lane r decodes row kb + r
+    if (lane < nrows) {
       const float* r = bag_rois + (size_t)k * 5;
       float dx = d[0] + breg[0], dy = d[1] + breg[1], dw = d[2] + breg[2], dh = d[3] + breg[3];
       if (out_deltas) { float* od = out_deltas + (size_t)k * 4; od[0] = dx; od[1] = dy; od[2] = dw; od[3] = dh; }
@@ -191,6 +224,8 @@ __global__ void reg_decode_kernel(const TH* __restrict__ H, long long ldh, int D
       part[2] += wv * best;
     }
   }
+#pragma unroll
+  for (int i = 0; i < 5; i++) part[i] = warp_sum(part[i]);
   block_accumulate(sums, part, 5, red);
 }
 
@@ -205,19 +240,20 @@ __global__ void cls_ins_kernel(const TH* __restrict__ H, long long ldh, int D, c
   for (int i = threadIdx.x; i < C * D; i += blockDim.x) { wsm[i] = Wcls[i]; wsm[C * D + i] = Wins[i]; }
   __syncthreads();
   const int lane = threadIdx.x & 31, nw = blockDim.x >> 5;
-  for (int k = blockIdx.x * nw + (threadIdx.x >> 5); k < M; k += gridDim.x * nw) {
-    float o[C2];
-    row_dot<TH, C2>(H + (size_t)k * ldh, wsm, D, lane, o);
-    // dynamic register indexing is avoided with a select chain
-    float v = 0.f;
+  for (int kb = (blockIdx.x * nw + (threadIdx.x >> 5)) * HEAD_ROWS; kb < M; kb += gridDim.x * nw * HEAD_ROWS) {
+    float o[HEAD_ROWS][C2];
+    const int nrows = M - kb < HEAD_ROWS ? M - kb : HEAD_ROWS;
+    rows_dot<TH, C2>(H + (size_t)kb * ldh, ldh, nrows, wsm, D, lane, o);
 #pragma unroll
-    for (int c = 0; c < C; c++) v = (lane == c) ? o[C + c] : v;
-    float u = 0.f;
+    for (int r = 0; r < HEAD_ROWS; r++) {
+      // dynamic register indexing is avoided with a select chain
+      float v = 0.f, u = 0.f;
 #pragma unroll
-    for (int c = 0; c < C; c++) u = (lane == c) ? o[c] : u;
-    if (lane < C) {
-      cls[(size_t)k * C + lane] = u + bcls[lane];
-      ins[(size_t)k * C + lane] = v + bins[lane];
+      for (int c = 0; c < C; c++) { v = (lane == c) ? o[r][C + c] : v; u = (lane == c) ? o[r][c] : u; }
+      if (lane < C && r < nrows) {
+        cls[(size_t)(kb + r) * C + lane] = u + bcls[lane];
+        ins[(size_t)(kb + r) * C + lane] = v + bins[lane];
+      }
     }
   }
 }
@@ -374,7 +410,8 @@ extern "C" int pt_prep_fc1_weight(const float* w, void* out_bf16, int N, int C, 
                                   void* stream) {
   const long long K = (long long)C * bins;
   if (ld < (x3 ? 3 : 1) * K) { set_error("pt_prep_fc1_weight: ld too small"); return PT_ERR_ARG; }
-  const size_t smem = (size_t)K * sizeof(float);
+  if (C % 8 != 0 || ld % 8 != 0) { set_error("pt_prep_fc1_weight: C and ld must be multiples of 8"); return PT_ERR_ARG; }
+  const size_t smem = (size_t)(C + 1) * bins * sizeof(float);
   if (smem > 200 * 1024) { set_error("pt_prep_fc1_weight: row of %lld floats does not fit shared memory", K); return PT_ERR_UNSUPPORTED; }
   cudaFuncSetAttribute(prep_fc1_weight_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   prep_fc1_weight_kernel<<<N, 512, smem, (cudaStream_t)stream>>>(w, (__nv_bfloat16*)out_bf16, C, bins, ld, x3);
@@ -397,8 +434,8 @@ extern "C" int pt_reg_decode(const void* H, int h_f32, long long ldh, int D, con
   const int threads = 256;
   const size_t smem = (size_t)(4 * D + 8 * 8) * sizeof(float);
   const float max_ratio = fabsf(logf(wh_ratio_clip));
-  int grid = (K + 7) / 8;
-  if (grid > 148 * 4) grid = 148 * 4;
+  int grid = (K + 8 * HEAD_ROWS - 1) / (8 * HEAD_ROWS);
+  if (grid > 148 * 2) grid = 148 * 2;
   if (h_f32) {
     cudaFuncSetAttribute(reg_decode_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     reg_decode_kernel<float><<<grid, threads, smem, (cudaStream_t)stream>>>(
@@ -419,8 +456,8 @@ static int launch_cls_ins(const void* H, long long ldh, int D, const float* Wcls
   const size_t smem = (size_t)C2 * D * sizeof(float);
   auto kern = cls_ins_kernel<TH, C2>;
   cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  int grid = (M + 7) / 8;
-  if (grid > 148 * 2) grid = 148 * 2;
+  int grid = (M + 8 * HEAD_ROWS - 1) / (8 * HEAD_ROWS);
+  if (grid > 148) grid = 148;
   kern<<<grid, 256, smem, s>>>((const TH*)H, ldh, D, Wcls, bcls, Wins, bins, M, cls, ins);
   return check_launch("cls_ins_kernel");
 }

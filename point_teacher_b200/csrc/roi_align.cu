@@ -18,6 +18,7 @@
 namespace ptb {
 
 constexpr int P7 = 7;
+constexpr int GW_CHUNK = 16;   // x samples per bin held in the shared sample table at a time
 
 // --------------------------------------------------------------------------------- NCHW -> NHWC
 template <typename TOut>
@@ -115,7 +116,7 @@ __device__ __forceinline__ void flush_stage(float* out, int roi, int C, const fl
   // coalesced write of one RoI's (C, 7, 7) block from the transposed smem staging
   const int n = C * P7 * P7;
   float* dst = out + (size_t)roi * n;
-  for (int o = threadIdx.x * 4; o < n; o += blockDim.x * 4) {
+  for (int o = threadIdx.x * 4; o < n; o += P7 * 32 * 4) {
     float v[4];
 #pragma unroll
     for (int i = 0; i < 4; i++) {
@@ -127,86 +128,183 @@ __device__ __forceinline__ void flush_stage(float* out, int roi, int C, const fl
 }
 
 // --------------------------------------------------------------------------------- horizontal RoIAlign
+// Separable formulation.  Bilinear average pooling is linear in the feature map and the sample grid is a
+// Cartesian product, so for one RoI
+//     out[ph][pw][c] = 1/count * sum_row sum_col  wy[ph][row] * wx[pw][col] * feat[row][col][c]
+// where wx[pw][col] (wy[ph][row]) accumulates the low/high bilinear weights of every x (y) sample of bin pw
+// (ph) that lands on that column (row); samples rejected by the border rule simply add no weight.
+// CTA = 7 compute warps (one output row each) + 1 builder warp that runs ONE RoI AHEAD: it loads the RoI,
+// builds the two tiny weight tables with the reference's exact coordinate arithmetic (double-buffered in
+// shared memory, handed over with named barriers) and prefetches the RoI's feature patch into L1, so the
+// compute warps never see the RoI-load / table-build latency and their pixel loads hit L1.
+struct RoiMeta {
+  int xmin, xmax, ymin, skip;
+  float inv_count;
+  int img;
+  int ylo[8], yhi[8];       // row range touched by output row ph
+};
+
+constexpr int RA_THREADS = (P7 + 1) * 32;
+enum { BAR_FULL0 = 1, BAR_EMPTY0 = 3, BAR_COMPUTE = 5 };
+
+__device__ __forceinline__ void nbar_sync(int id, int n) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n) : "memory"); }
+__device__ __forceinline__ void nbar_arrive(int id, int n) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(n) : "memory"); }
+
 template <typename TIn, int MODE>
-__global__ void __launch_bounds__(P7 * 32, 2)
+__global__ void __launch_bounds__(RA_THREADS, 2)
 roi_align_fwd_kernel(const TIn* __restrict__ feat, const float* __restrict__ rois, void* __restrict__ out,
                      long long ld_out, int K, int B, int C, int H, int W, float scale, int sampling_ratio,
                      int aligned, const int* __restrict__ roi_level, int level) {
-  extern __shared__ float stage[];
-  const int ph = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const float off = aligned ? 0.5f : 0.f;
-  for (int roi = blockIdx.x; roi < K; roi += gridDim.x) {
-    if (roi_level != nullptr && roi_level[roi] != level) continue;  // multi-level FPN: other level's RoI
-    const float* r = rois + (size_t)roi * 5;
-    const int b = (int)__ldg(r);
-    const float x1 = fsub(fmul(__ldg(r + 1), scale), off), y1 = fsub(fmul(__ldg(r + 2), scale), off);
-    const float x2 = fsub(fmul(__ldg(r + 3), scale), off), y2 = fsub(fmul(__ldg(r + 4), scale), off);
-    float rw = fsub(x2, x1), rh = fsub(y2, y1);
-    if (!aligned) { rw = fmaxf(rw, 1.f); rh = fmaxf(rh, 1.f); }
-    const float bh = fdiv(rh, (float)P7), bw = fdiv(rw, (float)P7);
-    const int gh = sampling_ratio > 0 ? sampling_ratio : (int)ceilf(bh);
-    const int gw = sampling_ratio > 0 ? sampling_ratio : (int)ceilf(bw);
-    const int cnt = gh * gw > 1 ? gh * gw : 1;
-    const float inv_count = 1.0f / (float)cnt;
-    const bool b_ok = b >= 0 && b < B;
-    const TIn* fb = feat + (size_t)(b_ok ? b : 0) * H * W * C;
-    const float ybase = fadd(y1, fmul((float)ph, bh));
+  extern __shared__ float smem_dyn[];
+  // [2 buffers][ (W+1)*8 wx | (H+1)*8 wy ] then the NCHW staging area
+  const int tab_floats = (W + 4) * 8 + (H + 1) * 8;
+  float* stage = smem_dyn + 2 * tab_floats;
+  __shared__ RoiMeta meta[2];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int n_iter = blockIdx.x < K ? (K - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
 
-    for (int c0 = lane * 8; c0 < C; c0 += 256) {
-      float acc[P7][8];
-#pragma unroll
-      for (int pw = 0; pw < P7; pw++)
-#pragma unroll
-        for (int j = 0; j < 8; j++) acc[pw][j] = 0.f;
-
-      for (int iy = 0; iy < gh && b_ok; iy++) {
-        const float y = fadd(ybase, fdiv(fmul((float)iy + .5f, bh), (float)gh));
-        int yl, yh; float ly, hy;
-        if (!axis_setup(y, H, yl, yh, ly, hy)) continue;
-        const TIn* row_lo = fb + (size_t)yl * W * C + c0;
-        const TIn* row_hi = fb + (size_t)yh * W * C + c0;
-        int i0 = -1, i1 = -1;   // cached feature columns (already blended in y)
-        float t0[8], t1[8];
-#pragma unroll
-        for (int pw = 0; pw < P7; pw++) {
-          const float xb = fadd(x1, fmul((float)pw, bw));
-          for (int ix = 0; ix < gw; ix++) {
-            const float x = fadd(xb, fdiv(fmul((float)ix + .5f, bw), (float)gw));
-            int xl, xh; float lx, hx;
-            if (!axis_setup(x, W, xl, xh, lx, hx)) continue;
-            if (xl != i0) {
-              if (xl == i1) {
-#pragma unroll
-                for (int j = 0; j < 8; j++) t0[j] = t1[j];
-              } else {
-                F8 a = load8(row_lo + (size_t)xl * C), c = load8(row_hi + (size_t)xl * C);
-#pragma unroll
-                for (int j = 0; j < 8; j++) t0[j] = hy * a.v[j] + ly * c.v[j];
-              }
-              i0 = xl;
-            }
-            if (xh != i1) {
-              if (xh == i0) {
-#pragma unroll
-                for (int j = 0; j < 8; j++) t1[j] = t0[j];
-              } else {
-                F8 a = load8(row_lo + (size_t)xh * C), c = load8(row_hi + (size_t)xh * C);
-#pragma unroll
-                for (int j = 0; j < 8; j++) t1[j] = hy * a.v[j] + ly * c.v[j];
-              }
-              i1 = xh;
-            }
-#pragma unroll
-            for (int j = 0; j < 8; j++) acc[pw][j] += hx * t0[j] + lx * t1[j];
-          }
+  if (warp == P7) {
+    // ------------------------------------------------------------------ builder warp
+    const float off = aligned ? 0.5f : 0.f;
+    for (int it = 0; it < n_iter; it++) {
+      const int roi = blockIdx.x + it * gridDim.x, buf = it & 1;
+      if (it >= 2) nbar_sync(BAR_EMPTY0 + buf, RA_THREADS);
+      float* wx = smem_dyn + buf * tab_floats;       // wx[col - xmin][pw]
+      float* wy = wx + (W + 4) * 8;                  // wy[row - ymin][ph]
+      RoiMeta& mt = meta[buf];
+      const bool skip = roi_level != nullptr && roi_level[roi] != level;   // multi-level FPN: other level's RoI
+      const float* r = rois + (size_t)roi * 5;
+      const int b = (int)__ldg(r);
+      const float x1 = fsub(fmul(__ldg(r + 1), scale), off), y1 = fsub(fmul(__ldg(r + 2), scale), off);
+      const float x2 = fsub(fmul(__ldg(r + 3), scale), off), y2 = fsub(fmul(__ldg(r + 4), scale), off);
+      float rw = fsub(x2, x1), rh = fsub(y2, y1);
+      if (!aligned) { rw = fmaxf(rw, 1.f); rh = fmaxf(rh, 1.f); }
+      const float bh = fdiv(rh, (float)P7), bw = fdiv(rw, (float)P7);
+      const int gh = sampling_ratio > 0 ? sampling_ratio : (int)ceilf(bh);
+      const int gw = sampling_ratio > 0 ? sampling_ratio : (int)ceilf(bw);
+      const int cnt = gh * gw > 1 ? gh * gw : 1;
+      const bool b_ok = b >= 0 && b < B && !skip;
+      // lanes 0..6 own the x bins, lanes 8..14 the y bins (shuffle groups of 8)
+      const bool isx = lane < 8;
+      const int bi = lane & 7;
+      const float start = isx ? x1 : y1, bin = isx ? bw : bh;
+      const int g = isx ? gw : gh, size = isx ? W : H;
+      float* tab = isx ? wx : wy;
+      const float base = fadd(start, fmul((float)bi, bin));
+      int lo = 1 << 30, hi = -1;
+      const bool owner = lane < 16 && bi < P7;
+      if (owner && b_ok) {
+        for (int i = 0; i < g; i++) {
+          const float v = fadd(base, fdiv(fmul((float)i + .5f, bin), (float)g));
+          int l, h; float fl, fh;
+          if (axis_setup(v, size, l, h, fl, fh)) { lo = min(lo, l); hi = max(hi, h); }
         }
       }
-      store_bins<MODE>(out, ld_out, roi, ph, C, c0, acc, inv_count, stage);
+      int glo = lo, ghi = hi;
+#pragma unroll
+      for (int o = 4; o > 0; o >>= 1) {
+        glo = min(glo, __shfl_xor_sync(0xffffffffu, glo, o));
+        ghi = max(ghi, __shfl_xor_sync(0xffffffffu, ghi, o));
+      }
+      if (ghi < 0) { glo = 0; ghi = -1; }
+      if (owner) {
+        const int npad = isx ? ((ghi - glo + 4) & ~3) : (ghi - glo + 1);   // x table zero-padded to 4 columns
+        for (int c = 0; c < npad; c++) tab[c * 8 + bi] = 0.f;
+        if (b_ok) {
+          for (int i = 0; i < g; i++) {
+            const float v = fadd(base, fdiv(fmul((float)i + .5f, bin), (float)g));
+            int l, h; float fl, fh;
+            if (axis_setup(v, size, l, h, fl, fh)) { tab[(l - glo) * 8 + bi] += fh; tab[(h - glo) * 8 + bi] += fl; }
+          }
+        }
+        if (!isx) { mt.ylo[bi] = lo; mt.yhi[bi] = hi; }
+      }
+      const int xmin = __shfl_sync(0xffffffffu, glo, 0), xmax = __shfl_sync(0xffffffffu, ghi, 0);
+      const int ymin = __shfl_sync(0xffffffffu, glo, 8), ymax = __shfl_sync(0xffffffffu, ghi, 8);
+      if (lane == 0) {
+        mt.xmin = xmin; mt.xmax = xmax; mt.ymin = ymin; mt.skip = skip ? 1 : 0;
+        mt.inv_count = 1.0f / (float)cnt; mt.img = b_ok ? b : 0;
+      }
+      nbar_arrive(BAR_FULL0 + buf, RA_THREADS);
+      // pull the RoI's feature patch into L1 one iteration before the compute warps ask for it
+      if (b_ok && xmax >= xmin && ymax >= ymin) {
+        const int row_lines = ((xmax - xmin + 1) * C * (int)sizeof(TIn) + 127) / 128;
+        const int nrows = ymax - ymin + 1;
+        int total = row_lines * nrows;
+        if (total > 256) total = 256;
+        const char* pbase = reinterpret_cast<const char*>(feat + ((size_t)b * H * W + (size_t)ymin * W + xmin) * C);
+        for (int i = lane; i < total; i += 32) {
+          const int rr = i / row_lines, ll = i - rr * row_lines;
+          asm volatile("prefetch.global.L1 [%0];" ::"l"(pbase + ((size_t)rr * W * C) * sizeof(TIn) + (size_t)ll * 128));
+        }
+      }
     }
-    if (MODE == OUT_F32_NCHW) {
-      __syncthreads();
+    return;
+  }
+
+  // -------------------------------------------------------------------- compute warps (warp = output row ph)
+  const int ph = warp;
+  for (int it = 0; it < n_iter; it++) {
+    const int roi = blockIdx.x + it * gridDim.x, buf = it & 1;
+    nbar_sync(BAR_FULL0 + buf, RA_THREADS);
+    const float* wx = smem_dyn + buf * tab_floats;
+    const float* wy = wx + (W + 4) * 8;
+    const RoiMeta& mt = meta[buf];
+    const int xmin = mt.xmin, xmax = mt.xmax, ymin = mt.ymin;
+    const int ylo = mt.ylo[ph], yhi = mt.yhi[ph];
+    const float inv_count = mt.inv_count;
+    const bool skip = mt.skip != 0;
+    const TIn* fb = feat + (size_t)mt.img * H * W * C;
+
+    if (!skip) {
+      for (int c0 = lane * 8; c0 - lane * 8 < C; c0 += 256) {
+        float acc[P7][8];
+#pragma unroll
+        for (int pw = 0; pw < P7; pw++)
+#pragma unroll
+          for (int j = 0; j < 8; j++) acc[pw][j] = 0.f;
+        if (c0 < C) {
+          for (int cc = xmin; cc <= xmax; cc += 4) {
+            float t[4][8];
+#pragma unroll
+            for (int q = 0; q < 4; q++)
+#pragma unroll
+              for (int j = 0; j < 8; j++) t[q][j] = 0.f;
+            // columns past xmax are clamped onto xmax: their (zero-padded) weights discard them
+            int coff[4];
+#pragma unroll
+            for (int q = 0; q < 4; q++) coff[q] = (min(cc + q, xmax) - cc) * C;
+#pragma unroll 2
+            for (int row = ylo; row <= yhi; row++) {
+              const float wyv = wy[(row - ymin) * 8 + ph];
+              const TIn* prow = fb + ((size_t)row * W + cc) * C + c0;
+#pragma unroll
+              for (int q = 0; q < 4; q++) {
+                const F8 v = load8(prow + coff[q]);
+#pragma unroll
+                for (int j = 0; j < 8; j++) t[q][j] = fmaf(wyv, v.v[j], t[q][j]);
+              }
+            }
+#pragma unroll
+            for (int q = 0; q < 4; q++) {
+              const float4* wp = reinterpret_cast<const float4*>(wx + (cc + q - xmin) * 8);
+              const float4 wa = wp[0], wb = wp[1];
+              const float wv[P7] = {wa.x, wa.y, wa.z, wa.w, wb.x, wb.y, wb.z};
+#pragma unroll
+              for (int pw = 0; pw < P7; pw++)
+#pragma unroll
+                for (int j = 0; j < 8; j++) acc[pw][j] = fmaf(wv[pw], t[q][j], acc[pw][j]);
+            }
+          }
+          store_bins<MODE>(out, ld_out, roi, ph, C, c0, acc, inv_count, stage);
+        }
+      }
+    }
+    if (it + 2 < n_iter) nbar_arrive(BAR_EMPTY0 + buf, RA_THREADS);
+    if (MODE == OUT_F32_NCHW && !skip) {
+      nbar_sync(BAR_COMPUTE, P7 * 32);
       flush_stage<MODE>(reinterpret_cast<float*>(out), roi, C, stage);
-      __syncthreads();
+      nbar_sync(BAR_COMPUTE, P7 * 32);
     }
   }
 }
@@ -312,7 +410,10 @@ template <typename TIn, int MODE>
 static int launch_fwd(bool rotated, const void* feat, const float* rois, void* out, long long ld_out, int K, int B,
                       int C, int H, int W, float scale, int sampling_ratio, int aligned, int clockwise,
                       const int* roi_level, int level, cudaStream_t stream) {
-  size_t smem = MODE == OUT_F32_NCHW ? (size_t)P7 * P7 * (C + 1) * sizeof(float) : 0;
+  const size_t stage_bytes = MODE == OUT_F32_NCHW ? (size_t)P7 * P7 * (C + 1) * sizeof(float) : 0;
+  const size_t tab_bytes = rotated ? 0 : 2 * ((size_t)(W + 4) * 8 + (size_t)(H + 1) * 8) * sizeof(float);
+  size_t smem = stage_bytes + tab_bytes;
+  if (smem > 100 * 1024) { set_error("roi_align: feature map %dx%d too large for the shared weight tables", H, W); return PT_ERR_UNSUPPORTED; }
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
@@ -325,8 +426,8 @@ static int launch_fwd(bool rotated, const void* feat, const float* rois, void* o
   } else {
     auto kern = roi_align_fwd_kernel<TIn, MODE>;
     if (smem > 48 * 1024) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    kern<<<grid, P7 * 32, smem, stream>>>(reinterpret_cast<const TIn*>(feat), rois, out, ld_out, K, B, C, H, W,
-                                           scale, sampling_ratio, aligned, roi_level, level);
+    kern<<<grid, RA_THREADS, smem, stream>>>(reinterpret_cast<const TIn*>(feat), rois, out, ld_out, K, B, C, H, W,
+                                              scale, sampling_ratio, aligned, roi_level, level);
   }
   return check_launch(rotated ? "roi_align_rotated_fwd_kernel" : "roi_align_fwd_kernel");
 }

@@ -29,6 +29,7 @@ class MILHeadMixin:
 
     bag_loss_pos_scale = 1.0   # OBB scales 0.25 * pos + 0.75 * neg (rotated_fcos_head_p2rb_ts.py:1272,1282)
     bag_loss_neg_scale = 1.0
+    bag_loss_bbox_scale = 1.0
     reg_dim = 4
 
     # ------------------------------------------------------------------ construction
@@ -210,6 +211,52 @@ class MILHeadMixin:
         b.update(sel_idx=idx, sel_score=sc, merged_points=pts)
         self.last_results = R
         return losses, tuple(torch.split(merged, per_img))
+
+    def mil_stage_packed(self, x, img_metas, img_wh, base_rois, U1, ref, real, neg_boxes, neg_img_idx, bag_offsets,
+                         labels, pseudo, cfg, stage, loss_scales=(1.0, 1.0)):
+        """One MIL stage on packed tensors (the fast path behind ``phase2_refine``): no per-image lists, no
+        replicated reference/real boxes (instance k belongs to GT k // (U1*U2)), negatives appended to the
+        classification pass.  base_rois (G*U1,5); ref/real/pseudo (G,4); labels (G,) int64;
+        neg_boxes (Nn,4)|None with neg_img_idx (Nn,) int32; bag_offsets (B+1,) int32 into base_rois.
+        Returns (merged (G,4), merged centres (G,2), losses dict)."""
+        dev = x[0].device
+        ebags, evalid = ops.bag_gen(base_rois, img_wh, cfg["base_ratios"], cfg["shake_ratio"], cfg["min_scale"])
+        K, G = ebags.shape[0], pseudo.shape[0]
+        U2 = K // max(base_rois.shape[0], 1)
+        sums = torch.zeros((8,), dtype=torch.float32, device=dev)
+        A = self._roi_operand(x, ebags)
+        H = self._fc_stack(A, self.shared_fcs_reg[stage], K)
+        n_neg = 0 if neg_boxes is None else neg_boxes.shape[0]
+        rois2 = torch.empty((K + n_neg, 5), dtype=torch.float32, device=dev)
+        neg_w = None
+        if n_neg:
+            ops.make_rois(neg_boxes, neg_img_idx, out=rois2[K:])
+            neg_w = ops.neg_weight(rois2[K:], base_rois, bag_offsets)
+        h0, w0, _ = img_metas[0]["img_shape"]
+        fr = self.fc_reg[stage]
+        _, _, iou_t = ops.reg_decode(H, fr.weight.detach(), fr.bias.detach(), ebags, evalid, ref, real, U1 * U2,
+                                     (w0, h0), sums, K=K, hyper=self.loss_bbox_denosing_hyper, out_rois=rois2)
+        del A, H
+        A2 = self._roi_operand(x, rois2)
+        H2 = self._fc_stack(A2, self.shared_fcs_bag[stage], K + n_neg)
+        fc, fi = self.fc_cls[stage], self.fc_ins[stage]
+        cls, ins = ops.cls_ins_heads(H2, fc.weight.detach(), fc.bias.detach(), fi.weight.detach(),
+                                     fi.bias.detach(), M=K + n_neg)
+        merged, pts, idx, sc = ops.score_select(cls, ins, evalid, rois2, labels, pseudo, img_wh, G, U1, U2,
+                                                self.topk, self.beta, sums)
+        if n_neg:
+            ops.neg_loss(cls[K:], neg_w, sums)
+        out = ops.finalize_losses(sums, K, bool(n_neg), loss_scales[0] * self.bag_loss_bbox_scale,
+                                  loss_scales[1])
+        losses = {f"stage{stage}_loss_mil_bbox": out[0], f"stage{stage}_loss_mil_bags": out[1],
+                  f"stage{stage}_coarse_bags_iou": out[2], f"stage{stage}_refine_bags_iou": out[3]}
+        self.last_results = dict(
+            cls_score=cls[:K].view(G, U1, U2, -1), ins_score=ins[:K].view(G, U1, U2, -1),
+            neg_cls_score=cls[K:] if n_neg else None, neg_weight=neg_w, iou_target=iou_t,
+            extensive_bags=[rois2[:K, 1:5]], base_shaking_num=U1, extensive_shaking_num=U2,
+            _b200=dict(sums=sums, K=K, evalid=evalid, refined=rois2[:K], coarse=ebags, img_wh=img_wh, cls=cls,
+                       ins=ins, n_neg=n_neg, U1=U1, U2=U2, sel_idx=idx, sel_score=sc, merged_points=pts))
+        return merged, pts, losses
 
     def MIL_head_burn_in_step1(self, x_ori, x_synethic, img_metas, proposals_list, proposals_valid_list,
                                proposals_reference_list, proposals_real_list, syn_proposals_list,

@@ -60,6 +60,17 @@ def bag_gen(in_rois, img_wh, base_ratios, shake_ratio, min_scale):
     return out, valid
 
 
+def make_rois(boxes, img_idx, out=None):
+    """boxes (n,4|5) + img_idx (n,) int32 -> rois (n,5|6); ``out`` may be a row-slice of a larger RoI buffer."""
+    _chk(boxes, "boxes", _f32, 2)
+    _chk(img_idx, "img_idx", _i32, 1)
+    n, d = boxes.shape
+    if out is None:
+        out = torch.empty((n, d + 1), dtype=_f32, device=boxes.device)
+    _lib.call("pt_make_rois", _p(boxes), d, _p(img_idx), n, d, _p(out), _stream())
+    return out
+
+
 def neg_weight(neg_rois, bag_rois, bag_offsets):
     _chk(neg_rois, "neg_rois", _f32, 2, 5)
     _chk(bag_rois, "bag_rois", _f32, 2, 5)
@@ -121,10 +132,24 @@ def roi_align_forward(feat_nhwc, rois, out_mode, spatial_scale, sampling_ratio=0
             out = torch.empty((rows or K, kcols * (3 if out_mode == OUT_BF16X3_BINMAJOR else 1)), dtype=_bf16,
                               device=rois.device)
     ld = out.shape[1] if out_mode != OUT_F32_NCHW else 0
+    if PROFILE["on"]:
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+    _roi_call(feat_nhwc, rois, out, ld, out_mode, K, B, C, H, W, pooled, spatial_scale, sampling_ratio, aligned,
+              rotated, clockwise, roi_level, level)
+    if PROFILE["on"]:
+        e1.record()
+        esz = 4 if out_mode == OUT_F32_NCHW else (6 if out_mode == OUT_BF16X3_BINMAJOR else 2)
+        nbytes = K * kcols * esz + feat_nhwc.numel() * feat_nhwc.element_size() + K * rois.shape[1] * 4
+        PROFILE["events"].append(("roi_align", e0, e1, float(nbytes), (K, C, out_mode)))
+    return out
+
+
+def _roi_call(feat_nhwc, rois, out, ld, out_mode, K, B, C, H, W, pooled, spatial_scale, sampling_ratio, aligned,
+              rotated, clockwise, roi_level, level):
     _lib.call("pt_roi_align_forward", _p(feat_nhwc), int(feat_nhwc.dtype == _bf16), _p(rois), _p(out), ld, out_mode,
               K, B, C, H, W, pooled, float(spatial_scale), int(sampling_ratio), int(aligned), int(rotated),
               int(clockwise), _p(roi_level), int(level), _stream())
-    return out
 
 
 def map_roi_levels(rois, num_levels, finest_scale=56, rotated=False):
@@ -145,6 +170,8 @@ def roi_rescale(rois, factor, rotated=False):
 
 # ------------------------------------------------------------------------------ FC GEMM
 _WS = {}
+# optional per-launch timing hook for bench.py: {"events": [(tag, start, stop, flops)], "on": bool}
+PROFILE = {"on": False, "events": []}
 
 
 def gemm_workspace(device):
@@ -170,8 +197,14 @@ def fc_gemm(A, B, bias=None, relu=False, out_dtype=_bf16, M=None, out=None, allo
     if out is None:
         out = torch.empty((A.shape[0], N), dtype=out_dtype, device=A.device)
     ws = gemm_workspace(A.device)
+    if PROFILE["on"]:
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
     _lib.call("pt_fc_gemm_bf16", _p(A), A.shape[1], _p(B), B.shape[1], _p(bias), _p(out), out.shape[1], M, N, K,
               int(relu), int(out.dtype == _f32), _p(ws), ws.numel(), num_sms(), int(allow_split), _stream())
+    if PROFILE["on"]:
+        e1.record()
+        PROFILE["events"].append(("fc_gemm", e0, e1, 2.0 * M * N * K, (M, N, K)))
     return out
 
 

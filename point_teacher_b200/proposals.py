@@ -11,21 +11,42 @@ import torch
 from . import ops
 
 
+_CONST = {}
+
+
+def const_tensor(values, dtype, device):
+    """Small host-side metadata (image sizes, per-image offsets) as a device tensor, uploaded once per distinct
+    value: steady-state steps do no H2D copy for it, which keeps the step CUDA-graph capturable."""
+    key = (tuple(map(tuple, values)) if values and isinstance(values[0], (list, tuple)) else tuple(values),
+           dtype, str(device))
+    t = _CONST.get(key)
+    if t is None:
+        if len(_CONST) > 4096:
+            _CONST.clear()
+        t = torch.tensor(values, dtype=dtype, device=device)
+        _CONST[key] = t
+    return t
+
+
 def img_wh_tensor(img_meta, device):
     """(B,2) float tensor of (w, h) from ``img_meta[i]['img_shape'] = (h, w, c)``."""
-    return torch.tensor([[float(m["img_shape"][1]), float(m["img_shape"][0])] for m in img_meta],
-                        dtype=torch.float32, device=device)
+    return const_tensor([[float(m["img_shape"][1]), float(m["img_shape"][0])] for m in img_meta],
+                        torch.float32, device)
 
 
 def boxes_to_rois(box_list):
     """``bbox2roi`` (core/bbox/transforms.py:58-78): list of (n_i, >=4) -> (sum n_i, 5)."""
-    parts = []
+    n = sum(b.size(0) for b in box_list)
+    ref = box_list[0]
+    out = ref.new_empty((n, 5))
+    o = 0
     for i, b in enumerate(box_list):
-        if b.size(0) > 0:
-            parts.append(torch.cat([b.new_full((b.size(0), 1), i), b[:, :4]], dim=-1))
-        else:
-            parts.append(b.new_zeros((0, 5)))
-    return torch.cat(parts, 0).contiguous()
+        k = b.size(0)
+        if k:
+            out[o:o + k, 0] = float(i)
+            out[o:o + k, 1:5] = b[:, :4]
+        o += k
+    return out
 
 
 def _split(t, sizes):
@@ -86,8 +107,10 @@ def gen_negative_proposals(gt_points, proposal_cfg, aug_generate_proposals, img_
                      for i in range(len(gt_points))]
     neg_rois = boxes_to_rois(neg_boxes)
     bag_rois = boxes_to_rois(aug_generate_proposals)
-    counts = [0] + [p.shape[0] for p in aug_generate_proposals]
-    offsets = torch.tensor(counts, dtype=torch.int64).cumsum(0).to(torch.int32).to(dev)
+    offs = [0]
+    for p in aug_generate_proposals:
+        offs.append(offs[-1] + p.shape[0])
+    offsets = const_tensor(offs, torch.int32, dev)
     w = ops.neg_weight(neg_rois, bag_rois, offsets).bool()
     sizes = [b.shape[0] for b in neg_boxes]
     return list(neg_boxes), _split(w, sizes)
