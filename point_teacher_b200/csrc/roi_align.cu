@@ -21,21 +21,50 @@ constexpr int P7 = 7;
 constexpr int GW_CHUNK = 16;   // x samples per bin held in the shared sample table at a time
 
 // --------------------------------------------------------------------------------- NCHW -> NHWC
+// 64 channels x 64 positions per CTA: 16-byte loads along HW, 16-/8-byte stores along C.
 template <typename TOut>
-__global__ void nchw_to_nhwc_kernel(const float* __restrict__ in, TOut* __restrict__ out, int C, int HW) {
-  __shared__ float tile[32][33];
+__global__ void __launch_bounds__(256)
+nchw_to_nhwc_kernel(const float* __restrict__ in, TOut* __restrict__ out, int C, int HW) {
+  __shared__ float tile[64][65];
   const int b = blockIdx.z;
-  const int c0 = blockIdx.y * 32, p0 = blockIdx.x * 32;
+  const int c0 = blockIdx.y * 64, p0 = blockIdx.x * 64;
   const float* src = in + (size_t)b * C * HW;
   TOut* dst = out + (size_t)b * C * HW;
-  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
-    int c = c0 + i, p = p0 + threadIdx.x;
-    tile[i][threadIdx.x] = (c < C && p < HW) ? src[(size_t)c * HW + p] : 0.f;
+  const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;     // 16 x 16
+  const bool vec_in = (HW & 3) == 0;
+#pragma unroll
+  for (int i = 0; i < 4; i++) {
+    const int c = c0 + ty + 16 * i, p = p0 + tx * 4;
+    float v[4] = {0.f, 0.f, 0.f, 0.f};
+    if (c < C) {
+      if (vec_in && p + 3 < HW) {
+        const float4 f = *reinterpret_cast<const float4*>(src + (size_t)c * HW + p);
+        v[0] = f.x; v[1] = f.y; v[2] = f.z; v[3] = f.w;
+      } else {
+#pragma unroll
+        for (int j = 0; j < 4; j++) if (p + j < HW) v[j] = src[(size_t)c * HW + p + j];
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < 4; j++) tile[ty + 16 * i][tx * 4 + j] = v[j];
   }
   __syncthreads();
-  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
-    int p = p0 + i, c = c0 + threadIdx.x;
-    if (c < C && p < HW) dst[(size_t)p * C + c] = (TOut)tile[threadIdx.x][i];
+#pragma unroll
+  for (int i = 0; i < 4; i++) {
+    const int p = p0 + ty + 16 * i, c = c0 + tx * 4;
+    if (p < HW && c < C) {
+      float v[4];
+#pragma unroll
+      for (int j = 0; j < 4; j++) v[j] = tile[tx * 4 + j][ty + 16 * i];
+      TOut* o = dst + (size_t)p * C + c;
+      if ((C & 3) == 0) {
+        if (sizeof(TOut) == 4) *reinterpret_cast<float4*>(o) = make_float4(v[0], v[1], v[2], v[3]);
+        else *reinterpret_cast<uint2*>(o) = make_uint2(pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]));
+      } else {
+#pragma unroll
+        for (int j = 0; j < 4; j++) if (c + j < C) o[j] = (TOut)v[j];
+      }
+    }
   }
 }
 
@@ -439,7 +468,7 @@ using namespace ptb;
 extern "C" int pt_nchw_to_nhwc(const float* in, void* out, int B, int C, int H, int W, int out_bf16, void* stream) {
   if (B <= 0 || C <= 0 || H <= 0 || W <= 0) return PT_OK;
   const int HW = H * W;
-  dim3 grid((HW + 31) / 32, (C + 31) / 32, B), block(32, 8);
+  dim3 grid((HW + 63) / 64, (C + 63) / 64, B), block(256);
   if (out_bf16)
     nchw_to_nhwc_kernel<__nv_bfloat16><<<grid, block, 0, (cudaStream_t)stream>>>(in, (__nv_bfloat16*)out, C, HW);
   else
