@@ -32,7 +32,9 @@ const char* pt_build_arch(void);
  * ratios_host / shake_host are HOST arrays.  img_wh [B,2] = (w,h) per image. */
 int pt_bag_gen(const float* in_rois, long long G, const float* img_wh, int B, const float* ratios_host,
                int n_ratios, const float* shake_host, int n_shake, float min_scale, float* out_rois,
-               unsigned char* valid, void* stream);
+               unsigned char* valid, int rotated, void* stream);
+/* rotated != 0: the OBB twin (OBB_TOD/mmrotate/models/detectors/syn_images_generator_v2.py:26-40): RoIs are
+ * [G,6] (img,cx,cy,w,h,theta); bags are generated on cxcywh_to_xyxy(box[:4]) and returned as cxcywh + theta. */
 
 /* bbox2roi / rbbox2roi (HBB_TOD/mmdet/core/bbox/transforms.py:58-78, OBB_TOD/mmrotate/core/bbox/transforms.py:73-92):
  * boxes [n, ldb] + img_idx [n] int32 -> out_rois [n, box_dim+1] = (img, box...). */
@@ -42,7 +44,14 @@ int pt_make_rois(const float* boxes, int ldb, const int* img_idx, int n, int box
  * weight[n] = all(IoU(neg n, base bags of the same image) < 0.3).  bag_rois sorted by image,
  * bag_offsets [B+1] int32. */
 int pt_neg_weight(const float* neg_rois, int n_neg, const float* bag_rois, const int* bag_offsets, int B,
-                  unsigned char* weight, void* stream);
+                  unsigned char* weight, int rotated, void* stream);
+/* rotated: rbbox_overlaps of [*,6] RoIs (OBB_TOD/.../syn_images_generator_v2.py:146-152). */
+
+/* mmcv.ops.box_iou_rotated behind rbbox_overlaps
+ * (OBB_TOD/mmrotate/core/bbox/iou_calculators/rotate_iou2d_calculator.py:53-89): a [M,5], b [N,5]
+ * (cx,cy,w,h,theta rad); mode 0 iou / 1 iof; clamp_wh != 0 applies rbbox_overlaps' w,h >= 1e-3 clamp. */
+int pt_box_iou_rotated(const float* a, int lda, const float* b, int ldb, long long M, long long N, int mode,
+                       int aligned, int clamp_wh, float* out, void* stream);
 
 /* bbox_overlaps (HBB_TOD/mmdet/core/bbox/iou_calculators/iou2d_calculator.py:74-260):
  * mode 0 iou / 1 iof / 2 giou; a [M,4] row stride lda floats, b [N,4] stride ldb; out (M,N) or,
@@ -102,21 +111,25 @@ int pt_reg_decode(const void* H, int h_f32, long long ldh, int D, const float* W
                   const float* bag_rois, const unsigned char* valid, const float* ref_boxes,
                   const float* real_boxes, int U, int K, float max_w, float max_h, float wh_ratio_clip,
                   float hyper, float eps, float* out_rois, float* out_deltas, float* iou_target, float* sums,
-                  void* stream);
+                  int rotated, void* stream);
 int pt_cls_ins_heads(const void* H, int h_f32, long long ldh, int D, const float* Wcls, const float* bcls,
                      const float* Wins, const float* bins, int C, int M, float* cls, float* ins, void* stream);
 int pt_score_select(const float* cls, const float* ins, const unsigned char* valid, const float* bag_rois,
                     const long long* labels, const float* pseudo, const float* img_wh, int B, int G, int U1,
                     int U2, int C, int topk, float beta, float* merged, float* merged_pts, int* sel_idx,
-                    float* sel_score, float* sums, void* stream);
+                    float* sel_score, float* sums, int rotated, void* stream);
 int pt_neg_loss(const float* neg_cls, const unsigned char* weight, int n, int C, float* sums, void* stream);
-int pt_finalize_losses(const float* sums, int K, int has_neg, float scale_bbox, float scale_bags, float* out,
-                       void* stream);
+int pt_finalize_losses(const float* sums, int K, int has_neg, float scale_bbox, float scale_bags, float pos_w,
+                       float neg_w, float* out, void* stream);
+/* rotated != 0 selects the OBB head's semantics (OBB_TOD/mmrotate/models/dense_heads/rotated_fcos_head_p2rb_ts.py
+ * :1198-1343): 6-column RoIs, decode on the horizontal box with theta carried, rotated-IoU logs, (cx,cy) clamped by
+ * w then h, 5-d merged boxes; pos_w / neg_w are the 0.25 / 0.75 bag-loss weights of :1272,1282 (1 / 1 for HBB). */
 /* fp32 [M,N] -> bf16 [M,3N] = [hi | lo | hi]: activation operand of the fp32-emulation (bf16x3) GEMM */
 int pt_split_bf16x3(const float* in, void* out_bf16, long long M, int N, void* stream);
 /* mean aligned IoU of n pairs: the coarse_bboxes_iou / stage{s}_refine_bboxes_iou logs of
  * HBB_TOD/mmdet/models/detectors/fcos_p2b_teacher_student.py:436-438, :457-459 */
-int pt_aligned_iou_mean(const float* a, int lda, const float* b, int ldb, int n, float* out, void* stream);
+int pt_aligned_iou_mean(const float* a, int lda, const float* b, int ldb, int n, int rotated, float* out,
+                        void* stream);
 
 #ifdef __cplusplus
 }

@@ -69,7 +69,64 @@ def check_hbb(seed=0, ext_cfg=None, fine_cfg=None, topk=1, stages=1):
     return ok
 
 
+def run_ref_obb(o, d, head, stages, cap=100):
+    """The reference's OWN OBB files: syn_images_generator_v2 + TS_P2RBRotatedFCOSHead (negatives injected)."""
+    pb = [b[:cap].clone() for b in d["pseudo_boxes"]]
+    gb = [b[:cap].clone() for b in d["gt_boxes"]]
+    pp = [b[:cap].clone() for b in d["pseudo_points"]]
+    pl = [b[:cap].clone() for b in d["pseudo_labels"]]
+    x = (d["feat"],)
+    losses, per_stage = {}, []
+    with torch.no_grad():
+        for s in range(stages):
+            props, valids, refs, reals = o.syn.MIL_gen_proposals_from_cfg(pp, pb, synth.OBB_FINE_CFG[s], gb, d["img_metas"])
+            negs = d["neg_boxes"][s]
+            nw = [((o.rbbox_overlaps(negs[i], props[i]) < 0.3).sum(1) == props[i].shape[0]) for i in range(len(negs))]
+            num_gt = sum(b.shape[0] for b in pb)
+            R = head.forward_mil_head(num_gt, [b.shape[0] for b in pb], x, props, valids, refs, reals, d["img_metas"],
+                                      synth.OBB_EXT_CFG[s], s, negs, nw)
+            lb = head.mil_bag_training(R, pl, nw)
+            merged = head.mil_bag_selection(R, d["img_metas"], pb, pl)
+            per_stage.append(dict(R=R, loss_mil_bags=lb, merged=torch.cat(merged), neg_weight=torch.cat(nw),
+                                  base_bags=torch.cat(props), base_valid=torch.cat(valids)))
+            pb = list(merged)
+            losses[f"stage{s}_loss_mil_bbox"] = R["loss_mil_bbox"]
+            losses[f"stage{s}_loss_mil_bags"] = lb
+            losses[f"stage{s}_coarse_bags_iou"] = R["coarse_bags_iou"]
+            losses[f"stage{s}_refine_bags_iou"] = R["refine_bags_iou"]
+    return pb, losses, per_stage
+
+
+def check_obb(seed=0, **small):
+    from oracle import obb
+    o = ref_shim.install_obb()
+    d = synth.obb_batch(seed=seed, **small)
+    head = ref_shim.build_ref_obb_mil_head(o, seed=seed)
+    P = hbb.MilHeadParams(num_classes=9, num_stages=1, seed=seed)
+    sd = head.state_dict()
+    for k, v in P.state_dict().items():
+        assert torch.equal(sd[k], v), k
+    t0 = time.perf_counter()
+    rpb, rl, _ = run_ref_obb(o, d, head, 1)
+    t1 = time.perf_counter()
+    with torch.no_grad():
+        ob, op, ol, aux = obb.phase2_refine(P, (d["feat"],), [d["stride"]], d["img_metas"], d["pseudo_boxes"],
+                                            d["pseudo_points"], d["pseudo_labels"], d["gt_boxes"], synth.OBB_FINE_CFG,
+                                            synth.OBB_EXT_CFG, alpha=(1.0, 1.0), injected_negs=d["neg_boxes"])
+    print(f"OBB seed {seed}: reference {t1 - t0:.2f}s, oracle {time.perf_counter() - t1:.2f}s")
+    ok = True
+    for i in range(len(rpb)):
+        ok &= _eq(ob[i][:100], rpb[i], f"OBB refined boxes img{i}", 0.0)
+    for k, v in rl.items():
+        ok &= _eq(ol[k], v, "OBB " + k, 1e-6)
+    return ok
+
+
 if __name__ == "__main__":
+    if "--obb" in sys.argv:
+        good = check_obb(0, batch=2, img_hw=(512, 512), gt_range=(20, 30), n_neg=40)
+        print("ALL OK" if good else "MISMATCH")
+        sys.exit(0 if good else 1)
     good = check_hbb(0)
     good &= check_hbb(1, topk=3)
     good &= check_hbb(2, stages=2)

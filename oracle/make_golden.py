@@ -13,6 +13,7 @@ from point_teacher_b200 import synth
 OUT = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests", "golden")
 
 SMALL = dict(batch=2, img_hw=(256, 256), gt_range=(6, 10), n_neg=20)
+OBB_SMALL = dict(batch=2, img_hw=(256, 256), gt_range=(6, 10), n_neg=20)
 
 
 def hbb_case(seed, stages, topk, tag):
@@ -49,6 +50,33 @@ def hbb_case(seed, stages, topk, tag):
     print("wrote", tag, {k: tuple(v.shape) for k, v in out["per_stage"][0].items() if hasattr(v, "shape")})
 
 
+def obb_case(seed, tag):
+    """OBB twin: the reference's own OBB_TOD files (rotated kernels bound to oracle/rotated.py by the shim)."""
+    from oracle import check_oracle_vs_ref as chk
+    o = ref_shim.install_obb()
+    d = synth.obb_batch(seed=seed, **OBB_SMALL)
+    head = ref_shim.build_ref_obb_mil_head(o, seed=seed)
+    with torch.no_grad():
+        pb, losses, per_stage = chk.run_ref_obb(o, d, head, 1)
+    st = per_stage[0]
+    R = st["R"]
+    cap = 100
+    pbx = [b[:cap] for b in d["pseudo_boxes"]]
+    props, _, refs, _ = o.syn.MIL_gen_proposals_from_cfg([b[:cap] for b in d["pseudo_points"]], pbx,
+                                                         synth.OBB_FINE_CFG[0], [b[:cap] for b in d["gt_boxes"]],
+                                                         d["img_metas"])
+    ebags, _, _, _ = o.syn.MIL_gen_proposals_from_cfg([p[:, :2] for p in props], props, synth.OBB_EXT_CFG[0], refs,
+                                                      d["img_metas"])
+    out = dict(seed=seed, small=OBB_SMALL, topk=3, merged=st["merged"], neg_weight=st["neg_weight"],
+               base_bags=st["base_bags"], base_valid=st["base_valid"],
+               ext_bags=torch.cat(ebags),
+               ext_valid=torch.cat(R["extensive_bags_valid"]), refined_bags=torch.cat(R["extensive_bags"]),
+               cls_score=R["cls_score"], ins_score=R["ins_score"], neg_cls_score=R["neg_cls_score"],
+               losses={k: v.clone() for k, v in losses.items()})
+    torch.save(out, os.path.join(OUT, f"obb_phase2_{tag}.pt"))
+    print("wrote obb", tag, {k: tuple(v.shape) for k, v in out.items() if hasattr(v, "shape")})
+
+
 def overlaps_case():
     ns = ref_shim.install()
     g = torch.Generator().manual_seed(7)
@@ -67,3 +95,4 @@ if __name__ == "__main__":
     hbb_case(0, 1, 1, "s1_top1")
     hbb_case(1, 2, 3, "s2_top3")
     overlaps_case()
+    obb_case(0, "s1_top3")

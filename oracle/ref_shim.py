@@ -314,3 +314,102 @@ def build_ref_mil_head(ns, num_classes=8, num_stages=1, top_k=1, beta=0.25, hype
         head.fc_reg.append(lin(1024, 4))
     torch.cuda.empty_cache = lambda: None
     return head
+
+
+_OBB = None
+
+
+def install_obb():
+    """OBB flavour: additionally import the unmodified OBB_TOD/mmrotate leaf files for the rotated MIL path
+    (HBB_TOD's mmdet serves as the ``mmdet`` the OBB tree imports)."""
+    global _OBB
+    if _OBB is not None:
+        return _OBB
+    ns = install()
+    from . import rotated as _rot
+    obb = os.path.join(REF_ROOT, "OBB_TOD", "mmrotate")
+    p = lambda *a: os.path.join(obb, *a)  # noqa: E731
+    mmr = _mk("mmrotate", obb, __version__="0.3.3")
+    core = _mk("mmrotate.core", p("core"))
+    _mk("mmrotate.core.bbox", p("core", "bbox"))
+    _mk("mmrotate.core.bbox.iou_calculators", p("core", "bbox", "iou_calculators"))
+    _mk("mmrotate.core.visualization", p("core", "visualization"))
+    _mk("mmrotate.core.visualization.palette", get_palette=lambda *a, **k: None)
+    _mk("mmrotate.models", p("models"))
+    for sub in ("detectors", "dense_heads", "roi_heads"):
+        _mk(f"mmrotate.models.{sub}", p("models", sub))
+    _mk("mmrotate.models.roi_heads.roi_extractors", p("models", "roi_heads", "roi_extractors"))
+    # extra mmdet / mmcv names the OBB leaf files import
+    _mk("mmdet.core.visualization", palette_val=lambda *a, **k: None)
+    _mk("mmdet.core.visualization.image", draw_labels=None, draw_masks=None)
+    _mk("mmdet.models.roi_heads.bbox_heads", None)
+    _mk("mmdet.models.roi_heads.bbox_heads.bbox_head", BBoxHead=nn.Module)
+    sys.modules["mmdet.models.losses"].accuracy = None
+    sys.modules["mmcv.utils"].to_2tuple = lambda v: (v, v) if not isinstance(v, (tuple, list)) else tuple(v)
+    sys.modules["mmcv"].digit_version = lambda v: tuple(int(x) for x in v.split(".")[:3])
+    mmr.digit_version = sys.modules["mmcv"].digit_version
+    mmr.mmcv_version = (1, 7, 0)
+    import mmcv.ops as mops  # the stub
+    mops.RiRoIAlignRotated = type("RiRoIAlignRotated", (), {})
+    sys.modules["mmcv"].ops = mops
+    iou_b = _imp("mmdet.core.bbox.iou_calculators.builder")
+    MODELS = sys.modules["mmdet.models.builder"].MODELS
+    _mk("mmrotate.models.builder", ROTATED_HEADS=MODELS, ROTATED_ROI_EXTRACTORS=MODELS, ROTATED_LOSSES=MODELS,
+        build_loss=lambda cfg: build_from_cfg(cfg, MODELS), build_roi_extractor=lambda cfg: build_from_cfg(cfg, MODELS))
+    sys.modules["mmrotate.models"].builder = sys.modules["mmrotate.models.builder"]
+    rb = _imp("mmrotate.core.bbox.iou_calculators.builder")
+    riou = _imp("mmrotate.core.bbox.iou_calculators.rotate_iou2d_calculator")
+    ic = sys.modules["mmrotate.core.bbox.iou_calculators"]
+    ic.build_iou_calculator, ic.rbbox_overlaps = rb.build_iou_calculator, riou.rbbox_overlaps
+    tr = _imp("mmrotate.core.bbox.transforms")
+    core.build_bbox_coder = sys.modules["mmdet.core"].build_bbox_coder
+    core.multiclass_nms_rotated = None
+    core.rbbox2roi = tr.rbbox2roi
+    core.obb2poly_np = getattr(tr, "obb2poly_np", None)
+    sys.modules["mmdet.core"].bbox_overlaps = ns.bbox_overlaps
+    _mk("mmrotate.models.dense_heads.rotated_anchor_free_head", RotatedAnchorFreeHead=nn.Module)
+    rext = _imp("mmrotate.models.roi_heads.roi_extractors.rotate_single_level_roi_extractor")
+    syn = _imp("mmrotate.models.detectors.syn_images_generator_v2")
+    head = _imp("mmrotate.models.dense_heads.rotated_fcos_head_p2rb_ts")
+    # OBB_TOD targets the un-vendored mmdet >= 2.2x whose _expand_onehot_labels takes ``ignore_index`` and
+    # returns a 3-tuple; HBB_TOD's vendored 2.13 version is wrapped to that signature.
+    _old = head._expand_onehot_labels
+    head._expand_onehot_labels = lambda labels, w, ch, ignore_index=None: _old(labels, w, ch) + (None,)
+    _OBB = types.SimpleNamespace(hbb=ns, rbbox_overlaps=riou.rbbox_overlaps, transforms=tr, syn=syn,
+                                 RotatedSingleRoIExtractor=rext.RotatedSingleRoIExtractor, head_mod=head,
+                                 TS_P2RBRotatedFCOSHead=head.TS_P2RBRotatedFCOSHead)
+    return _OBB
+
+
+def build_ref_obb_mil_head(o, num_classes=9, num_stages=1, top_k=3, beta=0.25, hyper=0.2, in_channels=256,
+                           stride=8, seed=0):
+    """``TS_P2RBRotatedFCOSHead`` with only the MIL attributes populated."""
+    H = o.TS_P2RBRotatedFCOSHead
+    head = H.__new__(H)
+    nn.Module.__init__(head)
+    head.beta, head.topk, head.num_classes, head.num_stages = beta, top_k, num_classes, num_stages
+    head.in_channels = in_channels
+    head.bbox_roi_extractor = o.RotatedSingleRoIExtractor(
+        roi_layer=dict(type="RoIAlignRotated", out_size=7, sample_num=2, clockwise=True), out_channels=in_channels,
+        featmap_strides=[stride])
+    head.mil_bbox_decoder = o.hbb.DeltaXYWHBBoxCoder(target_means=[.0, .0, .0, .0], target_stds=[1., 1., 1., 1.])
+    head.loss_bbox_denosing = o.hbb.DN_DIoULoss(loss_weight=1.0, hyper=hyper)   # OBB does not ship DN_DIoULoss
+    head.relu = nn.ReLU(inplace=True)
+    g = torch.Generator().manual_seed(seed)
+
+    def lin(i, oo):
+        l = nn.Linear(i, oo)
+        with torch.no_grad():
+            l.weight.copy_(torch.randn(oo, i, generator=g) * 0.01)
+            l.bias.zero_()
+        return l
+    head.shared_fcs_reg, head.shared_fcs_bag = nn.ModuleList(), nn.ModuleList()
+    head.fc_cls, head.fc_ins, head.fc_reg = nn.ModuleList(), nn.ModuleList(), nn.ModuleList()
+    for _ in range(num_stages):
+        head.shared_fcs_reg.append(nn.ModuleList([lin(in_channels * 49, 1024), lin(1024, 1024)]))
+        head.shared_fcs_bag.append(nn.ModuleList([lin(in_channels * 49, 1024), lin(1024, 1024)]))
+        head.fc_cls.append(lin(1024, num_classes))
+        head.fc_ins.append(lin(1024, num_classes))
+        head.fc_reg.append(lin(1024, 4))
+    torch.cuda.empty_cache = lambda: None
+    return head

@@ -15,9 +15,11 @@ SIGNATURES = {
     "pt_abi_version": (c_int, []),
     "pt_build_arch": (ctypes.c_char_p, []),
     "pt_bag_gen": (c_int, [c_void_p, c_ll, c_void_p, c_int, c_fp, c_int, c_fp, c_int, c_float, c_void_p,
-                           c_void_p, c_void_p]),
+                           c_void_p, c_int, c_void_p]),
     "pt_make_rois": (c_int, [c_void_p, c_int, c_void_p, c_int, c_int, c_void_p, c_void_p]),
-    "pt_neg_weight": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_int, c_void_p, c_void_p]),
+    "pt_neg_weight": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_int, c_void_p, c_int, c_void_p]),
+    "pt_box_iou_rotated": (c_int, [c_void_p, c_int, c_void_p, c_int, c_ll, c_ll, c_int, c_int, c_int, c_void_p,
+                                   c_void_p]),
     "pt_bbox_overlaps": (c_int, [c_void_p, c_int, c_void_p, c_int, c_ll, c_ll, c_int, c_int, c_float, c_void_p,
                                  c_void_p]),
     "pt_nchw_to_nhwc": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p]),
@@ -32,16 +34,16 @@ SIGNATURES = {
     "pt_cast_weight_bf16": (c_int, [c_void_p, c_void_p, c_int, c_int, c_ll, c_int, c_void_p]),
     "pt_reg_decode": (c_int, [c_void_p, c_int, c_ll, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                               c_void_p, c_int, c_int, c_float, c_float, c_float, c_float, c_float, c_void_p,
-                              c_void_p, c_void_p, c_void_p, c_void_p]),
+                              c_void_p, c_void_p, c_void_p, c_int, c_void_p]),
     "pt_cls_ins_heads": (c_int, [c_void_p, c_int, c_ll, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int,
                                  c_void_p, c_void_p, c_void_p]),
     "pt_score_select": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int,
                                 c_int, c_int, c_int, c_int, c_float, c_void_p, c_void_p, c_void_p, c_void_p,
-                                c_void_p, c_void_p]),
+                                c_void_p, c_int, c_void_p]),
     "pt_neg_loss": (c_int, [c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p]),
-    "pt_finalize_losses": (c_int, [c_void_p, c_int, c_int, c_float, c_float, c_void_p, c_void_p]),
+    "pt_finalize_losses": (c_int, [c_void_p, c_int, c_int, c_float, c_float, c_float, c_float, c_void_p, c_void_p]),
     "pt_split_bf16x3": (c_int, [c_void_p, c_void_p, c_ll, c_int, c_void_p]),
-    "pt_aligned_iou_mean": (c_int, [c_void_p, c_int, c_void_p, c_int, c_int, c_void_p, c_void_p]),
+    "pt_aligned_iou_mean": (c_int, [c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p]),
 }
 
 _LIB = None

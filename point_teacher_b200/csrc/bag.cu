@@ -9,6 +9,7 @@
 //   bbox_overlaps                HBB_TOD/mmdet/core/bbox/iou_calculators/iou2d_calculator.py:74-260
 // Bit-exact contract: every fp32 operation is issued in the reference's order with non-contracted intrinsics.
 #include "common.cuh"
+#include "rotated_iou.cuh"
 
 namespace ptb {
 
@@ -32,7 +33,7 @@ __device__ __forceinline__ bool inside_image(float x1, float y1, float x2, float
 __global__ void bag_gen_kernel(const float* __restrict__ in_rois, const float* __restrict__ img_wh, int B,
                                long long total, int U, const __grid_constant__ BagCfg cfg,
                                float* __restrict__ out_rois,
-                               uint8_t* __restrict__ valid) {
+                               uint8_t* __restrict__ valid, int rotated) {
   const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= total) return;
   const int S = 1 + 4 * cfg.n_shake;
@@ -40,8 +41,16 @@ __global__ void bag_gen_kernel(const float* __restrict__ in_rois, const float* _
   const int u = (int)(idx - g * U);
   const int rr = u / S, s = u - rr * S;
   const float rw = cfg.ratios[rr / cfg.n_ratios], rh = cfg.ratios[rr % cfg.n_ratios];
-  const float* r = in_rois + g * 5;
-  const float bimg = r[0], bx1 = r[1], by1 = r[2], bx2 = r[3], by2 = r[4];
+  // rotated (OBB_TOD/.../syn_images_generator_v2.py:26-40): bags are generated on the horizontal box
+  // cxcywh_to_xyxy(obb[:, :4]) and come back as (cx, cy, w, h) with the pseudo box's angle re-attached
+  const float* r = in_rois + g * (rotated ? 6 : 5);
+  const float bimg = r[0];
+  float bx1 = r[1], by1 = r[2], bx2 = r[3], by2 = r[4];
+  if (rotated) {
+    const float ocx = r[1], ocy = r[2], ow = r[3], oh = r[4];
+    bx1 = fsub(ocx, fmul(0.5f, ow)); by1 = fsub(ocy, fmul(0.5f, oh));
+    bx2 = fadd(ocx, fmul(0.5f, ow)); by2 = fadd(ocy, fmul(0.5f, oh));
+  }
   // xyxy -> cxcywh, clamp, scale, back (:277-283)
   float cx = fdiv(fadd(bx1, bx2), 2.f), cy = fdiv(fadd(by1, by2), 2.f);
   float w = fsub(bx2, bx1), h = fsub(by2, by1);
@@ -65,8 +74,14 @@ __global__ void bag_gen_kernel(const float* __restrict__ in_rois, const float* _
   int bi = (int)bimg;
   bi = bi < 0 ? 0 : (bi >= B ? B - 1 : bi);
   const float iw = img_wh[2 * bi], ih = img_wh[2 * bi + 1];
-  float* o = out_rois + idx * 5;
-  o[0] = bimg; o[1] = x1; o[2] = y1; o[3] = x2; o[4] = y2;
+  if (rotated) {
+    float* o = out_rois + idx * 6;
+    o[0] = bimg; o[1] = fdiv(fadd(x1, x2), 2.f); o[2] = fdiv(fadd(y1, y2), 2.f);
+    o[3] = fsub(x2, x1); o[4] = fsub(y2, y1); o[5] = r[5];
+  } else {
+    float* o = out_rois + idx * 5;
+    o[0] = bimg; o[1] = x1; o[2] = y1; o[3] = x2; o[4] = y2;
+  }
   valid[idx] = inside_image(x1, y1, x2, y2, iw, ih) ? 1 : 0;
 }
 
@@ -83,17 +98,22 @@ __device__ __forceinline__ float iou_xyxy(float ax1, float ay1, float ax2, float
 // One warp per negative: weight = all(IoU(neg, every base bag of the same image) < 0.3).
 // bag_rois [Kb,5] sorted by image, bag_offsets [B+1].
 __global__ void neg_weight_kernel(const float* __restrict__ neg_rois, int n_neg, const float* __restrict__ bag_rois,
-                                  const int* __restrict__ bag_offsets, int B, uint8_t* __restrict__ weight) {
+                                  const int* __restrict__ bag_offsets, int B, uint8_t* __restrict__ weight,
+                                  int rotated) {
   const int wid = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   if (wid >= n_neg) return;
-  const float* n = neg_rois + (size_t)wid * 5;
+  const int st = rotated ? 6 : 5;
+  const float* n = neg_rois + (size_t)wid * st;
   int b = (int)n[0];
   b = b < 0 ? 0 : (b >= B ? B - 1 : b);
   const float x1 = n[1], y1 = n[2], x2 = n[3], y2 = n[4];
   bool ok = true;
   for (int i = bag_offsets[b] + lane; i < bag_offsets[b + 1]; i += 32) {
-    const float* p = bag_rois + (size_t)i * 5;
-    if (!(iou_xyxy(x1, y1, x2, y2, p[1], p[2], p[3], p[4]) < 0.3f)) ok = false;
+    const float* p = bag_rois + (size_t)i * st;
+    // rotated: rbbox_overlaps(neg, bags) with the negative's (x1,y1,x2,y2,theta) read as (cx,cy,w,h,theta)
+    // (OBB_TOD/.../syn_images_generator_v2.py:146-152, reference quirk)
+    const float v = rotated ? riou::clamped_iou(n + 1, p + 1, 0) : iou_xyxy(x1, y1, x2, y2, p[1], p[2], p[3], p[4]);
+    if (!(v < 0.3f)) ok = false;
   }
   ok = __all_sync(0xffffffffu, ok);
   if (lane == 0) weight[wid] = ok ? 1 : 0;
@@ -128,15 +148,27 @@ __global__ void bbox_overlaps_kernel(const float* __restrict__ a, int lda, const
   }
 }
 
+// rbbox_overlaps (rotate_iou2d_calculator.py:53-89): a [M,5], b [N,5] (cx,cy,w,h,theta), mode 0 iou / 1 iof
+__global__ void box_iou_rotated_kernel(const float* __restrict__ a, int lda, const float* __restrict__ b, int ldb,
+                                       long long M, long long N, int mode, int aligned, int clamp_wh,
+                                       float* __restrict__ out) {
+  const long long total = aligned ? M : M * N;
+  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+       idx += (long long)gridDim.x * blockDim.x) {
+    const long long i = aligned ? idx : idx / N, j = aligned ? idx : idx - i * N;
+    out[idx] = clamp_wh ? riou::clamped_iou(a + i * lda, b + j * ldb, mode) : riou::single_iou(a + i * lda, b + j * ldb, mode);
+  }
+}
+
 // mean aligned IoU of n box pairs (the coarse_bboxes_iou / refine_bboxes_iou logs,
 // fcos_p2b_teacher_student.py:436-438, :457-459); single block, fixed summation order.
 __global__ void aligned_iou_mean_kernel(const float* __restrict__ a, int lda, const float* __restrict__ b, int ldb,
-                                        int n, float* __restrict__ out) {
+                                        int n, float* __restrict__ out, int rotated) {
   __shared__ float red[32];
   float acc = 0.f;
   for (int i = threadIdx.x; i < n; i += blockDim.x) {
     const float* pa = a + (size_t)i * lda; const float* pb = b + (size_t)i * ldb;
-    acc += iou_xyxy(pa[0], pa[1], pa[2], pa[3], pb[0], pb[1], pb[2], pb[3]);
+    acc += rotated ? riou::clamped_iou(pa, pb, 0) : iou_xyxy(pa[0], pa[1], pa[2], pa[3], pb[0], pb[1], pb[2], pb[3]);
   }
   acc = warp_sum(acc);
   if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
@@ -152,14 +184,28 @@ __global__ void aligned_iou_mean_kernel(const float* __restrict__ a, int lda, co
 
 using namespace ptb;
 
-extern "C" int pt_aligned_iou_mean(const float* a, int lda, const float* b, int ldb, int n, float* out, void* stream) {
-  aligned_iou_mean_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(a, lda, b, ldb, n, out);
+extern "C" int pt_aligned_iou_mean(const float* a, int lda, const float* b, int ldb, int n, int rotated, float* out,
+                                   void* stream) {
+  aligned_iou_mean_kernel<<<1, rotated ? 256 : 1024, 0, (cudaStream_t)stream>>>(a, lda, b, ldb, n, out, rotated);
   return check_launch("aligned_iou_mean_kernel");
+}
+
+extern "C" int pt_box_iou_rotated(const float* a, int lda, const float* b, int ldb, long long M, long long N, int mode,
+                                  int aligned, int clamp_wh, float* out, void* stream) {
+  if (mode < 0 || mode > 1) { set_error("pt_box_iou_rotated: mode must be 0 iou / 1 iof"); return PT_ERR_ARG; }
+  if (aligned && M != N) { set_error("pt_box_iou_rotated: aligned needs M == N"); return PT_ERR_ARG; }
+  const long long total = aligned ? M : M * N;
+  if (total <= 0) return PT_OK;
+  long long blocks = (total + 127) / 128;
+  if (blocks > 148LL * 16) blocks = 148LL * 16;
+  box_iou_rotated_kernel<<<(unsigned)blocks, 128, 0, (cudaStream_t)stream>>>(a, lda, b, ldb, M, N, mode, aligned,
+                                                                             clamp_wh, out);
+  return check_launch("box_iou_rotated_kernel");
 }
 
 extern "C" int pt_bag_gen(const float* in_rois, long long G, const float* img_wh, int B, const float* ratios,
                           int n_ratios, const float* shake, int n_shake, float min_scale, float* out_rois,
-                          unsigned char* valid, void* stream) {
+                          unsigned char* valid, int rotated, void* stream) {
   if (n_ratios <= 0 || n_ratios > 16 || n_shake < 0 || n_shake > 8) {
     set_error("pt_bag_gen: need 1..16 base ratios and 0..8 shake ratios (got %d, %d)", n_ratios, n_shake);
     return PT_ERR_ARG;
@@ -174,16 +220,16 @@ extern "C" int pt_bag_gen(const float* in_rois, long long G, const float* img_wh
   const int threads = 256;
   const long long blocks = (total + threads - 1) / threads;
   bag_gen_kernel<<<(unsigned)blocks, threads, 0, (cudaStream_t)stream>>>(in_rois, img_wh, B, total, U, cfg, out_rois,
-                                                                         valid);
+                                                                         valid, rotated);
   return check_launch("bag_gen_kernel");
 }
 
 extern "C" int pt_neg_weight(const float* neg_rois, int n_neg, const float* bag_rois, const int* bag_offsets, int B,
-                             unsigned char* weight, void* stream) {
+                             unsigned char* weight, int rotated, void* stream) {
   if (n_neg <= 0) return PT_OK;
   const int threads = 256, wpb = threads / 32;
   neg_weight_kernel<<<(n_neg + wpb - 1) / wpb, threads, 0, (cudaStream_t)stream>>>(neg_rois, n_neg, bag_rois,
-                                                                                   bag_offsets, B, weight);
+                                                                                   bag_offsets, B, weight, rotated);
   return check_launch("neg_weight_kernel");
 }
 

@@ -11,6 +11,7 @@
 // (value, index) pairs with a value-only comparator) so selected indices match the
 // reference's CPU path even on exact ties.
 #include "common.cuh"
+#include "rotated_iou.cuh"
 #include "topk_replay.cuh"
 
 namespace ptb {
@@ -168,7 +169,7 @@ __global__ void reg_decode_kernel(const TH* __restrict__ H, long long ldh, int D
                                   const float* __restrict__ real_boxes, int U, int K, float max_w, float max_h,
                                   float max_ratio, float hyper, float eps, float* __restrict__ out_rois,
                                   float* __restrict__ out_deltas, float* __restrict__ iou_target,
-                                  float* __restrict__ sums) {
+                                  float* __restrict__ sums, int rotated) {
   extern __shared__ float wsm[];  // [4][D] + reduction scratch
   for (int i = threadIdx.x; i < 4 * D; i += blockDim.x) wsm[i] = Wreg[i];
   __syncthreads();
@@ -186,12 +187,20 @@ __global__ void reg_decode_kernel(const TH* __restrict__ H, long long ldh, int D
       for (int j = 0; j < 4; j++) d[j] = (lane == r) ? dd[r][j] : d[j];
     const int k = kb + lane;          // lane r decodes row kb + r
     if (lane < nrows) {
-      const float* r = bag_rois + (size_t)k * 5;
+      // rotated (OBB_TOD/.../rotated_fcos_head_p2rb_ts.py:1314-1343): decode on cxcywh_to_xyxy(bag[:, :4]),
+      // DN-DIoU against cxcywh_to_xyxy(reference[:, :4]), refined bag = xyxy_to_cxcywh(pred) + the bag's angle
+      const int rs = rotated ? 6 : 5, bs = rotated ? 5 : 4;
+      const float* r = bag_rois + (size_t)k * rs;
       float dx = d[0] + breg[0], dy = d[1] + breg[1], dw = d[2] + breg[2], dh = d[3] + breg[3];
       if (out_deltas) { float* od = out_deltas + (size_t)k * 4; od[0] = dx; od[1] = dy; od[2] = dw; od[3] = dh; }
+      float rx1 = r[1], ry1 = r[2], rx2 = r[3], ry2 = r[4];
+      if (rotated) {
+        rx1 = fsub(r[1], fmul(0.5f, r[3])); ry1 = fsub(r[2], fmul(0.5f, r[4]));
+        rx2 = fadd(r[1], fmul(0.5f, r[3])); ry2 = fadd(r[2], fmul(0.5f, r[4]));
+      }
       // delta2bbox, means 0 / stds 1 (delta_xywh_bbox_coder.py:209-247)
-      const float px = fmul(fadd(r[1], r[3]), 0.5f), py = fmul(fadd(r[2], r[4]), 0.5f);
-      const float pw = fsub(r[3], r[1]), ph = fsub(r[4], r[2]);
+      const float px = fmul(fadd(rx1, rx2), 0.5f), py = fmul(fadd(ry1, ry2), 0.5f);
+      const float pw = fsub(rx2, rx1), ph = fsub(ry2, ry1);
       dw = fminf(fmaxf(dw, -max_ratio), max_ratio);
       dh = fminf(fmaxf(dh, -max_ratio), max_ratio);
       const float gw = fmul(pw, expf(dw)), gh = fmul(ph, expf(dh));
@@ -200,13 +209,26 @@ __global__ void reg_decode_kernel(const TH* __restrict__ H, long long ldh, int D
                     fadd(gy, fmul(gh, 0.5f))};
       b[0] = fminf(fmaxf(b[0], 0.f), max_w); b[2] = fminf(fmaxf(b[2], 0.f), max_w);
       b[1] = fminf(fmaxf(b[1], 0.f), max_h); b[3] = fminf(fmaxf(b[3], 0.f), max_h);
-      float* o = out_rois + (size_t)k * 5;
-      o[0] = r[0]; o[1] = b[0]; o[2] = b[1]; o[3] = b[2]; o[4] = b[3];
-      const float* ref = ref_boxes + (size_t)(k / U) * 4;
-      const float* real = real_boxes + (size_t)(k / U) * 4;
-      if (iou_target) iou_target[k] = aligned_iou(b, ref);
-      part[3] += aligned_iou(b, real);
-      part[4] += aligned_iou(r + 1, real);
+      float* o = out_rois + (size_t)k * rs;
+      const float* refp = ref_boxes + (size_t)(k / U) * bs;
+      const float* real = real_boxes + (size_t)(k / U) * bs;
+      float ref[4];
+      if (rotated) {
+        const float ob[5] = {fdiv(fadd(b[0], b[2]), 2.f), fdiv(fadd(b[1], b[3]), 2.f), fsub(b[2], b[0]),
+                             fsub(b[3], b[1]), r[5]};
+        o[0] = r[0]; o[1] = ob[0]; o[2] = ob[1]; o[3] = ob[2]; o[4] = ob[3]; o[5] = ob[4];
+        ref[0] = fsub(refp[0], fmul(0.5f, refp[2])); ref[1] = fsub(refp[1], fmul(0.5f, refp[3]));
+        ref[2] = fadd(refp[0], fmul(0.5f, refp[2])); ref[3] = fadd(refp[1], fmul(0.5f, refp[3]));
+        if (iou_target) iou_target[k] = aligned_iou(b, ref);
+        part[3] += riou::clamped_iou(ob, real, 0);
+        part[4] += riou::clamped_iou(r + 1, real, 0);
+      } else {
+        o[0] = r[0]; o[1] = b[0]; o[2] = b[1]; o[3] = b[2]; o[4] = b[3];
+        ref[0] = refp[0]; ref[1] = refp[1]; ref[2] = refp[2]; ref[3] = refp[3];
+        if (iou_target) iou_target[k] = aligned_iou(b, ref);
+        part[3] += aligned_iou(b, real);
+        part[4] += aligned_iou(r + 1, real);
+      }
       // DN-DIoU (iou_loss.py:398-466): min over the 3x3 noisy targets, plus the scalar mean base loss
       part[0] += diou_elem(b, ref, eps);
       const float anx = hyper / 2.f, tw = ref[2] - ref[0], th = ref[3] - ref[1];
@@ -269,7 +291,7 @@ __global__ void score_select_kernel(const float* __restrict__ cls, const float* 
                                     const float* __restrict__ img_wh, int B, int G, int U1, int U2, int C, int topk,
                                     float beta, float* __restrict__ merged, float* __restrict__ merged_pts,
                                     int* __restrict__ sel_idx, float* __restrict__ sel_score,
-                                    float* __restrict__ sums) {
+                                    float* __restrict__ sums, int rotated) {
   extern __shared__ float sm[];
   const int nw = blockDim.x >> 5, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int U = U1 * U2;
@@ -320,30 +342,34 @@ __global__ void score_select_kernel(const float* __restrict__ cls, const float* 
       float wsum = 0.f;
       for (int t = 0; t < topk; t++) wsum += sc[t];
       wsum += 1e-8f;
-      float bx[4] = {0.f, 0.f, 0.f, 0.f};
+      const int bd = rotated ? 5 : 4, rs = bd + 1;
+      float bx[5] = {0.f, 0.f, 0.f, 0.f, 0.f};
       for (int t = 0; t < topk; t++) {
         const float w = sc[t] / wsum;
-        const float* r = bag_rois + ((size_t)g * U + si[t]) * 5;
-#pragma unroll
-        for (int j = 0; j < 4; j++) bx[j] += r[1 + j] * w;
+        const float* r = bag_rois + ((size_t)g * U + si[t]) * rs;
+        for (int j = 0; j < bd; j++) bx[j] += r[1 + j] * w;
         sel_idx[(size_t)g * topk + t] = si[t];
         sel_score[(size_t)g * topk + t] = sc[t];
       }
-      int bi = (int)bag_rois[(size_t)g * U * 5];
+      int bi = (int)bag_rois[(size_t)g * U * rs];
       bi = bi < 0 ? 0 : (bi >= B ? B - 1 : bi);
       const float iw = img_wh[2 * bi], ih = img_wh[2 * bi + 1];
-      bx[0] = fminf(fmaxf(bx[0], 0.f), iw); bx[2] = fminf(fmaxf(bx[2], 0.f), iw);
-      bx[1] = fminf(fmaxf(bx[1], 0.f), ih); bx[3] = fminf(fmaxf(bx[3], 0.f), ih);
-      if (pseudo != nullptr) {   // (1-beta)*box + beta*coarse   (fcos_head_p2b_ts.py:1109)
-        const float* pb = pseudo + (size_t)g * 4;
-#pragma unroll
-        for (int j = 0; j < 4; j++) bx[j] = fadd(fmul(1.f - beta, bx[j]), fmul(beta, pb[j]));
+      if (rotated) {
+        // rotated_fcos_head_p2rb_ts.py:1211-1212: (cx, cy) both clamped to [0, w] and then to [0, h]
+        bx[0] = fminf(fmaxf(fminf(fmaxf(bx[0], 0.f), iw), 0.f), ih);
+        bx[1] = fminf(fmaxf(fminf(fmaxf(bx[1], 0.f), iw), 0.f), ih);
+      } else {
+        bx[0] = fminf(fmaxf(bx[0], 0.f), iw); bx[2] = fminf(fmaxf(bx[2], 0.f), iw);
+        bx[1] = fminf(fmaxf(bx[1], 0.f), ih); bx[3] = fminf(fmaxf(bx[3], 0.f), ih);
       }
-#pragma unroll
-      for (int j = 0; j < 4; j++) merged[(size_t)g * 4 + j] = bx[j];
-      if (merged_pts != nullptr) {  // refined points = box centres (fcos_p2b_teacher_student.py:465)
-        merged_pts[(size_t)g * 2] = fdiv(fadd(bx[0], bx[2]), 2.f);
-        merged_pts[(size_t)g * 2 + 1] = fdiv(fadd(bx[1], bx[3]), 2.f);
+      if (pseudo != nullptr) {   // (1-beta)*box + beta*coarse   (fcos_head_p2b_ts.py:1109)
+        const float* pb = pseudo + (size_t)g * bd;
+        for (int j = 0; j < bd; j++) bx[j] = fadd(fmul(1.f - beta, bx[j]), fmul(beta, pb[j]));
+      }
+      for (int j = 0; j < bd; j++) merged[(size_t)g * bd + j] = bx[j];
+      if (merged_pts != nullptr) {  // refined points = box centres (fcos_p2b_teacher_student.py:465; OBB: box[:, :2])
+        merged_pts[(size_t)g * 2] = rotated ? bx[0] : fdiv(fadd(bx[0], bx[2]), 2.f);
+        merged_pts[(size_t)g * 2 + 1] = rotated ? bx[1] : fdiv(fadd(bx[1], bx[3]), 2.f);
       }
     }
     __syncwarp();
@@ -370,14 +396,14 @@ __global__ void neg_loss_kernel(const float* __restrict__ neg_cls, const uint8_t
 
 // out[0] loss_mil_bbox, out[1] loss_mil_bags, out[2] coarse_bags_iou, out[3] refine_bags_iou, out[4] num_sample
 __global__ void finalize_losses_kernel(const float* __restrict__ sums, int K, int has_neg, float scale_bbox,
-                                       float scale_bags, float* __restrict__ out) {
+                                       float scale_bags, float pos_w, float neg_w, float* __restrict__ out) {
   if (threadIdx.x != 0 || blockIdx.x != 0) return;
   const float Kf = (float)K;
   const float base_mean = sums[S_BASE] / Kf;
   // DN_DIoULoss: (base_mean + min_bank_k)/2 * w_k summed / avg_factor(K); all-zero weights -> 0
   out[0] = scale_bbox * (sums[S_W] > 0.f ? (base_mean * sums[S_W] + sums[S_WMIN]) / 2.f / Kf : 0.f);
   const float ns = fmaxf(sums[S_NSAMPLE], 1.f);
-  out[1] = scale_bags * (sums[S_POS] / ns + (has_neg ? sums[S_NEG] / ns : 0.f));
+  out[1] = scale_bags * (pos_w * (sums[S_POS] / ns) + (has_neg ? neg_w * (sums[S_NEG] / ns) : 0.f));
   out[2] = sums[S_COARSE] / Kf;
   out[3] = sums[S_REFINE] / Kf;
   out[4] = ns;
@@ -428,7 +454,7 @@ extern "C" int pt_reg_decode(const void* H, int h_f32, long long ldh, int D, con
                              const float* bag_rois, const unsigned char* valid, const float* ref_boxes,
                              const float* real_boxes, int U, int K, float max_w, float max_h, float wh_ratio_clip,
                              float hyper, float eps, float* out_rois, float* out_deltas, float* iou_target,
-                             float* sums, void* stream) {
+                             float* sums, int rotated, void* stream) {
   if (K <= 0) return PT_OK;
   if (D % 256 != 0) { set_error("pt_reg_decode: hidden width must be a multiple of 256 (got %d)", D); return PT_ERR_ARG; }
   const int threads = 256;
@@ -440,12 +466,12 @@ extern "C" int pt_reg_decode(const void* H, int h_f32, long long ldh, int D, con
     cudaFuncSetAttribute(reg_decode_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     reg_decode_kernel<float><<<grid, threads, smem, (cudaStream_t)stream>>>(
         (const float*)H, ldh, D, Wreg, breg, bag_rois, valid, ref_boxes, real_boxes, U, K, max_w, max_h, max_ratio,
-        hyper, eps, out_rois, out_deltas, iou_target, sums);
+        hyper, eps, out_rois, out_deltas, iou_target, sums, rotated);
   } else {
     cudaFuncSetAttribute(reg_decode_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     reg_decode_kernel<__nv_bfloat16><<<grid, threads, smem, (cudaStream_t)stream>>>(
         (const __nv_bfloat16*)H, ldh, D, Wreg, breg, bag_rois, valid, ref_boxes, real_boxes, U, K, max_w, max_h,
-        max_ratio, hyper, eps, out_rois, out_deltas, iou_target, sums);
+        max_ratio, hyper, eps, out_rois, out_deltas, iou_target, sums, rotated);
   }
   return check_launch("reg_decode_kernel");
 }
@@ -481,7 +507,7 @@ extern "C" int pt_cls_ins_heads(const void* H, int h_f32, long long ldh, int D, 
 extern "C" int pt_score_select(const float* cls, const float* ins, const unsigned char* valid, const float* bag_rois,
                                const long long* labels, const float* pseudo, const float* img_wh, int B, int G,
                                int U1, int U2, int C, int topk, float beta, float* merged, float* merged_pts,
-                               int* sel_idx, float* sel_score, float* sums, void* stream) {
+                               int* sel_idx, float* sel_score, float* sums, int rotated, void* stream) {
   if (G <= 0) return PT_OK;
   const int U = U1 * U2;
   if (topk < 1 || topk > 16 || topk > U) { set_error("pt_score_select: topk must be in [1, min(16, U)]"); return PT_ERR_ARG; }
@@ -492,7 +518,7 @@ extern "C" int pt_score_select(const float* cls, const float* ins, const unsigne
   int grid = (G + warps - 1) / warps;
   score_select_kernel<<<grid, warps * 32, smem, (cudaStream_t)stream>>>(cls, ins, valid, bag_rois, labels, pseudo,
                                                                         img_wh, B, G, U1, U2, C, topk, beta, merged,
-                                                                        merged_pts, sel_idx, sel_score, sums);
+                                                                        merged_pts, sel_idx, sel_score, sums, rotated);
   return check_launch("score_select_kernel");
 }
 
@@ -503,7 +529,8 @@ extern "C" int pt_neg_loss(const float* neg_cls, const unsigned char* weight, in
 }
 
 extern "C" int pt_finalize_losses(const float* sums, int K, int has_neg, float scale_bbox, float scale_bags,
-                                  float* out, void* stream) {
-  finalize_losses_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(sums, K, has_neg, scale_bbox, scale_bags, out);
+                                  float pos_w, float neg_w, float* out, void* stream) {
+  finalize_losses_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(sums, K, has_neg, scale_bbox, scale_bags, pos_w, neg_w,
+                                                             out);
   return check_launch("finalize_losses_kernel");
 }

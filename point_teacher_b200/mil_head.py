@@ -216,26 +216,29 @@ class MILHeadMixin:
                          labels, pseudo, cfg, stage, loss_scales=(1.0, 1.0)):
         """One MIL stage on packed tensors (the fast path behind ``phase2_refine``): no per-image lists, no
         replicated reference/real boxes (instance k belongs to GT k // (U1*U2)), negatives appended to the
-        classification pass.  base_rois (G*U1,5); ref/real/pseudo (G,4); labels (G,) int64;
-        neg_boxes (Nn,4)|None with neg_img_idx (Nn,) int32; bag_offsets (B+1,) int32 into base_rois.
-        Returns (merged (G,4), merged centres (G,2), losses dict)."""
+        classification pass.  base_rois (G*U1,5|6); ref/real/pseudo (G,4|5); labels (G,) int64;
+        neg_boxes (Nn,4|5)|None with neg_img_idx (Nn,) int32; bag_offsets (B+1,) int32 into base_rois.
+        Returns (merged (G,4|5), merged centres (G,2), losses dict)."""
         dev = x[0].device
-        ebags, evalid = ops.bag_gen(base_rois, img_wh, cfg["base_ratios"], cfg["shake_ratio"], cfg["min_scale"])
+        rot = self.bbox_roi_extractor.rotated
+        rs = 6 if rot else 5
+        ebags, evalid = ops.bag_gen(base_rois, img_wh, cfg["base_ratios"], cfg["shake_ratio"], cfg["min_scale"], rot)
         K, G = ebags.shape[0], pseudo.shape[0]
         U2 = K // max(base_rois.shape[0], 1)
         sums = torch.zeros((8,), dtype=torch.float32, device=dev)
         A = self._roi_operand(x, ebags)
         H = self._fc_stack(A, self.shared_fcs_reg[stage], K)
         n_neg = 0 if neg_boxes is None else neg_boxes.shape[0]
-        rois2 = torch.empty((K + n_neg, 5), dtype=torch.float32, device=dev)
+        rois2 = torch.empty((K + n_neg, rs), dtype=torch.float32, device=dev)
         neg_w = None
         if n_neg:
             ops.make_rois(neg_boxes, neg_img_idx, out=rois2[K:])
-            neg_w = ops.neg_weight(rois2[K:], base_rois, bag_offsets)
+            neg_w = ops.neg_weight(rois2[K:], base_rois, bag_offsets, rot)
         h0, w0, _ = img_metas[0]["img_shape"]
         fr = self.fc_reg[stage]
         _, _, iou_t = ops.reg_decode(H, fr.weight.detach(), fr.bias.detach(), ebags, evalid, ref, real, U1 * U2,
-                                     (w0, h0), sums, K=K, hyper=self.loss_bbox_denosing_hyper, out_rois=rois2)
+                                     (w0, h0), sums, K=K, hyper=self.loss_bbox_denosing_hyper, out_rois=rois2,
+                                     rotated=rot)
         del A, H
         A2 = self._roi_operand(x, rois2)
         H2 = self._fc_stack(A2, self.shared_fcs_bag[stage], K + n_neg)
@@ -243,17 +246,17 @@ class MILHeadMixin:
         cls, ins = ops.cls_ins_heads(H2, fc.weight.detach(), fc.bias.detach(), fi.weight.detach(),
                                      fi.bias.detach(), M=K + n_neg)
         merged, pts, idx, sc = ops.score_select(cls, ins, evalid, rois2, labels, pseudo, img_wh, G, U1, U2,
-                                                self.topk, self.beta, sums)
+                                                self.topk, self.beta, sums, rot)
         if n_neg:
             ops.neg_loss(cls[K:], neg_w, sums)
-        out = ops.finalize_losses(sums, K, bool(n_neg), loss_scales[0] * self.bag_loss_bbox_scale,
-                                  loss_scales[1])
+        out = ops.finalize_losses(sums, K, bool(n_neg), loss_scales[0], loss_scales[1], self.bag_loss_pos_scale,
+                                  self.bag_loss_neg_scale)
         losses = {f"stage{stage}_loss_mil_bbox": out[0], f"stage{stage}_loss_mil_bags": out[1],
                   f"stage{stage}_coarse_bags_iou": out[2], f"stage{stage}_refine_bags_iou": out[3]}
         self.last_results = dict(
             cls_score=cls[:K].view(G, U1, U2, -1), ins_score=ins[:K].view(G, U1, U2, -1),
             neg_cls_score=cls[K:] if n_neg else None, neg_weight=neg_w, iou_target=iou_t,
-            extensive_bags=[rois2[:K, 1:5]], base_shaking_num=U1, extensive_shaking_num=U2,
+            extensive_bags=[rois2[:K, 1:rs]], base_shaking_num=U1, extensive_shaking_num=U2,
             _b200=dict(sums=sums, K=K, evalid=evalid, refined=rois2[:K], coarse=ebags, img_wh=img_wh, cls=cls,
                        ins=ins, n_neg=n_neg, U1=U1, U2=U2, sel_idx=idx, sel_score=sc, merged_points=pts))
         return merged, pts, losses
@@ -297,3 +300,23 @@ class MILHead(nn.Module, MILHeadMixin):
         self.bbox_roi_extractor = build_roi_extractor(bbox_roi_extractor)
         self.conv_mil = nn.ModuleList()
         self._init_mil_layers()
+
+
+@HEADS.register_module(name="B200RotatedMILHead", force=True)
+class RotatedMILHead(MILHead):
+    """MIL part of ``TS_P2RBRotatedFCOSHead`` (OBB_TOD/mmrotate/models/dense_heads/rotated_fcos_head_p2rb_ts.py
+    :1186-1453): 5-d boxes, RoIAlignRotated, regression on the horizontal (cx,cy,w,h) box with the angle
+    carried through (:1314-1334), rotated-IoU logs, bag loss 0.25 * pos + 0.75 * neg (:1272,1282) and the
+    top-k score-weighted merge with the (cx,cy) clamp quirk (:1198-1216)."""
+    bag_loss_pos_scale = 0.25
+    bag_loss_neg_scale = 0.75
+
+    def __init__(self, num_classes, in_channels=256, beta=0.25, top_k=3, num_stages=2,
+                 bbox_roi_extractor=dict(type="RotatedSingleRoIExtractor",
+                                         roi_layer=dict(type="RoIAlignRotated", out_size=7, sample_num=2,
+                                                        clockwise=True),
+                                         out_channels=256, featmap_strides=[8]), **kwargs):
+        super().__init__(num_classes, in_channels=in_channels, beta=beta, top_k=top_k, num_stages=num_stages,
+                         bbox_roi_extractor=bbox_roi_extractor, **kwargs)
+        if not self.bbox_roi_extractor.rotated:
+            raise ValueError("RotatedMILHead needs a RotatedSingleRoIExtractor")

@@ -45,18 +45,18 @@ def num_sms():
 
 
 # ------------------------------------------------------------------------------ bags
-def bag_gen(in_rois, img_wh, base_ratios, shake_ratio, min_scale):
-    """in_rois (G,5) -> (rois (G*U,5), valid (G*U,) uint8)."""
-    _chk(in_rois, "in_rois", _f32, 2, 5)
+def bag_gen(in_rois, img_wh, base_ratios, shake_ratio, min_scale, rotated=False):
+    """in_rois (G,5) -> (rois (G*U,5), valid (G*U,) uint8); rotated: 6-column RoIs (img,cx,cy,w,h,theta)."""
+    _chk(in_rois, "in_rois", _f32, 2, 6 if rotated else 5)
     _chk(img_wh, "img_wh", _f32, 2, 2)
     ratios, nr = _farr(base_ratios)
     shake, ns = _farr(shake_ratio or [])
     U = nr * nr * (1 + 4 * ns)
     G = in_rois.shape[0]
-    out = torch.empty((G * U, 5), dtype=_f32, device=in_rois.device)
+    out = torch.empty((G * U, in_rois.shape[1]), dtype=_f32, device=in_rois.device)
     valid = torch.empty((G * U,), dtype=_u8, device=in_rois.device)
     _lib.call("pt_bag_gen", _p(in_rois), G, _p(img_wh), img_wh.shape[0], ratios, nr, shake, ns, float(min_scale),
-              _p(out), _p(valid), _stream())
+              _p(out), _p(valid), int(rotated), _stream())
     return out, valid
 
 
@@ -71,14 +71,33 @@ def make_rois(boxes, img_idx, out=None):
     return out
 
 
-def neg_weight(neg_rois, bag_rois, bag_offsets):
-    _chk(neg_rois, "neg_rois", _f32, 2, 5)
-    _chk(bag_rois, "bag_rois", _f32, 2, 5)
+def neg_weight(neg_rois, bag_rois, bag_offsets, rotated=False):
+    _chk(neg_rois, "neg_rois", _f32, 2, 6 if rotated else 5)
+    _chk(bag_rois, "bag_rois", _f32, 2, 6 if rotated else 5)
     _chk(bag_offsets, "bag_offsets", _i32, 1)
     w = torch.empty((neg_rois.shape[0],), dtype=_u8, device=neg_rois.device)
     _lib.call("pt_neg_weight", _p(neg_rois), neg_rois.shape[0], _p(bag_rois), _p(bag_offsets),
-              bag_offsets.shape[0] - 1, _p(w), _stream())
+              bag_offsets.shape[0] - 1, _p(w), int(rotated), _stream())
     return w
+
+
+def box_iou_rotated(b1, b2, mode="iou", aligned=False, clamp_wh=False):
+    """(M,5) x (N,5) (cx,cy,w,h,theta) -> (M,N) | aligned (M,)."""
+    if mode not in ("iou", "iof"):
+        raise ValueError(f"Unsupported mode {mode}")
+    _chk(b1, "bboxes1", _f32, 2)
+    _chk(b2, "bboxes2", _f32, 2)
+    M, N = b1.shape[0], b2.shape[0]
+    if aligned and M != N:
+        raise ValueError("aligned requires the same number of boxes")
+    out = torch.empty((M,) if aligned else (M, N), dtype=_f32, device=b1.device)
+    if M * N == 0:
+        return out
+    if b1.shape[1] < 5 or b2.shape[1] < 5:
+        raise ValueError("rotated boxes need 5 columns")
+    _lib.call("pt_box_iou_rotated", _p(b1), b1.shape[1], _p(b2), b2.shape[1], M, N, 0 if mode == "iou" else 1,
+              int(aligned), int(clamp_wh), _p(out), _stream())
+    return out
 
 
 _MODES = {"iou": 0, "iof": 1, "giou": 2}
@@ -228,18 +247,19 @@ def cast_weight(w, x3=False):
 
 # ------------------------------------------------------------------------------ head tails
 def reg_decode(H, Wreg, breg, bag_rois, valid, ref_boxes, real_boxes, U, max_wh, sums, K=None, hyper=0.2,
-               eps=1e-6, wh_ratio_clip=16 / 1000, want_deltas=False, out_rois=None):
+               eps=1e-6, wh_ratio_clip=16 / 1000, want_deltas=False, out_rois=None, rotated=False):
     if H.dtype not in (_f32, _bf16):
         raise ValueError("hidden must be fp32 or bf16")
     _chk(H, "hidden", None, 2)
     _chk(Wreg, "fc_reg.weight", _f32, 2)
-    _chk(bag_rois, "bag_rois", _f32, 2, 5)
+    rs = 6 if rotated else 5
+    _chk(bag_rois, "bag_rois", _f32, 2, rs)
     K = bag_rois.shape[0] if K is None else K
     dev = H.device
     if out_rois is None:
-        out_rois = torch.empty((K, 5), dtype=_f32, device=dev)
+        out_rois = torch.empty((K, rs), dtype=_f32, device=dev)
     else:
-        _chk(out_rois, "out_rois", _f32, 2, 5)
+        _chk(out_rois, "out_rois", _f32, 2, rs)
         if out_rois.shape[0] < K:
             raise ValueError("out_rois has fewer rows than K")
     deltas = torch.empty((K, 4), dtype=_f32, device=dev) if want_deltas else None
@@ -247,7 +267,7 @@ def reg_decode(H, Wreg, breg, bag_rois, valid, ref_boxes, real_boxes, U, max_wh,
     _lib.call("pt_reg_decode", _p(H), int(H.dtype == _f32), H.shape[1], Wreg.shape[1], _p(Wreg), _p(breg),
               _p(bag_rois), _p(valid), _p(ref_boxes), _p(real_boxes), U, K, float(max_wh[0]), float(max_wh[1]),
               float(wh_ratio_clip), float(hyper), float(eps), _p(out_rois), _p(deltas), _p(iou_t), _p(sums),
-              _stream())
+              int(rotated), _stream())
     return out_rois, deltas, iou_t
 
 
@@ -262,22 +282,23 @@ def cls_ins_heads(H, Wcls, bcls, Wins, bins, M=None):
     return cls, ins
 
 
-def score_select(cls, ins, valid, bag_rois, labels, pseudo, img_wh, G, U1, U2, topk, beta, sums):
+def score_select(cls, ins, valid, bag_rois, labels, pseudo, img_wh, G, U1, U2, topk, beta, sums, rotated=False):
     """Returns (merged (G,4), merged centres (G,2), selected idx (G,topk) int32, scores (G,topk))."""
     _chk(cls, "cls", _f32, 2)
     _chk(ins, "ins", _f32, 2)
     _chk(labels, "labels", _i64, 1)
+    bd = 5 if rotated else 4
     if pseudo is not None:
-        _chk(pseudo, "pseudo_boxes", _f32, 2, 4)
+        _chk(pseudo, "pseudo_boxes", _f32, 2, bd)
     C = cls.shape[1]
     dev = cls.device
-    merged = torch.empty((G, 4), dtype=_f32, device=dev)
+    merged = torch.empty((G, bd), dtype=_f32, device=dev)
     pts = torch.empty((G, 2), dtype=_f32, device=dev)
     idx = torch.empty((G, topk), dtype=_i32, device=dev)
     sc = torch.empty((G, topk), dtype=_f32, device=dev)
     _lib.call("pt_score_select", _p(cls), _p(ins), _p(valid), _p(bag_rois), _p(labels), _p(pseudo), _p(img_wh),
               img_wh.shape[0], G, U1, U2, C, topk, float(beta), _p(merged), _p(pts), _p(idx), _p(sc), _p(sums),
-              _stream())
+              int(rotated), _stream())
     return merged, pts, idx, sc
 
 
@@ -286,10 +307,10 @@ def neg_loss(neg_cls, weight, sums, n=None):
     _lib.call("pt_neg_loss", _p(neg_cls), _p(weight), n, neg_cls.shape[1], _p(sums), _stream())
 
 
-def finalize_losses(sums, K, has_neg, scale_bbox=1.0, scale_bags=1.0):
+def finalize_losses(sums, K, has_neg, scale_bbox=1.0, scale_bags=1.0, pos_w=1.0, neg_w=1.0):
     out = torch.empty((5,), dtype=_f32, device=sums.device)
-    _lib.call("pt_finalize_losses", _p(sums), K, int(has_neg), float(scale_bbox), float(scale_bags), _p(out),
-              _stream())
+    _lib.call("pt_finalize_losses", _p(sums), K, int(has_neg), float(scale_bbox), float(scale_bags), float(pos_w),
+              float(neg_w), _p(out), _stream())
     return out
 
 
@@ -300,11 +321,12 @@ def split_bf16x3(x):
     return out
 
 
-def aligned_iou_mean(a, b):
+def aligned_iou_mean(a, b, rotated=False):
     _chk(a, "a", _f32, 2)
     _chk(b, "b", _f32, 2)
     if a.shape[0] != b.shape[0]:
         raise ValueError("aligned IoU needs the same number of boxes")
     out = torch.empty((1,), dtype=_f32, device=a.device)
-    _lib.call("pt_aligned_iou_mean", _p(a), a.shape[1], _p(b), b.shape[1], a.shape[0], _p(out), _stream())
+    _lib.call("pt_aligned_iou_mean", _p(a), a.shape[1], _p(b), b.shape[1], a.shape[0], int(rotated), _p(out),
+              _stream())
     return out[0]

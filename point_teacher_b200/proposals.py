@@ -84,14 +84,20 @@ def MIL_gen_proposals_from_cfg(pseudo_points, pseudo_boxes, fine_proposal_cfg, g
     return proposals_list, proposals_valid_list, ref, real
 
 
-def sample_negative_boxes(num, img_shape, generator=None):
+def sample_negative_boxes(num, img_shape, generator=None, rotated=False):
     """The reference's four CPU ``torch.rand`` draws (:247-250).  Kept on the host generator so a run
-    with the same CPU seed sees the same negatives as the reference."""
+    with the same CPU seed sees the same negatives as the reference.  rotated: the OBB variant
+    (OBB_TOD/.../syn_images_generator_v2.py:142-148): spans of 200 px and a fifth draw for theta."""
+    import math
     h, w, _ = img_shape
+    span = 200 if rotated else 100
     x1 = torch.rand(num, generator=generator) * w * 0.8
     y1 = torch.rand(num, generator=generator) * h * 0.8
-    x2 = x1 + torch.rand(num, generator=generator) * 100
-    y2 = y1 + torch.rand(num, generator=generator) * 100
+    x2 = x1 + torch.rand(num, generator=generator) * span
+    y2 = y1 + torch.rand(num, generator=generator) * span
+    if rotated:
+        th = torch.rand(num, generator=generator) * math.pi - math.pi / 2
+        return torch.stack([x1, y1, x2, y2, th], dim=1)
     return torch.stack([x1, y1, x2, y2], dim=1)
 
 

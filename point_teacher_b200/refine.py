@@ -24,24 +24,25 @@ def phase2_refine(head, x_ori, img_metas, pseudo_bboxes, pseudo_points, pseudo_l
     no host synchronisation, so the whole call is CUDA-graph capturable (``CapturedPhase2``)."""
     cap = num_training_burninstep2
     dev = pseudo_bboxes[0].device
+    rot = head.bbox_roi_extractor.rotated       # OBB twin: rotated_fcos_teacher_student.py:494-535
     counts = [min(int(b.shape[0]), cap) for b in pseudo_bboxes]
     pb = torch.cat([b[:cap, :] for b in pseudo_bboxes]).float().contiguous()
     gb = torch.cat([b[:cap, :] for b in gt_bboxes]).float().contiguous()
     labels = torch.cat([l[:cap] for l in pseudo_labels]).long().contiguous()
     img_idx = const_tensor([i for i, c in enumerate(counts) for _ in range(c)], torch.int32, dev)
     img_wh = img_wh_tensor(img_metas, dev)
-    losses = {"coarse_bboxes_iou": ops.aligned_iou_mean(pb, gb)}
+    losses = {"coarse_bboxes_iou": ops.aligned_iou_mean(pb, gb, rot)}
     pts = None
     for stage in range(num_stages):
         cfg = fine_proposal_cfg[stage]
         base_rois, _ = ops.bag_gen(ops.make_rois(pb, img_idx), img_wh, cfg["base_ratios"], cfg["shake_ratio"],
-                                   cfg["min_scale"])
+                                   cfg["min_scale"], rot)
         U1 = base_rois.shape[0] // max(pb.shape[0], 1)
         negs = neg_idx = offs = None
         n_neg = cfg["gen_num_neg"]
         if n_neg:
             nl = neg_boxes[stage] if neg_boxes is not None else \
-                [sample_negative_boxes(n_neg, m["img_shape"]).to(dev) for m in img_metas]
+                [sample_negative_boxes(n_neg, m["img_shape"], rotated=rot).to(dev) for m in img_metas]
             negs = torch.cat(list(nl)).float().contiguous()
             neg_idx = const_tensor([i for i, t in enumerate(nl) for _ in range(int(t.shape[0]))], torch.int32, dev)
             o = [0]
@@ -52,7 +53,7 @@ def phase2_refine(head, x_ori, img_metas, pseudo_bboxes, pseudo_points, pseudo_l
                                                       offs, labels, pb, fine_proposal_extensive_cfg[stage], stage,
                                                       loss_scales=alpha)
         pb = pb_new
-        losses[f"stage{stage}_refine_bboxes_iou"] = ops.aligned_iou_mean(pb, gb)
+        losses[f"stage{stage}_refine_bboxes_iou"] = ops.aligned_iou_mean(pb, gb, rot)
         losses.update(mil_loss)
     # write-back (:463-465): refined head + untouched tail, one concat for boxes and one for points
     mb, mp = torch.split(pb, counts), torch.split(pts, counts)

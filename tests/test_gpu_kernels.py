@@ -216,3 +216,61 @@ def test_weight_prep_layouts(cuda):
     assert _rel(p3[:, :K] + p3[:, 2 * K:], ref) < 1e-4
     c3 = ops.cast_weight(w[:, :1024].contiguous().to(cuda), x3=True).float().cpu()
     assert _rel(c3[:, :1024] + c3[:, 2048:], w[:, :1024]) < 1e-4
+
+
+# ------------------------------------------------------------------------------ rotated IoU / OBB bags
+def _rboxes(g, n, img=512, median=20.0, hi=120.0):
+    b = hbb.xyxy_to_cxcywh(synth.make_boxes(g, n, (img, img), median=median, hi=hi))
+    th = torch.rand(n, 1, generator=g) * math.pi - math.pi / 2
+    return torch.cat([b, th], 1)
+
+
+@pytest.mark.parametrize("mode", ["iou", "iof"])
+def test_box_iou_rotated_vs_oracle(cuda, mode):
+    from point_teacher_b200 import ops
+    g = torch.Generator().manual_seed(31)
+    a = _rboxes(g, 90)
+    b = _rboxes(g, 70)
+    b[:40, :2] = a[:40, :2] + torch.randn(40, 2, generator=g) * 4        # many true overlaps
+    b[40:45] = a[40:45]                                                  # identical boxes
+    b[45, 2:4] = 0.0                                                     # degenerate
+    ref = rotated.box_iou_rotated(a, b, mode)
+    got = ops.box_iou_rotated(a.to(cuda), b.to(cuda), mode).cpu()
+    assert (got - ref).abs().max() < 1e-3, (got - ref).abs().max()
+    ref_al = rotated.box_iou_rotated(a[:70], b, mode, True)
+    got_al = ops.box_iou_rotated(a[:70].contiguous().to(cuda), b.to(cuda), mode, aligned=True).cpu()
+    assert (got_al - ref_al.reshape(-1)).abs().max() < 1e-3
+    # threshold decisions the path consumes (neg weights: iou < 0.3)
+    dis = ((got < 0.3) != (ref < 0.3)).float().mean().item()
+    assert dis < 1e-3, dis
+    # theta = 0 degenerates to bbox_overlaps
+    a0, b0 = a.clone(), b.clone()
+    a0[:, 4] = 0
+    b0[:, 4] = 0
+    if mode == "iou":
+        ax = hbb.bbox_overlaps(hbb.cxcywh_to_xyxy(a0[:, :4]), hbb.cxcywh_to_xyxy(b0[:, :4]))
+        assert (ops.box_iou_rotated(a0.to(cuda), b0.to(cuda)).cpu() - ax).abs().max() < 1e-3
+
+
+def test_obb_bag_gen_bit_exact_and_neg_weight(cuda):
+    from oracle import obb
+    from point_teacher_b200 import ops
+    g = torch.Generator().manual_seed(32)
+    metas = [dict(img_shape=(512, 512, 3))] * 2
+    boxes = [_rboxes(g, 11), _rboxes(g, 17)]
+    boxes[0][0, :2] = torch.tensor([3., 3.])           # mostly outside -> invalid instances
+    pts = [b[:, :2] for b in boxes]
+    cfg = synth.OBB_EXT_CFG[0]
+    ref, rvalid, _, _ = obb.mil_gen_proposals(pts, boxes, cfg, boxes, metas)
+    rois = obb.rbbox2roi(boxes).to(cuda)
+    wh = torch.tensor([[512., 512.], [512., 512.]], device=cuda)
+    out, valid = ops.bag_gen(rois, wh, cfg["base_ratios"], cfg["shake_ratio"], cfg["min_scale"], rotated=True)
+    assert torch.equal(out[:, 1:].cpu(), torch.cat(ref))
+    assert torch.equal(valid.bool().cpu().reshape(-1, 1), torch.cat(rvalid))
+    # negatives: the reference passes (x1,y1,x2,y2,theta) AS (cx,cy,w,h,theta)
+    negs = [obb.sample_negative_boxes(50, (512, 512, 3), g) for _ in range(2)]
+    rw = torch.cat([obb.negative_weights(negs[i], ref[i]) for i in range(2)])
+    nrois = obb.rbbox2roi(negs).to(cuda)
+    offs = torch.tensor([0, ref[0].shape[0], ref[0].shape[0] + ref[1].shape[0]], dtype=torch.int32, device=cuda)
+    w = ops.neg_weight(nrois, out, offs, rotated=True)
+    assert (w.bool().cpu() != rw).float().mean().item() <= 0.01

@@ -228,3 +228,68 @@ def test_captured_graph_replay_matches_eager(cuda):
     gb2, _, _ = cap.replay()
     torch.cuda.synchronize()
     assert not torch.equal(gb2[0].cpu(), eb[0].cpu().clone()) or True  # outputs alias the static graph buffers
+
+
+# ------------------------------------------------------------------------------ OBB twin (config #3)
+OBB_SMALL = dict(batch=2, img_hw=(256, 256), gt_range=(6, 10), n_neg=20)
+
+
+def _run_cuda_obb(cuda, d, P, precision, alpha=(1.0, 1.0), topk=3):
+    from point_teacher_b200.mil_head import RotatedMILHead
+    from point_teacher_b200.refine import phase2_refine
+    head = RotatedMILHead(num_classes=9, num_stages=1, top_k=topk, precision=precision).to(cuda)
+    head.load_state_dict(P.state_dict(), strict=False)
+    to = lambda l: [t.to(cuda) for t in l]  # noqa: E731
+    with torch.no_grad():
+        out = phase2_refine(head, (d["feat"].to(cuda),), d["img_metas"], to(d["pseudo_boxes"]),
+                            to(d["pseudo_points"]), to(d["pseudo_labels"]), to(d["gt_boxes"]), synth.OBB_FINE_CFG,
+                            synth.OBB_EXT_CFG, num_stages=1, alpha=alpha, neg_boxes=[to(d["neg_boxes"][0])])
+    torch.cuda.synchronize()
+    return out, head
+
+
+@pytest.mark.parametrize("precision,tol", [("fp32", 1e-3), ("bf16", 2e-2)])
+@pytest.mark.parametrize("seed,small", [(0, OBB_SMALL), (2, dict(batch=2, img_hw=(512, 512), gt_range=(20, 30), n_neg=40))])
+def test_obb_phase2_refine_vs_oracle(cuda, precision, tol, seed, small):
+    from oracle import obb
+    d = synth.obb_batch(seed=seed, **small)
+    P = hbb.MilHeadParams(num_classes=9, num_stages=1, seed=seed)
+    with torch.no_grad():
+        ob, op, ol, aux = obb.phase2_refine(P, (d["feat"],), [d["stride"]], d["img_metas"], d["pseudo_boxes"],
+                                            d["pseudo_points"], d["pseudo_labels"], d["gt_boxes"],
+                                            synth.OBB_FINE_CFG, synth.OBB_EXT_CFG, alpha=(0.01, 0.25),
+                                            injected_negs=d["neg_boxes"])
+    (gb, gp, gl), head = _run_cuda_obb(cuda, d, P, precision, alpha=(0.01, 0.25))
+    R, ref = head.last_results, aux[-1]
+    assert torch.equal(R["_b200"]["coarse"][:, 1:6].cpu(), torch.cat(ref["coarse_extensive_bags"]))   # bit-exact
+    assert torch.equal(R["_b200"]["evalid"].bool().cpu().reshape(-1, 1), torch.cat(ref["extensive_bags_valid"]))
+    assert _rel(R["cls_score"], ref["cls_score"]) < tol
+    assert _rel(R["ins_score"], ref["ins_score"]) < tol
+    assert _rel(R["neg_cls_score"], ref["neg_cls_score"]) < tol
+    assert _rel(torch.cat(R["extensive_bags"]), torch.cat(ref["extensive_bags"])) < tol
+    for k in ol:
+        assert abs(float(gl[k]) - float(ol[k])) <= tol * max(abs(float(ol[k])), 1e-3), (k, float(gl[k]), float(ol[k]))
+    for i in range(len(ob)):
+        assert gb[i].shape == ob[i].shape and gb[i].shape[1] == 5
+        assert _rel(gb[i], ob[i]) < tol
+        assert _rel(gp[i], op[i]) < tol
+    if precision == "fp32":
+        agree = (R["_b200"]["sel_idx"].cpu().long() == ref["selected_idx"]).float().mean().item()
+        assert agree >= 0.999, agree
+
+
+def test_obb_phase2_against_reference_golden(cuda, golden_dir):
+    g = torch.load(os.path.join(golden_dir, "obb_phase2_s1_top3.pt"))
+    d = synth.obb_batch(seed=g["seed"], **g["small"])
+    P = hbb.MilHeadParams(num_classes=9, num_stages=1, seed=g["seed"])
+    (gb, gp, gl), head = _run_cuda_obb(cuda, d, P, "fp32", topk=g["topk"])
+    R = head.last_results
+    assert torch.equal(R["_b200"]["coarse"][:, 1:6].cpu(), g["ext_bags"])
+    assert torch.equal(R["_b200"]["evalid"].bool().cpu().reshape(-1, 1), g["ext_valid"])
+    assert torch.equal(R["neg_weight"].bool().cpu(), g["neg_weight"])
+    assert _rel(torch.cat(R["extensive_bags"]), g["refined_bags"]) < 1e-3
+    assert _rel(R["cls_score"], g["cls_score"]) < 1e-3
+    assert _rel(R["ins_score"], g["ins_score"]) < 1e-3
+    assert _rel(torch.cat([b[:100] for b in gb]), g["merged"]) < 1e-3
+    for k, v in g["losses"].items():
+        assert abs(float(gl[k]) - float(v)) <= 1e-3 * max(abs(float(v)), 1e-3), k

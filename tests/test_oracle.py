@@ -137,3 +137,26 @@ def test_rotated_nms_keeps_descending_score_order():
     out, keep = rotated.nms_rotated(dets, scores, 0.05)
     assert keep.tolist() == [3, 2]
     assert out.shape == (2, 6)
+
+
+def test_obb_oracle_reproduces_reference_golden(golden_dir):
+    """OBB twin: oracle/obb.py against outputs of the reference's own OBB_TOD files (oracle/make_golden.py)."""
+    from oracle import obb
+    g = torch.load(os.path.join(golden_dir, "obb_phase2_s1_top3.pt"))
+    d = synth.obb_batch(seed=g["seed"], **g["small"])
+    P = hbb.MilHeadParams(num_classes=9, num_stages=1, seed=g["seed"])
+    with torch.no_grad():
+        ob, _, losses, aux = obb.phase2_refine(P, (d["feat"],), [d["stride"]], d["img_metas"], d["pseudo_boxes"],
+                                               d["pseudo_points"], d["pseudo_labels"], d["gt_boxes"],
+                                               synth.OBB_FINE_CFG, synth.OBB_EXT_CFG, alpha=(1.0, 1.0),
+                                               topk=g["topk"], injected_negs=d["neg_boxes"])
+    R = aux[0]
+    assert torch.equal(torch.cat(R["coarse_extensive_bags"]), g["ext_bags"])            # bag geometry: bit-exact
+    assert torch.equal(torch.cat(R["extensive_bags_valid"]), g["ext_valid"])
+    assert torch.equal(torch.cat(R["extensive_bags"]), g["refined_bags"])
+    assert torch.equal(R["cls_score"], g["cls_score"])
+    assert torch.equal(R["ins_score"], g["ins_score"])
+    assert torch.equal(torch.cat(R["neg_weight"]), g["neg_weight"])
+    assert torch.equal(torch.cat([b[:100] for b in ob]), g["merged"])
+    for k, v in g["losses"].items():
+        assert torch.allclose(losses[k], v, rtol=1e-6), k
