@@ -67,12 +67,17 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
   return ok != 0;
 }
 // Bounded wait: a protocol bug must trap (the launch fails with an error the host reports)
-// instead of hanging the GPU box.
+// instead of hanging the GPU box.  The clock is only consulted every 256 failed polls.
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   if (mbar_try_wait(bar, parity)) return;
-  long long t0 = clock64();
-  while (!mbar_try_wait(bar, parity)) {
-    if (clock64() - t0 > 4000000000LL) __trap();  // ~2 s at 1.9 GHz
+  long long t0 = 0;
+  for (uint32_t spins = 1;; spins++) {
+    if (mbar_try_wait(bar, parity)) return;
+    if ((spins & 255u) == 0) {
+      const long long now = clock64();
+      if (t0 == 0) t0 = now;
+      else if (now - t0 > 4000000000LL) __trap();  // ~2 s at 1.9 GHz
+    }
   }
 }
 __device__ __forceinline__ void fence_barrier_init() {

@@ -17,6 +17,12 @@
 
 namespace ptb {
 
+namespace ramma {   // roi_align_mma.cu: TMA + mma.sync bf16 throughput path
+bool supported(int C, int H, int W);
+int launch(const void* feat_bf16_nhwc, const float* rois, void* out, long long ld_out, int K, int B, int C, int H,
+           int W, float scale, int sampling_ratio, int aligned, const int* roi_level, int level, cudaStream_t stream);
+}  // namespace ramma
+
 constexpr int P7 = 7;
 constexpr int GW_CHUNK = 16;   // x samples per bin held in the shared sample table at a time
 
@@ -493,6 +499,9 @@ extern "C" int pt_roi_align_forward(const void* feat, int feat_bf16, const float
   }
   cudaStream_t s = (cudaStream_t)stream;
   const bool rot = rotated != 0;
+  if (feat_bf16 && !rot && out_mode == OUT_BF16_BINMAJOR && ramma::supported(C, H, W))
+    return ramma::launch(feat, rois, out, ld_out, K, B, C, H, W, spatial_scale, sampling_ratio, aligned, roi_level,
+                         level, s);
 #define PT_DISPATCH(T, M) return launch_fwd<T, M>(rot, feat, rois, out, ld_out, K, B, C, H, W, spatial_scale, sampling_ratio, aligned, clockwise, roi_level, level, s)
   if (feat_bf16) {
     if (out_mode == OUT_BF16_BINMAJOR) PT_DISPATCH(__nv_bfloat16, OUT_BF16_BINMAJOR);

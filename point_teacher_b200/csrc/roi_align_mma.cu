@@ -1,0 +1,417 @@
+// RoIAlign forward, bf16 throughput path for sm_100a: TMA patch loads + warp-level tensor-core interpolation.
+//
+// Same operator as roi_align.cu's roi_align_fwd_kernel (mmcv.ops.RoIAlign(output_size=7, sampling_ratio=0|n,
+// pool_mode='avg', aligned) reached through
+//   HBB_TOD/mmdet/models/roi_heads/roi_extractors/single_level_roi_extractor.py:56-114),
+// specialised for the MIL path's operand: bf16 NHWC feature map in, bf16 bin-major (K, 49*C) FC1 operand out.
+//
+// Why tensor cores on an HBM-bound op: bilinear average pooling of one RoI is the small contraction
+//     out[bin, c] = sum_pix Wmat[bin, pix] * patch[pix, c]          (49 x npix) * (npix x 256)
+// with Wmat[bin=(ph,pw), pix=(row,col)] = wy[ph][row] * wx[pw][col] / count (the separable tables of the
+// reference's sample grid).  Tiny objects touch a 3x3..4x4 pixel patch, so one m16n8k16 k-step covers a whole
+// RoI.  Doing the contraction with mma.sync cuts the issue slots per RoI ~7x against the FFMA formulation
+// (6 000 -> ~900 warp instructions), which is what lets the SMs saturate the 25 KB/RoI store stream.  The
+// tensor pipe itself stays almost idle; the bound is the HBM/L2 write path.
+//
+// CTA = 8 MMA warps (32 channels each, all 49 bins -> 64 fp32 accumulators/thread) + 2 builder warps that take
+// alternate RoIs (a single builder warp is latency-bound at ~4 700 cycles per RoI and starves the MMA warps).
+//   builder : reads the RoI (prefetched one iteration ahead), builds wx/wy with the reference's exact (non-contracted) coordinate arithmetic,
+//             walks the patch in 4x4-pixel chunks; per chunk it issues ONE 5-D TMA box load
+//             (64 ch x 4 cols x 4 rows x 1 img x 4 channel-quarters = 8 KB, SWIZZLE_128B, OOB zero fill) into a
+//             its own 2-deep mbarrier ring and writes the chunk's A fragments (Wmat in mma register order) next to it.
+//   MMA     : per chunk 4 x LDS.128 (A) + 2 x ldmatrix.x4.trans (B) + 16 x mma.m16n8k16; after the RoI's last
+//             chunk: bf16 pack -> stmatrix into a padded (conflict free), double-buffered smem staging ->
+//             512 B-per-warp coalesced 16 B global stores.
+#include <cuda.h>
+
+#include "common.cuh"
+
+namespace ptb {
+namespace ramma {
+
+constexpr int P7 = 7, NBIN = 49;
+constexpr int BUILDERS = 2, DEPTH = 2, STAGES = BUILDERS * DEPTH;   // every builder warp owns a DEPTH-deep ring
+constexpr int MMA_WARPS = 8;
+constexpr int THREADS = (MMA_WARPS + BUILDERS) * 32;
+constexpr int QUARTER_BYTES = 16 * 128;           // 16 pixels x 64 channels bf16
+constexpr int PATCH_BYTES = 4 * QUARTER_BYTES;    // 8 KB
+constexpr int AFRAG_BYTES = 4 * 32 * 16;          // 4 m-tiles x 32 lanes x uint4
+constexpr int STG_LD = 264;                       // staging row: 256 channels + 8 pad (bank-conflict free)
+constexpr int STG_ROW_BYTES = STG_LD * 2;
+constexpr int STG_BYTES = ((NBIN * STG_ROW_BYTES + 127) / 128) * 128;
+enum { F_LAST = 2, F_ZERO = 4, F_SKIP = 8 };
+
+__device__ __forceinline__ void tma_load_5d(uint32_t dst, const void* desc, uint32_t bar, int c0, int c1, int c2,
+                                            int c3, int c4) {
+  asm volatile(
+      "cp.async.bulk.tensor.5d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], [%2];"
+      ::"r"(dst), "l"(desc), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
+      : "memory");
+}
+__device__ __forceinline__ void ldsm_x4_trans(uint32_t addr, uint32_t (&r)[4]) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0, %1, %2, %3}, [%4];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3])
+               : "r"(addr));
+}
+__device__ __forceinline__ void stsm_x4(uint32_t addr, uint32_t r0, uint32_t r1, uint32_t r2, uint32_t r3) {
+  asm volatile("stmatrix.sync.aligned.m8n8.x4.shared.b16 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(r0), "r"(r1),
+               "r"(r2), "r"(r3)
+               : "memory");
+}
+__device__ __forceinline__ uint4 lds128(uint32_t addr) {
+  uint4 v;
+  asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr));
+  return v;
+}
+__device__ __forceinline__ void sts128(uint32_t addr, const uint4& v) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+__device__ __forceinline__ void sts32(uint32_t addr, uint32_t v) {
+  asm volatile("st.shared.b32 [%0], %1;" ::"r"(addr), "r"(v) : "memory");
+}
+__device__ __forceinline__ uint2 lds64(uint32_t addr) {
+  uint2 v;
+  asm volatile("ld.shared.v2.b32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(addr));
+  return v;
+}
+__device__ __forceinline__ void mma_bf16(float (&d)[4], const uint4& a, uint32_t b0, uint32_t b1) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, "
+      "{%0, %1, %2, %3};"
+      : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+      : "r"(a.x), "r"(a.y), "r"(a.z), "r"(a.w), "r"(b0), "r"(b1));
+}
+
+// one axis of the Detectron2 bilinear rule (same as roi_align.cu)
+__device__ __forceinline__ bool axis_setup(float v, int size, int& lo, int& hi, float& l, float& h) {
+  if (v < -1.0f || v > (float)size) return false;
+  if (v <= 0.f) v = 0.f;
+  lo = (int)v;
+  if (lo >= size - 1) { hi = lo = size - 1; v = (float)lo; } else hi = lo + 1;
+  l = fsub(v, (float)lo);
+  h = fsub(1.0f, l);
+  return true;
+}
+
+__global__ void __launch_bounds__(THREADS, 2)
+roi_align_mma_kernel(const __grid_constant__ CUtensorMap tmap, const float* __restrict__ rois,
+                     __nv_bfloat16* __restrict__ out, long long ld_out, int K, int B, int C, int H, int W,
+                     float scale, int sampling_ratio, int aligned, const int* __restrict__ roi_level, int level) {
+  extern __shared__ uint8_t smem_raw[];
+  // shared-window byte addresses (explicit .shared accesses below; generic pointers would cost LD/ST.E)
+  const uint32_t sbase = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t s_patch = sbase;                                    // [STAGES][PATCH_BYTES], 1 KB aligned
+  const uint32_t s_afrag = s_patch + STAGES * PATCH_BYTES;           // [STAGES][AFRAG_BYTES]
+  const uint32_t s_stg = s_afrag + STAGES * AFRAG_BYTES;             // [2][STG_BYTES]
+  const uint32_t s_tab = s_stg + 2 * STG_BYTES;                      // [BUILDERS][(W+4)*8 + (H+4)*8] floats
+  const int tab_floats = (W + 4) * 8 + (H + 4) * 8;
+  const uint32_t s_full = s_tab + BUILDERS * tab_floats * 4;         // [STAGES] mbarriers
+  const uint32_t s_empty = s_full + STAGES * 8;
+  const uint32_t s_meta = s_empty + STAGES * 8;                      // [STAGES] {roi, flags}
+  uint8_t* gen = smem_raw + (sbase - smem_u32(smem_raw));            // generic view of the same window
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(gen + (s_full - sbase));
+  uint64_t* empty_bar = reinterpret_cast<uint64_t*>(gen + (s_empty - sbase));
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) {
+    tma_prefetch_desc(&tmap);
+    for (int i = 0; i < STAGES; i++) { mbar_init(full_bar + i, 1); mbar_init(empty_bar + i, MMA_WARPS); }
+    fence_barrier_init();
+  }
+  __syncthreads();
+  const int n_iter = blockIdx.x < K ? (K - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+  const int g = lane >> 2, t = lane & 3;
+
+  if (warp >= MMA_WARPS) {
+    // ---------------------------------------------------------------------------------- builder warps
+    const int bw_id = warp - MMA_WARPS;                 // RoIs bw_id, bw_id + BUILDERS, ... of this CTA
+    float* wx = reinterpret_cast<float*>(gen + (s_tab - sbase)) + bw_id * tab_floats;   // wx[col - xmin][pw]
+    float* wy = wx + (W + 4) * 8;                                                        // wy[row - ymin][ph]
+    const float off = aligned ? 0.5f : 0.f;
+    const uint32_t tx_bytes = (uint32_t)(C / 64) * QUARTER_BYTES;
+    int slot = 0; uint32_t phase = 0;
+    // bins owned by this lane in the A fragments: m-tile mt -> rows mt*16+g (lo) and +8 (hi)
+    int phs[8], pws[8];
+#pragma unroll
+    for (int i = 0; i < 8; i++) {
+      const int b = (i >> 1) * 16 + g + (i & 1) * 8;
+      phs[i] = b < NBIN ? b / P7 : -1;
+      pws[i] = b < NBIN ? b % P7 : 0;
+    }
+    // software prefetch of the RoI record one iteration ahead (lanes 0..4 hold the 5 floats)
+    float rnext = 0.f;
+    if (bw_id < n_iter && lane < 5) rnext = __ldg(rois + (size_t)(blockIdx.x + bw_id * gridDim.x) * 5 + lane);
+    for (int it = bw_id; it < n_iter; it += BUILDERS) {
+      const int roi = blockIdx.x + it * gridDim.x;
+      const float rcur = rnext;
+      if (it + BUILDERS < n_iter && lane < 5)
+        rnext = __ldg(rois + (size_t)(blockIdx.x + (it + BUILDERS) * gridDim.x) * 5 + lane);
+      const bool skip = roi_level != nullptr && roi_level[roi] != level;   // another FPN level owns this RoI
+      const int b = (int)__shfl_sync(0xffffffffu, rcur, 0);
+      const float x1 = fsub(fmul(__shfl_sync(0xffffffffu, rcur, 1), scale), off);
+      const float y1 = fsub(fmul(__shfl_sync(0xffffffffu, rcur, 2), scale), off);
+      const float x2 = fsub(fmul(__shfl_sync(0xffffffffu, rcur, 3), scale), off);
+      const float y2 = fsub(fmul(__shfl_sync(0xffffffffu, rcur, 4), scale), off);
+      float rw = fsub(x2, x1), rh = fsub(y2, y1);
+      if (!aligned) { rw = fmaxf(rw, 1.f); rh = fmaxf(rh, 1.f); }
+      // lanes 0..6 own the x bins, lanes 8..14 the y bins (lanes 16..31 mirror them so that every lane sees
+      // both bin sizes through one xor-8 shuffle)
+      const bool isx = (lane & 8) == 0;
+      const int bi = lane & 7;
+      const float bin = fdiv(isx ? rw : rh, (float)P7);
+      const float bin_o = __shfl_xor_sync(0xffffffffu, bin, 8);       // the other axis' bin size
+      const int gs = sampling_ratio > 0 ? sampling_ratio : (int)ceilf(bin);
+      const int gs_o = sampling_ratio > 0 ? sampling_ratio : (int)ceilf(bin_o);
+      const int cnt = gs * gs_o > 1 ? gs * gs_o : 1;
+      const float inv_count = 1.0f / (float)cnt;
+      const bool b_ok = b >= 0 && b < B && !skip;
+      const float start = isx ? x1 : y1;
+      const int size = isx ? W : H;
+      float* tab = isx ? wx : wy;
+      const float base = fadd(start, fmul((float)bi, bin));
+      int lo = 1 << 30, hi = -1;
+      const bool owner = lane < 16 && bi < P7;
+      // gs == 1 (every RoI up to 7 feature pixels wide): the single sample is kept in registers
+      int l1 = 0, h1 = 0; float fl1 = 0.f, fh1 = 0.f; bool ok1 = false;
+      if (owner && b_ok) {
+        if (gs == 1) {
+          ok1 = axis_setup(fadd(base, fmul(.5f, bin)), size, l1, h1, fl1, fh1);   // x/1.0f is exact: no division
+          if (ok1) { lo = l1; hi = h1; }
+        } else {
+          for (int i = 0; i < gs; i++) {
+            const float v = fadd(base, fdiv(fmul((float)i + .5f, bin), (float)gs));
+            int l, h; float fl, fh;
+            if (axis_setup(v, size, l, h, fl, fh)) { lo = min(lo, l); hi = max(hi, h); }
+          }
+        }
+      }
+      int glo = lo, ghi = hi;
+#pragma unroll
+      for (int o = 4; o > 0; o >>= 1) {
+        glo = min(glo, __shfl_xor_sync(0xffffffffu, glo, o));
+        ghi = max(ghi, __shfl_xor_sync(0xffffffffu, ghi, o));
+      }
+      if (ghi < 0) { glo = 0; ghi = -1; }
+      __syncwarp();   // the previous RoI's fragment builds are done reading the tables
+      if (owner) {
+        const int npad = (ghi - glo + 4) & ~3;   // zero-padded to whole 4-pixel chunks
+        for (int c = 0; c < npad; c++) tab[c * 8 + bi] = 0.f;
+        if (gs == 1) {
+          if (ok1) { tab[(l1 - glo) * 8 + bi] += fh1; tab[(h1 - glo) * 8 + bi] += fl1; }
+        } else if (b_ok) {
+          for (int i = 0; i < gs; i++) {
+            const float v = fadd(base, fdiv(fmul((float)i + .5f, bin), (float)gs));
+            int l, h; float fl, fh;
+            if (axis_setup(v, size, l, h, fl, fh)) { tab[(l - glo) * 8 + bi] += fh; tab[(h - glo) * 8 + bi] += fl; }
+          }
+        }
+      }
+      __syncwarp();
+      const int xmin = __shfl_sync(0xffffffffu, glo, 0), xmax = __shfl_sync(0xffffffffu, ghi, 0);
+      const int ymin = __shfl_sync(0xffffffffu, glo, 8), ymax = __shfl_sync(0xffffffffu, ghi, 8);
+      const bool empty = !b_ok || xmax < xmin || ymax < ymin;
+      const int ncx = empty ? 1 : (xmax - xmin) / 4 + 1, ncy = empty ? 1 : (ymax - ymin) / 4 + 1;
+      for (int cy = 0; cy < ncy; cy++) {
+        for (int cx = 0; cx < ncx; cx++) {
+          const int stage = bw_id * DEPTH + slot;
+          mbar_wait(empty_bar + stage, phase ^ 1);
+          int flags = (cy == ncy - 1 && cx == ncx - 1 ? F_LAST : 0);
+          if (empty) {
+            flags |= skip ? F_SKIP : F_ZERO;
+          } else {
+            const int r0 = cy * 4 + (t >> 1), c0 = cx * 4 + 2 * (t & 1);
+            const uint32_t dst = s_afrag + stage * AFRAG_BYTES + lane * 16;
+#pragma unroll
+            for (int mt = 0; mt < 4; mt++) {
+              uint32_t a[4];
+#pragma unroll
+              for (int hl = 0; hl < 2; hl++) {
+                const int i = mt * 2 + hl;
+                float wy0 = 0.f, wy2 = 0.f, wxa = 0.f, wxb = 0.f;
+                if (phs[i] >= 0) {
+                  wy0 = wy[r0 * 8 + phs[i]] * inv_count;
+                  wy2 = wy[(r0 + 2) * 8 + phs[i]] * inv_count;
+                  wxa = wx[c0 * 8 + pws[i]];
+                  wxb = wx[(c0 + 1) * 8 + pws[i]];
+                }
+                a[hl] = pack_bf16(wy0 * wxa, wy0 * wxb);        // k = 2t, 2t+1   (rows r0)
+                a[2 + hl] = pack_bf16(wy2 * wxa, wy2 * wxb);    // k = 2t+8, 2t+9 (rows r0+2)
+              }
+              sts128(dst + mt * 512, make_uint4(a[0], a[1], a[2], a[3]));
+            }
+          }
+          if (lane == 0) asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(s_meta + stage * 8), "r"(roi), "r"(flags) : "memory");
+          __syncwarp();
+          if (lane == 0) {
+            if (empty) {
+              mbar_arrive(full_bar + stage);
+            } else {
+              mbar_expect_tx(full_bar + stage, tx_bytes);
+              tma_load_5d(s_patch + stage * PATCH_BYTES, &tmap, s_full + stage * 8, 0, xmin + cx * 4, ymin + cy * 4, b, 0);
+            }
+          }
+          if (++slot == DEPTH) { slot = 0; phase ^= 1; }
+        }
+      }
+    }
+    return;
+  }
+
+  // ------------------------------------------------------------------------------------ MMA warps
+  const int cb = warp * 32;                      // first channel of this warp
+  const bool active = cb < C;
+  const int q = warp >> 1, j0 = (warp & 1) * 4;  // channel quarter, first 16 B chunk inside the quarter's 128 B row
+  uint32_t boff[2];
+  {
+    const int i = lane >> 3, rr = lane & 7;
+    const int p = (i & 1) * 8 + rr;
+#pragma unroll
+    for (int np = 0; np < 2; np++) {
+      const int jj = j0 + np * 2 + (i >> 1);
+      boff[np] = (uint32_t)(q * QUARTER_BYTES + p * 128 + ((jj ^ rr) << 4));
+    }
+  }
+  // stmatrix row address of this lane inside a staging buffer: matrix (lane>>3) = n-tile, row (lane&7) = bin
+  const uint32_t stsm_off = (uint32_t)((lane & 7) * STG_ROW_BYTES + (cb + (lane >> 3) * 8) * 2);
+  float acc[4][4][4];
+#pragma unroll
+  for (int mt = 0; mt < 4; mt++)
+#pragma unroll
+    for (int nt = 0; nt < 4; nt++)
+#pragma unroll
+      for (int e = 0; e < 4; e++) acc[mt][nt][e] = 0.f;
+
+  uint32_t slotbits = 0, phasebits = 0;          // per-builder ring position / parity (bit = builder id)
+  int sbuf = 0;
+  for (int it = 0; it < n_iter; it++) {
+    const int bw_id = it % BUILDERS;
+    int roi, flags;
+    do {
+      const int slot = (slotbits >> bw_id) & 1;
+      const int stage = bw_id * DEPTH + slot;
+      mbar_wait(full_bar + stage, (phasebits >> bw_id) & 1);
+      {
+        const uint2 m = lds64(s_meta + stage * 8);
+        roi = (int)m.x; flags = (int)m.y;
+      }
+      if (!(flags & (F_ZERO | F_SKIP)) && active) {
+        const uint32_t af = s_afrag + stage * AFRAG_BYTES + lane * 16;
+        uint4 a[4];
+#pragma unroll
+        for (int mt = 0; mt < 4; mt++) a[mt] = lds128(af + mt * 512);
+        const uint32_t pb = s_patch + stage * PATCH_BYTES;
+        uint32_t b01[4], b23[4];
+        ldsm_x4_trans(pb + boff[0], b01);
+        ldsm_x4_trans(pb + boff[1], b23);
+#pragma unroll
+        for (int mt = 0; mt < 4; mt++) {
+          mma_bf16(acc[mt][0], a[mt], b01[0], b01[1]);
+          mma_bf16(acc[mt][1], a[mt], b01[2], b01[3]);
+          mma_bf16(acc[mt][2], a[mt], b23[0], b23[1]);
+          mma_bf16(acc[mt][3], a[mt], b23[2], b23[3]);
+        }
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(empty_bar + stage);
+      if (slot == DEPTH - 1) phasebits ^= 1u << bw_id;
+      slotbits ^= 1u << bw_id;
+    } while (!(flags & F_LAST));
+    if (flags & F_SKIP) continue;
+
+    const uint32_t sg = s_stg + sbuf * STG_BYTES;
+    if (active) {
+#pragma unroll
+      for (int mt = 0; mt < 3; mt++) {
+        stsm_x4(sg + mt * 16 * STG_ROW_BYTES + stsm_off,
+                pack_bf16(acc[mt][0][0], acc[mt][0][1]), pack_bf16(acc[mt][1][0], acc[mt][1][1]),
+                pack_bf16(acc[mt][2][0], acc[mt][2][1]), pack_bf16(acc[mt][3][0], acc[mt][3][1]));
+        stsm_x4(sg + (mt * 16 + 8) * STG_ROW_BYTES + stsm_off,
+                pack_bf16(acc[mt][0][2], acc[mt][0][3]), pack_bf16(acc[mt][1][2], acc[mt][1][3]),
+                pack_bf16(acc[mt][2][2], acc[mt][2][3]), pack_bf16(acc[mt][3][2], acc[mt][3][3]));
+      }
+      if (g == 0) {   // bin 48: row 0 of m-tile 3
+#pragma unroll
+        for (int nt = 0; nt < 4; nt++)
+          sts32(sg + 48 * STG_ROW_BYTES + (cb + nt * 8 + 2 * t) * 2, pack_bf16(acc[3][nt][0], acc[3][nt][1]));
+      }
+#pragma unroll
+      for (int mt = 0; mt < 4; mt++)
+#pragma unroll
+        for (int nt = 0; nt < 4; nt++)
+#pragma unroll
+          for (int e = 0; e < 4; e++) acc[mt][nt][e] = 0.f;
+    }
+    asm volatile("bar.sync 1, %0;" ::"n"(MMA_WARPS * 32) : "memory");
+    // double-buffered staging: the next RoI's writes go to the other buffer, and buffer reuse two RoIs later
+    // is ordered by the next barrier (every warp has finished this copy-out before it arrives there)
+    if (lane * 8 < C) {
+      __nv_bfloat16* gp = out + (size_t)roi * ld_out + (size_t)warp * C + lane * 8;
+      const uint32_t sp = sg + warp * STG_ROW_BYTES + lane * 16;
+      const size_t gstep = (size_t)MMA_WARPS * C;
+      uint4 v[6];
+#pragma unroll
+      for (int i = 0; i < 6; i++) v[i] = lds128(sp + i * MMA_WARPS * STG_ROW_BYTES);
+#pragma unroll
+      for (int i = 0; i < 6; i++) *reinterpret_cast<uint4*>(gp + i * gstep) = v[i];
+      if (warp == 0) *reinterpret_cast<uint4*>(gp + 6 * gstep) = lds128(sp + 6 * MMA_WARPS * STG_ROW_BYTES);
+    }
+    sbuf ^= 1;
+  }
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode() {
+  static EncodeTiledFn fn = nullptr;
+  if (fn == nullptr) {
+    void* ptr = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres);
+    if (e != cudaSuccess || qres != cudaDriverEntryPointSuccess || ptr == nullptr) return nullptr;
+    fn = reinterpret_cast<EncodeTiledFn>(ptr);
+  }
+  return fn;
+}
+
+size_t smem_bytes(int H, int W) {
+  return 1024 + (size_t)STAGES * (PATCH_BYTES + AFRAG_BYTES) + 2 * (size_t)STG_BYTES +
+         BUILDERS * ((size_t)(W + 4) * 8 + (size_t)(H + 4) * 8) * sizeof(float) + 3 * STAGES * 8 + 64;
+}
+
+bool supported(int C, int H, int W) {
+  return C % 64 == 0 && C >= 64 && C <= 256 && smem_bytes(H, W) <= 113 * 1024;
+}
+
+int launch(const void* feat_bf16_nhwc, const float* rois, void* out, long long ld_out, int K, int B, int C, int H,
+           int W, float scale, int sampling_ratio, int aligned, const int* roi_level, int level,
+           cudaStream_t stream) {
+  EncodeTiledFn enc = get_encode();
+  if (enc == nullptr) { set_error("cuTensorMapEncodeTiled entry point not found"); return PT_ERR_DRIVER; }
+  if ((uintptr_t)feat_bf16_nhwc & 15) { set_error("roi_align_mma: feature map must be 16-byte aligned"); return PT_ERR_ARG; }
+  CUtensorMap map;
+  // NHWC bf16 viewed as (64 ch, W, H, B, C/64): the channel quarter is the slowest box dimension so that each
+  // quarter lands as a [16 pixels][128 B] SWIZZLE_128B tile, the ldmatrix-friendly layout
+  cuuint64_t dims[5] = {64, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B, (cuuint64_t)(C / 64)};
+  cuuint64_t strides[4] = {(cuuint64_t)C * 2, (cuuint64_t)W * C * 2, (cuuint64_t)H * W * C * 2, 128};
+  cuuint32_t box[5] = {64, 4, 4, 1, (cuuint32_t)(C / 64)};
+  cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+  CUresult r = enc(&map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<void*>(feat_bf16_nhwc), dims, strides, box,
+                   estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) { set_error("roi_align_mma: cuTensorMapEncodeTiled failed: CUresult %d", (int)r); return PT_ERR_DRIVER; }
+  const size_t smem = smem_bytes(H, W);
+  cudaError_t e = cudaFuncSetAttribute(roi_align_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) { set_error("cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return PT_ERR_CUDA; }
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const int grid = K < 2 * sms ? K : 2 * sms;
+  roi_align_mma_kernel<<<grid, THREADS, smem, stream>>>(map, rois, reinterpret_cast<__nv_bfloat16*>(out), ld_out, K, B,
+                                                        C, H, W, scale, sampling_ratio, aligned, roi_level, level);
+  return check_launch("roi_align_mma_kernel");
+}
+
+}  // namespace ramma
+}  // namespace ptb

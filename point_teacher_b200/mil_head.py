@@ -289,10 +289,13 @@ class MILHead(nn.Module, MILHeadMixin):
                  bbox_roi_extractor=dict(type="SingleRoIExtractor", roi_layer=dict(type="RoIAlign", output_size=7),
                                          out_channels=256, featmap_strides=[8]),
                  loss_bbox_denosing=dict(type="DN_DIoULoss", loss_weight=1.0, hyper=0.2), precision="bf16",
-                 feat_dtype=torch.float32, **kwargs):
+                 feat_dtype=None, **kwargs):
         super().__init__()
         self.num_classes, self.in_channels = num_classes, in_channels
         self.beta, self.topk, self.num_stages = beta, top_k, num_stages
+        # bf16 precision: bf16 NHWC feature map (TMA + tensor-core RoIAlign); fp32 precision: fp32 feature map
+        if feat_dtype is None:
+            feat_dtype = torch.bfloat16 if precision == "bf16" else torch.float32
         self.precision, self.feat_dtype = precision, feat_dtype
         if loss_bbox_denosing.get("type") != "DN_DIoULoss" or loss_bbox_denosing.get("loss_weight", 1.0) != 1.0:
             raise NotImplementedError("the fused decode kernel implements DN_DIoULoss(loss_weight=1.0)")

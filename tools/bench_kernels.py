@@ -58,6 +58,17 @@ def main():
             t = timeit(lambda: ops.roi_align_forward(feat, r, mode, 0.125, out=o), a.iters, flush)
             nb = r.shape[0] * 12544 * (4 if mode == 1 else 2) + feat.numel() * feat.element_size() + r.numel() * 4
             res[name] = {"us": t, "GBps": nb / t / 1e3}
+        # stress config #4 (one image): 1500 GT x 64 instances = 96 000 RoIs, 2.4 GB bf16 out
+        ds = synth.hbb_batch(seed=1, batch=1, gt_range=(1500, 1500))
+        props, _ = hbb.fine_proposals(ds["pseudo_boxes"], synth.stress_ext_cfg(8)[0], ds["img_metas"])
+        rs = hbb.bbox2roi(props).to(dev)
+        xs = ds["feat"].to(dev)
+        outs = torch.empty((rs.shape[0], 12544), dtype=torch.bfloat16, device=dev)
+        for name, feat in [("roi_stress96k_f32in", ops.nchw_to_nhwc(xs)), ("roi_stress96k_bf16in", ops.nchw_to_nhwc(xs, torch.bfloat16))]:
+            t = timeit(lambda: ops.roi_align_forward(feat, rs, 0, 0.125, out=outs), max(a.iters // 4, 3), flush)
+            nb = rs.shape[0] * 12544 * 2 + feat.numel() * feat.element_size() + rs.numel() * 4
+            res[name] = {"us": t, "GBps": nb / t / 1e3, "K": rs.shape[0]}
+        del outs
     if a.what in ("gemm", "all"):
         for M, N, K in [(5000, 1024, 12544), (5400, 1024, 12544), (5000, 1024, 1024), (4736, 1024, 12544)]:
             A = torch.randn(M, K, device=dev).to(torch.bfloat16)
