@@ -20,8 +20,9 @@
 //             (64 ch x 4 cols x 4 rows x 1 img x 4 channel-quarters = 8 KB, SWIZZLE_128B, OOB zero fill) into a
 //             its own 2-deep mbarrier ring and writes the chunk's A fragments (Wmat in mma register order) next to it.
 //   MMA     : per chunk 4 x LDS.128 (A) + 2 x ldmatrix.x4.trans (B) + 16 x mma.m16n8k16; after the RoI's last
-//             chunk: bf16 pack -> stmatrix into a padded (conflict free), double-buffered smem staging ->
-//             512 B-per-warp coalesced 16 B global stores.
+//             chunk: bf16 pack -> stmatrix into a warp-private SWIZZLE_64B staging -> one TMA tensor store of the
+//             warp's 49 bins x 32 channels (no CTA-wide barrier in the steady state; the output never touches
+//             the LSU pipe, which the ncu captures showed to be the limiter of the LDS+STG copy-out).
 #include <cuda.h>
 
 #include "common.cuh"
@@ -36,9 +37,10 @@ constexpr int THREADS = (MMA_WARPS + BUILDERS) * 32;
 constexpr int QUARTER_BYTES = 16 * 128;           // 16 pixels x 64 channels bf16
 constexpr int PATCH_BYTES = 4 * QUARTER_BYTES;    // 8 KB
 constexpr int AFRAG_BYTES = 4 * 32 * 16;          // 4 m-tiles x 32 lanes x uint4
-constexpr int STG_LD = 264;                       // staging row: 256 channels + 8 pad (bank-conflict free)
-constexpr int STG_ROW_BYTES = STG_LD * 2;
-constexpr int STG_BYTES = ((NBIN * STG_ROW_BYTES + 127) / 128) * 128;
+// warp-private output staging, double buffered: 49 bins x 32 channels (64 B rows) in the TMA SWIZZLE_64B layout
+// (16 B chunk index ^= (row >> 1) & 3), which also makes the stmatrix writes bank-conflict free
+constexpr int STG_ROW_BYTES = 64;
+constexpr int STG_BYTES = ((NBIN * STG_ROW_BYTES + 511) / 512) * 512;   // per MMA warp and buffer
 enum { F_LAST = 2, F_ZERO = 4, F_SKIP = 8 };
 
 __device__ __forceinline__ void tma_load_5d(uint32_t dst, const void* desc, uint32_t bar, int c0, int c1, int c2,
@@ -74,6 +76,14 @@ __device__ __forceinline__ uint2 lds64(uint32_t addr) {
   asm volatile("ld.shared.v2.b32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(addr));
   return v;
 }
+// D = A * B (no accumulator input: the first chunk of a RoI starts from zero without clearing registers)
+__device__ __forceinline__ void mma_bf16_z(float (&d)[4], const uint4& a, uint32_t b0, uint32_t b1) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, "
+      "{%10, %10, %10, %10};"
+      : "=f"(d[0]), "=f"(d[1]), "=f"(d[2]), "=f"(d[3])
+      : "r"(a.x), "r"(a.y), "r"(a.z), "r"(a.w), "r"(b0), "r"(b1), "f"(0.f));
+}
 __device__ __forceinline__ void mma_bf16(float (&d)[4], const uint4& a, uint32_t b0, uint32_t b1) {
   asm volatile(
       "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, "
@@ -94,16 +104,17 @@ __device__ __forceinline__ bool axis_setup(float v, int size, int& lo, int& hi, 
 }
 
 __global__ void __launch_bounds__(THREADS, 2)
-roi_align_mma_kernel(const __grid_constant__ CUtensorMap tmap, const float* __restrict__ rois,
-                     __nv_bfloat16* __restrict__ out, long long ld_out, int K, int B, int C, int H, int W,
-                     float scale, int sampling_ratio, int aligned, const int* __restrict__ roi_level, int level) {
+roi_align_mma_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ CUtensorMap omap,
+                     const float* __restrict__ rois, int K, int B, int C, int H, int W,
+                     float scale, int sampling_ratio, int aligned, const int* __restrict__ roi_level, int level,
+                     int stg_bufs) {
   extern __shared__ uint8_t smem_raw[];
   // shared-window byte addresses (explicit .shared accesses below; generic pointers would cost LD/ST.E)
   const uint32_t sbase = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t s_patch = sbase;                                    // [STAGES][PATCH_BYTES], 1 KB aligned
   const uint32_t s_afrag = s_patch + STAGES * PATCH_BYTES;           // [STAGES][AFRAG_BYTES]
-  const uint32_t s_stg = s_afrag + STAGES * AFRAG_BYTES;             // [2][STG_BYTES]
-  const uint32_t s_tab = s_stg + 2 * STG_BYTES;                      // [BUILDERS][(W+4)*8 + (H+4)*8] floats
+  const uint32_t s_stg = s_afrag + STAGES * AFRAG_BYTES;             // [MMA_WARPS][2][STG_BYTES]
+  const uint32_t s_tab = s_stg + MMA_WARPS * stg_bufs * STG_BYTES;                      // [BUILDERS][(W+4)*8 + (H+4)*8] floats
   const int tab_floats = (W + 4) * 8 + (H + 4) * 8;
   const uint32_t s_full = s_tab + BUILDERS * tab_floats * 4;         // [STAGES] mbarriers
   const uint32_t s_empty = s_full + STAGES * 8;
@@ -115,6 +126,7 @@ roi_align_mma_kernel(const __grid_constant__ CUtensorMap tmap, const float* __re
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (threadIdx.x == 0) {
     tma_prefetch_desc(&tmap);
+    tma_prefetch_desc(&omap);
     for (int i = 0; i < STAGES; i++) { mbar_init(full_bar + i, 1); mbar_init(empty_bar + i, MMA_WARPS); }
     fence_barrier_init();
   }
@@ -271,21 +283,18 @@ roi_align_mma_kernel(const __grid_constant__ CUtensorMap tmap, const float* __re
       boff[np] = (uint32_t)(q * QUARTER_BYTES + p * 128 + ((jj ^ rr) << 4));
     }
   }
-  // stmatrix row address of this lane inside a staging buffer: matrix (lane>>3) = n-tile, row (lane&7) = bin
-  const uint32_t stsm_off = (uint32_t)((lane & 7) * STG_ROW_BYTES + (cb + (lane >> 3) * 8) * 2);
+  // stmatrix row address of this lane inside the warp's staging: matrix (lane>>3) = n-tile = 16 B chunk,
+  // row (lane&7) = bin; SWIZZLE_64B: chunk ^= (row >> 1) & 3 (buffers are 512 B aligned)
+  const uint32_t sg0 = s_stg + warp * stg_bufs * STG_BYTES;
+  const uint32_t stsm_off = (uint32_t)((lane & 7) * STG_ROW_BYTES + (((lane >> 3) ^ ((lane & 7) >> 1)) << 4));
+  int sbuf = 0;
   float acc[4][4][4];
-#pragma unroll
-  for (int mt = 0; mt < 4; mt++)
-#pragma unroll
-    for (int nt = 0; nt < 4; nt++)
-#pragma unroll
-      for (int e = 0; e < 4; e++) acc[mt][nt][e] = 0.f;
 
   uint32_t slotbits = 0, phasebits = 0;          // per-builder ring position / parity (bit = builder id)
-  int sbuf = 0;
   for (int it = 0; it < n_iter; it++) {
     const int bw_id = it % BUILDERS;
     int roi, flags;
+    bool first = true;
     do {
       const int slot = (slotbits >> bw_id) & 1;
       const int stage = bw_id * DEPTH + slot;
@@ -303,60 +312,72 @@ roi_align_mma_kernel(const __grid_constant__ CUtensorMap tmap, const float* __re
         uint32_t b01[4], b23[4];
         ldsm_x4_trans(pb + boff[0], b01);
         ldsm_x4_trans(pb + boff[1], b23);
+        if (first) {
 #pragma unroll
-        for (int mt = 0; mt < 4; mt++) {
-          mma_bf16(acc[mt][0], a[mt], b01[0], b01[1]);
-          mma_bf16(acc[mt][1], a[mt], b01[2], b01[3]);
-          mma_bf16(acc[mt][2], a[mt], b23[0], b23[1]);
-          mma_bf16(acc[mt][3], a[mt], b23[2], b23[3]);
+          for (int mt = 0; mt < 4; mt++) {
+            mma_bf16_z(acc[mt][0], a[mt], b01[0], b01[1]);
+            mma_bf16_z(acc[mt][1], a[mt], b01[2], b01[3]);
+            mma_bf16_z(acc[mt][2], a[mt], b23[0], b23[1]);
+            mma_bf16_z(acc[mt][3], a[mt], b23[2], b23[3]);
+          }
+        } else {
+#pragma unroll
+          for (int mt = 0; mt < 4; mt++) {
+            mma_bf16(acc[mt][0], a[mt], b01[0], b01[1]);
+            mma_bf16(acc[mt][1], a[mt], b01[2], b01[3]);
+            mma_bf16(acc[mt][2], a[mt], b23[0], b23[1]);
+            mma_bf16(acc[mt][3], a[mt], b23[2], b23[3]);
+          }
         }
+      } else if (first) {
+#pragma unroll
+        for (int mt = 0; mt < 4; mt++)
+#pragma unroll
+          for (int nt = 0; nt < 4; nt++)
+#pragma unroll
+            for (int e = 0; e < 4; e++) acc[mt][nt][e] = 0.f;
       }
+      first = false;
       __syncwarp();
       if (lane == 0) mbar_arrive(empty_bar + stage);
       if (slot == DEPTH - 1) phasebits ^= 1u << bw_id;
       slotbits ^= 1u << bw_id;
     } while (!(flags & F_LAST));
-    if (flags & F_SKIP) continue;
+    if ((flags & F_SKIP) || !active) continue;
 
-    const uint32_t sg = s_stg + sbuf * STG_BYTES;
-    if (active) {
-#pragma unroll
-      for (int mt = 0; mt < 3; mt++) {
-        stsm_x4(sg + mt * 16 * STG_ROW_BYTES + stsm_off,
-                pack_bf16(acc[mt][0][0], acc[mt][0][1]), pack_bf16(acc[mt][1][0], acc[mt][1][1]),
-                pack_bf16(acc[mt][2][0], acc[mt][2][1]), pack_bf16(acc[mt][3][0], acc[mt][3][1]));
-        stsm_x4(sg + (mt * 16 + 8) * STG_ROW_BYTES + stsm_off,
-                pack_bf16(acc[mt][0][2], acc[mt][0][3]), pack_bf16(acc[mt][1][2], acc[mt][1][3]),
-                pack_bf16(acc[mt][2][2], acc[mt][2][3]), pack_bf16(acc[mt][3][2], acc[mt][3][3]));
-      }
-      if (g == 0) {   // bin 48: row 0 of m-tile 3
-#pragma unroll
-        for (int nt = 0; nt < 4; nt++)
-          sts32(sg + 48 * STG_ROW_BYTES + (cb + nt * 8 + 2 * t) * 2, pack_bf16(acc[3][nt][0], acc[3][nt][1]));
-      }
-#pragma unroll
-      for (int mt = 0; mt < 4; mt++)
-#pragma unroll
-        for (int nt = 0; nt < 4; nt++)
-#pragma unroll
-          for (int e = 0; e < 4; e++) acc[mt][nt][e] = 0.f;
+    // epilogue, warp-private (no CTA barrier): bf16 pack -> stmatrix into the swizzled staging -> ONE TMA tensor
+    // store of the warp's 49 x 32-channel slice (the LSU pipe never sees the 25 KB/RoI output again)
+    const uint32_t sg = sg0 + sbuf * STG_BYTES;
+    if (lane == 0) {   // buffer free: the store issued stg_bufs RoIs ago has finished reading it
+      if (stg_bufs == 2) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+      else asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
     }
-    asm volatile("bar.sync 1, %0;" ::"n"(MMA_WARPS * 32) : "memory");
-    // double-buffered staging: the next RoI's writes go to the other buffer, and buffer reuse two RoIs later
-    // is ordered by the next barrier (every warp has finished this copy-out before it arrives there)
-    if (lane * 8 < C) {
-      __nv_bfloat16* gp = out + (size_t)roi * ld_out + (size_t)warp * C + lane * 8;
-      const uint32_t sp = sg + warp * STG_ROW_BYTES + lane * 16;
-      const size_t gstep = (size_t)MMA_WARPS * C;
-      uint4 v[6];
+    __syncwarp();
 #pragma unroll
-      for (int i = 0; i < 6; i++) v[i] = lds128(sp + i * MMA_WARPS * STG_ROW_BYTES);
-#pragma unroll
-      for (int i = 0; i < 6; i++) *reinterpret_cast<uint4*>(gp + i * gstep) = v[i];
-      if (warp == 0) *reinterpret_cast<uint4*>(gp + 6 * gstep) = lds128(sp + 6 * MMA_WARPS * STG_ROW_BYTES);
+    for (int mt = 0; mt < 3; mt++) {
+      stsm_x4(sg + mt * 16 * STG_ROW_BYTES + stsm_off,
+              pack_bf16(acc[mt][0][0], acc[mt][0][1]), pack_bf16(acc[mt][1][0], acc[mt][1][1]),
+              pack_bf16(acc[mt][2][0], acc[mt][2][1]), pack_bf16(acc[mt][3][0], acc[mt][3][1]));
+      stsm_x4(sg + (mt * 16 + 8) * STG_ROW_BYTES + stsm_off,
+              pack_bf16(acc[mt][0][2], acc[mt][0][3]), pack_bf16(acc[mt][1][2], acc[mt][1][3]),
+              pack_bf16(acc[mt][2][2], acc[mt][2][3]), pack_bf16(acc[mt][3][2], acc[mt][3][3]));
     }
-    sbuf ^= 1;
+    if (g == 0) {   // bin 48: row 0 of m-tile 3 ((48 >> 1) & 3 == 0: unswizzled)
+#pragma unroll
+      for (int nt = 0; nt < 4; nt++)
+        sts32(sg + 48 * STG_ROW_BYTES + nt * 16 + t * 4, pack_bf16(acc[3][nt][0], acc[3][nt][1]));
+    }
+    fence_proxy_async();      // generic-proxy smem writes -> visible to the async proxy (TMA)
+    __syncwarp();
+    if (lane == 0) {
+      asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%1, %2, %3}], [%4];" ::"l"(&omap),
+                   "r"(cb), "r"(0), "r"(roi), "r"(sg)
+                   : "memory");
+      asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+    }
+    sbuf ^= stg_bufs - 1;
   }
+  if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // smem must outlive the reads
 }
 
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
@@ -375,13 +396,15 @@ static EncodeTiledFn get_encode() {
   return fn;
 }
 
-size_t smem_bytes(int H, int W) {
-  return 1024 + (size_t)STAGES * (PATCH_BYTES + AFRAG_BYTES) + 2 * (size_t)STG_BYTES +
+constexpr size_t SMEM_LIMIT = 113 * 1024;   // two CTAs per SM
+
+size_t smem_bytes(int H, int W, int stg_bufs) {
+  return 1024 + (size_t)STAGES * (PATCH_BYTES + AFRAG_BYTES) + MMA_WARPS * stg_bufs * (size_t)STG_BYTES +
          BUILDERS * ((size_t)(W + 4) * 8 + (size_t)(H + 4) * 8) * sizeof(float) + 3 * STAGES * 8 + 64;
 }
 
 bool supported(int C, int H, int W) {
-  return C % 64 == 0 && C >= 64 && C <= 256 && smem_bytes(H, W) <= 113 * 1024;
+  return C % 64 == 0 && C >= 64 && C <= 256 && smem_bytes(H, W, 1) <= SMEM_LIMIT;
 }
 
 int launch(const void* feat_bf16_nhwc, const float* rois, void* out, long long ld_out, int K, int B, int C, int H,
@@ -401,15 +424,28 @@ int launch(const void* feat_bf16_nhwc, const float* rois, void* out, long long l
                    estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) { set_error("roi_align_mma: cuTensorMapEncodeTiled failed: CUresult %d", (int)r); return PT_ERR_DRIVER; }
-  const size_t smem = smem_bytes(H, W);
+  // output (K, 49, C) bf16, row pitch ld_out: one box = one warp's slice of one RoI (32 ch x 49 bins), SWIZZLE_64B
+  CUtensorMap omap;
+  {
+    cuuint64_t od[3] = {(cuuint64_t)C, (cuuint64_t)NBIN, (cuuint64_t)K};
+    cuuint64_t os[2] = {(cuuint64_t)C * 2, (cuuint64_t)ld_out * 2};
+    cuuint32_t ob[3] = {32, (cuuint32_t)NBIN, 1};
+    cuuint32_t oe[3] = {1, 1, 1};
+    if ((uintptr_t)out & 15) { set_error("roi_align_mma: output must be 16-byte aligned"); return PT_ERR_ARG; }
+    r = enc(&omap, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, out, od, os, ob, oe, CU_TENSOR_MAP_INTERLEAVE_NONE,
+            CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { set_error("roi_align_mma: output cuTensorMapEncodeTiled failed: CUresult %d", (int)r); return PT_ERR_DRIVER; }
+  }
+  const int stg_bufs = smem_bytes(H, W, 2) <= SMEM_LIMIT ? 2 : 1;   // large maps: single-buffered staging
+  const size_t smem = smem_bytes(H, W, stg_bufs);
   cudaError_t e = cudaFuncSetAttribute(roi_align_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) { set_error("cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return PT_ERR_CUDA; }
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   const int grid = K < 2 * sms ? K : 2 * sms;
-  roi_align_mma_kernel<<<grid, THREADS, smem, stream>>>(map, rois, reinterpret_cast<__nv_bfloat16*>(out), ld_out, K, B,
-                                                        C, H, W, scale, sampling_ratio, aligned, roi_level, level);
+  roi_align_mma_kernel<<<grid, THREADS, smem, stream>>>(map, omap, rois, K, B, C, H, W, scale, sampling_ratio, aligned,
+                                                        roi_level, level, stg_bufs);
   return check_launch("roi_align_mma_kernel");
 }
 
