@@ -63,7 +63,9 @@ int pt_bbox_overlaps(const float* a, int lda, const float* b, int ldb, long long
  * mmcv.ops.RoIAlign / RoIAlignRotated forward as built by
  *   HBB_TOD/mmdet/models/roi_heads/roi_extractors/base_roi_extractor.py:50-59 and called from
  *   single_level_roi_extractor.py:56-114 / OBB_TOD/.../rotate_single_level_roi_extractor.py:90-167.
- * pt_nchw_to_nhwc: [B,C,H,W] fp32 -> [B,H,W,C] fp32 or bf16 (done once per step).
+ * pt_nchw_to_nhwc: [B,C,H,W] fp32 -> [B,H,W,C] fp32 (out_bf16 = 0), bf16 (1) or saturating fp16 (2); once per step.
+ * feat_bf16 of pt_roi_align_forward uses the same dtype code.  bf16/fp16 feature maps with out_mode 0 take the
+ * TMA + mma.sync throughput kernel (roi_align_mma.cu) when C % 64 == 0 and C <= 256.
  * pt_roi_align_forward: feat NHWC; rois [K,5] or rotated [K,6] (img,cx,cy,w,h,theta rad).
  *   out_mode 0: bf16 [K, ld_out], column (ph*7+pw)*C + c (the FC1 operand layout)
  *   out_mode 1: fp32 [K,C,7,7] (the extractor's public layout)

@@ -13,14 +13,17 @@
 // sample crosses a pixel boundary -- tiny objects (2x2 feature pixels) touch ~3 columns for 7 bins.
 // Sample coordinates use non-contracted fp32 arithmetic in the reference's operation order so the adaptive
 // grid size and the border rule are decided identically.
+#include <cuda_fp16.h>
+
 #include "common.cuh"
 
 namespace ptb {
 
 namespace ramma {   // roi_align_mma.cu: TMA + mma.sync bf16 throughput path
 bool supported(int C, int H, int W);
-int launch(const void* feat_bf16_nhwc, const float* rois, void* out, long long ld_out, int K, int B, int C, int H,
-           int W, float scale, int sampling_ratio, int aligned, const int* roi_level, int level, cudaStream_t stream);
+int launch(const void* feat_nhwc, int feat_f16, const float* rois, void* out, long long ld_out, int K, int B, int C,
+           int H, int W, float scale, int sampling_ratio, int aligned, const int* roi_level, int level,
+           cudaStream_t stream);
 }  // namespace ramma
 
 constexpr int P7 = 7;
@@ -28,6 +31,18 @@ constexpr int GW_CHUNK = 16;   // x samples per bin held in the shared sample ta
 
 // --------------------------------------------------------------------------------- NCHW -> NHWC
 // 64 channels x 64 positions per CTA: 16-byte loads along HW, 16-/8-byte stores along C.
+template <typename T> struct IS_HALF { static constexpr bool value = false; };
+template <> struct IS_HALF<__half> { static constexpr bool value = true; };
+// fp16 feature maps saturate to +-65504 instead of overflowing to inf
+__device__ __forceinline__ uint32_t pack_f16_sat(float lo, float hi) {
+  uint32_t r;
+  asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+  return r;
+}
+template <typename TOut> __device__ __forceinline__ TOut cvt_out(float v) { return (TOut)v; }
+template <> __device__ __forceinline__ __half cvt_out<__half>(float v) {
+  return __float2half_rn(fminf(fmaxf(v, -65504.f), 65504.f));
+}
 template <typename TOut>
 __global__ void __launch_bounds__(256)
 nchw_to_nhwc_kernel(const float* __restrict__ in, TOut* __restrict__ out, int C, int HW) {
@@ -65,10 +80,11 @@ nchw_to_nhwc_kernel(const float* __restrict__ in, TOut* __restrict__ out, int C,
       TOut* o = dst + (size_t)p * C + c;
       if ((C & 3) == 0) {
         if (sizeof(TOut) == 4) *reinterpret_cast<float4*>(o) = make_float4(v[0], v[1], v[2], v[3]);
+        else if (IS_HALF<TOut>::value) *reinterpret_cast<uint2*>(o) = make_uint2(pack_f16_sat(v[0], v[1]), pack_f16_sat(v[2], v[3]));
         else *reinterpret_cast<uint2*>(o) = make_uint2(pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]));
       } else {
 #pragma unroll
-        for (int j = 0; j < 4; j++) if (c + j < C) o[j] = (TOut)v[j];
+        for (int j = 0; j < 4; j++) if (c + j < C) o[j] = cvt_out<TOut>(v[j]);
       }
     }
   }
@@ -104,6 +120,19 @@ __device__ __forceinline__ bool axis_setup(float v, int size, int& lo, int& hi, 
   l = fsub(v, (float)lo);
   h = fsub(1.0f, l);
   return true;
+}
+
+__device__ __forceinline__ F8 load8(const __half* p) {
+  F8 r;
+  uint4 u = __ldg(reinterpret_cast<const uint4*>(p));
+  const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+  for (int i = 0; i < 4; i++) {
+    const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&w[i]));
+    r.v[2 * i] = f.x;
+    r.v[2 * i + 1] = f.y;
+  }
+  return r;
 }
 
 enum { OUT_BF16_BINMAJOR = 0, OUT_F32_NCHW = 1, OUT_BF16X3_BINMAJOR = 2 };
@@ -475,14 +504,16 @@ extern "C" int pt_nchw_to_nhwc(const float* in, void* out, int B, int C, int H, 
   if (B <= 0 || C <= 0 || H <= 0 || W <= 0) return PT_OK;
   const int HW = H * W;
   dim3 grid((HW + 63) / 64, (C + 63) / 64, B), block(256);
-  if (out_bf16)
+  if (out_bf16 == 2)
+    nchw_to_nhwc_kernel<__half><<<grid, block, 0, (cudaStream_t)stream>>>(in, (__half*)out, C, HW);
+  else if (out_bf16)
     nchw_to_nhwc_kernel<__nv_bfloat16><<<grid, block, 0, (cudaStream_t)stream>>>(in, (__nv_bfloat16*)out, C, HW);
   else
     nchw_to_nhwc_kernel<float><<<grid, block, 0, (cudaStream_t)stream>>>(in, (float*)out, C, HW);
   return check_launch("nchw_to_nhwc_kernel");
 }
 
-// feat: NHWC [B,H,W,C] fp32 (feat_bf16=0) or bf16 (=1).  rois: [K,5] (b,x1,y1,x2,y2) or, rotated, [K,6]
+// feat: NHWC [B,H,W,C] fp32 (feat_bf16=0), bf16 (=1) or fp16 (=2).  rois: [K,5] (b,x1,y1,x2,y2) or, rotated, [K,6]
 // (b,cx,cy,w,h,theta).  out_mode 0: bf16 [K, ld_out] with k = (ph*7+pw)*C + c;  1: fp32 [K,C,7,7];
 // 2: bf16 [K, ld_out] three segments [hi | lo | hi] of 49*C each.
 extern "C" int pt_roi_align_forward(const void* feat, int feat_bf16, const float* rois, void* out, long long ld_out,
@@ -500,10 +531,14 @@ extern "C" int pt_roi_align_forward(const void* feat, int feat_bf16, const float
   cudaStream_t s = (cudaStream_t)stream;
   const bool rot = rotated != 0;
   if (feat_bf16 && !rot && out_mode == OUT_BF16_BINMAJOR && ramma::supported(C, H, W))
-    return ramma::launch(feat, rois, out, ld_out, K, B, C, H, W, spatial_scale, sampling_ratio, aligned, roi_level,
-                         level, s);
+    return ramma::launch(feat, feat_bf16 == 2, rois, out, ld_out, K, B, C, H, W, spatial_scale, sampling_ratio, aligned,
+                         roi_level, level, s);
 #define PT_DISPATCH(T, M) return launch_fwd<T, M>(rot, feat, rois, out, ld_out, K, B, C, H, W, spatial_scale, sampling_ratio, aligned, clockwise, roi_level, level, s)
-  if (feat_bf16) {
+  if (feat_bf16 == 2) {
+    if (out_mode == OUT_BF16_BINMAJOR) PT_DISPATCH(__half, OUT_BF16_BINMAJOR);
+    if (out_mode == OUT_F32_NCHW) PT_DISPATCH(__half, OUT_F32_NCHW);
+    if (out_mode == OUT_BF16X3_BINMAJOR) PT_DISPATCH(__half, OUT_BF16X3_BINMAJOR);
+  } else if (feat_bf16) {
     if (out_mode == OUT_BF16_BINMAJOR) PT_DISPATCH(__nv_bfloat16, OUT_BF16_BINMAJOR);
     if (out_mode == OUT_F32_NCHW) PT_DISPATCH(__nv_bfloat16, OUT_F32_NCHW);
     if (out_mode == OUT_BF16X3_BINMAJOR) PT_DISPATCH(__nv_bfloat16, OUT_BF16X3_BINMAJOR);

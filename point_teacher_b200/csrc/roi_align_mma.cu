@@ -24,6 +24,7 @@
 //             warp's 49 bins x 32 channels (no CTA-wide barrier in the steady state; the output never touches
 //             the LSU pipe, which the ncu captures showed to be the limiter of the LDS+STG copy-out).
 #include <cuda.h>
+#include <cuda_fp16.h>
 
 #include "common.cuh"
 
@@ -76,6 +77,24 @@ __device__ __forceinline__ uint2 lds64(uint32_t addr) {
   asm volatile("ld.shared.v2.b32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(addr));
   return v;
 }
+__device__ __forceinline__ uint32_t pack_f16(float lo, float hi) {
+  __half2 v = __floats2half2_rn(lo, hi);
+  return *reinterpret_cast<uint32_t*>(&v);
+}
+__device__ __forceinline__ void mma_f16_z(float (&d)[4], const uint4& a, uint32_t b0, uint32_t b1) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, "
+      "{%10, %10, %10, %10};"
+      : "=f"(d[0]), "=f"(d[1]), "=f"(d[2]), "=f"(d[3])
+      : "r"(a.x), "r"(a.y), "r"(a.z), "r"(a.w), "r"(b0), "r"(b1), "f"(0.f));
+}
+__device__ __forceinline__ void mma_f16(float (&d)[4], const uint4& a, uint32_t b0, uint32_t b1) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, "
+      "{%0, %1, %2, %3};"
+      : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+      : "r"(a.x), "r"(a.y), "r"(a.z), "r"(a.w), "r"(b0), "r"(b1));
+}
 // D = A * B (no accumulator input: the first chunk of a RoI starts from zero without clearing registers)
 __device__ __forceinline__ void mma_bf16_z(float (&d)[4], const uint4& a, uint32_t b0, uint32_t b1) {
   asm volatile(
@@ -103,6 +122,9 @@ __device__ __forceinline__ bool axis_setup(float v, int size, int& lo, int& hi, 
   return true;
 }
 
+// F16: the feature map (and therefore the interpolation weights) are fp16 instead of bf16 -- 3 more mantissa
+// bits on both mma operands, so the interpolation itself adds no visible error on top of the bf16 output.
+template <bool F16>
 __global__ void __launch_bounds__(THREADS, 2)
 roi_align_mma_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ CUtensorMap omap,
                      const float* __restrict__ rois, int K, int B, int C, int H, int W,
@@ -246,8 +268,8 @@ roi_align_mma_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_cons
                   wxa = wx[c0 * 8 + pws[i]];
                   wxb = wx[(c0 + 1) * 8 + pws[i]];
                 }
-                a[hl] = pack_bf16(wy0 * wxa, wy0 * wxb);        // k = 2t, 2t+1   (rows r0)
-                a[2 + hl] = pack_bf16(wy2 * wxa, wy2 * wxb);    // k = 2t+8, 2t+9 (rows r0+2)
+                a[hl] = F16 ? pack_f16(wy0 * wxa, wy0 * wxb) : pack_bf16(wy0 * wxa, wy0 * wxb);          // k = 2t, 2t+1
+                a[2 + hl] = F16 ? pack_f16(wy2 * wxa, wy2 * wxb) : pack_bf16(wy2 * wxa, wy2 * wxb);      // k = 2t+8, +9
               }
               sts128(dst + mt * 512, make_uint4(a[0], a[1], a[2], a[3]));
             }
@@ -315,18 +337,24 @@ roi_align_mma_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_cons
         if (first) {
 #pragma unroll
           for (int mt = 0; mt < 4; mt++) {
-            mma_bf16_z(acc[mt][0], a[mt], b01[0], b01[1]);
-            mma_bf16_z(acc[mt][1], a[mt], b01[2], b01[3]);
-            mma_bf16_z(acc[mt][2], a[mt], b23[0], b23[1]);
-            mma_bf16_z(acc[mt][3], a[mt], b23[2], b23[3]);
+            if (F16) {
+              mma_f16_z(acc[mt][0], a[mt], b01[0], b01[1]); mma_f16_z(acc[mt][1], a[mt], b01[2], b01[3]);
+              mma_f16_z(acc[mt][2], a[mt], b23[0], b23[1]); mma_f16_z(acc[mt][3], a[mt], b23[2], b23[3]);
+            } else {
+              mma_bf16_z(acc[mt][0], a[mt], b01[0], b01[1]); mma_bf16_z(acc[mt][1], a[mt], b01[2], b01[3]);
+              mma_bf16_z(acc[mt][2], a[mt], b23[0], b23[1]); mma_bf16_z(acc[mt][3], a[mt], b23[2], b23[3]);
+            }
           }
         } else {
 #pragma unroll
           for (int mt = 0; mt < 4; mt++) {
-            mma_bf16(acc[mt][0], a[mt], b01[0], b01[1]);
-            mma_bf16(acc[mt][1], a[mt], b01[2], b01[3]);
-            mma_bf16(acc[mt][2], a[mt], b23[0], b23[1]);
-            mma_bf16(acc[mt][3], a[mt], b23[2], b23[3]);
+            if (F16) {
+              mma_f16(acc[mt][0], a[mt], b01[0], b01[1]); mma_f16(acc[mt][1], a[mt], b01[2], b01[3]);
+              mma_f16(acc[mt][2], a[mt], b23[0], b23[1]); mma_f16(acc[mt][3], a[mt], b23[2], b23[3]);
+            } else {
+              mma_bf16(acc[mt][0], a[mt], b01[0], b01[1]); mma_bf16(acc[mt][1], a[mt], b01[2], b01[3]);
+              mma_bf16(acc[mt][2], a[mt], b23[0], b23[1]); mma_bf16(acc[mt][3], a[mt], b23[2], b23[3]);
+            }
           }
         }
       } else if (first) {
@@ -407,8 +435,8 @@ bool supported(int C, int H, int W) {
   return C % 64 == 0 && C >= 64 && C <= 256 && smem_bytes(H, W, 1) <= SMEM_LIMIT;
 }
 
-int launch(const void* feat_bf16_nhwc, const float* rois, void* out, long long ld_out, int K, int B, int C, int H,
-           int W, float scale, int sampling_ratio, int aligned, const int* roi_level, int level,
+int launch(const void* feat_bf16_nhwc, int feat_f16, const float* rois, void* out, long long ld_out, int K, int B, int C,
+           int H, int W, float scale, int sampling_ratio, int aligned, const int* roi_level, int level,
            cudaStream_t stream) {
   EncodeTiledFn enc = get_encode();
   if (enc == nullptr) { set_error("cuTensorMapEncodeTiled entry point not found"); return PT_ERR_DRIVER; }
@@ -420,7 +448,7 @@ int launch(const void* feat_bf16_nhwc, const float* rois, void* out, long long l
   cuuint64_t strides[4] = {(cuuint64_t)C * 2, (cuuint64_t)W * C * 2, (cuuint64_t)H * W * C * 2, 128};
   cuuint32_t box[5] = {64, 4, 4, 1, (cuuint32_t)(C / 64)};
   cuuint32_t estr[5] = {1, 1, 1, 1, 1};
-  CUresult r = enc(&map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<void*>(feat_bf16_nhwc), dims, strides, box,
+  CUresult r = enc(&map, feat_f16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<void*>(feat_bf16_nhwc), dims, strides, box,
                    estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) { set_error("roi_align_mma: cuTensorMapEncodeTiled failed: CUresult %d", (int)r); return PT_ERR_DRIVER; }
@@ -438,14 +466,20 @@ int launch(const void* feat_bf16_nhwc, const float* rois, void* out, long long l
   }
   const int stg_bufs = smem_bytes(H, W, 2) <= SMEM_LIMIT ? 2 : 1;   // large maps: single-buffered staging
   const size_t smem = smem_bytes(H, W, stg_bufs);
-  cudaError_t e = cudaFuncSetAttribute(roi_align_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  cudaError_t e = feat_f16
+      ? cudaFuncSetAttribute(roi_align_mma_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)
+      : cudaFuncSetAttribute(roi_align_mma_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) { set_error("cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return PT_ERR_CUDA; }
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   const int grid = K < 2 * sms ? K : 2 * sms;
-  roi_align_mma_kernel<<<grid, THREADS, smem, stream>>>(map, omap, rois, K, B, C, H, W, scale, sampling_ratio, aligned,
-                                                        roi_level, level, stg_bufs);
+  if (feat_f16)
+    roi_align_mma_kernel<true><<<grid, THREADS, smem, stream>>>(map, omap, rois, K, B, C, H, W, scale, sampling_ratio,
+                                                                aligned, roi_level, level, stg_bufs);
+  else
+    roi_align_mma_kernel<false><<<grid, THREADS, smem, stream>>>(map, omap, rois, K, B, C, H, W, scale, sampling_ratio,
+                                                                 aligned, roi_level, level, stg_bufs);
   return check_launch("roi_align_mma_kernel");
 }
 

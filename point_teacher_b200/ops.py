@@ -9,6 +9,8 @@ import torch
 from . import _lib
 
 _f32, _bf16, _u8, _i32, _i64 = torch.float32, torch.bfloat16, torch.uint8, torch.int32, torch.int64
+_f16 = torch.float16
+_FEAT_CODE = {_f32: 0, _bf16: 1, _f16: 2}     # feature-map dtype code of the C-ABI
 
 
 def _stream():
@@ -126,7 +128,9 @@ def nchw_to_nhwc(x, out_dtype=_f32):
     _chk(x, "feat", _f32, 4)
     B, C, H, W = x.shape
     out = torch.empty((B, H, W, C), dtype=out_dtype, device=x.device)
-    _lib.call("pt_nchw_to_nhwc", _p(x), _p(out), B, C, H, W, int(out_dtype == _bf16), _stream())
+    if out_dtype not in _FEAT_CODE:
+        raise ValueError("NHWC feature map must be fp32, bf16 or fp16")
+    _lib.call("pt_nchw_to_nhwc", _p(x), _p(out), B, C, H, W, _FEAT_CODE[out_dtype], _stream())
     return out
 
 
@@ -137,8 +141,8 @@ def roi_align_forward(feat_nhwc, rois, out_mode, spatial_scale, sampling_ratio=0
                       clockwise=True, pooled=7, out=None, rows=None, roi_level=None, level=0):
     """feat_nhwc (B,H,W,C) fp32|bf16; rois (K,5) or rotated (K,6).  ``out``/``rows`` let the caller
     hand in a (row-padded) GEMM operand buffer."""
-    if feat_nhwc.dtype not in (_f32, _bf16):
-        raise ValueError("feat must be fp32 or bf16")
+    if feat_nhwc.dtype not in _FEAT_CODE:
+        raise ValueError("feat must be fp32, bf16 or fp16")
     _chk(feat_nhwc, "feat_nhwc", None, 4)
     _chk(rois, "rois", _f32, 2, 6 if rotated else 5)
     B, H, W, C = feat_nhwc.shape
@@ -166,7 +170,7 @@ def roi_align_forward(feat_nhwc, rois, out_mode, spatial_scale, sampling_ratio=0
 
 def _roi_call(feat_nhwc, rois, out, ld, out_mode, K, B, C, H, W, pooled, spatial_scale, sampling_ratio, aligned,
               rotated, clockwise, roi_level, level):
-    _lib.call("pt_roi_align_forward", _p(feat_nhwc), int(feat_nhwc.dtype == _bf16), _p(rois), _p(out), ld, out_mode,
+    _lib.call("pt_roi_align_forward", _p(feat_nhwc), _FEAT_CODE[feat_nhwc.dtype], _p(rois), _p(out), ld, out_mode,
               K, B, C, H, W, pooled, float(spatial_scale), int(sampling_ratio), int(aligned), int(rotated),
               int(clockwise), _p(roi_level), int(level), _stream())
 

@@ -136,9 +136,10 @@ def test_roi_align_bf16_operand_layout(cuda):
     assert (gotb - ref_binmajor).abs().max() <= 2e-2 * ref_binmajor.abs().max()
 
 
+@pytest.mark.parametrize("fdt", [torch.bfloat16, torch.float16])
 @pytest.mark.parametrize("sr,C,hw", [(0, 256, (320, 320)), (2, 256, (320, 320)), (0, 128, (256, 512)), (0, 64, (800, 800))])
-def test_roi_align_mma_path_vs_oracle(cuda, sr, C, hw):
-    """TMA + mma.sync RoIAlign (bf16 NHWC in, bf16 bin-major out): tiny, large, whole-image, border, outside,
+def test_roi_align_mma_path_vs_oracle(cuda, sr, C, hw, fdt):
+    """TMA + mma.sync RoIAlign (bf16 / fp16 NHWC in, bf16 bin-major out): tiny, large, whole-image, border, outside,
     degenerate and negative-size RoIs; adaptive and fixed sampling; multi-level skip mask."""
     from point_teacher_b200 import ops
     x, rois = _roi_inputs(40 + sr + C, 400, hw=hw, C=C)
@@ -146,11 +147,13 @@ def test_roi_align_mma_path_vs_oracle(cuda, sr, C, hw):
     big = synth.make_boxes(g, 30, hw, median=150, sigma=0.6, lo=60, hi=700)      # many 4x4-pixel chunks per RoI
     rois[20:50, 1:] = big
     ref = rotated.roi_align(x, rois, 7, 0.125, sr, True).permute(0, 2, 3, 1).reshape(400, -1)
-    featb = ops.nchw_to_nhwc(x.to(cuda), torch.bfloat16)
+    featb = ops.nchw_to_nhwc(x.to(cuda), fdt)
+    assert featb.dtype == fdt
     got = ops.roi_align_forward(featb, rois.to(cuda), ops.OUT_BF16_BINMAJOR, 0.125, sampling_ratio=sr).float().cpu()
     err = (got - ref).abs()
     assert err.max() <= 2e-2 * ref.abs().max(), err.max()
-    assert err.mean() <= 4e-3 * ref.abs().mean() + 1e-6     # bf16 rounding of feature, weights and output
+    # mean error: bf16 rounding of feature, weights and output; with fp16 operands only the output rounding is left
+    assert err.mean() <= (4e-3 if fdt == torch.bfloat16 else 2e-3) * ref.abs().mean() + 1e-6
     assert torch.isfinite(got).all()
     if sr == 0:
         assert torch.count_nonzero(got[8]) == 0          # negative size: empty adaptive grid -> zeros
@@ -162,6 +165,14 @@ def test_roi_align_mma_path_vs_oracle(cuda, sr, C, hw):
     o = out.float().cpu()
     assert torch.equal(o[lv == 0], torch.full_like(o[lv == 0], 7.0))
     assert torch.equal(o[lv == 1], got[lv == 1])
+
+
+def test_nhwc_fp16_saturates(cuda):
+    from point_teacher_b200 import ops
+    x = torch.tensor([1e6, -1e6, 3.0, 65504.0, 7e4, -7e4, 0.5, -0.25]).reshape(1, 8, 1, 1).repeat(1, 1, 2, 2).contiguous()
+    f = ops.nchw_to_nhwc(x.to(cuda), torch.float16).float().cpu()
+    assert torch.isfinite(f).all()
+    assert torch.equal(f[0, 0, 0], torch.tensor([65504., -65504., 3., 65504., 65504., -65504., 0.5, -0.25]))
 
 
 def test_roi_align_rotated_vs_oracle(cuda):

@@ -49,16 +49,22 @@ def _rel(a, b):
     return ((a - b).abs().max() / b.abs().max().clamp_min(1e-12)).item()
 
 
-@pytest.mark.parametrize("precision,tol", [("fp32", 1e-3), ("bf16", 2e-2)])
-@pytest.mark.parametrize("seed,stages,topk", [(0, 1, 1), (1, 2, 3)])
-def test_phase2_refine_vs_oracle(cuda, precision, tol, seed, stages, topk):
-    d = synth.hbb_batch(seed=seed, num_stages=stages, **SMALL)
-    P = hbb.MilHeadParams(num_stages=stages, seed=seed)
-    ob, op, ol, aux = _run_oracle(d, P, stages, topk, alpha=(0.01, 0.25))
-    (gb, gp, gl), head = _run_cuda(cuda, d, P, stages, topk, precision, alpha=(0.01, 0.25))
-    R = head.last_results
-    ref = aux[-1]
-    # scores of the last stage
+def _compare_stage(cuda, d, P, stages, topk, precision, tol, fine, ext):
+    import copy
+    with torch.no_grad():
+        ob, op, ol, aux = hbb.phase2_refine(P, (d["feat"],), [d["stride"]], d["img_metas"], d["pseudo_boxes"],
+                                            d["pseudo_points"], d["pseudo_labels"], d["gt_boxes"], fine, ext,
+                                            num_stages=stages, cap=100, alpha=(0.01, 0.25), topk=topk,
+                                            injected_negs=d["neg_boxes"])
+    from point_teacher_b200.refine import phase2_refine
+    head = _make_head(cuda, P, stages, topk, precision)
+    to = lambda l: [t.to(cuda) for t in l]  # noqa: E731
+    with torch.no_grad():
+        gb, gp, gl = phase2_refine(head, (d["feat"].to(cuda),), d["img_metas"], to(d["pseudo_boxes"]),
+                                   to(d["pseudo_points"]), to(d["pseudo_labels"]), to(d["gt_boxes"]), fine, ext,
+                                   num_stages=stages, alpha=(0.01, 0.25), neg_boxes=[to(n) for n in d["neg_boxes"]])
+    torch.cuda.synchronize()
+    R, ref = head.last_results, aux[-1]
     assert _rel(R["cls_score"], ref["cls_score"]) < tol
     assert _rel(R["ins_score"], ref["ins_score"]) < tol
     assert _rel(R["neg_cls_score"], ref["neg_cls_score"]) < tol
@@ -71,6 +77,33 @@ def test_phase2_refine_vs_oracle(cuda, precision, tol, seed, stages, topk):
     if precision == "fp32":
         agree = (R["_b200"]["sel_idx"].cpu().long() == ref["selected_idx"]).float().mean().item()
         assert agree >= 0.999, agree
+    return ob, op
+
+
+@pytest.mark.parametrize("precision,tol", [("fp32", 1e-3), ("bf16", 2e-2)])
+@pytest.mark.parametrize("seed,stages,topk", [(0, 1, 1), (1, 2, 3)])
+def test_phase2_refine_vs_oracle(cuda, precision, tol, seed, stages, topk):
+    """fp32: the whole multi-stage run end to end.  bf16: every stage against the oracle FROM IDENTICAL STAGE
+    INPUTS (the oracle's previous-stage boxes) -- a top-k selection that flips on a 1e-3 score difference moves
+    a merged box by pixels, so errors of a later stage of an end-to-end bf16 run measure that chaos, not the
+    kernels (the end-to-end multi-stage comparison is made in fp32, where selections agree >= 99.9 %)."""
+    import copy
+    d = synth.hbb_batch(seed=seed, num_stages=stages, **SMALL)
+    P = hbb.MilHeadParams(num_stages=stages, seed=seed)
+    if precision == "fp32" or stages == 1:
+        _compare_stage(cuda, d, P, stages, topk, precision, tol, synth.HBB_FINE_CFG, synth.HBB_EXT_CFG)
+        return
+    for s in range(stages):
+        Ps = copy.copy(P)
+        Ps.num_stages = 1
+        for nm in ("shared_fcs_reg", "shared_fcs_bag", "fc_cls", "fc_ins", "fc_reg"):
+            setattr(Ps, nm, getattr(P, nm)[s:s + 1])
+        ds = dict(d)
+        ds["neg_boxes"] = [d["neg_boxes"][s]]
+        ob, op = _compare_stage(cuda, ds, Ps, 1, topk, precision, tol, synth.HBB_FINE_CFG[s:s + 1],
+                                synth.HBB_EXT_CFG[s:s + 1])
+        d = dict(d)
+        d["pseudo_boxes"], d["pseudo_points"] = ob, op       # the oracle's stage output feeds the next stage
 
 
 @pytest.mark.parametrize("tag", ["s1_top1", "s2_top3"])
