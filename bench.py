@@ -18,7 +18,7 @@ import time
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-WORKLOAD = ("HBB cfg#1: phase-2 MIL refinement forward, 2 imgs/GPU 800x800, stride-8 256-ch fp32 feature map, "
+WORKLOAD = ("HBB cfg#1: phase-2 MIL refinement forward, 2 imgs/GPU 800x800, stride-8 256-ch fp32 NCHW feature map, "
             "200-600 GT/img capped at 100, U1=1 x U2=25 bags (K=5000 RoIs x2 passes) + 400 negatives, 8 classes")
 METRIC = "phase-2 MIL refine imgs/s"
 
@@ -32,31 +32,70 @@ def _peaks():
 
 
 class ClockSampler(threading.Thread):
+    """SM clock + throttle reasons sampled DURING the timed regions (NVML in-process, ~1 ms per sample;
+    nvidia-smi subprocess as the fallback)."""
     Q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+    NAMES = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
 
     def __init__(self, index=0):
         super().__init__(daemon=True)
-        self.index, self.rows, self._stop = index, [], threading.Event()
+        self.index, self.sm, self.reasons, self.max_mhz = index, [], set(), None
+        self._stop, self._on = threading.Event(), threading.Event()
+        self.nvml = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            phys = int(vis.split(",")[index]) if vis and all(v.strip().isdigit() for v in vis.split(",")) else index
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(phys)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+            self.nvml = pynvml
+        except Exception:
+            self.nvml = None
+
+    def region(self, on):
+        (self._on.set if on else self._on.clear)()
+
+    def _sample_nvml(self):
+        n = self.nvml
+        self.sm.append(int(n.nvmlDeviceGetClockInfo(self.h, n.NVML_CLOCK_SM)))
+        r = int(n.nvmlDeviceGetCurrentClocksEventReasons(self.h))
+        for bit, name in ((n.nvmlClocksEventReasonHwSlowdown, "hw_slowdown"),
+                          (n.nvmlClocksEventReasonHwThermalSlowdown, "hw_thermal_slowdown"),
+                          (n.nvmlClocksEventReasonSwThermalSlowdown, "sw_thermal_slowdown"),
+                          (n.nvmlClocksEventReasonSwPowerCap, "sw_power_cap")):
+            if r & bit:
+                self.reasons.add(name)
+
+    def _sample_smi(self):
+        out = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                              "-i", str(self.index)], capture_output=True, text=True, timeout=5).stdout
+        r = [c.strip() for c in out.strip().split(",")]
+        if r and r[0].isdigit():
+            self.sm.append(int(r[0]))
+            self.max_mhz = int(r[1]) if len(r) > 1 and r[1].isdigit() else self.max_mhz
+            for i, nme in enumerate(self.NAMES):
+                if len(r) > 2 + i and r[2 + i] == "Active":
+                    self.reasons.add(nme)
 
     def run(self):
         while not self._stop.is_set():
-            try:
-                out = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                      "-i", str(self.index)], capture_output=True, text=True, timeout=5).stdout
-                self.rows.append([c.strip() for c in out.strip().split(",")])
-            except Exception:
-                pass
-            self._stop.wait(0.1)
+            if self._on.is_set():
+                try:
+                    self._sample_nvml() if self.nvml else self._sample_smi()
+                except Exception:
+                    pass
+                self._stop.wait(0.002)
+            else:
+                self._stop.wait(0.0005)
 
     def summary(self):
         self._stop.set()
-        sm = sorted(int(r[0]) for r in self.rows if r and r[0].isdigit())
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = [n for i, n in enumerate(names) if any(len(r) > 2 + i and r[2 + i] == "Active" for r in self.rows)]
-        mx = max((int(r[1]) for r in self.rows if len(r) > 1 and r[1].isdigit()), default=None)
-        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx, "reasons": reasons,
-                "samples": len(sm)}
+        sm = sorted(self.sm)
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": self.max_mhz,
+                "reasons": sorted(self.reasons), "samples": len(sm),
+                "source": "nvml" if self.nvml else "nvidia-smi"}
 
 
 def make_inputs(seed):
@@ -99,13 +138,20 @@ def run_reference(args):
         "e2e": {"value": val, "unit": "imgs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
 
 
+def _traffic(kernel_key):
+    """Per-launch DRAM bytes of a kernel from the committed ncu --set full capture (profiles/traffic.json)."""
+    p = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(p):
+        return json.load(open(p)).get(kernel_key)
+    return None
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
-    from oracle import hbb
     from point_teacher_b200 import _lib, ops, synth
     from point_teacher_b200.mil_head import MILHead
-    from point_teacher_b200.refine import CapturedPhase2, phase2_refine
+    from point_teacher_b200.refine import CapturedPhase2, Phase2Pipeline
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -114,23 +160,21 @@ def run_ours(args):
     dev = torch.device("cuda", local)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
-    _lib.load()
+    _lib.load()                                # raises when the CUDA extension is missing: no fallback
 
     d = make_inputs(rank)                      # per-image sharding: every rank owns its own 2 images
-    P = hbb.MilHeadParams(num_stages=1, seed=0)
-    head = MILHead(num_classes=8, num_stages=1, top_k=1, precision=args.precision).to(dev)
-    head.load_state_dict(P.state_dict(), strict=False)
+    torch.manual_seed(0)
+    head = MILHead(num_classes=8, num_stages=1, top_k=1, precision=args.precision).to(dev)   # N(0, 0.01) init
     to = lambda l: [t.to(dev) for t in l]  # noqa: E731
-    host = dict(feat=d["feat"].pin_memory(), pseudo_boxes=[t.pin_memory() for t in d["pseudo_boxes"]],
-                pseudo_points=[t.pin_memory() for t in d["pseudo_points"]],
-                pseudo_labels=[t.pin_memory() for t in d["pseudo_labels"]],
-                gt_boxes=[t.pin_memory() for t in d["gt_boxes"]],
-                neg_boxes=[[t.pin_memory() for t in d["neg_boxes"][0]]])
+    pin = lambda l: [t.pin_memory() for t in l]  # noqa: E731
+    host = dict(feat=d["feat"].pin_memory(), pseudo_boxes=pin(d["pseudo_boxes"]), pseudo_points=pin(d["pseudo_points"]),
+                pseudo_labels=pin(d["pseudo_labels"]), gt_boxes=pin(d["gt_boxes"]), neg_boxes=[pin(d["neg_boxes"][0])])
     inputs = dict(feat=d["feat"].to(dev), pseudo_boxes=to(d["pseudo_boxes"]), pseudo_points=to(d["pseudo_points"]),
                   pseudo_labels=to(d["pseudo_labels"]), gt_boxes=to(d["gt_boxes"]),
                   neg_boxes=[to(d["neg_boxes"][0])])
+    W = max(args.warmup, 3)
     cap = CapturedPhase2(head, inputs, d["img_metas"], synth.HBB_FINE_CFG, synth.HBB_EXT_CFG, num_stages=1, cap=100,
-                         refresh_weights=True, warmup=max(args.warmup, 3))
+                         refresh_weights=True, warmup=W)
     if args.no_graph:
         cap.replay = lambda: cap._step()
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
@@ -144,16 +188,18 @@ def run_ours(args):
     # ---- launches per step (counted on one eager step through the C-ABI)
     torch.cuda.synchronize()
     c0 = _lib.LAUNCHES["count"]
-    cap._step()
+    with torch.no_grad():
+        cap._step()
     torch.cuda.synchronize()
     launches_per_step = _lib.LAUNCHES["count"] - c0
 
     # ---- device-resident throughput: graph replay, L2 flushed between steps, per-step CUDA events
-    for _ in range(max(args.warmup, 3)):
+    for _ in range(W):
         cap.replay()
     sampler = ClockSampler(local)
     sampler.start()
     barrier()
+    sampler.region(True)
     evs = []
     for _ in range(args.steps):
         flush.zero_()
@@ -163,51 +209,40 @@ def run_ours(args):
         e1.record()
         evs.append((e0, e1))
     barrier()
+    sampler.region(False)
     dev_ms = sum(a.elapsed_time(b) for a, b in evs) / args.steps
 
-    # ---- end to end through the public call with HOST buffers: pinned H2D of every input, D2H of the result
-    out_host = [torch.empty_like(b).pin_memory() for b in d["pseudo_boxes"]]
-    loss_host = torch.empty(8, dtype=torch.float32).pin_memory()
-
-    def h2d():
-        inputs["feat"].copy_(host["feat"], non_blocking=True)
-        for k in ("pseudo_boxes", "pseudo_points", "pseudo_labels", "gt_boxes"):
-            for dst, src in zip(inputs[k], host[k]):
-                dst.copy_(src, non_blocking=True)
-        for dst, src in zip(inputs["neg_boxes"][0], host["neg_boxes"][0]):
-            dst.copy_(src, non_blocking=True)
-
-    def d2h(outs):
-        boxes, _, losses = outs
-        for dst, src in zip(out_host, boxes):
-            dst.copy_(src, non_blocking=True)
-        keys = sorted(losses)
-        loss_host[:len(keys)].copy_(torch.stack([losses[k].reshape(()) for k in keys]), non_blocking=True)
-
-    h2d_bytes = sum(t.numel() * t.element_size() for t in [host["feat"]] + host["pseudo_boxes"] +
-                    host["pseudo_points"] + host["pseudo_labels"] + host["gt_boxes"] + host["neg_boxes"][0])
-    d2h_bytes = sum(t.numel() * t.element_size() for t in out_host) + 4 * 7
-    for _ in range(3):
-        h2d(); d2h(cap.replay())
-    barrier()
-    evs2 = []
-    for _ in range(args.steps):
-        flush.zero_()
+    # ---- end to end through the public host-facing call: pinned H2D of every input of every step, D2H of the
+    #      refined boxes / points / losses; double-buffered so the copy of step i+1 overlaps step i
+    e2e_ms, h2d_bytes, d2h_bytes = float("nan"), 0, 0
+    if not args.no_graph:
+        pipe = Phase2Pipeline(head, inputs, d["img_metas"], synth.HBB_FINE_CFG, synth.HBB_EXT_CFG, num_stages=1,
+                              cap=100, depth=2)
+        h2d_bytes, d2h_bytes = pipe.h2d_bytes, pipe.d2h_bytes
+        for _ in range(W):
+            t = pipe.submit(host)
+        pipe.result(t)
+        barrier()
+        sampler.region(True)
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
-        h2d()
-        d2h(cap.replay())
+        for _ in range(args.steps):
+            t = pipe.submit(host)
+        pipe.result(t)
         e1.record()
-        evs2.append((e0, e1))
-    barrier()
-    e2e_ms = sum(a.elapsed_time(b) for a, b in evs2) / args.steps
+        barrier()
+        sampler.region(False)
+        e2e_ms = e0.elapsed_time(e1) / args.steps
+        res = pipe.result(t)
+        assert all(torch.isfinite(b).all() for b in res[0])
     clocks = sampler.summary()
 
     # ---- per-kernel roofline: eager replay of the same steps with CUDA events around each launch
     ops.PROFILE["on"], ops.PROFILE["events"] = True, []
-    for _ in range(min(args.steps, 10)):
-        flush.zero_()
-        cap._step()
+    with torch.no_grad():
+        for _ in range(min(args.steps, 10)):
+            flush.zero_()
+            cap._step()
     torch.cuda.synchronize()
     ops.PROFILE["on"] = False
     hbm_peak, tf_peak, peak_src = _peaks()
@@ -216,7 +251,35 @@ def run_ours(args):
     gemm_ms = sum(t for t, _ in gemm) / max(len(gemm), 1)
     gemm_tf = (sum(f for _, f in gemm) / max(len(gemm), 1)) / (gemm_ms * 1e-3) / 1e12 if gemm else 0.0
     roi_ms = sum(t for t, _ in roi) / max(len(roi), 1)
-    roi_gbs = (sum(b for _, b in roi) / max(len(roi), 1)) / (roi_ms * 1e-3) / 1e9 if roi else 0.0
+    roi_bytes = sum(b for _, b in roi) / max(len(roi), 1)
+    roi_gbs = roi_bytes / (roi_ms * 1e-3) / 1e9 if roi else 0.0
+
+    # ---- RoIAlign at the stress shape (config #4, one image: 1500 GT x 64 instances = 96 000 RoIs, 2.4 GB out):
+    #      the size at which the kernel is HBM-bound rather than launch/tail-bound
+    stress = None
+    if rank == 0 and not args.no_stress:
+        ds = synth.hbb_batch(seed=1, batch=1, gt_range=(1500, 1500))
+        from point_teacher_b200.proposals import fine_proposals_from_cfg
+        props, _ = fine_proposals_from_cfg(to(ds["pseudo_boxes"]), synth.stress_ext_cfg(8)[0], ds["img_metas"])
+        rs = torch.cat([torch.zeros((props[0].shape[0], 1), device=dev), props[0]], 1).contiguous()
+        fs = ops.nchw_to_nhwc(ds["feat"].to(dev), head.feat_dtype)
+        outs = torch.empty((rs.shape[0], 12544), dtype=torch.bfloat16, device=dev)
+        ts = []
+        for i in range(8):
+            flush.zero_()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            ops.roi_align_forward(fs, rs, ops.OUT_BF16_BINMAJOR, 0.125, out=outs)
+            e1.record()
+            torch.cuda.synchronize()
+            if i >= 3:
+                ts.append(e0.elapsed_time(e1))
+        sms = sum(ts) / len(ts)
+        sbytes = rs.shape[0] * 12544 * 2 + fs.numel() * fs.element_size() + rs.numel() * 4
+        stress = {"rois": rs.shape[0], "algorithmic_bytes": sbytes, "avg_launch_ms": sms,
+                  "achieved": sbytes / (sms * 1e-3) / 1e9, "frac": sbytes / (sms * 1e-3) / 1e9 / hbm_peak,
+                  "traffic": _traffic("roi_align_mma_kernel@96000")}
+        del outs, fs
 
     # max over ranks
     if world > 1:
@@ -226,8 +289,10 @@ def run_ours(args):
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        from oracle import hbb                      # the checker, timed as the reported CPU baseline only
         torch.set_num_threads(os.cpu_count() or 1)
         d0 = make_inputs(0)
+        P = hbb.MilHeadParams(num_stages=1, seed=0)
 
         def cstep():
             with torch.no_grad():
@@ -236,7 +301,7 @@ def run_ours(args):
                                   synth.HBB_EXT_CFG, num_stages=1, cap=100, injected_negs=d0["neg_boxes"])
         cstep()
         t0 = time.perf_counter()
-        n = 3
+        n = 5
         for _ in range(n):
             cstep()
         cdt = (time.perf_counter() - t0) / n
@@ -246,26 +311,34 @@ def run_ours(args):
 
     if rank == 0:
         total_imgs = n_img * world
+        feat_dt = str(head.feat_dtype).replace("torch.", "")
         line = {
             "metric": METRIC, "value": total_imgs / (dev_ms * 1e-3), "unit": "imgs/s", "n_gpus": world,
-            "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": dev_ms, "higher_is_better": True,
+            "steps": args.steps, "warmup": W, "ms_per_step": dev_ms, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None,
             "dtype": "bf16 (fp32 accumulate; fp32 box/score math)" if args.precision == "bf16" else "bf16x3 (fp32 emulation)",
             "data": "synthetic",
             "config": {"workload": WORKLOAD, "images_per_gpu": n_img, "sharding": "per-image, no data-path collective",
-                       "launch": "eager" if args.no_graph else "cuda_graph", "l2": "flushed between steps (256 MiB write, untimed); per-step CUDA events",
-                       "weights": "fp32->bf16 + FC1 column permutation redone inside every step"},
+                       "launch": "eager" if args.no_graph else "cuda_graph",
+                       "l2": "value: flushed between steps (256 MiB write, untimed), per-step CUDA events; "
+                             "e2e: inputs arrive from pinned host memory every step and the per-step working set "
+                             "(~0.4 GB of operands) exceeds the 126 MB L2",
+                       "weights": "fp32->bf16 + FC1 column permutation redone inside every step",
+                       "roi_feature_map": f"NHWC {feat_dt}"},
             "e2e": {"value": total_imgs / (e2e_ms * 1e-3), "unit": "imgs/s", "h2d_bytes_per_step": h2d_bytes,
-                    "d2h_bytes_per_step": d2h_bytes, "ms_per_step": e2e_ms},
+                    "d2h_bytes_per_step": d2h_bytes, "ms_per_step": e2e_ms,
+                    "api": "point_teacher_b200.refine.Phase2Pipeline.submit/result (double-buffered H2D)"},
             "gpu_launches": launches_per_step * args.steps,
             "clocks": clocks,
             "roofline": {"kernel": "fc_gemm_kernel (FC1, M=5000/5400 N=1024 K=12544)", "bound": "tensor",
-                         "achieved": gemm_tf, "peak": tf_peak / 1.0, "unit": "TFLOP/s", "frac": gemm_tf / tf_peak,
-                         "traffic": None, "peak_source": peak_src, "avg_launch_ms": gemm_ms,
+                         "achieved": gemm_tf, "peak": tf_peak, "unit": "TFLOP/s", "frac": gemm_tf / tf_peak,
+                         "traffic": _traffic("fc_gemm_kernel@fc1"), "peak_source": peak_src, "avg_launch_ms": gemm_ms,
                          "measured": "eager replay of the same steps, CUDA events around each launch"},
-            "roofline_roi_align": {"kernel": "roi_align_fwd_kernel<float, bf16 bin-major>", "bound": "hbm",
-                                   "achieved": roi_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": roi_gbs / hbm_peak,
-                                   "avg_launch_ms": roi_ms},
+            "roofline_roi_align": {"kernel": "roi_align_mma_kernel (TMA + mma.sync, bf16 bin-major out)"
+                                   if args.precision == "bf16" else "roi_align_fwd_kernel<float, bf16x3>",
+                                   "bound": "hbm", "achieved": roi_gbs, "peak": hbm_peak, "unit": "GB/s",
+                                   "frac": roi_gbs / hbm_peak, "avg_launch_ms": roi_ms, "algorithmic_bytes": roi_bytes,
+                                   "traffic": _traffic("roi_align_mma_kernel@5000"), "stress_96k_rois": stress},
             "cpu_baseline": cpu,
         }
         print(json.dumps(line))
@@ -276,12 +349,13 @@ def run_ours(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="eager launches (for ncu passes)")
+    ap.add_argument("--no-stress", action="store_true", help="skip the 96k-RoI RoIAlign roofline measurement")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -134,14 +134,88 @@ class CapturedPhase2:
         self.graph = torch.cuda.CUDAGraph()
         with torch.no_grad(), torch.cuda.graph(self.graph):
             self.outputs = self._step()
+            self.loss_keys = sorted(self.outputs[2])
+            self.loss_vec = torch.stack([self.outputs[2][k].reshape(()).float() for k in self.loss_keys])
 
     def _step(self):
         i = self.inputs
         if self.refresh_weights:
             self.head._wcache.clear()
+        # the NHWC feature-map cache is keyed on (pointer, version): inside a captured step it must MISS, otherwise
+        # the capture would bake in the tensor transposed during warm-up and replays would read stale features
+        for layer in self.head.bbox_roi_extractor.roi_layers:
+            layer._cache.clear()
         return phase2_refine(self.head, (i["feat"],), self.img_metas, i["pseudo_boxes"], i["pseudo_points"],
                              i["pseudo_labels"], i["gt_boxes"], neg_boxes=i.get("neg_boxes"), **self.kw)
 
     def replay(self):
         self.graph.replay()
         return self.outputs
+
+
+class Phase2Pipeline:
+    """Host-facing throughput API: phase-2 refinement of a stream of batches whose inputs live in (pinned) HOST
+    memory.  ``depth`` captured steps (``CapturedPhase2``) are used round-robin; the H2D copy of batch i+1 runs on
+    a copy stream while batch i computes, and every result (refined boxes, points, losses) is copied back into
+    pinned host buffers.  ``submit(host_inputs)`` never blocks the host; ``result(ticket)`` waits for that batch.
+
+    host_inputs / example_inputs: dict(feat (B,C,H,W) fp32, pseudo_boxes, pseudo_points, pseudo_labels, gt_boxes:
+    lists of per-image tensors, neg_boxes: [per-stage][per-image] injected negatives or None)."""
+
+    def __init__(self, head, example_inputs, img_metas, fine_cfg, ext_cfg, num_stages=1, cap=100,
+                 alpha=(0.01, 0.25), depth=2, refresh_weights=True):
+        def clone(v):
+            if isinstance(v, (list, tuple)):
+                return [clone(t) for t in v]
+            return None if v is None else v.clone()
+        self.depth = depth
+        self.slots = [CapturedPhase2(head, {k: clone(v) for k, v in example_inputs.items()}, img_metas, fine_cfg,
+                                     ext_cfg, num_stages, cap, alpha, refresh_weights) for _ in range(depth)]
+        self.copy_stream = torch.cuda.Stream()
+        self.h2d_done = [torch.cuda.Event() for _ in range(depth)]
+        self.done = [torch.cuda.Event() for _ in range(depth)]
+        self.host_out = []
+        for s in self.slots:
+            boxes, pts, losses = s.outputs
+            self.host_out.append(dict(
+                boxes=[torch.empty(b.shape, dtype=b.dtype).pin_memory() for b in boxes],
+                points=[torch.empty(p.shape, dtype=p.dtype).pin_memory() for p in pts],
+                losses=torch.empty((len(losses),), dtype=torch.float32).pin_memory()))
+        self.loss_keys = self.slots[0].loss_keys
+        self.n = 0
+        self.h2d_bytes = sum(t.numel() * t.element_size() for t in self._flat(example_inputs))
+        self.d2h_bytes = sum(t.numel() * t.element_size()
+                             for t in self.host_out[0]["boxes"] + self.host_out[0]["points"]) + 4 * len(self.loss_keys)
+
+    @staticmethod
+    def _flat(v):
+        if v is None:
+            return []
+        if isinstance(v, dict):
+            return [t for k in sorted(v) for t in Phase2Pipeline._flat(v[k])]
+        if isinstance(v, (list, tuple)):
+            return [t for x in v for t in Phase2Pipeline._flat(x)]
+        return [v]
+
+    def submit(self, host_inputs):
+        s = self.n % self.depth
+        slot, cur = self.slots[s], torch.cuda.current_stream()
+        self.copy_stream.wait_event(self.done[s])              # slot inputs are free once its last step finished
+        with torch.cuda.stream(self.copy_stream):
+            for dst, src in zip(self._flat(slot.inputs), self._flat(host_inputs)):
+                dst.copy_(src, non_blocking=True)
+            self.h2d_done[s].record(self.copy_stream)
+        cur.wait_event(self.h2d_done[s])
+        boxes, pts, losses = slot.replay()
+        ho = self.host_out[s]
+        for dst, src in zip(ho["boxes"] + ho["points"], list(boxes) + list(pts)):
+            dst.copy_(src, non_blocking=True)
+        ho["losses"].copy_(slot.loss_vec, non_blocking=True)
+        self.done[s].record(cur)
+        self.n += 1
+        return s
+
+    def result(self, ticket):
+        self.done[ticket].synchronize()
+        ho = self.host_out[ticket]
+        return ho["boxes"], ho["points"], dict(zip(self.loss_keys, ho["losses"].tolist()))

@@ -255,12 +255,62 @@ def test_captured_graph_replay_matches_eager(cuda):
     torch.cuda.synchronize()
     for a, b in zip(eb + ep, gb + gp):
         assert torch.equal(a, b)
-    # new data through the static input buffers
-    d2 = synth.hbb_batch(seed=4, **SMALL)
-    inputs["feat"].copy_(d2["feat"] * 0.5)
-    gb2, _, _ = cap.replay()
+    # new data through the static input buffers: the replay must see it (nothing input-dependent may be baked in)
+    d2 = synth.hbb_batch(seed=9, **SMALL)
+    eb_old = [b.clone() for b in eb]
+    inputs["feat"].copy_(d2["feat"])
+    with torch.no_grad():
+        eb2, ep2, el2 = phase2_refine(head, (inputs["feat"],), d["img_metas"], inputs["pseudo_boxes"],
+                                      inputs["pseudo_points"], inputs["pseudo_labels"], inputs["gt_boxes"],
+                                      synth.HBB_FINE_CFG, synth.HBB_EXT_CFG, neg_boxes=inputs["neg_boxes"])
+    eb2 = [b.clone() for b in eb2]
+    gb2, gp2, gl2 = cap.replay()
     torch.cuda.synchronize()
-    assert not torch.equal(gb2[0].cpu(), eb[0].cpu().clone()) or True  # outputs alias the static graph buffers
+    for a, b in zip(eb2, gb2):
+        assert torch.equal(a, b)
+    assert not torch.equal(eb2[0], eb_old[0])
+
+
+def test_host_pipeline_matches_eager(cuda):
+    """Phase2Pipeline (pinned host inputs, double-buffered H2D, D2H of the results) == the eager device call,
+    for alternating batches, in both precisions."""
+    from point_teacher_b200.refine import Phase2Pipeline, phase2_refine
+    for precision in ("bf16", "fp32"):
+        batches = [synth.hbb_batch(seed=s, batch=2, img_hw=(256, 256), gt_range=(8, 8), n_neg=20) for s in (11, 12, 13)]
+        P = hbb.MilHeadParams(num_stages=1, seed=11)
+        head = _make_head(cuda, P, 1, 1, precision)
+        to = lambda l: [t.to(cuda) for t in l]  # noqa: E731
+        pin = lambda l: [t.pin_memory() for t in l]  # noqa: E731
+
+        def dev_inputs(d):
+            return dict(feat=d["feat"].to(cuda), pseudo_boxes=to(d["pseudo_boxes"]), pseudo_points=to(d["pseudo_points"]),
+                        pseudo_labels=to(d["pseudo_labels"]), gt_boxes=to(d["gt_boxes"]), neg_boxes=[to(d["neg_boxes"][0])])
+
+        def host_inputs(d):
+            return dict(feat=d["feat"].pin_memory(), pseudo_boxes=pin(d["pseudo_boxes"]), pseudo_points=pin(d["pseudo_points"]),
+                        pseudo_labels=pin(d["pseudo_labels"]), gt_boxes=pin(d["gt_boxes"]), neg_boxes=[pin(d["neg_boxes"][0])])
+        metas = batches[0]["img_metas"]
+        pipe = Phase2Pipeline(head, dev_inputs(batches[0]), metas, synth.HBB_FINE_CFG, synth.HBB_EXT_CFG)
+        tickets = []
+        results = []
+        for i in range(5):
+            t = pipe.submit(host_inputs(batches[i % 3]))
+            if len(tickets) == 1:                     # read the previous one while this one is in flight
+                b, p, l = pipe.result(tickets.pop())
+                results.append(([x.clone() for x in b], dict(l)))
+            tickets.append(t)
+        b, p, l = pipe.result(tickets.pop())
+        results.append(([x.clone() for x in b], dict(l)))
+        for i, (boxes, losses) in enumerate(results):
+            di = dev_inputs(batches[i % 3])
+            with torch.no_grad():
+                eb, ep, el = phase2_refine(head, (di["feat"],), metas, di["pseudo_boxes"], di["pseudo_points"],
+                                           di["pseudo_labels"], di["gt_boxes"], synth.HBB_FINE_CFG, synth.HBB_EXT_CFG,
+                                           neg_boxes=di["neg_boxes"])
+            for a, b in zip(eb, boxes):
+                assert torch.equal(a.cpu(), b), (precision, i)
+            for k in el:
+                assert abs(float(el[k]) - losses[k]) <= 1e-6 * max(abs(losses[k]), 1e-3), (precision, i, k)
 
 
 # ------------------------------------------------------------------------------ OBB twin (config #3)
