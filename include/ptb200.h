@@ -133,6 +133,33 @@ int pt_split_bf16x3(const float* in, void* out_bf16, long long M, int N, void* s
 int pt_aligned_iou_mean(const float* a, int lda, const float* b, int ldb, int n, int rotated, float* out,
                         void* stream);
 
+/* ---- dense-head label assignment (rows a13-a15) -------------------------------------------------------------
+ * FocalLossCost table (HBB_TOD/mmdet/core/bbox/match_costs/match_cost.py:54-100): out[p,c] = (pos - neg) * weight. */
+int pt_focal_cost_table(const float* logits, long long n, float alpha, float gamma, float eps, float weight,
+                        float* out, void* stream);
+/* Stage 1 of TopkAssigner / FUSETopkAssigner (assigners/topk_assigner.py:118-125, fuse_topk_assigner.py:96-101):
+ * pre_idx [num_pre, G] int32 = indices of the num_pre smallest PointCost(pts, gts) per GT column, with the
+ * ATen CPU tie rule.  pts [P, ldp] (x, y first), gts [G, ldg] (cx, cy first); l2 selects PointCost mode 'L2'.
+ * scratch_v / scratch_i [G, P] are required only when num_pre * 64 > P (ATen's nth_element path). */
+int pt_topk_pre(const float* pts, int ldp, int P, const float* gts, int ldg, int G, int l2, float weight, int num_pre,
+                int* pre_idx, float* scratch_v, int* scratch_i, void* stream);
+/* Stage 2 (topk_assigner.py:128-145, fuse_topk_assigner.py:104-119): second cost = fl_table[p, label_c]
+ * (+ InsiderCost of pred [P, ldb] = (cx, cy, w, h) vs GT point c, times loc_weight, when pred != NULL); the
+ * all-columns top-k quirk and last-GT-wins overwrite are reproduced.  gt_inds / out_labels [P] int64. */
+int pt_topk_second(const int* pre_idx, int num_pre, int topk, int G, int P, const float* fl_table, int C,
+                   const long long* labels, const float* pred, int ldb, const float* gts, int ldg, float loc_weight,
+                   int* assigned_ws, long long* gt_inds, long long* out_labels, void* stream);
+/* BboxOverlaps2D (calc 0; iou2d_calculator.py:74-260) / BboxDistanceMetric (calc 1; metric_calculator.py:44-185)
+ * matrix [M, N]; modes 0 iou, 1 iof, 2 giou, 3 wd, 4 kl, 5 center_distance2, 6 exp_kl, 7 kl_10 (3.. calc 1 only). */
+int pt_bbox_metric(const float* a, int lda, const float* b, int ldb, long long M, long long N, int calc, int mode,
+                   float eps, float* out, void* stream);
+/* MaxIoUAssigner.assign (assigners/max_iou_assigner.py:60-212) on calc(gts, anchors, mode) without materialising
+ * the G x A matrix.  argmax_ws [A] int32, gt_ws [2*G] 32-bit words. */
+int pt_max_iou_assign(const float* gts, int ldg, int G, const float* anchors, int lda, int A, int calc, int mode,
+                      float eps, float pos_thr, float neg_lo, float neg_hi, float min_pos, int gt_max_assign_all,
+                      int match_low_quality, const long long* gt_labels, long long* gt_inds, float* max_overlaps,
+                      long long* labels, int* argmax_ws, unsigned* gt_ws, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -122,7 +122,56 @@ def check_obb(seed=0, **small):
     return ok
 
 
+def check_assign():
+    from oracle import assign
+    ns = ref_shim.install()
+    ok = True
+    for seed, ties, (npre, tk) in [(0, True, (3, 3)), (1, True, (1, 1)), (2, True, (5, 3)), (3, False, (5, 3)),
+                                   (4, True, (7, 2))]:
+        d = synth.assign_batch(seed, ties=ties)
+        ref = ns.TopkAssigner(num_pre=npre, topk=tk, cls_cost=dict(type="FocalLossCost", weight=1.0),
+                              reg_cost=dict(type="PointCost", mode="L1", weight=1.0))
+        r = ref.assign(d["pred"], d["logits"], d["gt"], d["labels"])
+        gi, lb = assign.topk_assign(d["pred"], d["logits"], d["gt"], d["labels"], npre, tk)
+        ok &= _eq(gi, r.gt_inds, f"TopkAssigner({npre},{tk}) gt_inds seed{seed}", 0.0)
+        ok &= _eq(lb, r.labels, f"TopkAssigner({npre},{tk}) labels seed{seed}", 0.0)
+        ref = ns.FUSETopkAssigner(num_pre=npre, topk=tk, cls_cost=dict(type="FocalLossCost", weight=1.0),
+                                  reg_cost=dict(type="PointCost", mode="L1", weight=1.0),
+                                  location_cost=dict(type="InsiderCost", weight=1.0))
+        r = ref.assign(d["pred"], d["points"], d["logits"], None, d["gt"], d["labels"])
+        gi, lb = assign.fuse_topk_assign(d["pred"], d["points"], d["logits"], d["gt"], d["labels"], npre, tk)
+        ok &= _eq(gi, r.gt_inds, f"FUSETopkAssigner({npre},{tk}) gt_inds seed{seed}", 0.0)
+        ok &= _eq(lb, r.labels, f"FUSETopkAssigner({npre},{tk}) labels seed{seed}", 0.0)
+    # metric matrix + MaxIoU
+    g = torch.Generator().manual_seed(9)
+    gts = synth.make_boxes(g, 23, (400, 400))
+    anchors = torch.cat([synth.jitter_boxes(g, gts.repeat(6, 1), 3.0, 0.4), synth.make_boxes(g, 300, (400, 400))])
+    anchors[5] = gts[5]
+    anchors[77] = gts[5]                      # exact duplicate maxima: gt_max_assign_all matters
+    for mode in ("iou", "iof", "giou", "wd", "kl", "center_distance2", "exp_kl", "kl_10"):
+        m = ns.BboxDistanceMetric()(gts, anchors, mode)
+        ok &= _eq(assign.bbox_metric(gts, anchors, mode), m, f"BboxDistanceMetric {mode}", 0.0)
+    for kw in (dict(pos_iou_thr=0.5, neg_iou_thr=0.4, min_pos_iou=0.0), dict(pos_iou_thr=0.7, neg_iou_thr=0.3, min_pos_iou=0.3),
+               dict(pos_iou_thr=0.5, neg_iou_thr=0.5, min_pos_iou=0.0, gt_max_assign_all=False),
+               dict(pos_iou_thr=0.5, neg_iou_thr=0.5, match_low_quality=False)):
+        for calc, mode in ((dict(type="BboxOverlaps2D"), "iou"), (dict(type="BboxDistanceMetric"), "wd")):
+            ref = ns.MaxIoUAssigner(iou_calculator=calc, **kw)
+            labels = torch.randint(0, 8, (23,), generator=g)
+            ov = ref.iou_calculator(gts, anchors, mode)
+            r = ref.assign_wrt_overlaps(ov, labels)
+            ours_ov = hbb.bbox_overlaps(gts, anchors, mode) if calc["type"] == "BboxOverlaps2D" else assign.bbox_metric(gts, anchors, mode)
+            gi, mx, lb = assign.max_iou_assign(ours_ov, labels, **kw)
+            ok &= _eq(gi, r.gt_inds, f"MaxIoU {calc['type']} {kw} gt_inds", 0.0)
+            ok &= _eq(mx, r.max_overlaps, "MaxIoU max_overlaps", 0.0)
+            ok &= _eq(lb, r.labels, "MaxIoU labels", 0.0)
+    return ok
+
+
 if __name__ == "__main__":
+    if "--assign" in sys.argv:
+        good = check_assign()
+        print("ALL OK" if good else "MISMATCH")
+        sys.exit(0 if good else 1)
     if "--obb" in sys.argv:
         good = check_obb(0, batch=2, img_hw=(512, 512), gt_range=(20, 30), n_neg=40)
         print("ALL OK" if good else "MISMATCH")

@@ -77,6 +77,44 @@ def obb_case(seed, tag):
     print("wrote obb", tag, {k: tuple(v.shape) for k, v in out.items() if hasattr(v, "shape")})
 
 
+def assign_case():
+    """Label assignment (rows a13-a15): outputs of the reference's own assigner / metric files."""
+    ns = ref_shim.install()
+    out = dict(cases=[])
+    for seed, ties, npre, tk in [(0, True, 3, 3), (1, True, 1, 1), (2, True, 5, 3), (3, False, 5, 3), (4, True, 7, 2)]:
+        d = synth.assign_batch(seed, ties=ties)
+        a = ns.TopkAssigner(num_pre=npre, topk=tk, cls_cost=dict(type="FocalLossCost", weight=1.0),
+                            reg_cost=dict(type="PointCost", mode="L1", weight=1.0))
+        r1 = a.assign(d["pred"], d["logits"], d["gt"], d["labels"])
+        f = ns.FUSETopkAssigner(num_pre=npre, topk=tk, cls_cost=dict(type="FocalLossCost", weight=1.0),
+                                reg_cost=dict(type="PointCost", mode="L1", weight=1.0),
+                                location_cost=dict(type="InsiderCost", weight=1.0))
+        r2 = f.assign(d["pred"], d["points"], d["logits"], None, d["gt"], d["labels"])
+        out["cases"].append(dict(seed=seed, ties=ties, num_pre=npre, topk=tk, topk_gt_inds=r1.gt_inds,
+                                 topk_labels=r1.labels, fuse_gt_inds=r2.gt_inds, fuse_labels=r2.labels,
+                                 fl_table=ns.match_cost.FocalLossCost()(d["logits"], torch.arange(8))))
+    g = torch.Generator().manual_seed(9)
+    gts = synth.make_boxes(g, 23, (400, 400))
+    anchors = torch.cat([synth.jitter_boxes(g, gts.repeat(6, 1), 3.0, 0.4), synth.make_boxes(g, 300, (400, 400))])
+    anchors[5] = gts[5]
+    anchors[77] = gts[5]
+    labels = torch.randint(0, 8, (23,), generator=g)
+    out["gts"], out["anchors"], out["labels"] = gts, anchors, labels
+    out["metric"] = {m: ns.BboxDistanceMetric()(gts, anchors, m)
+                     for m in ("iou", "iof", "giou", "wd", "kl", "center_distance2", "exp_kl", "kl_10")}
+    out["maxiou"] = []
+    for kw in (dict(pos_iou_thr=0.5, neg_iou_thr=0.4, min_pos_iou=0.0), dict(pos_iou_thr=0.7, neg_iou_thr=0.3, min_pos_iou=0.3),
+               dict(pos_iou_thr=0.5, neg_iou_thr=0.5, min_pos_iou=0.0, gt_max_assign_all=False),
+               dict(pos_iou_thr=0.5, neg_iou_thr=0.5, match_low_quality=False)):
+        for calc, mode in ((dict(type="BboxOverlaps2D"), "iou"), (dict(type="BboxDistanceMetric"), "wd")):
+            a = ns.MaxIoUAssigner(iou_calculator=calc, **kw)
+            r = a.assign_wrt_overlaps(a.iou_calculator(gts, anchors, mode), labels)
+            out["maxiou"].append(dict(kw=kw, calc=calc["type"], mode=mode, gt_inds=r.gt_inds, max_overlaps=r.max_overlaps,
+                                      labels=r.labels))
+    torch.save(out, os.path.join(OUT, "assign.pt"))
+    print("wrote assign", len(out["cases"]), len(out["maxiou"]))
+
+
 def overlaps_case():
     ns = ref_shim.install()
     g = torch.Generator().manual_seed(7)
@@ -96,3 +134,4 @@ if __name__ == "__main__":
     hbb_case(1, 2, 3, "s2_top3")
     overlaps_case()
     obb_case(0, "s1_top3")
+    assign_case()

@@ -43,6 +43,15 @@ SIGNATURES = {
     "pt_neg_loss": (c_int, [c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p]),
     "pt_finalize_losses": (c_int, [c_void_p, c_int, c_int, c_float, c_float, c_float, c_float, c_void_p, c_void_p]),
     "pt_split_bf16x3": (c_int, [c_void_p, c_void_p, c_ll, c_int, c_void_p]),
+    "pt_focal_cost_table": (c_int, [c_void_p, c_ll, c_float, c_float, c_float, c_float, c_void_p, c_void_p]),
+    "pt_topk_pre": (c_int, [c_void_p, c_int, c_int, c_void_p, c_int, c_int, c_int, c_float, c_int, c_void_p, c_void_p,
+                            c_void_p, c_void_p]),
+    "pt_topk_second": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_int, c_void_p, c_void_p, c_int,
+                               c_void_p, c_int, c_float, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "pt_bbox_metric": (c_int, [c_void_p, c_int, c_void_p, c_int, c_ll, c_ll, c_int, c_int, c_float, c_void_p, c_void_p]),
+    "pt_max_iou_assign": (c_int, [c_void_p, c_int, c_int, c_void_p, c_int, c_int, c_int, c_int, c_float, c_float,
+                                  c_float, c_float, c_float, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p,
+                                  c_void_p, c_void_p, c_void_p]),
     "pt_aligned_iou_mean": (c_int, [c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p]),
 }
 

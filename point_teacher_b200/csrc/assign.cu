@@ -1,0 +1,383 @@
+// Dense-head label assignment of Point Teacher for sm_100a, without ever
+// materialising the P x G cost / overlap matrices the reference builds.
+//
+//   TopkAssigner      HBB_TOD/mmdet/core/bbox/assigners/topk_assigner.py:54-147
+//   FUSETopkAssigner  HBB_TOD/mmdet/core/bbox/assigners/fuse_topk_assigner.py:56-121
+//   match costs       HBB_TOD/mmdet/core/bbox/match_costs/match_cost.py:54-100 (FocalLossCost), :188-214 (PointCost),
+//                     :217-252 (InsiderCost)
+//   MaxIoUAssigner    HBB_TOD/mmdet/core/bbox/assigners/max_iou_assigner.py:60-212
+//   BboxDistanceMetric / BboxOverlaps2D matrices: overlap_metric.cuh
+//
+// The assignment indices are "whatever ATen's CPU torch.topk / Tensor.max return" (tie rule):
+//   stage 1: per GT column the num_pre smallest point costs.  For k*64 <= P ATen runs std::partial_sort = a
+//            k-element max-heap streamed over the P points in index order.  One WARP per GT replays exactly those
+//            heap moves: 32 costs are evaluated per step, a ballot finds the lanes that beat the current heap top
+//            and only those are pushed (in index order, re-checked against the updated top) by lane 0.
+//            For k*64 > P ATen uses nth_element on the whole column: replayed by one thread per GT on a scratch
+//            column (tiny P only).
+//   stage 2: per GT i the reference ranks its num_pre candidate rows under EVERY column of the second cost
+//            (quirk) and assigns the union of the per-column top-`topk` rows to i; later GTs overwrite earlier
+//            ones.  One CTA per GT, one thread per column replaying the 5-element nth_element; winners are OR-ed
+//            into a bit mask and written with atomicMax(i + 1) (sequential overwrite == largest i wins).
+#include "overlap_metric.cuh"
+#include "topk_replay.cuh"
+
+namespace ptb {
+
+constexpr int MAXK = 16;
+
+__device__ __forceinline__ float sigmoid_ref(float x) { return fdiv(1.f, fadd(1.f, expf(-x))); }
+
+// FocalLossCost table (P, C): pos - neg at every class, times weight
+__global__ void focal_cost_table_kernel(const float* __restrict__ logits, long long n, float alpha, float gamma,
+                                        float eps, float weight, float* __restrict__ out) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float p = sigmoid_ref(logits[i]);
+  const float q = fsub(1.f, p);
+  const float pg = gamma == 2.f ? fmul(p, p) : powf(p, gamma);
+  const float qg = gamma == 2.f ? fmul(q, q) : powf(q, gamma);
+  const float neg = fmul(fmul(-logf(fadd(q, eps)), fsub(1.f, alpha)), pg);
+  const float pos = fmul(fmul(-logf(fadd(p, eps)), alpha), qg);
+  out[i] = fmul(fsub(pos, neg), weight);
+}
+
+__device__ __forceinline__ float point_cost(const float* __restrict__ pts, int ldp, int p, float gx, float gy, int l2,
+                                            float weight) {
+  const float dx = fsub(pts[(size_t)p * ldp], gx), dy = fsub(pts[(size_t)p * ldp + 1], gy);
+  const float d = l2 ? sqrtf(fadd(fmul(dx, dx), fmul(dy, dy))) : fadd(fabsf(dx), fabsf(dy));
+  return fmul(d, weight);
+}
+
+// ---- stage 1, partial_sort path: one warp per GT
+__global__ void __launch_bounds__(128)
+topk_pre_heap_kernel(const float* __restrict__ pts, int ldp, int P, const float* __restrict__ gts, int ldg, int G,
+                     int l2, float weight, int k, int* __restrict__ pre_idx) {
+  __shared__ float s_v[4][MAXK];
+  __shared__ int s_i[4][MAXK];
+  const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int g = blockIdx.x * 4 + w;
+  if (g >= G) return;
+  const float gx = gts[(size_t)g * ldg], gy = gts[(size_t)g * ldg + 1];
+  PairArray a{s_v[w], s_i[w]};
+  if (lane < k) { s_v[w][lane] = point_cost(pts, ldp, lane, gx, gy, l2, weight); s_i[w][lane] = lane; }
+  __syncwarp();
+  if (lane == 0) tk_make_heap<false>(a, 0, k);
+  __syncwarp();
+  for (int base = k; base < P; base += 32) {
+    const int p = base + lane;
+    VI mine; mine.i = p; mine.v = 0.f;
+    bool pass = false;
+    if (p < P) {
+      mine.v = point_cost(pts, ldp, p, gx, gy, l2, weight);
+      pass = tk_comp<false>(mine, a.get(0));
+    }
+    unsigned mask = __ballot_sync(0xffffffffu, pass);
+    while (mask) {
+      const int L = __ffs(mask) - 1;
+      VI cand;
+      cand.v = __shfl_sync(0xffffffffu, mine.v, L);
+      cand.i = base + L;
+      if (lane == 0 && tk_comp<false>(cand, a.get(0))) tk_adjust_heap<false>(a, 0, 0, k, cand);   // __pop_heap
+      __syncwarp();
+      pass = pass && lane > L && tk_comp<false>(mine, a.get(0));
+      mask = __ballot_sync(0xffffffffu, pass);
+    }
+  }
+  if (lane == 0) {
+    tk_sort_heap<false>(a, 0, k);
+    for (int j = 0; j < k; j++) pre_idx[(size_t)j * G + g] = s_i[w][j];
+  }
+}
+
+// ---- stage 1, nth_element path (k*64 > P): one thread per GT on a scratch column
+__global__ void topk_pre_full_kernel(const float* __restrict__ pts, int ldp, int P, const float* __restrict__ gts,
+                                     int ldg, int G, int l2, float weight, int k, float* __restrict__ sc_v,
+                                     int* __restrict__ sc_i, int* __restrict__ pre_idx) {
+  const int g = blockIdx.x * blockDim.x + threadIdx.x;
+  if (g >= G) return;
+  const float gx = gts[(size_t)g * ldg], gy = gts[(size_t)g * ldg + 1];
+  float* v = sc_v + (size_t)g * P;
+  int* ix = sc_i + (size_t)g * P;
+  for (int p = 0; p < P; p++) { v[p] = point_cost(pts, ldp, p, gx, gy, l2, weight); ix[p] = p; }
+  cpu_topk_replay(v, ix, P, k, false);
+  for (int j = 0; j < k; j++) pre_idx[(size_t)j * G + g] = ix[j];
+}
+
+// ---- stage 2: one CTA per GT i
+__global__ void __launch_bounds__(128)
+topk_second_kernel(const int* __restrict__ pre_idx, int num_pre, int topk, int G, const float* __restrict__ fl_table,
+                   int C, const long long* __restrict__ labels, const float* __restrict__ pred, int ldb,
+                   const float* __restrict__ gts, int ldg, float loc_weight, int* __restrict__ assigned) {
+  __shared__ int rows[MAXK];
+  __shared__ float bx1[MAXK], by1[MAXK], bx2[MAXK], by2[MAXK];
+  __shared__ unsigned win;
+  const int i = blockIdx.x;
+  if (threadIdx.x < num_pre) {
+    const int r = pre_idx[(size_t)threadIdx.x * G + i];
+    rows[threadIdx.x] = r;
+    if (pred != nullptr) {
+      const float* b = pred + (size_t)r * ldb;
+      const float hw = fdiv(b[2], 2.f), hh = fdiv(b[3], 2.f);
+      bx1[threadIdx.x] = fsub(b[0], hw); by1[threadIdx.x] = fsub(b[1], hh);
+      bx2[threadIdx.x] = fadd(b[0], hw); by2[threadIdx.x] = fadd(b[1], hh);
+    }
+  }
+  if (threadIdx.x == 0) win = 0;
+  __syncthreads();
+  if (num_pre <= topk) {
+    if (threadIdx.x < num_pre) atomicMax(assigned + rows[threadIdx.x], i + 1);
+    return;
+  }
+  unsigned mine = 0;
+  for (int c = threadIdx.x; c < G; c += blockDim.x) {
+    float v[MAXK]; int ix[MAXK];
+    const int lab = (int)labels[c];
+    const float gx = gts[(size_t)c * ldg], gy = gts[(size_t)c * ldg + 1];
+    for (int r = 0; r < num_pre; r++) {
+      float cost = fl_table[(size_t)rows[r] * C + lab];
+      if (pred != nullptr) {
+        const bool inside = gx >= bx1[r] && gx <= bx2[r] && gy >= by1[r] && gy <= by2[r];
+        cost = fadd(cost, fmul(inside ? 0.f : 1.f, loc_weight));
+      }
+      v[r] = cost; ix[r] = r;
+    }
+    cpu_topk_replay(v, ix, num_pre, topk, false);
+    for (int j = 0; j < topk; j++) mine |= 1u << ix[j];
+  }
+  if (mine) atomicOr(&win, mine);
+  __syncthreads();
+  if (threadIdx.x < num_pre && ((win >> threadIdx.x) & 1u)) atomicMax(assigned + rows[threadIdx.x], i + 1);
+}
+
+__global__ void assign_finalize_kernel(const int* __restrict__ assigned, const long long* __restrict__ gt_labels,
+                                       int P, long long* __restrict__ gt_inds, long long* __restrict__ labels) {
+  const int p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= P) return;
+  const int a = assigned[p];
+  gt_inds[p] = a;
+  if (labels != nullptr) labels[p] = (a > 0 && gt_labels != nullptr) ? gt_labels[a - 1] : -1;
+}
+
+// ---- metric matrix
+__global__ void bbox_metric_kernel(const float* __restrict__ a, int lda, const float* __restrict__ b, int ldb,
+                                   long long M, long long N, int calc, int mode, float eps, float* __restrict__ out) {
+  const long long total = M * N;
+  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+       idx += (long long)gridDim.x * blockDim.x) {
+    const long long i = idx / N, j = idx - i * N;
+    const float* pa = a + i * lda;
+    const float* pb = b + j * ldb;
+    out[idx] = pair_metric(calc, mode, pa[0], pa[1], pa[2], pa[3], pb[0], pb[1], pb[2], pb[3], eps);
+  }
+}
+
+// ---- MaxIoUAssigner without the G x A matrix
+// order-preserving float <-> uint32 so that atomicMax works on signed floats (GIoU is negative)
+__device__ __forceinline__ unsigned enc_f(float f) {
+  const unsigned u = __float_as_uint(f);
+  return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+__device__ __forceinline__ float dec_f(unsigned e) {
+  return __uint_as_float((e & 0x80000000u) ? (e & 0x7fffffffu) : ~e);
+}
+
+constexpr int GT_TILE = 256;
+
+// pass 1: per anchor max / first argmax over the GTs; per GT max over the anchors (atomicMax)
+__global__ void __launch_bounds__(256)
+max_iou_pass1_kernel(const float* __restrict__ gts, int ldg, int G, const float* __restrict__ anchors, int lda, int A,
+                     int calc, int mode, float eps, float* __restrict__ max_ov, int* __restrict__ argmax,
+                     unsigned* __restrict__ gt_max) {
+  __shared__ float4 sg[GT_TILE];
+  __shared__ unsigned smax[GT_TILE];
+  const int a = blockIdx.x * blockDim.x + threadIdx.x;
+  float4 bx = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (a < A) { const float* p = anchors + (size_t)a * lda; bx = make_float4(p[0], p[1], p[2], p[3]); }
+  float best = 0.f; int bi = 0; bool has = false;
+  for (int g0 = 0; g0 < G; g0 += GT_TILE) {
+    const int n = min(GT_TILE, G - g0);
+    __syncthreads();
+    if (threadIdx.x < n) {
+      const float* p = gts + (size_t)(g0 + threadIdx.x) * ldg;
+      sg[threadIdx.x] = make_float4(p[0], p[1], p[2], p[3]);
+      smax[threadIdx.x] = 0u;   // below enc_f of every float
+    }
+    __syncthreads();
+    if (a < A) {
+      for (int j = 0; j < n; j++) {
+        const float4 gb = sg[j];
+        const float v = pair_metric(calc, mode, gb.x, gb.y, gb.z, gb.w, bx.x, bx.y, bx.z, bx.w, eps);
+        if (!has || v > best) { best = v; bi = g0 + j; has = true; }     // first index among equal maxima
+        // the running maximum settles after a few anchors: a broadcast read filters almost every atomic
+        const unsigned e = enc_f(v);
+        if (e > smax[j]) atomicMax(&smax[j], e);
+      }
+    }
+    __syncthreads();
+    if (threadIdx.x < n && smax[threadIdx.x] != 0u) atomicMax(gt_max + g0 + threadIdx.x, smax[threadIdx.x]);
+  }
+  if (a < A) { max_ov[a] = best; argmax[a] = bi; }
+}
+
+// pass 1b (gt_max_assign_all == False): first anchor index achieving each GT's max
+__global__ void __launch_bounds__(256)
+max_iou_argmax_kernel(const float* __restrict__ gts, int ldg, int G, const float* __restrict__ anchors, int lda,
+                      int A, int calc, int mode, float eps, const unsigned* __restrict__ gt_max,
+                      int* __restrict__ gt_argmax) {
+  const int a = blockIdx.x * blockDim.x + threadIdx.x;
+  if (a >= A) return;
+  const float* p = anchors + (size_t)a * lda;
+  for (int g = 0; g < G; g++) {
+    const float* q = gts + (size_t)g * ldg;
+    const float v = pair_metric(calc, mode, q[0], q[1], q[2], q[3], p[0], p[1], p[2], p[3], eps);
+    if (v == dec_f(gt_max[g])) atomicMin(gt_argmax + g, a);
+  }
+}
+
+// pass 2: thresholds + low-quality matching (sequential "for i in range(num_gts)" == largest i wins)
+__global__ void __launch_bounds__(256)
+max_iou_pass2_kernel(const float* __restrict__ gts, int ldg, int G, const float* __restrict__ anchors, int lda, int A,
+                     int calc, int mode, float eps, const float* __restrict__ max_ov, const int* __restrict__ argmax,
+                     const unsigned* __restrict__ gt_max, const int* __restrict__ gt_argmax, float pos_thr,
+                     float neg_lo, float neg_hi, float min_pos, int assign_all, int low_quality,
+                     const long long* __restrict__ gt_labels, long long* __restrict__ gt_inds,
+                     long long* __restrict__ labels) {
+  __shared__ float4 sg[GT_TILE];
+  __shared__ float sm[GT_TILE];
+  const int a = blockIdx.x * blockDim.x + threadIdx.x;
+  float4 bx = make_float4(0.f, 0.f, 0.f, 0.f);
+  long long asg = -1;
+  if (a < A) {
+    const float* p = anchors + (size_t)a * lda;
+    bx = make_float4(p[0], p[1], p[2], p[3]);
+    const float m = max_ov[a];
+    if (m >= neg_lo && m < neg_hi) asg = 0;
+    if (m >= pos_thr) asg = argmax[a] + 1;
+  }
+  if (low_quality) {
+    for (int g0 = 0; g0 < G; g0 += GT_TILE) {
+      const int n = min(GT_TILE, G - g0);
+      __syncthreads();
+      if (threadIdx.x < n) {
+        const float* p = gts + (size_t)(g0 + threadIdx.x) * ldg;
+        sg[threadIdx.x] = make_float4(p[0], p[1], p[2], p[3]);
+        sm[threadIdx.x] = dec_f(gt_max[g0 + threadIdx.x]);
+      }
+      __syncthreads();
+      if (a < A) {
+        for (int j = 0; j < n; j++) {
+          const float gm = sm[j];
+          if (!(gm >= min_pos)) continue;
+          if (assign_all) {
+            const float4 gb = sg[j];
+            const float v = pair_metric(calc, mode, gb.x, gb.y, gb.z, gb.w, bx.x, bx.y, bx.z, bx.w, eps);
+            if (v == gm) asg = g0 + j + 1;
+          } else if (gt_argmax[g0 + j] == a) {
+            asg = g0 + j + 1;
+          }
+        }
+      }
+    }
+  }
+  if (a < A) {
+    gt_inds[a] = asg;
+    if (labels != nullptr) labels[a] = asg > 0 ? gt_labels[asg - 1] : -1;
+  }
+}
+
+}  // namespace ptb
+
+using namespace ptb;
+
+extern "C" int pt_focal_cost_table(const float* logits, long long n, float alpha, float gamma, float eps,
+                                   float weight, float* out, void* stream) {
+  if (n <= 0) return PT_OK;
+  focal_cost_table_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(logits, n, alpha, gamma, eps,
+                                                                                        weight, out);
+  return check_launch("focal_cost_table_kernel");
+}
+
+// Stage 1 of Topk/FUSETopkAssigner.  pts [P, ldp] (x, y first), gts [G, ldg] (cx, cy first); pre_idx [num_pre, G]
+// int32 = torch.topk(cost, num_pre, dim=0, largest=False).indices.  scratch_v / scratch_i ([G, P] each) are only
+// needed (and only touched) when num_pre * 64 > P.
+extern "C" int pt_topk_pre(const float* pts, int ldp, int P, const float* gts, int ldg, int G, int l2, float weight,
+                           int num_pre, int* pre_idx, float* scratch_v, int* scratch_i, void* stream) {
+  if (G <= 0) return PT_OK;
+  if (num_pre < 1 || num_pre > MAXK) { set_error("pt_topk_pre: num_pre must be in 1..%d (got %d)", MAXK, num_pre); return PT_ERR_UNSUPPORTED; }
+  if (num_pre > P) { set_error("pt_topk_pre: selected index k out of range (num_pre %d > %d points)", num_pre, P); return PT_ERR_ARG; }
+  cudaStream_t s = (cudaStream_t)stream;
+  if ((long long)num_pre * 64 <= P) {
+    topk_pre_heap_kernel<<<(G + 3) / 4, 128, 0, s>>>(pts, ldp, P, gts, ldg, G, l2, weight, num_pre, pre_idx);
+    return check_launch("topk_pre_heap_kernel");
+  }
+  if (scratch_v == nullptr || scratch_i == nullptr) { set_error("pt_topk_pre: scratch columns required when num_pre*64 > P"); return PT_ERR_ARG; }
+  topk_pre_full_kernel<<<(G + 63) / 64, 64, 0, s>>>(pts, ldp, P, gts, ldg, G, l2, weight, num_pre, scratch_v, scratch_i,
+                                                    pre_idx);
+  return check_launch("topk_pre_full_kernel");
+}
+
+// Stage 2 + write-out.  fl_table [P, C] (may be NULL when num_pre <= topk), labels [G] int64, pred [P, ldb]
+// (cx, cy, w, h) or NULL (TopkAssigner), assigned_ws [P] int32 scratch; gt_inds / out_labels [P] int64.
+extern "C" int pt_topk_second(const int* pre_idx, int num_pre, int topk, int G, int P, const float* fl_table, int C,
+                              const long long* labels, const float* pred, int ldb, const float* gts, int ldg,
+                              float loc_weight, int* assigned_ws, long long* gt_inds, long long* out_labels,
+                              void* stream) {
+  cudaStream_t s = (cudaStream_t)stream;
+  if (P <= 0) return PT_OK;
+  cudaMemsetAsync(assigned_ws, 0, (size_t)P * sizeof(int), s);
+  if (G > 0) {
+    if (num_pre < 1 || num_pre > MAXK || topk < 1) { set_error("pt_topk_second: bad num_pre/topk"); return PT_ERR_ARG; }
+    if (num_pre > topk && fl_table == nullptr) { set_error("pt_topk_second: cost table required when num_pre > topk"); return PT_ERR_ARG; }
+    topk_second_kernel<<<G, 128, 0, s>>>(pre_idx, num_pre, topk, G, fl_table, C, labels, pred, ldb, gts, ldg, loc_weight,
+                                         assigned_ws);
+    int rc = check_launch("topk_second_kernel");
+    if (rc != PT_OK) return rc;
+  }
+  assign_finalize_kernel<<<(P + 255) / 256, 256, 0, s>>>(assigned_ws, labels, P, gt_inds, out_labels);
+  return check_launch("assign_finalize_kernel");
+}
+
+extern "C" int pt_bbox_metric(const float* a, int lda, const float* b, int ldb, long long M, long long N, int calc,
+                              int mode, float eps, float* out, void* stream) {
+  if (M * N <= 0) return PT_OK;
+  if (calc < 0 || calc > 1 || mode < 0 || mode > METRIC_KL10 || (calc == 0 && mode > METRIC_GIOU)) {
+    set_error("pt_bbox_metric: unsupported calculator %d / mode %d", calc, mode);
+    return PT_ERR_ARG;
+  }
+  const long long total = M * N;
+  const int blocks = (int)((total + 255) / 256 < 148LL * 32 ? (total + 255) / 256 : 148LL * 32);
+  bbox_metric_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(a, lda, b, ldb, M, N, calc, mode, eps, out);
+  return check_launch("bbox_metric_kernel");
+}
+
+// MaxIoUAssigner.assign (overlaps = calc(gts, anchors, mode)); ws: G uint32 (gt max) + G int32 (gt argmax).
+extern "C" int pt_max_iou_assign(const float* gts, int ldg, int G, const float* anchors, int lda, int A, int calc,
+                                 int mode, float eps, float pos_thr, float neg_lo, float neg_hi, float min_pos,
+                                 int gt_max_assign_all, int match_low_quality, const long long* gt_labels,
+                                 long long* gt_inds, float* max_overlaps, long long* labels, int* argmax_ws,
+                                 unsigned* gt_ws, void* stream) {
+  cudaStream_t s = (cudaStream_t)stream;
+  if (A <= 0) return PT_OK;
+  if (G <= 0) { set_error("pt_max_iou_assign: G must be > 0 (the host wrapper handles the empty case)"); return PT_ERR_ARG; }
+  if (calc < 0 || calc > 1 || mode < 0 || mode > METRIC_KL10 || (calc == 0 && mode > METRIC_GIOU)) {
+    set_error("pt_max_iou_assign: unsupported calculator %d / mode %d", calc, mode);
+    return PT_ERR_ARG;
+  }
+  int* gt_argmax = reinterpret_cast<int*>(gt_ws + G);
+  cudaMemsetAsync(gt_ws, 0, (size_t)G * sizeof(unsigned), s);
+  cudaMemsetAsync(gt_argmax, 0x7f, (size_t)G * sizeof(int), s);
+  const int blocks = (A + 255) / 256;
+  max_iou_pass1_kernel<<<blocks, 256, 0, s>>>(gts, ldg, G, anchors, lda, A, calc, mode, eps, max_overlaps, argmax_ws, gt_ws);
+  int rc = check_launch("max_iou_pass1_kernel");
+  if (rc != PT_OK) return rc;
+  if (match_low_quality && !gt_max_assign_all) {
+    max_iou_argmax_kernel<<<blocks, 256, 0, s>>>(gts, ldg, G, anchors, lda, A, calc, mode, eps, gt_ws, gt_argmax);
+    rc = check_launch("max_iou_argmax_kernel");
+    if (rc != PT_OK) return rc;
+  }
+  max_iou_pass2_kernel<<<blocks, 256, 0, s>>>(gts, ldg, G, anchors, lda, A, calc, mode, eps, max_overlaps, argmax_ws, gt_ws,
+                                              gt_argmax, pos_thr, neg_lo, neg_hi, min_pos, gt_max_assign_all,
+                                              match_low_quality, gt_labels, gt_inds, labels);
+  return check_launch("max_iou_pass2_kernel");
+}

@@ -334,3 +334,91 @@ def aligned_iou_mean(a, b, rotated=False):
     _lib.call("pt_aligned_iou_mean", _p(a), a.shape[1], _p(b), b.shape[1], a.shape[0], int(rotated), _p(out),
               _stream())
     return out[0]
+
+
+# ------------------------------------------------------------------------------ dense-head label assignment
+METRIC_MODES = {"iou": 0, "iof": 1, "giou": 2, "wd": 3, "kl": 4, "center_distance2": 5, "exp_kl": 6, "kl_10": 7}
+
+
+def focal_cost_table(logits, alpha=0.25, gamma=2.0, eps=1e-12, weight=1.0):
+    """(P, C) logits -> (P, C) FocalLossCost table (pos - neg) * weight."""
+    _chk(logits, "cls_pred", _f32, 2)
+    out = torch.empty_like(logits)
+    _lib.call("pt_focal_cost_table", _p(logits), logits.numel(), float(alpha), float(gamma), float(eps), float(weight),
+              _p(out), _stream())
+    return out
+
+
+def topk_pre(points, gts, num_pre, mode="L1", weight=1.0):
+    """torch.topk(PointCost(points, gts), num_pre, dim=0, largest=False).indices as (num_pre, G) int32."""
+    _chk(points, "points", _f32, 2)
+    _chk(gts, "gt_bboxes", _f32, 2)
+    if points.shape[1] < 2 or gts.shape[1] < 2:
+        raise ValueError("points / gt_bboxes need at least 2 columns")
+    P, G = points.shape[0], gts.shape[0]
+    if num_pre > P:
+        raise RuntimeError("selected index k out of range")          # what torch.topk raises
+    pre = torch.empty((num_pre, G), dtype=_i32, device=points.device)
+    sv = si = None
+    if num_pre * 64 > P:
+        sv = torch.empty((G, P), dtype=_f32, device=points.device)
+        si = torch.empty((G, P), dtype=_i32, device=points.device)
+    _lib.call("pt_topk_pre", _p(points), points.shape[1], P, _p(gts), gts.shape[1], G, int(mode == "L2"), float(weight),
+              int(num_pre), _p(pre), _p(sv), _p(si), _stream())
+    return pre
+
+
+def topk_second(pre_idx, topk, P, fl_table, gt_labels, gts, pred=None, loc_weight=1.0):
+    """-> (gt_inds (P,) int64, labels (P,) int64)."""
+    num_pre, G = pre_idx.shape
+    _chk(gt_labels, "gt_labels", _i64, 1)
+    dev = pre_idx.device
+    ws = torch.empty((P,), dtype=_i32, device=dev)
+    gt_inds = torch.empty((P,), dtype=_i64, device=dev)
+    labels = torch.empty((P,), dtype=_i64, device=dev)
+    C = fl_table.shape[1] if fl_table is not None else 0
+    _lib.call("pt_topk_second", _p(pre_idx), num_pre, int(topk), G, P, _p(fl_table), C, _p(gt_labels), _p(pred),
+              pred.shape[1] if pred is not None else 0, _p(gts), gts.shape[1], float(loc_weight), _p(ws), _p(gt_inds),
+              _p(labels), _stream())
+    return gt_inds, labels
+
+
+def bbox_metric(b1, b2, mode="iou", calc=1, eps=1e-6):
+    """(M,4) x (N,4) -> (M,N): calc 0 BboxOverlaps2D, calc 1 BboxDistanceMetric."""
+    if mode not in METRIC_MODES or (calc == 0 and METRIC_MODES[mode] > 2):
+        raise AssertionError(f"Unsupported mode {mode}")
+    _chk(b1, "bboxes1", _f32, 2)
+    _chk(b2, "bboxes2", _f32, 2)
+    M, N = b1.shape[0], b2.shape[0]
+    out = torch.empty((M, N), dtype=_f32, device=b1.device)
+    if M * N == 0:
+        return out
+    if b1.shape[1] < 4 or b2.shape[1] < 4:
+        raise ValueError("boxes must have at least 4 columns")
+    _lib.call("pt_bbox_metric", _p(b1), b1.shape[1], _p(b2), b2.shape[1], M, N, int(calc), METRIC_MODES[mode], float(eps),
+              _p(out), _stream())
+    return out
+
+
+def max_iou_assign(gts, anchors, calc, mode, pos_iou_thr, neg_iou_thr, min_pos_iou, gt_max_assign_all,
+                   match_low_quality, gt_labels=None, eps=1e-6):
+    """-> (gt_inds (A,) int64, max_overlaps (A,) fp32, labels (A,) int64 | None); G > 0 and A > 0."""
+    _chk(gts, "gt_bboxes", _f32, 2)
+    _chk(anchors, "bboxes", _f32, 2)
+    G, A = gts.shape[0], anchors.shape[0]
+    dev = anchors.device
+    gt_inds = torch.empty((A,), dtype=_i64, device=dev)
+    mx = torch.empty((A,), dtype=_f32, device=dev)
+    labels = torch.empty((A,), dtype=_i64, device=dev) if gt_labels is not None else None
+    if gt_labels is not None:
+        _chk(gt_labels, "gt_labels", _i64, 1)
+    amx = torch.empty((A,), dtype=_i32, device=dev)
+    ws = torch.empty((2 * G,), dtype=_i32, device=dev)
+    if isinstance(neg_iou_thr, (tuple, list)):
+        lo, hi = float(neg_iou_thr[0]), float(neg_iou_thr[1])
+    else:
+        lo, hi = 0.0, float(neg_iou_thr)
+    _lib.call("pt_max_iou_assign", _p(gts), gts.shape[1], G, _p(anchors), anchors.shape[1], A, int(calc),
+              METRIC_MODES[mode], float(eps), float(pos_iou_thr), lo, hi, float(min_pos_iou), int(gt_max_assign_all),
+              int(match_low_quality), _p(gt_labels), _p(gt_inds), _p(mx), _p(labels), _p(amx), _p(ws), _stream())
+    return gt_inds, mx, labels

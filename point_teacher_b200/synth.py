@@ -112,3 +112,23 @@ def obb_batch(seed=0, batch=2, img_hw=(1024, 1024), stride=8, channels=256, num_
     return dict(feat=feat, gt_boxes=gts, pseudo_boxes=pseudo, pseudo_points=[b[:, :2] for b in pseudo],
                 pseudo_labels=labels, neg_boxes=negs, img_metas=metas, stride=stride,
                 num_classes=num_classes)
+
+
+def assign_batch(seed, P_hw=(40, 40), G=37, C=8, stride=8, ties=True):
+    """Grid points of a stride-8 map, GT points (integer-valued when ``ties`` so that L1 ties are everywhere),
+    logits, decoded boxes."""
+    g = torch.Generator().manual_seed(seed)
+    h, w = P_hw
+    ys, xs = torch.meshgrid(torch.arange(h), torch.arange(w), indexing="ij")
+    points = torch.stack([xs.reshape(-1), ys.reshape(-1)], 1).float() * stride + stride // 2
+    P = points.shape[0]
+    ctr = torch.rand(G, 2, generator=g) * torch.tensor([w * stride - 16.0, h * stride - 16.0]) + 8
+    if ties:
+        ctr = ctr.round()
+    wh = (torch.randn(G, 2, generator=g) * 0.5 + 2.5).exp().clamp(2, 64)
+    gt_cxcywh = torch.cat([ctr, wh], 1)
+    labels = torch.randint(0, C, (G,), generator=g)
+    logits = torch.randn(P, C, generator=g) * 2 - 2
+    pred_wh = (torch.randn(P, 2, generator=g) * 0.6 + 2.8).exp()
+    pred = torch.cat([points + torch.randn(P, 2, generator=g) * 4, pred_wh], 1)       # (cx, cy, w, h)
+    return dict(points=points, gt=gt_cxcywh, labels=labels, logits=logits, pred=pred)

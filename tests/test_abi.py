@@ -55,6 +55,16 @@ def test_reference_surface_names():
     assert registry.ROI_EXTRACTORS.get("SingleRoIExtractor") is roi_extractors.SingleRoIExtractor
     assert registry.ROI_EXTRACTORS.get("RotatedSingleRoIExtractor") is roi_extractors.RotatedSingleRoIExtractor
     assert callable(refine.P2BRefineMixin.forward_mil_head_burn_in_step2)
+    from point_teacher_b200 import assigners
+    for n in ("TopkAssigner", "FUSETopkAssigner", "MaxIoUAssigner"):
+        assert registry.BBOX_ASSIGNERS.get(n) is getattr(assigners, n)
+    for n in ("BboxOverlaps2D", "BboxDistanceMetric"):
+        assert registry.IOU_CALCULATORS.get(n) is getattr(assigners, n)
+    a = registry.build_assigner(dict(type="FUSETopkAssigner", num_pre=5, topk=3,
+                                     cls_cost=dict(type="FocalLossCost", weight=1.0),
+                                     reg_cost=dict(type="PointCost", mode="L1", weight=1.0),
+                                     location_cost=dict(type="InsiderCost", weight=1.0)))
+    assert a.num_pre == 5 and a.topk == 3 and callable(a.assign)
 
 
 def test_head_parameter_names_match_reference_checkpoints():

@@ -160,3 +160,44 @@ def test_obb_oracle_reproduces_reference_golden(golden_dir):
     assert torch.equal(torch.cat([b[:100] for b in ob]), g["merged"])
     for k, v in g["losses"].items():
         assert torch.allclose(losses[k], v, rtol=1e-6), k
+
+
+def test_assign_oracle_reproduces_reference_golden(golden_dir):
+    """Rows a13-a15: oracle/assign.py against outputs of the reference's own assigner / metric files."""
+    from oracle import assign
+    g = torch.load(os.path.join(golden_dir, "assign.pt"))
+    for c in g["cases"]:
+        d = synth.assign_batch(c["seed"], ties=c["ties"])
+        gi, lb = assign.topk_assign(d["pred"], d["logits"], d["gt"], d["labels"], c["num_pre"], c["topk"])
+        assert torch.equal(gi, c["topk_gt_inds"]) and torch.equal(lb, c["topk_labels"])
+        gi, lb = assign.fuse_topk_assign(d["pred"], d["points"], d["logits"], d["gt"], d["labels"], c["num_pre"], c["topk"])
+        assert torch.equal(gi, c["fuse_gt_inds"]) and torch.equal(lb, c["fuse_labels"])
+        assert torch.equal(assign.focal_loss_table(d["logits"]), c["fl_table"])
+    for m, ref in g["metric"].items():
+        assert torch.equal(assign.bbox_metric(g["gts"], g["anchors"], m), ref), m
+    for c in g["maxiou"]:
+        ov = hbb.bbox_overlaps(g["gts"], g["anchors"], c["mode"]) if c["calc"] == "BboxOverlaps2D" else \
+            assign.bbox_metric(g["gts"], g["anchors"], c["mode"])
+        gi, mx, lb = assign.max_iou_assign(ov, g["labels"], **c["kw"])
+        assert torch.equal(gi, c["gt_inds"]) and torch.equal(mx, c["max_overlaps"]) and torch.equal(lb, c["labels"])
+
+
+def test_max_iou_known_answers_from_reference_tests():
+    # HBB_TOD/tests/test_utils/test_assigner.py:15-63
+    from oracle import assign
+    bboxes = torch.FloatTensor([[0, 0, 10, 10], [10, 10, 20, 20], [5, 5, 15, 15], [32, 32, 38, 42]])
+    gts = torch.FloatTensor([[0, 0, 10, 9], [0, 10, 10, 19]])
+    gi, _, lb = assign.max_iou_assign(hbb.bbox_overlaps(gts, bboxes), torch.LongTensor([2, 3]), 0.5, 0.5)
+    assert gi.tolist() == [1, 0, 2, 0]
+    assert lb.tolist() == [2, -1, 3, -1]
+
+
+def test_focal_loss_cost_docstring_shape_and_sign():
+    # match_cost.py:66-74: costs are negative for confident positives; table column gather == direct call
+    from oracle import assign
+    g = torch.Generator().manual_seed(0)
+    x = torch.rand(4, 3, generator=g)
+    lab = torch.tensor([0, 1, 2])
+    c = assign.focal_loss_cost(x, lab)
+    assert c.shape == (4, 3) and (c < 0).all()
+    assert torch.equal(c, assign.focal_loss_table(x)[:, lab])
