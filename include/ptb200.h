@@ -160,6 +160,21 @@ int pt_max_iou_assign(const float* gts, int ldg, int G, const float* anchors, in
                       int match_low_quality, const long long* gt_labels, long long* gt_inds, float* max_overlaps,
                       long long* labels, int* argmax_ws, unsigned* gt_ws, void* stream);
 
+/* ---- phase-1 random region masking (row a16) --------------------------------------------------------------
+ * The deterministic tail of generate_black_paper (HBB_TOD/mmdet/models/detectors/syn_images_generator_v2.py:664-690).
+ * pt_nms_rotated: mmcv.ops.nms_rotated(dets [N, ld>=5], scores (stride lds), thr): order [N] int32 = box indices by
+ *   descending score (stable), keep_sorted [N] uint8 = survivor flags in that order.
+ * pt_black_paper_select: score < 1 and inside-image filters (:668-675), obb2poly_le90 + int32 truncation (:678-682);
+ *   bb [N,7]; the first *count rows of out_bb [N,7] / out_sel [N] / polys [N,8] are valid (score order).
+ * pt_fill_polys: cv2.fillPoly of integer quadrilaterals into img [C,H,W] fp32 (<- value) and / or mask [H,W] uint8. */
+long long pt_nms_rotated_workspace_bytes(int N);
+int pt_nms_rotated(const float* dets, int ld, const float* scores, int lds, int N, float thr, int* order,
+                   unsigned char* keep_sorted, void* workspace, long long workspace_bytes, void* stream);
+int pt_black_paper_select(const float* bb, int N, const int* order, const unsigned char* keep_sorted, float imgsize,
+                          float* out_bb, int* out_sel, int* polys, int* count, void* stream);
+int pt_fill_polys(const int* polys, const int* count, int max_polys, float* img, unsigned char* mask, int C, int H,
+                  int W, float value, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -167,7 +167,37 @@ def check_assign():
     return ok
 
 
+def check_mask():
+    """Row a16: the reference's own generate_black_paper (seeded torch + numpy RNG) against
+    sample_candidates + black_paper_from_candidates of oracle/mask.py."""
+    import numpy as np
+    from oracle import mask
+    ns = ref_shim.install()
+    ok = True
+    for seed in range(4):
+        d = synth.mask_batch(seed)
+        pattern, prior = ns.syn.load_basic_shape(synth.SHAPE_LIST)
+        dense = range(int(len(pattern) / 2))
+        torch.manual_seed(seed)
+        np.random.seed(seed)
+        img_ref, bb_ref = ns.syn.generate_black_paper(d["img"].clone(), d["bb_occupied"].clone(), d["img"].clone(), pattern,
+                                                      prior, dense, d["imgsize"])
+        torch.manual_seed(seed)
+        np.random.seed(seed)
+        allb = mask.sample_candidates(d["bb_occupied"], prior, dense, d["imgsize"])
+        img_o, bb_o, sel, polys, m = mask.black_paper_from_candidates(d["img"].clone(), allb, d["imgsize"])
+        ok &= _eq(bb_o, bb_ref, f"black paper kept boxes seed{seed} ({bb_ref.shape[0]} kept of {allb.shape[0]})", 0.0)
+        ok &= _eq(img_o, img_ref, f"black paper image seed{seed} ({int(m.sum())} px)", 0.0)
+        img_r, _, _, _, m2 = mask.black_paper_from_candidates(d["img"].clone(), allb, d["imgsize"], use_cv2=False)
+        ok &= _eq(torch.from_numpy(m2), torch.from_numpy(m), f"fill replay == cv2.fillPoly seed{seed}", 0.0)
+    return ok
+
+
 if __name__ == "__main__":
+    if "--mask" in sys.argv:
+        good = check_mask()
+        print("ALL OK" if good else "MISMATCH")
+        sys.exit(0 if good else 1)
     if "--assign" in sys.argv:
         good = check_assign()
         print("ALL OK" if good else "MISMATCH")

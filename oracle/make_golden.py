@@ -115,6 +115,26 @@ def assign_case():
     print("wrote assign", len(out["cases"]), len(out["maxiou"]))
 
 
+def mask_case():
+    """Row a16: outputs of the reference's own generate_black_paper (seeded torch + numpy RNG)."""
+    import numpy as np
+    ns = ref_shim.install()
+    out = []
+    for seed in (0, 3):
+        d = synth.mask_batch(seed)
+        pattern, prior = ns.syn.load_basic_shape(synth.SHAPE_LIST)
+        torch.manual_seed(seed)
+        np.random.seed(seed)
+        img_ref, bb_ref = ns.syn.generate_black_paper(d["img"].clone(), d["bb_occupied"].clone(), d["img"].clone(), pattern,
+                                                      prior, range(int(len(pattern) / 2)), d["imgsize"])
+        filled = (img_ref != d["img"]).any(0) | ((img_ref == 255).all(0) & (d["img"] == 255).all(0))
+        m = (img_ref == 255).all(0)
+        out.append(dict(seed=seed, kept=bb_ref, mask_bits=torch.from_numpy(np.packbits(m.numpy())),
+                        n_px=int(m.sum()), changed=int(filled.sum())))
+    torch.save(out, os.path.join(OUT, "black_paper.pt"))
+    print("wrote black_paper", [(o["kept"].shape[0], o["n_px"]) for o in out])
+
+
 def overlaps_case():
     ns = ref_shim.install()
     g = torch.Generator().manual_seed(7)
@@ -135,3 +155,4 @@ if __name__ == "__main__":
     overlaps_case()
     obb_case(0, "s1_top3")
     assign_case()
+    mask_case()

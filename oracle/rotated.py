@@ -63,7 +63,10 @@ def nms_rotated(dets, scores, iou_threshold, labels=None, clockwise=True):
     if not clockwise:
         d = d.copy()
         d[:, 4] *= -1
-    order = torch.sort(scores.detach().cpu(), 0, descending=True)[1].numpy().astype(np.int64)
+    # mmcv's wrapper calls scores.sort(0, descending=True) WITHOUT stable=True: the order of equal scores is then
+    # implementation-defined (ATen dispatches to an ISA-specific vectorised quicksort on recent builds), so it
+    # cannot be part of a parity contract.  Oracle and product both fix it to the stable order.
+    order = torch.sort(scores.detach().cpu(), stable=True, dim=0, descending=True)[1].numpy().astype(np.int64)
     n = d.shape[0]
     keep_mask = np.zeros((n,), np.uint8)
     _lib().oracle_nms_rotated(d.ctypes.data_as(ctypes.c_void_p),

@@ -52,6 +52,12 @@ SIGNATURES = {
     "pt_max_iou_assign": (c_int, [c_void_p, c_int, c_int, c_void_p, c_int, c_int, c_int, c_int, c_float, c_float,
                                   c_float, c_float, c_float, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p,
                                   c_void_p, c_void_p, c_void_p]),
+    "pt_nms_rotated_workspace_bytes": (c_ll, [c_int]),
+    "pt_nms_rotated": (c_int, [c_void_p, c_int, c_void_p, c_int, c_int, c_float, c_void_p, c_void_p, c_void_p, c_ll,
+                               c_void_p]),
+    "pt_black_paper_select": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_float, c_void_p, c_void_p, c_void_p,
+                                      c_void_p, c_void_p]),
+    "pt_fill_polys": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_int, c_int, c_int, c_float, c_void_p]),
     "pt_aligned_iou_mean": (c_int, [c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p]),
 }
 
@@ -81,7 +87,8 @@ def load():
 
 
 LAUNCHES = {"count": 0}   # kernels enqueued through the C-ABI (every launching entry point = one kernel)
-_NO_KERNEL = {"pt_last_error", "pt_abi_version", "pt_build_arch", "pt_fc_gemm_workspace_bytes"}
+_NO_KERNEL = {"pt_last_error", "pt_abi_version", "pt_build_arch", "pt_fc_gemm_workspace_bytes",
+              "pt_nms_rotated_workspace_bytes"}
 
 
 def call(name, *args):

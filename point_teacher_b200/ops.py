@@ -422,3 +422,56 @@ def max_iou_assign(gts, anchors, calc, mode, pos_iou_thr, neg_iou_thr, min_pos_i
               METRIC_MODES[mode], float(eps), float(pos_iou_thr), lo, hi, float(min_pos_iou), int(gt_max_assign_all),
               int(match_low_quality), _p(gt_labels), _p(gt_inds), _p(mx), _p(labels), _p(amx), _p(ws), _stream())
     return gt_inds, mx, labels
+
+
+# ------------------------------------------------------------------------------ phase-1 region masking
+def nms_rotated(dets, scores, iou_threshold):
+    """mmcv.ops.nms_rotated decision list: (order (N,) int32 by descending score, keep_sorted (N,) uint8)."""
+    _chk(dets, "dets", _f32, 2)
+    if dets.shape[1] < 5:
+        raise ValueError("dets need (cx, cy, w, h, theta)")
+    if scores.dtype != _f32 or scores.dim() != 1 or not scores.is_cuda or scores.shape[0] != dets.shape[0]:
+        raise ValueError("scores must be a CUDA fp32 vector with one entry per box")
+    N = dets.shape[0]
+    dev = dets.device
+    order = torch.empty((N,), dtype=_i32, device=dev)
+    keep = torch.empty((N,), dtype=_u8, device=dev)
+    if N == 0:
+        return order, keep
+    nbytes = _lib.load().pt_nms_rotated_workspace_bytes(N)
+    ws = torch.empty((nbytes,), dtype=_u8, device=dev)
+    _lib.call("pt_nms_rotated", _p(dets), dets.stride(0), _p(scores), scores.stride(0), N, float(iou_threshold),
+              _p(order), _p(keep), _p(ws), nbytes, _stream())
+    return order, keep
+
+
+def black_paper_select(bb, order, keep_sorted, imgsize):
+    """-> (kept boxes (N,7) padded, sel (N,) int32 padded, polys (N,4,2) int32 padded, count (1,) int32)."""
+    _chk(bb, "bb", _f32, 2, 7)
+    N, dev = bb.shape[0], bb.device
+    out = torch.zeros((N, 7), dtype=_f32, device=dev)
+    sel = torch.zeros((N,), dtype=_i32, device=dev)
+    polys = torch.zeros((N, 4, 2), dtype=_i32, device=dev)
+    count = torch.zeros((1,), dtype=_i32, device=dev)
+    _lib.call("pt_black_paper_select", _p(bb), N, _p(order), _p(keep_sorted), float(imgsize), _p(out), _p(sel),
+              _p(polys), _p(count), _stream())
+    return out, sel, polys, count
+
+
+def fill_polys(polys, img=None, mask=None, value=255.0, count=None):
+    """cv2.fillPoly of (M,4,2) int32 quadrilaterals into img (C,H,W) fp32 (<- value) and/or mask (H,W) uint8."""
+    _chk(polys, "polygons", _i32, 3, 2)
+    if polys.shape[1] != 4:
+        raise ValueError("only quadrilaterals are on the Point Teacher path")
+    if img is None and mask is None:
+        raise ValueError("nothing to draw into")
+    if img is not None:
+        _chk(img, "img", _f32, 3)
+        C, H, W = img.shape
+    if mask is not None:
+        _chk(mask, "mask", _u8, 2)
+        if img is not None and tuple(mask.shape) != (H, W):
+            raise ValueError("mask and img disagree on (H, W)")
+        C, (H, W) = (C if img is not None else 0), mask.shape
+    _lib.call("pt_fill_polys", _p(polys), _p(count), polys.shape[0], _p(img), _p(mask), C, H, W, float(value),
+              _stream())

@@ -132,3 +132,21 @@ def assign_batch(seed, P_hw=(40, 40), G=37, C=8, stride=8, ties=True):
     pred_wh = (torch.randn(P, 2, generator=g) * 0.6 + 2.8).exp()
     pred = torch.cat([points + torch.randn(P, 2, generator=g) * 4, pred_wh], 1)       # (cx, cy, w, h)
     return dict(points=points, gt=gt_cxcywh, labels=labels, logits=logits, pred=pred)
+
+
+# HBB_TOD/configs/point_teacher/aitodv2_point_teacher_0%.py: shape_list of the phase-1 masking priors
+SHAPE_LIST = [[20, 20, 0.5, 0.5], [30, 120, 0.5, 0.5], [10, 20, 0.5, 0.5], [20, 50, 0.5, 0.5], [30, 20, 0.5, 0.5]]
+
+
+def mask_batch(seed, imgsize=800, n_gt=(150, 300), n_shapes=5):
+    """Phase-1 masking inputs: one uint8-valued float image (3,H,W) and bb_occupied (G,7) =
+    (cx, cy, w, h, 0, 1, shape class) as built by fcos_p2b_teacher_student.py:470-479."""
+    g = torch.Generator().manual_seed(1000 + seed)
+    n = int(torch.randint(n_gt[0], n_gt[1] + 1, (1,), generator=g))
+    img = torch.randint(0, 256, (3, imgsize, imgsize), generator=g).float()
+    xyxy = make_boxes(g, n, (imgsize, imgsize))
+    cxcywh = torch.stack([(xyxy[:, 0] + xyxy[:, 2]) / 2, (xyxy[:, 1] + xyxy[:, 3]) / 2, xyxy[:, 2] - xyxy[:, 0],
+                          xyxy[:, 3] - xyxy[:, 1]], 1)
+    cls = torch.randint(0, n_shapes, (n, 1), generator=g).float()
+    bb = torch.cat([cxcywh, torch.zeros(n, 1), torch.ones(n, 1), cls], 1)
+    return dict(img=img, bb_occupied=bb, imgsize=imgsize)

@@ -1,0 +1,126 @@
+"""Phase-1 region masking kernels on a B200 against cv2.fillPoly, the CPU oracle and the
+golden vectors produced by the reference's own generate_black_paper."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import mask as M
+from oracle import rotated
+from point_teacher_b200 import synth
+
+pytestmark = pytest.mark.gpu
+
+
+def _quads(n, seed, size=300):
+    rng = np.random.default_rng(seed)
+    out = []
+    while len(out) < n:
+        cx, cy = rng.uniform(40, size - 40, 2)
+        w, h = rng.uniform(0.3, 90, 2)
+        a = rng.uniform(-np.pi / 2, np.pi / 2)
+        if len(out) % 10 == 0:
+            a = 0.0
+        if len(out) % 17 == 0:
+            a = float(np.pi / 2 * rng.integers(-1, 2))
+        p = M.obb2poly_le90(torch.tensor([[cx, cy, w, h, a]], dtype=torch.float32)).view(4, 2).numpy().astype(np.int32)
+        if p.min() >= 0 and p.max() < size:
+            out.append(p)
+    return out
+
+
+def test_fill_polys_bit_exact_vs_cv2(cuda):
+    """Every polygon rasterised alone (per-polygon pixel sets) and all together, against cv2.fillPoly."""
+    import cv2
+    from point_teacher_b200 import ops
+    quads = _quads(1500, 7)
+    polys = torch.from_numpy(np.stack(quads)).to(cuda)
+    for i in range(0, 1500, 97):                               # individual polygons
+        ref = np.zeros((300, 300), np.uint8)
+        cv2.fillPoly(ref, [quads[i]], 1)
+        m = torch.zeros((300, 300), dtype=torch.uint8, device=cuda)
+        ops.fill_polys(polys[i:i + 1].contiguous(), mask=m)
+        assert np.array_equal(m.cpu().numpy(), ref), quads[i].tolist()
+    ref = np.zeros((300, 300), np.uint8)
+    for q in quads[:200]:
+        cv2.fillPoly(ref, [q], 1)
+    img = torch.zeros((3, 300, 300), device=cuda)
+    m = torch.zeros((300, 300), dtype=torch.uint8, device=cuda)
+    ops.fill_polys(polys[:200].contiguous(), img=img, mask=m, value=255.0)
+    assert np.array_equal(m.cpu().numpy(), ref)
+    assert torch.equal(img.cpu(), torch.from_numpy(ref).float()[None].repeat(3, 1, 1) * 255)
+    # per-polygon bit-exactness over the whole set: draw each polygon into its own tile of a tall mask
+    tall = torch.zeros((300 * 64, 300), dtype=torch.uint8, device=cuda)
+    sub = np.stack(quads[200:264]).copy()
+    sub[:, :, 1] += (np.arange(64) * 300)[:, None]
+    ops.fill_polys(torch.from_numpy(sub).to(cuda), mask=tall)
+    ref = np.zeros((300 * 64, 300), np.uint8)
+    for q in sub:
+        cv2.fillPoly(ref, [q], 1)
+    assert np.array_equal(tall.cpu().numpy(), ref)
+
+
+def test_nms_rotated_vs_oracle(cuda):
+    from point_teacher_b200 import ops
+    g = torch.Generator().manual_seed(5)
+    n = 700
+    c = torch.rand(n, 2, generator=g) * 600 + 100
+    wh = (torch.randn(n, 2, generator=g) * 0.5 + 3.3).exp()
+    th = torch.rand(n, 1, generator=g) * np.pi - np.pi / 2
+    dets = torch.cat([c, wh, th], 1)
+    scores = torch.rand(n, generator=g)
+    scores[:100] = 1.0                                   # tied scores: stable order decides who suppresses whom
+    _, keep_ref = rotated.nms_rotated(dets, scores, 0.05)
+    order, keep = ops.nms_rotated(dets.to(cuda), scores.to(cuda), 0.05)
+    order, keep = order.cpu().long(), keep.cpu().bool()
+    assert torch.equal(order, torch.sort(scores, descending=True, stable=True).indices)
+    got = order[keep]
+    assert torch.equal(got, keep_ref), (got.shape, keep_ref.shape)
+
+
+def test_black_paper_against_reference_golden(cuda, golden_dir):
+    from point_teacher_b200 import masking
+    g = torch.load(os.path.join(golden_dir, "black_paper.pt"))
+    for c in g:
+        d = synth.mask_batch(c["seed"])
+        pattern, prior = masking.load_basic_shape(synth.SHAPE_LIST)
+        torch.manual_seed(c["seed"])
+        np.random.seed(c["seed"])
+        img = d["img"].to(cuda)
+        out_img, bb = masking.generate_black_paper(img, d["bb_occupied"], img, pattern, prior,
+                                                   range(int(len(pattern) / 2)), d["imgsize"])
+        assert out_img.data_ptr() == img.data_ptr()
+        assert torch.equal(bb.cpu(), c["kept"])               # NMS keep list + both filters: exact, in order
+        ref = torch.from_numpy(np.unpackbits(c["mask_bits"].numpy())[:800 * 800].reshape(800, 800)).bool()
+        got = (out_img == 255).all(0).cpu()
+        agree = (got == ref).float().mean().item()
+        # polygon corners go through sin / cos: the device rounds them once from double, the CPU reference uses its
+        # vector libm (<= 1 ulp); a corner sitting on an integer boundary may truncate differently
+        assert agree >= 0.9999, agree
+        untouched = ~got
+        assert torch.equal(out_img.cpu()[:, untouched], d["img"][:, untouched])
+
+
+def test_black_paper_polygons_and_fill_vs_oracle(cuda):
+    """Same candidate list through the oracle and the device tail: identical survivors; integer polygons equal up
+    to the sin / cos rounding; with the oracle's polygons the filled pixel set is bit-exact."""
+    from point_teacher_b200 import masking, ops
+    d = synth.mask_batch(7, n_gt=(80, 120))
+    pattern, prior = masking.load_basic_shape(synth.SHAPE_LIST)
+    torch.manual_seed(7)
+    np.random.seed(7)
+    allb = masking.sample_black_paper_candidates(d["bb_occupied"], prior, range(2), d["imgsize"])
+    _, bb_o, sel_o, polys_o, m_o = M.black_paper_from_candidates(d["img"].clone(), allb, d["imgsize"])
+    img = d["img"].to(cuda)
+    _, bb, dbg = masking.black_paper_from_candidates(img, allb.to(cuda), d["imgsize"], return_debug=True)
+    assert torch.equal(bb.cpu(), bb_o)
+    assert torch.equal(dbg["sel"].cpu().long(), sel_o)
+    pd = dbg["polys"].cpu().numpy()
+    assert pd.shape == polys_o.shape
+    assert np.abs(pd - polys_o).max() <= 1 and (pd != polys_o).mean() < 0.01
+    m = torch.zeros((800, 800), dtype=torch.uint8, device=cuda)
+    ops.fill_polys(torch.from_numpy(polys_o).to(cuda), mask=m)
+    assert np.array_equal(m.cpu().numpy(), m_o)
+    with pytest.raises(ValueError):
+        masking.generate_black_paper(d["img"], d["bb_occupied"], d["img"], pattern, prior, range(2), 800, candidates=allb)

@@ -201,3 +201,56 @@ def test_focal_loss_cost_docstring_shape_and_sign():
     c = assign.focal_loss_cost(x, lab)
     assert c.shape == (4, 3) and (c < 0).all()
     assert torch.equal(c, assign.focal_loss_table(x)[:, lab])
+
+
+def _random_quads(n, seed, size=300):
+    from oracle import mask as M
+    rng = np.random.default_rng(seed)
+    out = []
+    while len(out) < n:
+        cx, cy = rng.uniform(40, size - 40, 2)
+        w, h = rng.uniform(0.3, 80, 2)
+        a = rng.uniform(-np.pi / 2, np.pi / 2)
+        if len(out) % 10 == 0:
+            a = 0.0
+        if len(out) % 17 == 0:
+            a = float(np.pi / 2 * rng.integers(-1, 2))
+        p = M.obb2poly_le90(torch.tensor([[cx, cy, w, h, a]], dtype=torch.float32)).view(4, 2).numpy().astype(np.int32)
+        if p.min() >= 0 and p.max() < size:
+            out.append(p)
+    return out
+
+
+def test_fill_poly_replay_equals_cv2():
+    """The rasteriser restatement against the installed OpenCV (the reference calls cv2.fillPoly)."""
+    import cv2
+    from oracle import mask as M
+    for p in _random_quads(400, 3):
+        ref = np.zeros((300, 300), np.uint8)
+        cv2.fillPoly(ref, [p], 1)
+        got = np.zeros((300, 300), np.uint8)
+        M.fill_poly_replay(got, p)
+        assert np.array_equal(got, ref), p.tolist()
+
+
+def test_black_paper_oracle_reproduces_reference_golden(golden_dir):
+    from oracle import mask as M
+    from point_teacher_b200 import masking
+    g = torch.load(os.path.join(golden_dir, "black_paper.pt"))
+    for c in g:
+        d = synth.mask_batch(c["seed"])
+        pattern, prior = masking.load_basic_shape(synth.SHAPE_LIST)
+        dense = range(int(len(pattern) / 2))
+        torch.manual_seed(c["seed"])
+        np.random.seed(c["seed"])
+        allb = M.sample_candidates(d["bb_occupied"], prior, dense, d["imgsize"])
+        torch.manual_seed(c["seed"])
+        np.random.seed(c["seed"])
+        allb2 = masking.sample_black_paper_candidates(d["bb_occupied"], prior, dense, d["imgsize"])
+        assert torch.equal(allb, allb2)                       # the product's host-side draw == the oracle's
+        img, bb, sel, polys, m = M.black_paper_from_candidates(d["img"].clone(), allb, d["imgsize"])
+        assert torch.equal(bb, c["kept"])
+        assert np.array_equal(np.packbits(m.astype(bool)), c["mask_bits"].numpy())
+        assert int(m.sum()) == c["n_px"]
+        _, _, _, _, m2 = M.black_paper_from_candidates(d["img"].clone(), allb, d["imgsize"], use_cv2=False)
+        assert np.array_equal(m, m2)
