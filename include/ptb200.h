@@ -175,6 +175,37 @@ int pt_black_paper_select(const float* bb, int N, const int* order, const unsign
 int pt_fill_polys(const int* polys, const int* count, int max_polys, float* img, unsigned char* mask, int C, int H,
                   int W, float value, void* stream);
 
+/* ---- backward of the MIL head (training step; gradients all-reduced by point_teacher_b200/dist.py) -----------
+ * Autograd graph of fcos_head_p2b_ts.py:1147-1236 + delta_xywh_bbox_coder.py:144-250 + iou_loss.py:139-190,398-466.
+ * pt_fc_gemm_bf16_ex: pt_fc_gemm_bf16 with an optional bf16 mask [M, ldmask]: out = mask > 0 ? out : 0 (ReLU
+ *   backward by the saved forward activation), used for the dgrad GEMMs.
+ * pt_reg_loss_grad: g [K,4] = gscale[0] * scale * d loss_mil_bbox / d deltas (sums = the forward's loss sums).
+ * pt_bag_loss_grad: g [K + n_neg, 2C] = d loss_mil_bags / d (cls logits | ins logits), positives scaled by
+ *   gscale[0] * pos_scale, negatives by gscale[0] * neg_scale.
+ * pt_head_bwd: small heads (nout = 4 | 2C): dZ [M,D] bf16 = (g W) masked by H > 0, dW [nout,D] += g^T H, db += sum g.
+ * pt_transpose_pad_bf16: [R, C] -> [C, ldout >= R] zero padded (wgrad operands).
+ * pt_unpermute_dw1: fp32 [N, bins*C] bin-major FC1 weight gradient -> the parameter's c*bins + bin column order.
+ * pt_colsum_bf16: db [N] += column sums of bf16 [M, N].   pt_nhwc_to_nchw_f32: feature-gradient layout change.
+ * pt_roi_align_backward: mmcv RoIAlign backward (aligned avg pooling): dfeat NHWC fp32 (zeroed by the caller) +=
+ *   scatter of dA bf16 [K, ld] (bin-major columns). */
+int pt_fc_gemm_bf16_ex(const void* A, long long lda, const void* B, long long ldb, const float* bias, void* C,
+                       long long ldc, int M, int N, int K, int relu, int out_f32, const void* mask, long long ldmask,
+                       void* workspace, long long workspace_bytes, int num_sms, int allow_split, void* stream);
+int pt_reg_loss_grad(const float* deltas, const float* bag_rois, const unsigned char* valid, const float* ref_boxes,
+                     int U, int K, float max_w, float max_h, float wh_ratio_clip, float hyper, float eps,
+                     const float* sums, const float* gscale, float scale, float* g, void* stream);
+int pt_bag_loss_grad(const float* cls, const float* ins, const unsigned char* valid, const long long* labels, int G,
+                     int U1, int U2, int C, const unsigned char* neg_weight, int n_neg, const float* sums,
+                     const float* gscale, float pos_scale, float neg_scale, float* g, void* stream);
+int pt_head_bwd(const float* g, int nout, const void* H_bf16, long long ldh, int D, const float* W, int M,
+                void* dZ_bf16, long long ldz, float* dW, float* db, void* stream);
+int pt_transpose_pad_bf16(const void* in, long long ldin, int R, int C, void* out, long long ldout, void* stream);
+int pt_unpermute_dw1(const float* dw_binmajor, int N, int C, int bins, float* grad, int accumulate, void* stream);
+int pt_colsum_bf16(const void* dZ, long long ld, int M, int N, float* db, void* stream);
+int pt_nhwc_to_nchw_f32(const float* in, float* out, int B, int C, int H, int W, int accumulate, void* stream);
+int pt_roi_align_backward(const void* dA_bf16, long long ld, const float* rois, int K, int B, int C, int H, int W,
+                          float spatial_scale, int sampling_ratio, int aligned, float* dfeat, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -58,6 +58,20 @@ SIGNATURES = {
     "pt_black_paper_select": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_float, c_void_p, c_void_p, c_void_p,
                                       c_void_p, c_void_p]),
     "pt_fill_polys": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_int, c_int, c_int, c_float, c_void_p]),
+    "pt_fc_gemm_bf16_ex": (c_int, [c_void_p, c_ll, c_void_p, c_ll, c_void_p, c_void_p, c_ll, c_int, c_int, c_int, c_int,
+                                   c_int, c_void_p, c_ll, c_void_p, c_ll, c_int, c_int, c_void_p]),
+    "pt_reg_loss_grad": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_float, c_float, c_float,
+                                 c_float, c_float, c_void_p, c_void_p, c_float, c_void_p, c_void_p]),
+    "pt_bag_loss_grad": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_int,
+                                 c_void_p, c_void_p, c_float, c_float, c_void_p, c_void_p]),
+    "pt_head_bwd": (c_int, [c_void_p, c_int, c_void_p, c_ll, c_int, c_void_p, c_int, c_void_p, c_ll, c_void_p, c_void_p,
+                            c_void_p]),
+    "pt_transpose_pad_bf16": (c_int, [c_void_p, c_ll, c_int, c_int, c_void_p, c_ll, c_void_p]),
+    "pt_unpermute_dw1": (c_int, [c_void_p, c_int, c_int, c_int, c_void_p, c_int, c_void_p]),
+    "pt_colsum_bf16": (c_int, [c_void_p, c_ll, c_int, c_int, c_void_p, c_void_p]),
+    "pt_nhwc_to_nchw_f32": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p]),
+    "pt_roi_align_backward": (c_int, [c_void_p, c_ll, c_void_p, c_int, c_int, c_int, c_int, c_int, c_float, c_int, c_int,
+                                      c_void_p, c_void_p]),
     "pt_aligned_iou_mean": (c_int, [c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p]),
 }
 

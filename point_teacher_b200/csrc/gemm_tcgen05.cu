@@ -34,6 +34,8 @@ struct Params {
   int* counters;      // [tail_tiles], zero on entry / exit
   int M, N, K, ldc;
   int relu, out_f32;
+  const __nv_bfloat16* mask;  // optional [M, ldmask]: out = mask > 0 ? out : 0 (ReLU backward by the forward activation)
+  int ldmask;
   int tiles_n, tiles_total, split;  // split = S (>=2) when the tail wave is K-split, else 0
   int full_rounds;
 };
@@ -102,6 +104,20 @@ __device__ __forceinline__ void store_chunk(const Params& p, int row, int col0, 
     for (int j = 0; j < 32; j++) v[j] = fmaxf(v[j], 0.f);
   }
   if (!row_ok) return;
+  if (p.mask != nullptr) {
+    const uint4* m4 = reinterpret_cast<const uint4*>(p.mask + (size_t)row * p.ldmask + col0);
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+      const uint4 m = __ldg(m4 + j);
+      const uint32_t w[4] = {m.x, m.y, m.z, m.w};
+#pragma unroll
+      for (int q = 0; q < 4; q++) {
+        // bf16 > 0  <=>  sign bit clear and magnitude non-zero
+        if (!((w[q] & 0x7fffu) != 0 && (w[q] & 0x8000u) == 0)) v[8 * j + 2 * q] = 0.f;
+        if (!((w[q] & 0x7fff0000u) != 0 && (w[q] & 0x80000000u) == 0)) v[8 * j + 2 * q + 1] = 0.f;
+      }
+    }
+  }
   if (p.out_f32) {
     float4* dst = reinterpret_cast<float4*>(reinterpret_cast<float*>(p.C) + (size_t)row * p.ldc + col0);
 #pragma unroll
@@ -306,10 +322,27 @@ extern "C" long long pt_fc_gemm_workspace_bytes(int num_sms) {
   return tiles * ((long long)gemm::BM * gemm::BN * 4) + tiles * 4 + 256;
 }
 
+extern "C" int pt_fc_gemm_bf16_ex(const void* A, long long lda, const void* B, long long ldb, const float* bias,
+                                  void* C, long long ldc, int M, int N, int K, int relu, int out_f32, const void* mask,
+                                  long long ldmask, void* workspace, long long workspace_bytes, int num_sms,
+                                  int allow_split, void* stream);
+
 extern "C" int pt_fc_gemm_bf16(const void* A, long long lda, const void* B, long long ldb, const float* bias,
                                void* C, long long ldc, int M, int N, int K, int relu, int out_f32, void* workspace,
                                long long workspace_bytes, int num_sms, int allow_split, void* stream) {
+  return pt_fc_gemm_bf16_ex(A, lda, B, ldb, bias, C, ldc, M, N, K, relu, out_f32, nullptr, 0, workspace, workspace_bytes,
+                            num_sms, allow_split, stream);
+}
+
+extern "C" int pt_fc_gemm_bf16_ex(const void* A, long long lda, const void* B, long long ldb, const float* bias,
+                                  void* C, long long ldc, int M, int N, int K, int relu, int out_f32, const void* mask,
+                                  long long ldmask, void* workspace, long long workspace_bytes, int num_sms,
+                                  int allow_split, void* stream) {
   using namespace gemm;
+  if (mask != nullptr && (((uintptr_t)mask & 15) || (ldmask % 8))) {
+    set_error("pt_fc_gemm_bf16_ex: mask must be 16-byte aligned with ldmask a multiple of 8");
+    return PT_ERR_ARG;
+  }
   if (M <= 0) return PT_OK;
   if (N % BN != 0 || K % BK != 0 || K <= 0) {
     set_error("pt_fc_gemm_bf16: N must be a multiple of %d and K of %d (got N=%d K=%d)", BN, BK, N, K);
@@ -331,6 +364,7 @@ extern "C" int pt_fc_gemm_bf16(const void* A, long long lda, const void* B, long
   if (rc != PT_OK) return rc;
 
   Params p;
+  p.mask = reinterpret_cast<const __nv_bfloat16*>(mask); p.ldmask = (int)ldmask;
   p.bias = bias; p.C = C; p.M = M; p.N = N; p.K = K; p.ldc = (int)ldc; p.relu = relu; p.out_f32 = out_f32;
   p.tiles_n = N / BN;
   const int tiles_m = (M + BM - 1) / BM;

@@ -79,12 +79,17 @@ class MILHeadMixin:
             hit = self._wcache[key]
         return hit[1]
 
-    def _fc_stack(self, A, fcs, M):
+    def _fc_stack(self, A, fcs, M, keep=None):
         w1, w2 = self._weight(fcs[0], True), self._weight(fcs[1], False)
         b1, b2 = fcs[0].bias.detach(), fcs[1].bias.detach()
         if not self._x3():
             h1 = ops.fc_gemm(A, w1, b1, relu=True, out_dtype=torch.bfloat16, M=M)
-            return ops.fc_gemm(h1, w2, b2, relu=True, out_dtype=torch.bfloat16, M=M)
+            h2 = ops.fc_gemm(h1, w2, b2, relu=True, out_dtype=torch.bfloat16, M=M)
+            if keep is not None:                      # training: the backward needs both activations and operands
+                keep.update(A=A, H1=h1, H2=h2, W1=w1, W2=w2, M=M)
+            return h2
+        if keep is not None:
+            raise NotImplementedError("the backward runs in bf16 precision (precision='bf16')")
         h1 = ops.fc_gemm(A, w1, b1, relu=True, out_dtype=torch.float32, M=M)
         return ops.fc_gemm(ops.split_bf16x3(h1), w2, b2, relu=True, out_dtype=torch.float32, M=M)
 
@@ -213,7 +218,7 @@ class MILHeadMixin:
         return losses, tuple(torch.split(merged, per_img))
 
     def mil_stage_packed(self, x, img_metas, img_wh, base_rois, U1, ref, real, neg_boxes, neg_img_idx, bag_offsets,
-                         labels, pseudo, cfg, stage, loss_scales=(1.0, 1.0)):
+                         labels, pseudo, cfg, stage, loss_scales=(1.0, 1.0), keep=None):
         """One MIL stage on packed tensors (the fast path behind ``phase2_refine``): no per-image lists, no
         replicated reference/real boxes (instance k belongs to GT k // (U1*U2)), negatives appended to the
         classification pass.  base_rois (G*U1,5|6); ref/real/pseudo (G,4|5); labels (G,) int64;
@@ -226,8 +231,10 @@ class MILHeadMixin:
         K, G = ebags.shape[0], pseudo.shape[0]
         U2 = K // max(base_rois.shape[0], 1)
         sums = torch.zeros((8,), dtype=torch.float32, device=dev)
+        kreg = {} if keep is not None else None
+        kbag = {} if keep is not None else None
         A = self._roi_operand(x, ebags)
-        H = self._fc_stack(A, self.shared_fcs_reg[stage], K)
+        H = self._fc_stack(A, self.shared_fcs_reg[stage], K, kreg)
         n_neg = 0 if neg_boxes is None else neg_boxes.shape[0]
         rois2 = torch.empty((K + n_neg, rs), dtype=torch.float32, device=dev)
         neg_w = None
@@ -236,12 +243,12 @@ class MILHeadMixin:
             neg_w = ops.neg_weight(rois2[K:], base_rois, bag_offsets, rot)
         h0, w0, _ = img_metas[0]["img_shape"]
         fr = self.fc_reg[stage]
-        _, _, iou_t = ops.reg_decode(H, fr.weight.detach(), fr.bias.detach(), ebags, evalid, ref, real, U1 * U2,
-                                     (w0, h0), sums, K=K, hyper=self.loss_bbox_denosing_hyper, out_rois=rois2,
-                                     rotated=rot)
+        _, deltas, iou_t = ops.reg_decode(H, fr.weight.detach(), fr.bias.detach(), ebags, evalid, ref, real, U1 * U2,
+                                          (w0, h0), sums, K=K, hyper=self.loss_bbox_denosing_hyper, out_rois=rois2,
+                                          rotated=rot, want_deltas=keep is not None)
         del A, H
         A2 = self._roi_operand(x, rois2)
-        H2 = self._fc_stack(A2, self.shared_fcs_bag[stage], K + n_neg)
+        H2 = self._fc_stack(A2, self.shared_fcs_bag[stage], K + n_neg, kbag)
         fc, fi = self.fc_cls[stage], self.fc_ins[stage]
         cls, ins = ops.cls_ins_heads(H2, fc.weight.detach(), fc.bias.detach(), fi.weight.detach(),
                                      fi.bias.detach(), M=K + n_neg)
@@ -253,6 +260,13 @@ class MILHeadMixin:
                                   self.bag_loss_neg_scale)
         losses = {f"stage{stage}_loss_mil_bbox": out[0], f"stage{stage}_loss_mil_bags": out[1],
                   f"stage{stage}_coarse_bags_iou": out[2], f"stage{stage}_refine_bags_iou": out[3]}
+        self.last_losses = losses
+        if keep is not None:
+            if rot:
+                raise NotImplementedError("the backward is built for the HBB head")
+            keep.update(reg=kreg, bag=kbag, deltas=deltas, ebags=ebags, evalid=evalid, ref=ref, rois2=rois2, cls=cls,
+                        ins=ins, neg_w=neg_w, n_neg=n_neg, labels=labels, sums=sums, K=K, G=G, U1=U1, U2=U2,
+                        max_wh=(w0, h0), stage=stage, loss_scales=loss_scales)
         self.last_results = dict(
             cls_score=cls[:K].view(G, U1, U2, -1), ins_score=ins[:K].view(G, U1, U2, -1),
             neg_cls_score=cls[K:] if n_neg else None, neg_weight=neg_w, iou_target=iou_t,

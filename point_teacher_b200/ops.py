@@ -475,3 +475,101 @@ def fill_polys(polys, img=None, mask=None, value=255.0, count=None):
         C, (H, W) = (C if img is not None else 0), mask.shape
     _lib.call("pt_fill_polys", _p(polys), _p(count), polys.shape[0], _p(img), _p(mask), C, H, W, float(value),
               _stream())
+
+
+# ------------------------------------------------------------------------------ backward of the MIL head
+def fc_gemm_masked(A, B, mask, out_dtype=_bf16, M=None, allow_split=True):
+    """C = (A @ B^T) * (mask > 0): dgrad through a ReLU layer, mask = the saved bf16 forward activation."""
+    _chk(A, "A", _bf16, 2)
+    _chk(B, "B", _bf16, 2)
+    _chk(mask, "mask", _bf16, 2)
+    M = A.shape[0] if M is None else M
+    N, K = B.shape
+    if A.shape[1] != K or mask.shape[1] != N or mask.shape[0] < M:
+        raise ValueError("fc_gemm_masked: shape mismatch")
+    out = torch.empty((A.shape[0], N), dtype=out_dtype, device=A.device)
+    ws = gemm_workspace(A.device)
+    _lib.call("pt_fc_gemm_bf16_ex", _p(A), A.shape[1], _p(B), B.shape[1], _p(None), _p(out), out.shape[1], M, N, K, 0,
+              int(out.dtype == _f32), _p(mask), mask.shape[1], _p(ws), ws.numel(), num_sms(), int(allow_split), _stream())
+    return out
+
+
+def reg_loss_grad(deltas, bag_rois, valid, ref_boxes, U, max_wh, sums, gscale, scale, hyper=0.2, eps=1e-6,
+                  wh_ratio_clip=16 / 1000):
+    _chk(deltas, "deltas", _f32, 2, 4)
+    _chk(bag_rois, "bag_rois", _f32, 2, 5)
+    K = deltas.shape[0]
+    g = torch.empty((K, 4), dtype=_f32, device=deltas.device)
+    _lib.call("pt_reg_loss_grad", _p(deltas), _p(bag_rois), _p(valid), _p(ref_boxes), int(U), K, float(max_wh[0]),
+              float(max_wh[1]), float(wh_ratio_clip), float(hyper), float(eps), _p(sums), _p(gscale), float(scale), _p(g),
+              _stream())
+    return g
+
+
+def bag_loss_grad(cls, ins, valid, labels, G, U1, U2, neg_weight, n_neg, sums, gscale, pos_scale, neg_scale):
+    _chk(cls, "cls", _f32, 2)
+    _chk(ins, "ins", _f32, 2)
+    C = cls.shape[1]
+    M = G * U1 * U2 + n_neg
+    if cls.shape[0] < M:
+        raise ValueError("cls has fewer rows than bags + negatives")
+    g = torch.zeros((M, 2 * C), dtype=_f32, device=cls.device)
+    _lib.call("pt_bag_loss_grad", _p(cls), _p(ins), _p(valid), _p(labels), G, U1, U2, C, _p(neg_weight), int(n_neg),
+              _p(sums), _p(gscale), float(pos_scale), float(neg_scale), _p(g), _stream())
+    return g
+
+
+def head_bwd(g, H, W, dW, db, M=None):
+    """g [M,nout] fp32, H [M,D] bf16, W [nout,D] fp32 -> dZ [M,D] bf16; dW / db accumulated in place."""
+    _chk(g, "g", _f32, 2)
+    _chk(H, "hidden", _bf16, 2)
+    _chk(W, "weight", _f32, 2)
+    M = g.shape[0] if M is None else M
+    dZ = torch.empty((H.shape[0], H.shape[1]), dtype=_bf16, device=H.device)
+    _lib.call("pt_head_bwd", _p(g), g.shape[1], _p(H), H.shape[1], H.shape[1], _p(W), M, _p(dZ), dZ.shape[1], _p(dW),
+              _p(db), _stream())
+    return dZ
+
+
+def transpose_pad(x, rows=None, pad_to=64):
+    """bf16 [R, C] -> [C, Rp] with Rp = R rounded up to ``pad_to``, zero padded."""
+    _chk(x, "x", _bf16, 2)
+    R = x.shape[0] if rows is None else rows
+    Rp = (R + pad_to - 1) // pad_to * pad_to
+    out = torch.empty((x.shape[1], Rp), dtype=_bf16, device=x.device)
+    _lib.call("pt_transpose_pad_bf16", _p(x), x.shape[1], R, x.shape[1], _p(out), Rp, _stream())
+    return out
+
+
+def unpermute_dw1(dw_binmajor, C, bins, grad, accumulate):
+    _chk(dw_binmajor, "dW1", _f32, 2)
+    _lib.call("pt_unpermute_dw1", _p(dw_binmajor), dw_binmajor.shape[0], C, bins, _p(grad), int(accumulate), _stream())
+    return grad
+
+
+def colsum_bf16(dZ, db, M=None):
+    _chk(dZ, "dZ", _bf16, 2)
+    _lib.call("pt_colsum_bf16", _p(dZ), dZ.shape[1], dZ.shape[0] if M is None else M, dZ.shape[1], _p(db), _stream())
+    return db
+
+
+def nhwc_to_nchw_f32(x, out=None, accumulate=False):
+    _chk(x, "x", _f32, 4)
+    B, H, W, C = x.shape
+    if out is None:
+        out = torch.empty((B, C, H, W), dtype=_f32, device=x.device)
+    _lib.call("pt_nhwc_to_nchw_f32", _p(x), _p(out), B, C, H, W, int(accumulate), _stream())
+    return out
+
+
+def roi_align_backward(dA, rois, feat_shape_nhwc, spatial_scale, sampling_ratio=0, aligned=True, dfeat=None, K=None):
+    """dA bf16 [K, 49*C] bin-major -> dfeat NHWC fp32 (accumulated into ``dfeat`` when given, else zero-initialised)."""
+    _chk(dA, "dA", _bf16, 2)
+    _chk(rois, "rois", _f32, 2, 5)
+    B, H, W, C = feat_shape_nhwc
+    if dfeat is None:
+        dfeat = torch.zeros((B, H, W, C), dtype=_f32, device=dA.device)
+    K = rois.shape[0] if K is None else K
+    _lib.call("pt_roi_align_backward", _p(dA), dA.shape[1], _p(rois), K, B, C, H, W, float(spatial_scale),
+              int(sampling_ratio), int(aligned), _p(dfeat), _stream())
+    return dfeat

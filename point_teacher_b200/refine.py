@@ -15,7 +15,7 @@ from .proposals import (MIL_gen_proposals_from_cfg, const_tensor, gen_negative_p
 
 def phase2_refine(head, x_ori, img_metas, pseudo_bboxes, pseudo_points, pseudo_labels, gt_bboxes,
                   fine_proposal_cfg, fine_proposal_extensive_cfg, num_stages=1, num_training_burninstep2=100,
-                  alpha=(0.01, 0.25), neg_boxes=None):
+                  alpha=(0.01, 0.25), neg_boxes=None, train=False):
     """Returns (refined_pseudo_bboxes, refined_pseudo_points, losses) like the reference method.
     ``neg_boxes[stage][img]`` optionally injects the negative boxes the reference samples on the CPU.
 
@@ -49,9 +49,15 @@ def phase2_refine(head, x_ori, img_metas, pseudo_bboxes, pseudo_points, pseudo_l
             for c in counts:
                 o.append(o[-1] + c * U1)
             offs = const_tensor(o, torch.int32, dev)
-        pb_new, pts, mil_loss = head.mil_stage_packed(x_ori, img_metas, img_wh, base_rois, U1, pb, gb, negs, neg_idx,
-                                                      offs, labels, pb, fine_proposal_extensive_cfg[stage], stage,
-                                                      loss_scales=alpha)
+        if train:      # the two MIL losses carry a grad_fn (feature map + head parameters), see train.py
+            from .train import mil_stage_train
+            pb_new, pts, mil_loss = mil_stage_train(head, x_ori, img_metas, img_wh, base_rois, U1, pb, gb, negs, neg_idx,
+                                                    offs, labels, pb, fine_proposal_extensive_cfg[stage], stage,
+                                                    loss_scales=alpha)
+        else:
+            pb_new, pts, mil_loss = head.mil_stage_packed(x_ori, img_metas, img_wh, base_rois, U1, pb, gb, negs, neg_idx,
+                                                          offs, labels, pb, fine_proposal_extensive_cfg[stage], stage,
+                                                          loss_scales=alpha)
         pb = pb_new
         losses[f"stage{stage}_refine_bboxes_iou"] = ops.aligned_iou_mean(pb, gb, rot)
         losses.update(mil_loss)

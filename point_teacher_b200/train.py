@@ -1,0 +1,121 @@
+"""Training step of the MIL head: forward (``MILHeadMixin.mil_stage_packed``) + hand-written backward, exposed as a
+``torch.autograd.Function`` so that the reference's ``loss.backward()`` flow keeps working
+(HBB_TOD/mmdet/models/detectors/fcos_p2b_teacher_student.py:425-466 returns the loss dict that
+``BaseDetector._parse_losses`` sums and back-propagates; HBB_TOD/mmdet/models/dense_heads/fcos_head_p2b_ts.py:1318-1344).
+
+Differentiable outputs: ``stage{s}_loss_mil_bbox`` and ``stage{s}_loss_mil_bags``.  Differentiable inputs: the
+feature map (gradient returned in NCHW fp32, through RoIAlign backward) and the 14 parameter tensors of the stage
+(``shared_fcs_reg.{s}.{0,1}``, ``shared_fcs_bag.{s}.{0,1}``, ``fc_reg.{s}``, ``fc_cls.{s}``, ``fc_ins.{s}``).  The
+refined boxes are detached exactly where the reference detaches them (``pred.clone().detach()`` :1212; scores
+``.detach()`` :1126-1127), so no gradient flows through box coordinates.
+
+The big contractions run on the tcgen05 GEMM: dgrad = GEMM against a transposed bf16 weight copy with the ReLU mask
+fused in the epilogue; wgrad = GEMM over transposed (row-padded) copies of the activation gradient and the layer
+input.  bf16 operands, fp32 accumulation, fp32 parameter gradients."""
+import torch
+
+from . import ops
+
+
+def stage_params(head, stage):
+    fr, fb = head.shared_fcs_reg[stage], head.shared_fcs_bag[stage]
+    mods = [fr[0], fr[1], fb[0], fb[1], head.fc_reg[stage], head.fc_cls[stage], head.fc_ins[stage]]
+    return [t for m in mods for t in (m.weight, m.bias)]
+
+
+def _fc_branch_backward(head, k, dZ2, need_dA):
+    """k: what ``_fc_stack`` kept (A, H1, H2, W1 (bin-major bf16), W2 (bf16), M).  dZ2 bf16 [rows, 1024] = gradient
+    at the pre-activation of the second FC (already ReLU-masked).  Returns (dW1 in the parameter's column order, db1,
+    dW2, db2, dA | None)."""
+    M, dev = k["M"], dZ2.device
+    N1 = k["W1"].shape[0]
+    w2t = ops.transpose_pad(k["W2"])                                   # [in, out]: dgrad operand
+    dZ1 = ops.fc_gemm_masked(dZ2, w2t, k["H1"], M=M)                   # (dZ2 @ W2) * (H1 > 0)
+    dZ2t, H1t = ops.transpose_pad(dZ2, rows=M), ops.transpose_pad(k["H1"], rows=M)
+    dW2 = ops.fc_gemm(dZ2t, H1t, None, relu=False, out_dtype=torch.float32)
+    db2 = ops.colsum_bf16(dZ2, torch.zeros((dZ2.shape[1],), dtype=torch.float32, device=dev), M=M)
+    dZ1t, At = ops.transpose_pad(dZ1, rows=M), ops.transpose_pad(k["A"], rows=M)
+    dW1p = ops.fc_gemm(dZ1t, At, None, relu=False, out_dtype=torch.float32)      # [N1, 49*C] bin-major columns
+    del At
+    dW1 = torch.empty_like(dW1p)
+    ops.unpermute_dw1(dW1p, head.in_channels, head.roi_feat_area, dW1, accumulate=False)
+    db1 = ops.colsum_bf16(dZ1, torch.zeros((N1,), dtype=torch.float32, device=dev), M=M)
+    dA = None
+    if need_dA:
+        w1t = ops.transpose_pad(k["W1"])                               # [49*C, N1]
+        dA = ops.fc_gemm(dZ1, w1t, None, relu=False, out_dtype=torch.bfloat16, M=M)
+    return dW1, db1, dW2, db2, dA
+
+
+def mil_stage_backward(head, keep, x, g_bbox, g_bags, need_feat_grad=True):
+    """Gradients of (g_bbox * loss_mil_bbox + g_bags * loss_mil_bags) for one stage.  g_* are 1-element fp32 CUDA
+    tensors (no host read).  Returns (dfeat NCHW fp32 | None, [14 parameter gradients in ``stage_params`` order])."""
+    stage, dev = keep["stage"], keep["cls"].device
+    K, G, U1, U2, n_neg = keep["K"], keep["G"], keep["U1"], keep["U2"], keep["n_neg"]
+    s_bbox, s_bags = keep["loss_scales"]
+    fr, fc, fi = head.fc_reg[stage], head.fc_cls[stage], head.fc_ins[stage]
+    C = fc.weight.shape[0]
+    layer = head.bbox_roi_extractor.roi_layers[0]
+    # ---- regression branch: DN-DIoU -> delta2bbox -> fc_reg -> FC2 -> FC1 -> RoIAlign
+    g4 = ops.reg_loss_grad(keep["deltas"], keep["ebags"], keep["evalid"], keep["ref"], U1 * U2, keep["max_wh"],
+                           keep["sums"], g_bbox, s_bbox, hyper=head.loss_bbox_denosing_hyper)
+    dWreg, dbreg = torch.zeros_like(fr.weight), torch.zeros_like(fr.bias)
+    dZ2 = ops.head_bwd(g4, keep["reg"]["H2"], fr.weight.detach(), dWreg, dbreg, M=K)
+    r = _fc_branch_backward(head, keep["reg"], dZ2, need_feat_grad)
+    # ---- bag branch: gfocal -> bag score -> (sigmoid, softmax x valid x L1) -> fc_cls / fc_ins -> FC2 -> FC1
+    g16 = ops.bag_loss_grad(keep["cls"], keep["ins"], keep["evalid"], keep["labels"], G, U1, U2, keep["neg_w"], n_neg,
+                            keep["sums"], g_bags, s_bags * head.bag_loss_pos_scale, s_bags * head.bag_loss_neg_scale)
+    Wci = torch.cat([fc.weight.detach(), fi.weight.detach()], 0).contiguous()
+    dWci, dbci = torch.zeros_like(Wci), torch.zeros((2 * C,), dtype=torch.float32, device=dev)
+    dZ2b = ops.head_bwd(g16, keep["bag"]["H2"], Wci, dWci, dbci, M=K + n_neg)
+    b = _fc_branch_backward(head, keep["bag"], dZ2b, need_feat_grad)
+    dfeat = None
+    if need_feat_grad:
+        Bn, _, H, W = x.shape
+        shape = (Bn, H, W, x.shape[1])
+        dn = ops.roi_align_backward(r[4], keep["ebags"], shape, layer.spatial_scale, layer.sampling_ratio, layer.aligned, K=K)
+        ops.roi_align_backward(b[4], keep["rois2"], shape, layer.spatial_scale, layer.sampling_ratio, layer.aligned,
+                               dfeat=dn, K=K + n_neg)
+        dfeat = ops.nhwc_to_nchw_f32(dn)
+    grads = [r[0], r[1], r[2], r[3], b[0], b[1], b[2], b[3], dWreg, dbreg, dWci[:C], dbci[:C], dWci[C:], dbci[C:]]
+    return dfeat, grads
+
+
+class _MILStageFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, feat, head, args, *params):
+        keep = {}
+        with torch.no_grad():
+            merged, pts, losses = head.mil_stage_packed((feat,), *args, keep=keep)
+        ctx.head, ctx.keep, ctx.feat_needs = head, keep, feat.requires_grad
+        ctx.save_for_backward(feat)
+        s = keep["stage"]
+        ctx.mark_non_differentiable(merged, pts)
+        return losses[f"stage{s}_loss_mil_bbox"].reshape(()), losses[f"stage{s}_loss_mil_bags"].reshape(()), merged, pts
+
+    @staticmethod
+    def backward(ctx, g_bbox, g_bags, _gm, _gp):
+        (feat,) = ctx.saved_tensors
+        dev = feat.device
+        one = lambda g: (torch.zeros((1,), dtype=torch.float32, device=dev) if g is None  # noqa: E731
+                         else g.detach().float().reshape(1).contiguous())
+        dfeat, grads = mil_stage_backward(ctx.head, ctx.keep, feat, one(g_bbox), one(g_bags), ctx.feat_needs)
+        ctx.keep = None
+        return (dfeat, None, None, *grads)
+
+
+def mil_stage_train(head, x, img_metas, img_wh, base_rois, U1, ref, real, neg_boxes, neg_img_idx, bag_offsets, labels,
+                    pseudo, cfg, stage, loss_scales=(1.0, 1.0)):
+    """Differentiable twin of ``mil_stage_packed``: same arguments and return value, but the two loss entries carry a
+    ``grad_fn`` (feature map + the stage's parameters)."""
+    if getattr(head, "precision", "bf16") != "bf16":
+        raise NotImplementedError("the backward runs in bf16 precision")
+    if len(x[:head.bbox_roi_extractor.num_inputs]) != 1:
+        raise NotImplementedError("single feature level (both shipped configs)")
+    head._wcache.clear()                               # parameters change every iteration
+    args = (img_metas, img_wh, base_rois, U1, ref, real, neg_boxes, neg_img_idx, bag_offsets, labels, pseudo, cfg, stage,
+            loss_scales)
+    lb, lg, merged, pts = _MILStageFn.apply(x[0], head, args, *stage_params(head, stage))
+    losses = dict(head.last_losses)                    # detached logs (bag IoUs) + the two differentiable losses
+    losses[f"stage{stage}_loss_mil_bbox"], losses[f"stage{stage}_loss_mil_bags"] = lb, lg
+    return merged, pts, losses
