@@ -281,11 +281,35 @@ def run_ours(args):
                   "traffic": _traffic("roi_align_mma_kernel@96000")}
         del outs, fs
 
+    # ---- training step: forward + hand-written backward + ONE all-reduce of the MIL-head gradients (NCCL over
+    #      NVLink when N > 1).  Eager launches (the all-reduce is not graph-captured); reported beside the headline.
+    train_ms = float("nan")
+    if not args.no_train:
+        from point_teacher_b200.train import Phase2Trainer
+        trainer = Phase2Trainer(head, synth.HBB_FINE_CFG, synth.HBB_EXT_CFG, num_stages=1, cap=100)
+        xin = inputs["feat"].clone().requires_grad_(True)
+        targs = (d["img_metas"], inputs["pseudo_boxes"], inputs["pseudo_points"], inputs["pseudo_labels"], inputs["gt_boxes"])
+        for _ in range(3):
+            xin.grad = None
+            trainer.step((xin,), *targs, neg_boxes=inputs["neg_boxes"], reduce_logs=False)
+        barrier()
+        n_train = max(min(args.steps // 4, 50), 5)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(n_train):
+            xin.grad = None
+            trainer.step((xin,), *targs, neg_boxes=inputs["neg_boxes"], reduce_logs=False)
+        e1.record()
+        barrier()
+        train_ms = e0.elapsed_time(e1) / n_train
+        gnorm = float(torch.sqrt(sum((p.grad.float() ** 2).sum() for _, p in trainer.bucket.named)))
+        assert gnorm == gnorm and gnorm > 0
+
     # max over ranks
     if world > 1:
-        t = torch.tensor([dev_ms, e2e_ms], device=dev)
+        t = torch.tensor([dev_ms, e2e_ms, train_ms], device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        dev_ms, e2e_ms = t.tolist()
+        dev_ms, e2e_ms, train_ms = t.tolist()
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
@@ -339,6 +363,10 @@ def run_ours(args):
                                    "bound": "hbm", "achieved": roi_gbs, "peak": hbm_peak, "unit": "GB/s",
                                    "frac": roi_gbs / hbm_peak, "avg_launch_ms": roi_ms, "algorithmic_bytes": roi_bytes,
                                    "traffic": _traffic("roi_align_mma_kernel@5000"), "stress_96k_rois": stress},
+            "train_step": None if args.no_train else {
+                "ms_per_step": train_ms, "imgs_per_s": total_imgs / (train_ms * 1e-3), "launch": "eager",
+                "what": "forward + backward (head parameter grads + feature-map grad) + one flat-bucket all-reduce "
+                        "(average) of the 27.8 M MIL-head gradients" + (" over NCCL" if world > 1 else " (single rank: no-op)")},
             "cpu_baseline": cpu,
         }
         print(json.dumps(line))
@@ -356,6 +384,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="eager launches (for ncu passes)")
     ap.add_argument("--no-stress", action="store_true", help="skip the 96k-RoI RoIAlign roofline measurement")
+    ap.add_argument("--no-train", action="store_true", help="skip the training-step (fwd+bwd+all-reduce) measurement")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -119,3 +119,32 @@ def mil_stage_train(head, x, img_metas, img_wh, base_rois, U1, ref, real, neg_bo
     losses = dict(head.last_losses)                    # detached logs (bag IoUs) + the two differentiable losses
     losses[f"stage{stage}_loss_mil_bbox"], losses[f"stage{stage}_loss_mil_bags"] = lb, lg
     return merged, pts, losses
+
+
+class Phase2Trainer:
+    """One data-parallel training step of the phase-2 MIL path: forward + backward on this rank's images, then ONE
+    flat-bucket all-reduce (average) of the MIL-head gradients over NCCL / NVLink (``dist.MILGradBucket``), and the
+    rank-mean of the logged scalars -- the only two exchange steps of the path.  Loss
+    denominators stay per rank, as under the reference's DDP."""
+
+    def __init__(self, head, fine_cfg, ext_cfg, num_stages=1, cap=100, alpha=(0.01, 0.25)):
+        from .dist import MILGradBucket
+        self.head, self.kw = head, dict(fine_proposal_cfg=fine_cfg, fine_proposal_extensive_cfg=ext_cfg,
+                                        num_stages=num_stages, num_training_burninstep2=cap, alpha=alpha)
+        self.bucket = MILGradBucket(head)
+
+    def step(self, x, img_metas, pseudo_bboxes, pseudo_points, pseudo_labels, gt_bboxes, neg_boxes=None,
+             reduce_logs=True):
+        """x: tuple with the (B,C,H,W) fp32 feature map (``requires_grad`` decides whether its gradient is produced).
+        Returns (refined boxes, refined points, losses dict); parameter gradients are left in ``param.grad``
+        (already averaged over ranks), the feature gradient in ``x[0].grad``."""
+        from .dist import reduce_mean_losses
+        from .refine import phase2_refine
+        for _, p in self.bucket.named:
+            p.grad = None
+        boxes, pts, losses = phase2_refine(self.head, x, img_metas, pseudo_bboxes, pseudo_points, pseudo_labels,
+                                           gt_bboxes, neg_boxes=neg_boxes, train=True, **self.kw)
+        total = sum(v for k, v in losses.items() if "loss" in k)       # BaseDetector._parse_losses
+        total.backward()
+        self.bucket.all_reduce_()
+        return boxes, pts, (reduce_mean_losses(losses) if reduce_logs else losses)

@@ -172,3 +172,40 @@ def test_training_step_gradients_vs_oracle(cuda, seed, alpha):
     close(x.grad, feat.grad, "feature map")
     for a, b in zip(gb, ob):                               # the forward results are unchanged by train=True
         assert _rel(a.detach(), b) < 2e-2
+
+
+def test_phase2_trainer_single_process(cuda):
+    """Trainer step == plain backward when there is one rank; two stages chain through detached boxes."""
+    from point_teacher_b200.mil_head import MILHead
+    from point_teacher_b200.refine import phase2_refine
+    from point_teacher_b200.train import Phase2Trainer
+    d = synth.hbb_batch(seed=5, num_stages=2, **SMALL)
+    torch.manual_seed(0)
+    head = MILHead(num_classes=8, num_stages=2, top_k=3, precision="bf16").to(cuda)
+    to = lambda l: [t.to(cuda) for t in l]  # noqa: E731
+    args = (d["img_metas"], to(d["pseudo_boxes"]), to(d["pseudo_points"]), to(d["pseudo_labels"]), to(d["gt_boxes"]))
+    negs = [to(n) for n in d["neg_boxes"]]
+    x = d["feat"].to(cuda).requires_grad_(True)
+    tr = Phase2Trainer(head, synth.HBB_FINE_CFG, synth.HBB_EXT_CFG, num_stages=2)
+    boxes, pts, losses = tr.step((x,), *args, neg_boxes=negs)
+    g1 = {n: p.grad.clone() for n, p in head.named_parameters() if p.grad is not None}
+    gx1 = x.grad.clone()
+    assert set(k.split(".")[0] for k in g1) == {"shared_fcs_reg", "shared_fcs_bag", "fc_cls", "fc_ins", "fc_reg"}
+    assert all(k.split(".")[1] in ("0", "1") for k in g1) and len(g1) == 28          # both stages got gradients
+    for p in head.parameters():
+        p.grad = None
+    x.grad = None
+    b2, p2, l2 = phase2_refine(head, (x,), *args, synth.HBB_FINE_CFG, synth.HBB_EXT_CFG, num_stages=2, neg_boxes=negs,
+                               train=True)
+    sum(v for k, v in l2.items() if "loss" in k).backward()
+    for n, p in head.named_parameters():
+        if p.grad is not None:
+            # atomics (small-head dW, split-K GEMM tails) make the summation order run-dependent
+            assert torch.allclose(p.grad, g1[n], rtol=0, atol=1e-5 * float(g1[n].abs().max()) + 1e-9), n
+    assert torch.allclose(x.grad, gx1, rtol=0, atol=1e-6 * float(gx1.abs().max()))      # red.add order only
+    with torch.no_grad():
+        b3, _, l3 = phase2_refine(head, (x.detach(),), *args, synth.HBB_FINE_CFG, synth.HBB_EXT_CFG, num_stages=2,
+                                  neg_boxes=negs)
+    for a, b in zip(boxes, b3):
+        assert torch.equal(a, b)
+    assert all(torch.isfinite(v).all() for v in losses.values())

@@ -58,7 +58,7 @@ def launches_md():
     tot = sum(a[1] for a in agg.values())
     lines = ["# Round 1 - ncu launch list of the phase-2 step (current kernels)", "",
              "Command: `ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv python bench.py --steps 2 "
-             "--warmup 1 --no-graph --no-cpu-baseline --no-stress` (cold-cache, serialised launches: compare SHARES, "
+             "--warmup 1 --no-graph --no-cpu-baseline --no-stress --no-train` (cold-cache, serialised launches: compare SHARES, "
              "not absolutes; the capture spans ~8 eager steps).", "",
              "| kernel | launches | total ns | avg ns | share |", "|---|---:|---:|---:|---:|"]
     for k, a in sorted(agg.items(), key=lambda kv: -kv[1][1]):
