@@ -113,7 +113,12 @@ int pt_reg_decode(const void* H, int h_f32, long long ldh, int D, const float* W
                   const float* bag_rois, const unsigned char* valid, const float* ref_boxes,
                   const float* real_boxes, int U, int K, float max_w, float max_h, float wh_ratio_clip,
                   float hyper, float eps, float* out_rois, float* out_deltas, float* iou_target, float* sums,
-                  int rotated, void* stream);
+                  int rotated, const float* deltas_in, void* stream);
+/* deltas_in != NULL: [K,4] = H . Wreg^T (no bias) already computed by pt_small_heads_bf16; only the decode runs.
+ * pt_small_heads_bf16: out0 [M,n0] = H W0^T + b0, out1 [M,n1] = H W1^T + b1 on mma.sync (H bf16; W1/b0/b1 may be
+ * NULL): fc_reg (fcos_head_p2b_ts.py:1207) and fc_cls + fc_ins (:1250-1251). */
+int pt_small_heads_bf16(const void* H, long long ldh, int D, const float* W0, int n0, const float* b0, const float* W1,
+                        int n1, const float* b1, int M, float* out0, float* out1, void* stream);
 int pt_cls_ins_heads(const void* H, int h_f32, long long ldh, int D, const float* Wcls, const float* bcls,
                      const float* Wins, const float* bins, int C, int M, float* cls, float* ins, void* stream);
 int pt_score_select(const float* cls, const float* ins, const unsigned char* valid, const float* bag_rois,

@@ -34,7 +34,9 @@ SIGNATURES = {
     "pt_cast_weight_bf16": (c_int, [c_void_p, c_void_p, c_int, c_int, c_ll, c_int, c_void_p]),
     "pt_reg_decode": (c_int, [c_void_p, c_int, c_ll, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                               c_void_p, c_int, c_int, c_float, c_float, c_float, c_float, c_float, c_void_p,
-                              c_void_p, c_void_p, c_void_p, c_int, c_void_p]),
+                              c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p]),
+    "pt_small_heads_bf16": (c_int, [c_void_p, c_ll, c_int, c_void_p, c_int, c_void_p, c_void_p, c_int, c_void_p, c_int,
+                                    c_void_p, c_void_p, c_void_p]),
     "pt_cls_ins_heads": (c_int, [c_void_p, c_int, c_ll, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int,
                                  c_void_p, c_void_p, c_void_p]),
     "pt_score_select": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int,

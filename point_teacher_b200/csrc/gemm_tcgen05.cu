@@ -377,8 +377,10 @@ extern "C" int pt_fc_gemm_bf16_ex(const void* A, long long lda, const void* B, l
   if (allow_split && tail > 0 && workspace != nullptr) {
     int S = grid / tail;
     const int kb_total = K / BK;
-    // every split must keep >= 8 k-blocks of MMA work, otherwise the fp32 reduction costs more than it saves
+    // every split must keep >= 8 k-blocks of MMA work, otherwise the fp32 reduction costs more than it saves; short
+    // contractions (K < 4096: FC2, measured 43 us split vs 27 us unsplit at 5000x1024x1024) are never split
     if (S > kb_total / 8) S = kb_total / 8;
+    if (kb_total < 64) S = 0;
     const long long need = (long long)tail * BM * BN * 4 + (long long)tail * 4;
     if (S >= 2 && need <= workspace_bytes) {
       p.split = S;

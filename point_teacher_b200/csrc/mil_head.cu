@@ -24,9 +24,37 @@ __global__ void prep_fc1_weight_kernel(const float* __restrict__ w, __nv_bfloat1
   extern __shared__ float srow[];   // transposed staging [bin][C+1] (the +1 keeps both phases conflict-free)
   const int n = blockIdx.x, K = C * bins, S = C + 1;
   const float* src = w + (size_t)n * K;
-  for (int i = threadIdx.x; i < K; i += blockDim.x) {     // coalesced read, k = c*bins + bin
-    const int c = i / bins, bin = i - c * bins;
-    srow[bin * S + c] = src[i];
+  // coalesced 16-byte reads (k = c*bins + bin), 4 independent loads in flight per thread: the kernel is a pure
+  // HBM stream (77 MB per FC1 weight) and needs ~32 KB in flight per SM to reach the copy bandwidth
+  if ((K & 3) == 0) {
+    const float4* src4 = reinterpret_cast<const float4*>(src);
+    const int K4 = K >> 2;
+    for (int i0 = threadIdx.x; i0 < K4; i0 += blockDim.x * 4) {
+      float4 v[4];
+#pragma unroll
+      for (int u = 0; u < 4; u++) {
+        const int i = i0 + u * blockDim.x;
+        v[u] = i < K4 ? __ldg(src4 + i) : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+#pragma unroll
+      for (int u = 0; u < 4; u++) {
+        const int i = i0 + u * blockDim.x;
+        if (i < K4) {
+          const float e[4] = {v[u].x, v[u].y, v[u].z, v[u].w};
+          int c = (4 * i) / bins, bin = 4 * i - c * bins;
+#pragma unroll
+          for (int j = 0; j < 4; j++) {
+            srow[bin * S + c] = e[j];
+            if (++bin == bins) { bin = 0; c++; }
+          }
+        }
+      }
+    }
+  } else {
+    for (int i = threadIdx.x; i < K; i += blockDim.x) {
+      const int c = i / bins, bin = i - c * bins;
+      srow[bin * S + c] = src[i];
+    }
   }
   __syncthreads();
   __nv_bfloat16* dst = out + (size_t)n * ld;
@@ -169,9 +197,11 @@ __global__ void reg_decode_kernel(const TH* __restrict__ H, long long ldh, int D
                                   const float* __restrict__ real_boxes, int U, int K, float max_w, float max_h,
                                   float max_ratio, float hyper, float eps, float* __restrict__ out_rois,
                                   float* __restrict__ out_deltas, float* __restrict__ iou_target,
-                                  float* __restrict__ sums, int rotated) {
+                                  float* __restrict__ sums, int rotated, const float* __restrict__ deltas_in) {
   extern __shared__ float wsm[];  // [4][D] + reduction scratch
-  for (int i = threadIdx.x; i < 4 * D; i += blockDim.x) wsm[i] = Wreg[i];
+  // deltas_in != NULL: H . Wreg^T was already computed on tensor cores (heads_mma.cu); only the decode runs here
+  if (deltas_in == nullptr)
+    for (int i = threadIdx.x; i < 4 * D; i += blockDim.x) wsm[i] = Wreg[i];
   __syncthreads();
   float* red = wsm + 4 * D;
   const int lane = threadIdx.x & 31, nw = blockDim.x >> 5;
@@ -179,12 +209,19 @@ __global__ void reg_decode_kernel(const TH* __restrict__ H, long long ldh, int D
   for (int kb = (blockIdx.x * nw + (threadIdx.x >> 5)) * HEAD_ROWS; kb < K; kb += gridDim.x * nw * HEAD_ROWS) {
     float dd[HEAD_ROWS][4];
     const int nrows = K - kb < HEAD_ROWS ? K - kb : HEAD_ROWS;
-    rows_dot<TH, 4>(H + (size_t)kb * ldh, ldh, nrows, wsm, D, lane, dd);
     float d[4] = {0.f, 0.f, 0.f, 0.f};
+    if (deltas_in != nullptr) {
+      if (lane < nrows) {
+        const float4 v = *reinterpret_cast<const float4*>(deltas_in + (size_t)(kb + lane) * 4);
+        d[0] = v.x; d[1] = v.y; d[2] = v.z; d[3] = v.w;
+      }
+    } else {
+      rows_dot<TH, 4>(H + (size_t)kb * ldh, ldh, nrows, wsm, D, lane, dd);
 #pragma unroll
-    for (int r = 0; r < HEAD_ROWS; r++)
+      for (int r = 0; r < HEAD_ROWS; r++)
 #pragma unroll
-      for (int j = 0; j < 4; j++) d[j] = (lane == r) ? dd[r][j] : d[j];
+        for (int j = 0; j < 4; j++) d[j] = (lane == r) ? dd[r][j] : d[j];
+    }
     const int k = kb + lane;          // lane r decodes row kb + r
     if (lane < nrows) {
       // rotated (OBB_TOD/.../rotated_fcos_head_p2rb_ts.py:1314-1343): decode on cxcywh_to_xyxy(bag[:, :4]),
@@ -454,7 +491,7 @@ extern "C" int pt_reg_decode(const void* H, int h_f32, long long ldh, int D, con
                              const float* bag_rois, const unsigned char* valid, const float* ref_boxes,
                              const float* real_boxes, int U, int K, float max_w, float max_h, float wh_ratio_clip,
                              float hyper, float eps, float* out_rois, float* out_deltas, float* iou_target,
-                             float* sums, int rotated, void* stream) {
+                             float* sums, int rotated, const float* deltas_in, void* stream) {
   if (K <= 0) return PT_OK;
   if (D % 256 != 0) { set_error("pt_reg_decode: hidden width must be a multiple of 256 (got %d)", D); return PT_ERR_ARG; }
   const int threads = 256;
@@ -466,12 +503,12 @@ extern "C" int pt_reg_decode(const void* H, int h_f32, long long ldh, int D, con
     cudaFuncSetAttribute(reg_decode_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     reg_decode_kernel<float><<<grid, threads, smem, (cudaStream_t)stream>>>(
         (const float*)H, ldh, D, Wreg, breg, bag_rois, valid, ref_boxes, real_boxes, U, K, max_w, max_h, max_ratio,
-        hyper, eps, out_rois, out_deltas, iou_target, sums, rotated);
+        hyper, eps, out_rois, out_deltas, iou_target, sums, rotated, deltas_in);
   } else {
     cudaFuncSetAttribute(reg_decode_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     reg_decode_kernel<__nv_bfloat16><<<grid, threads, smem, (cudaStream_t)stream>>>(
         (const __nv_bfloat16*)H, ldh, D, Wreg, breg, bag_rois, valid, ref_boxes, real_boxes, U, K, max_w, max_h,
-        max_ratio, hyper, eps, out_rois, out_deltas, iou_target, sums, rotated);
+        max_ratio, hyper, eps, out_rois, out_deltas, iou_target, sums, rotated, deltas_in);
   }
   return check_launch("reg_decode_kernel");
 }
