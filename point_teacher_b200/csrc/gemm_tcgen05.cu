@@ -11,9 +11,9 @@
 //   warp 1      MMA issuer (one elected lane): 4 x tcgen05.mma 128x256x16 per stage, accumulators in TMEM,
 //               two 256-column accumulator stages so the epilogue of tile i overlaps the MMAs of tile i+1
 //   warps 2..5  epilogue: tcgen05.ld 32x32b -> +bias -> ReLU -> bf16 pack (or fp32) -> 16-byte global stores
-// Tail balancing: when tiles % CTAs != 0 the last partial wave is split along K across the idle CTAs;
-// partial tiles are reduced with fp32 red.global.add into a (self re-zeroing) workspace and the last CTA to
-// arrive applies bias/activation (no spinning: an arrival counter elects the finaliser).
+// Tail balancing: when tiles % CTAs != 0 the last partial wave is split along K across the idle CTAs; the S
+// partials of a tile are parked in private fp32 workspace slots and reduced all-to-all (each CTA finalises 1/S of
+// the rows), which is deterministic and free of same-address atomics.
 #include <cuda.h>
 
 #include "common.cuh"
@@ -30,8 +30,8 @@ constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 256 + 1024;
 struct Params {
   const float* bias;  // [N] or nullptr
   void* C;            // bf16 or fp32 [M, ldc]
-  float* ws;          // split-K workspace, zero on entry, zero on exit: [tail_tiles][BM][BN]
-  int* counters;      // [tail_tiles], zero on entry / exit
+  float* ws;          // split-K workspace: [tail_tiles][S][BM][BN] private fp32 partial slots (no initialisation needed)
+  int* counters;      // [tail_tiles][2] (arrived, finished), zero on entry / exit
   int M, N, K, ldc;
   int relu, out_f32;
   const __nv_bfloat16* mask;  // optional [M, ldmask]: out = mask > 0 ? out : 0 (ReLU backward by the forward activation)
@@ -228,45 +228,83 @@ fc_gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
         __syncwarp();
         if (lane == 0) mbar_arrive(tempty_bar + acc);
       } else {
-        // split-K partial: reduce into the fp32 workspace tile
-        float* wrow = p.ws + ((size_t)u.tail_idx * BM + q * 32 + lane) * BN;
+        // split-K partial (tail wave): the S CTAs of a tile each park their fp32 partial in a private workspace
+        // slot (plain 16-byte stores), meet at a counter, and then each CTA reduces and finalises 1/S of the tile's
+        // rows from all S slots -- a deterministic all-to-all reduction, 2 x 128 KB of L2 traffic per CTA.  (The
+        // earlier red.global.add version serialised S-way on every address and cost ~25 us per FC1 launch.)
+        const int s_idx = blockIdx.x % p.split;
+        float* slot = p.ws + ((size_t)u.tail_idx * p.split + s_idx) * (BM * BN);
+        float* wrow = slot + (size_t)(q * 32 + lane) * BN;
 #pragma unroll 1
         for (int ch = 0; ch < BN / 32; ch++) {
           uint32_t r[32];
           tmem_ld_32x32(taddr + ch * 32, r);
           tmem_ld_wait();
 #pragma unroll
-          for (int j = 0; j < 8; j++)   // fire-and-forget 16-byte reductions at L2 (REDG.F32x4)
-            asm volatile("red.relaxed.gpu.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(wrow + ch * 32 + 4 * j),
-                         "r"(r[4 * j]), "r"(r[4 * j + 1]), "r"(r[4 * j + 2]), "r"(r[4 * j + 3])
-                         : "memory");
+          for (int j = 0; j < 8; j++)
+            __stcg(reinterpret_cast<float4*>(wrow + ch * 32) + j,
+                   make_float4(__uint_as_float(r[4 * j]), __uint_as_float(r[4 * j + 1]), __uint_as_float(r[4 * j + 2]),
+                               __uint_as_float(r[4 * j + 3])));
         }
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(tempty_bar + acc);
         __threadfence();
         asm volatile("bar.sync 1, 128;" ::: "memory");  // the 4 epilogue warps
+        int* cnt = p.counters + 2 * u.tail_idx;
         if (threadIdx.x == 64) {
-          int old = atomicAdd(p.counters + u.tail_idx, 1);
-          *fin_flag = (old == p.split - 1) ? 1 : 0;
+          atomicAdd(cnt, 1);
+          // all S CTAs of the tile are co-resident (grid <= #SMs, one CTA per SM): bounded spin
+          long long t0 = clock64();
+          while (*reinterpret_cast<volatile int*>(cnt) < p.split) {
+            if (clock64() - t0 > 4000000000LL) __trap();
+          }
           __threadfence();
         }
         asm volatile("bar.sync 1, 128;" ::: "memory");
-        if (*fin_flag) {
-#pragma unroll 1
-          for (int ch = 0; ch < BN / 32; ch++) {
-            uint32_t r[32];
-            float4* w4 = reinterpret_cast<float4*>(wrow + ch * 32);
-#pragma unroll
-            for (int j = 0; j < 8; j++) {
-              float4 t = __ldcg(w4 + j);
-              r[4 * j] = __float_as_uint(t.x); r[4 * j + 1] = __float_as_uint(t.y);
-              r[4 * j + 2] = __float_as_uint(t.z); r[4 * j + 3] = __float_as_uint(t.w);
-              __stcg(w4 + j, make_float4(0.f, 0.f, 0.f, 0.f));  // leave the workspace zeroed
+        {
+          const int r_lo = (int)(((long long)s_idx * BM) / p.split), r_hi = (int)(((long long)(s_idx + 1) * BM) / p.split);
+          const float* tile_ws = p.ws + (size_t)u.tail_idx * p.split * (BM * BN);
+          const int items = (r_hi - r_lo) * (BN / 4);
+          for (int idx = threadIdx.x - 64; idx < items; idx += 128) {
+            const int rr = r_lo + idx / (BN / 4), c4 = idx % (BN / 4);
+            float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+            for (int sp = 0; sp < p.split; sp++) {
+              const float4 t = __ldcg(reinterpret_cast<const float4*>(tile_ws + ((size_t)sp * BM + rr) * BN) + c4);
+              a.x += t.x; a.y += t.y; a.z += t.z; a.w += t.w;
             }
-            store_chunk(p, row, u.n_blk * BN + ch * 32, r, row_ok);
+            const int grow = u.m_blk * BM + rr, gcol = u.n_blk * BN + c4 * 4;
+            if (grow < p.M) {
+              float v[4] = {a.x, a.y, a.z, a.w};
+              if (p.bias != nullptr) {
+                const float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + gcol));
+                v[0] += b.x; v[1] += b.y; v[2] += b.z; v[3] += b.w;
+              }
+              if (p.relu) {
+#pragma unroll
+                for (int j = 0; j < 4; j++) v[j] = fmaxf(v[j], 0.f);
+              }
+              if (p.mask != nullptr) {
+                const uint2 m = __ldg(reinterpret_cast<const uint2*>(p.mask + (size_t)grow * p.ldmask + gcol));
+                if (!((m.x & 0x7fffu) != 0 && (m.x & 0x8000u) == 0)) v[0] = 0.f;
+                if (!((m.x & 0x7fff0000u) != 0 && (m.x & 0x80000000u) == 0)) v[1] = 0.f;
+                if (!((m.y & 0x7fffu) != 0 && (m.y & 0x8000u) == 0)) v[2] = 0.f;
+                if (!((m.y & 0x7fff0000u) != 0 && (m.y & 0x80000000u) == 0)) v[3] = 0.f;
+              }
+              if (p.out_f32)
+                *reinterpret_cast<float4*>(reinterpret_cast<float*>(p.C) + (size_t)grow * p.ldc + gcol) =
+                    make_float4(v[0], v[1], v[2], v[3]);
+              else
+                *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(p.C) + (size_t)grow * p.ldc + gcol) =
+                    make_uint2(pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]));
+            }
           }
-          if (threadIdx.x == 64) p.counters[u.tail_idx] = 0;
+        }
+        // the last CTA to finish its slice re-arms the counters for the next launch
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        if (threadIdx.x == 64) {
+          const int done = atomicAdd(cnt + 1, 1);
+          if (done == p.split - 1) { cnt[0] = 0; cnt[1] = 0; __threadfence(); }
         }
       }
       if (++acc == ACC_STAGES) { acc = 0; acc_phase ^= 1; }
@@ -317,9 +355,8 @@ static int make_map(CUtensorMap* map, const void* base, long long rows, long lon
 using namespace ptb;
 
 extern "C" long long pt_fc_gemm_workspace_bytes(int num_sms) {
-  // worst case: tail tiles < num_sms/2, one BMxBN fp32 tile each, + one int counter each
-  long long tiles = num_sms / 2 + 1;
-  return tiles * ((long long)gemm::BM * gemm::BN * 4) + tiles * 4 + 256;
+  // tail tiles x splits <= num_sms private fp32 BMxBN slots, + two int counters per tail tile (zero on entry / exit)
+  return (long long)num_sms * ((long long)gemm::BM * gemm::BN * 4) + 4096;
 }
 
 extern "C" int pt_fc_gemm_bf16_ex(const void* A, long long lda, const void* B, long long ldb, const float* bias,
@@ -374,18 +411,19 @@ extern "C" int pt_fc_gemm_bf16_ex(const void* A, long long lda, const void* B, l
   const int tail = p.tiles_total - p.full_rounds * grid;
   p.split = 0;
   p.ws = nullptr; p.counters = nullptr;
-  if (allow_split && tail > 0 && workspace != nullptr) {
+  if (allow_split && tail > 0 && tail * 8 <= 4096 && workspace != nullptr) {
     int S = grid / tail;
     const int kb_total = K / BK;
     // every split must keep >= 8 k-blocks of MMA work, otherwise the fp32 reduction costs more than it saves; short
     // contractions (K < 4096: FC2, measured 43 us split vs 27 us unsplit at 5000x1024x1024) are never split
     if (S > kb_total / 8) S = kb_total / 8;
     if (kb_total < 64) S = 0;
-    const long long need = (long long)tail * BM * BN * 4 + (long long)tail * 4;
+    const long long need = (long long)tail * S * BM * BN * 4 + 4096;
     if (S >= 2 && need <= workspace_bytes) {
       p.split = S;
-      p.ws = reinterpret_cast<float*>(workspace);
-      p.counters = reinterpret_cast<int*>(reinterpret_cast<char*>(workspace) + (long long)tail * BM * BN * 4);
+      // counters first (they must stay zero between launches; the partial slots need no initialisation)
+      p.counters = reinterpret_cast<int*>(workspace);
+      p.ws = reinterpret_cast<float*>(reinterpret_cast<char*>(workspace) + 4096);   // counters live in the first 4 KB
     }
   }
   static bool attr_set = false;

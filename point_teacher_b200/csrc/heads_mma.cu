@@ -12,7 +12,8 @@
 
 namespace ptb {
 
-constexpr int SH_WARPS = 4;     // 2 row tiles x 2 K halves per CTA
+constexpr int SH_KS = 8;        // K slices per row tile: D/8 = 128 hidden units = 4 fully unrolled 32-wide steps per warp
+constexpr int SH_WARPS = 2 * SH_KS;   // 2 row tiles x 8 K slices per CTA: one round of load latency per tile
 
 template <int NT>
 __global__ void __launch_bounds__(SH_WARPS * 32)
@@ -23,7 +24,7 @@ small_head_mma_kernel(const __nv_bfloat16* __restrict__ H, long long ldh, int D,
   const int row_bytes = D * 2 + 16;                               // padded: conflict-free LDS.128 across 8 rows
   // weights as bf16 hi + bf16 lo (w ~= hi + lo to 16 mantissa bits): [2][NT*8][D + 8]
   const size_t lo_off = (size_t)NT * 8 * row_bytes;
-  float* part = reinterpret_cast<float*>(smem_h + 2 * lo_off);    // [2 tiles][32 lanes][NT*4]
+  float* part = reinterpret_cast<float*>(smem_h + 2 * lo_off);    // [2 tiles][SH_KS][32 lanes][NT*4]
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   {
     const int total = NT * 8 * (D / 4);
@@ -57,8 +58,8 @@ small_head_mma_kernel(const __nv_bfloat16* __restrict__ H, long long ldh, int D,
   }
   __syncthreads();
   const int g = lane >> 2, t = lane & 3;
-  const int tile = warp >> 1, khalf = warp & 1;
-  const int kbeg = khalf * (D / 2), kend = kbeg + D / 2;
+  const int tile = warp / SH_KS, ks = warp % SH_KS;
+  const int kbeg = ks * (D / SH_KS), kend = kbeg + D / SH_KS;
   for (int rp = blockIdx.x * 32; rp < M; rp += gridDim.x * 32) {    // trip count uniform over the CTA (barriers inside)
     const int r0 = rp + tile * 16;
     const int ra = min(r0 + g, M - 1), rb = min(r0 + g + 8, M - 1);
@@ -90,21 +91,21 @@ small_head_mma_kernel(const __nv_bfloat16* __restrict__ H, long long ldh, int D,
         }
       }
     }
-    // reduce the two K halves through shared memory, then bias + store (fp32)
+    // reduce the K slices through shared memory, then bias + store (fp32)
     __syncthreads();
-    if (khalf == 1) {
 #pragma unroll
-      for (int nt = 0; nt < NT; nt++)
+    for (int nt = 0; nt < NT; nt++)
 #pragma unroll
-        for (int e = 0; e < 4; e++) part[((size_t)tile * 32 + lane) * NT * 4 + nt * 4 + e] = acc[nt][e];
-    }
+      for (int e = 0; e < 4; e++) part[(((size_t)tile * SH_KS + ks) * 32 + lane) * NT * 4 + nt * 4 + e] = acc[nt][e];
     __syncthreads();
-    if (khalf == 0) {
+    if (ks == 0) {
 #pragma unroll
       for (int nt = 0; nt < NT; nt++) {
 #pragma unroll
         for (int e = 0; e < 4; e++) {
-          const float v = acc[nt][e] + part[((size_t)tile * 32 + lane) * NT * 4 + nt * 4 + e];
+          float v = 0.f;
+#pragma unroll
+          for (int q = 0; q < SH_KS; q++) v += part[(((size_t)tile * SH_KS + q) * 32 + lane) * NT * 4 + nt * 4 + e];
           const int row = r0 + g + (e >> 1) * 8, col = nt * 8 + 2 * t + (e & 1);
           if (row < M) {
             if (col < n0) out0[(size_t)row * n0 + col] = v + (b0 != nullptr ? b0[col] : 0.f);
@@ -119,7 +120,7 @@ small_head_mma_kernel(const __nv_bfloat16* __restrict__ H, long long ldh, int D,
 template <int NT>
 static int launch_small_head(const void* H, long long ldh, int D, const float* W0, int n0, const float* b0,
                              const float* W1, int n1, const float* b1, int M, float* out0, float* out1, cudaStream_t s) {
-  const size_t smem = (size_t)2 * NT * 8 * (D * 2 + 16) + (size_t)2 * 32 * NT * 4 * sizeof(float);
+  const size_t smem = (size_t)2 * NT * 8 * (D * 2 + 16) + (size_t)2 * SH_KS * 32 * NT * 4 * sizeof(float);
   auto kern = small_head_mma_kernel<NT>;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) { set_error("cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return PT_ERR_CUDA; }
@@ -139,7 +140,7 @@ extern "C" int pt_small_heads_bf16(const void* H, long long ldh, int D, const fl
                                    const float* W1, int n1, const float* b1, int M, float* out0, float* out1,
                                    void* stream) {
   if (M <= 0) return PT_OK;
-  if (D % 64 != 0 || (ldh % 8) != 0 || ((uintptr_t)H & 15)) { set_error("pt_small_heads_bf16: D %% 64, ldh %% 8 and 16-byte alignment required"); return PT_ERR_ARG; }
+  if (D % (32 * SH_KS) != 0 || (ldh % 8) != 0 || ((uintptr_t)H & 15)) { set_error("pt_small_heads_bf16: D %% 256, ldh %% 8 and 16-byte alignment required"); return PT_ERR_ARG; }
   if (W1 == nullptr) n1 = 0;
   const int n = n0 + n1;
   cudaStream_t s = (cudaStream_t)stream;

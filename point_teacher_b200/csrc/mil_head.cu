@@ -320,98 +320,106 @@ __global__ void cls_ins_kernel(const TH* __restrict__ H, long long ldh, int D, c
 // --------------------------------------------------------------------------------- score + select
 __device__ __forceinline__ float sigmoidf_(float x) { return 1.f / (1.f + expf(-x)); }
 
-// One warp per GT.  cls / ins [G*U1*U2, C]; valid [G*U1*U2]; bag_rois [G*U1*U2, 5] (refined bags);
-// labels [G] int64; pseudo [G,4]; gt_img [G] image index -> img_wh.
-__global__ void score_select_kernel(const float* __restrict__ cls, const float* __restrict__ ins,
-                                    const uint8_t* __restrict__ valid, const float* __restrict__ bag_rois,
-                                    const long long* __restrict__ labels, const float* __restrict__ pseudo,
-                                    const float* __restrict__ img_wh, int B, int G, int U1, int U2, int C, int topk,
-                                    float beta, float* __restrict__ merged, float* __restrict__ merged_pts,
-                                    int* __restrict__ sel_idx, float* __restrict__ sel_score,
-                                    float* __restrict__ sums, int rotated) {
+// One CTA per GT.  cls / ins [G*U1*U2, C]; valid [G*U1*U2]; bag_rois [G*U1*U2, 5] (refined bags);
+// labels [G] int64; pseudo [G,4].  The GT's score tiles are staged in shared memory with coalesced loads, the
+// (U1 group, class) softmax columns are spread over the warps, thread 0 replays the CPU top-k and merges.
+constexpr int SS_WARPS = 4;
+__global__ void __launch_bounds__(SS_WARPS * 32)
+score_select_kernel(const float* __restrict__ cls, const float* __restrict__ ins, const uint8_t* __restrict__ valid,
+                    const float* __restrict__ bag_rois, const long long* __restrict__ labels,
+                    const float* __restrict__ pseudo, const float* __restrict__ img_wh, int B, int G, int U1, int U2,
+                    int C, int topk, float beta, float* __restrict__ merged, float* __restrict__ merged_pts,
+                    int* __restrict__ sel_idx, float* __restrict__ sel_score, float* __restrict__ sums, int rotated) {
   extern __shared__ float sm[];
-  const int nw = blockDim.x >> 5, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int U = U1 * U2;
-  float* sc = sm + (size_t)warp * 2 * U;           // selection scores of this warp's GT
-  int* si = reinterpret_cast<int*>(sc + U);        // companion indices for the replay
-  float* red = sm + (size_t)nw * 2 * U;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int U = U1 * U2, g = blockIdx.x;
+  float* cls_s = sm;                                 // [U][C]
+  float* ins_s = cls_s + (size_t)U * C;              // [U][C]
+  float* sc = ins_s + (size_t)U * C;                 // [U] selection scores
+  int* si = reinterpret_cast<int*>(sc + U);          // [U] companion indices for the replay
+  float* red = reinterpret_cast<float*>(si + U);     // [SS_WARPS][2]
+  uint8_t* val_s = reinterpret_cast<uint8_t*>(red + 2 * SS_WARPS);   // [U]
+  const size_t row0 = (size_t)g * U;
+  for (int i = threadIdx.x; i < U * C; i += blockDim.x) { cls_s[i] = cls[row0 * C + i]; ins_s[i] = ins[row0 * C + i]; }
+  for (int i = threadIdx.x; i < U; i += blockDim.x) val_s[i] = valid[row0 + i];
+  __syncthreads();
+  const int label = (int)labels[g];
   float part[2] = {0.f, 0.f};
-  for (int g = blockIdx.x * nw + warp; g < G; g += gridDim.x * nw) {
-    const int label = (int)labels[g];
-    for (int u1 = 0; u1 < U1; u1++) {
-      const size_t base = ((size_t)g * U1 + u1) * U2;
-      bool any_valid = false;
-      for (int u = lane; u < U2; u += 32) any_valid |= valid[base + u] != 0;
-      any_valid = __any_sync(0xffffffffu, any_valid);
-      float bag_loss = 0.f;
-      for (int c = 0; c < C; c++) {
-        // softmax over the U2 instances of this class column, masked by validity, L1-normalised
-        float mx = -3.0e38f;
-        for (int u = lane; u < U2; u += 32) mx = fmaxf(mx, ins[(base + u) * C + c]);
-        mx = warp_max(mx);
-        float se = 0.f;
-        for (int u = lane; u < U2; u += 32) se += expf(ins[(base + u) * C + c] - mx);
-        se = warp_sum(se);
-        float sv = 0.f;
-        for (int u = lane; u < U2; u += 32) sv += valid[base + u] ? expf(ins[(base + u) * C + c] - mx) / se : 0.f;
-        sv = warp_sum(sv);
-        const float den = fmaxf(sv, 1e-12f);
-        float bag = 0.f;
-        for (int u = lane; u < U2; u += 32) {
-          const float insn = (valid[base + u] ? expf(ins[(base + u) * C + c] - mx) / se : 0.f) / den;
-          const float p = sigmoidf_(cls[(base + u) * C + c]);
-          bag += p * insn;
-          if (c == label) { sc[u1 * U2 + u] = p * insn; si[u1 * U2 + u] = u1 * U2 + u; }
-        }
-        bag = warp_sum(bag);
-        // gfocal (fcos_head_p2b_ts.py:1074-1078) against the one-hot label, weight = bag has a valid instance
-        const float q = (c == label) ? 1.f : 0.f;
-        const float l1 = (bag - q) * (bag - q);
-        const float l2 = q * logf(bag + 1e-6f) + (1.f - q) * logf(1.f - bag + 1e-6f);
-        bag_loss += -(l1 * l2);
-      }
-      if (lane == 0 && any_valid) { part[0] += bag_loss; part[1] += 1.f; }
+  for (int p = warp; p < U1 * C; p += SS_WARPS) {
+    const int u1 = p / C, c = p - u1 * C;
+    const int base = u1 * U2;
+    bool any_valid = false;
+    for (int u = lane; u < U2; u += 32) any_valid |= val_s[base + u] != 0;
+    any_valid = __any_sync(0xffffffffu, any_valid);
+    // softmax over the U2 instances of this class column, masked by validity, L1-normalised
+    float mx = -3.0e38f;
+    for (int u = lane; u < U2; u += 32) mx = fmaxf(mx, ins_s[(base + u) * C + c]);
+    mx = warp_max(mx);
+    float se = 0.f;
+    for (int u = lane; u < U2; u += 32) se += expf(ins_s[(base + u) * C + c] - mx);
+    se = warp_sum(se);
+    float sv = 0.f;
+    for (int u = lane; u < U2; u += 32) sv += val_s[base + u] ? expf(ins_s[(base + u) * C + c] - mx) / se : 0.f;
+    sv = warp_sum(sv);
+    const float den = fmaxf(sv, 1e-12f);
+    float bag = 0.f;
+    for (int u = lane; u < U2; u += 32) {
+      const float insn = (val_s[base + u] ? expf(ins_s[(base + u) * C + c] - mx) / se : 0.f) / den;
+      const float pr = sigmoidf_(cls_s[(base + u) * C + c]);
+      bag += pr * insn;
+      if (c == label) { sc[base + u] = pr * insn; si[base + u] = base + u; }
     }
-    __syncwarp();
-    if (lane == 0) {
-      // replay of torch.topk(largest=True) on CPU over the flattened U1*U2 axis
-      cpu_topk_replay(sc, si, U, topk, /*largest=*/true);
-      float wsum = 0.f;
-      for (int t = 0; t < topk; t++) wsum += sc[t];
-      wsum += 1e-8f;
-      const int bd = rotated ? 5 : 4, rs = bd + 1;
-      float bx[5] = {0.f, 0.f, 0.f, 0.f, 0.f};
-      for (int t = 0; t < topk; t++) {
-        const float w = sc[t] / wsum;
-        const float* r = bag_rois + ((size_t)g * U + si[t]) * rs;
-        for (int j = 0; j < bd; j++) bx[j] += r[1 + j] * w;
-        sel_idx[(size_t)g * topk + t] = si[t];
-        sel_score[(size_t)g * topk + t] = sc[t];
-      }
-      int bi = (int)bag_rois[(size_t)g * U * rs];
-      bi = bi < 0 ? 0 : (bi >= B ? B - 1 : bi);
-      const float iw = img_wh[2 * bi], ih = img_wh[2 * bi + 1];
-      if (rotated) {
-        // rotated_fcos_head_p2rb_ts.py:1211-1212: (cx, cy) both clamped to [0, w] and then to [0, h]
-        bx[0] = fminf(fmaxf(fminf(fmaxf(bx[0], 0.f), iw), 0.f), ih);
-        bx[1] = fminf(fmaxf(fminf(fmaxf(bx[1], 0.f), iw), 0.f), ih);
-      } else {
-        bx[0] = fminf(fmaxf(bx[0], 0.f), iw); bx[2] = fminf(fmaxf(bx[2], 0.f), iw);
-        bx[1] = fminf(fmaxf(bx[1], 0.f), ih); bx[3] = fminf(fmaxf(bx[3], 0.f), ih);
-      }
-      if (pseudo != nullptr) {   // (1-beta)*box + beta*coarse   (fcos_head_p2b_ts.py:1109)
-        const float* pb = pseudo + (size_t)g * bd;
-        for (int j = 0; j < bd; j++) bx[j] = fadd(fmul(1.f - beta, bx[j]), fmul(beta, pb[j]));
-      }
-      for (int j = 0; j < bd; j++) merged[(size_t)g * bd + j] = bx[j];
-      if (merged_pts != nullptr) {  // refined points = box centres (fcos_p2b_teacher_student.py:465; OBB: box[:, :2])
-        merged_pts[(size_t)g * 2] = rotated ? bx[0] : fdiv(fadd(bx[0], bx[2]), 2.f);
-        merged_pts[(size_t)g * 2 + 1] = rotated ? bx[1] : fdiv(fadd(bx[1], bx[3]), 2.f);
-      }
-    }
-    __syncwarp();
+    bag = warp_sum(bag);
+    // gfocal (fcos_head_p2b_ts.py:1074-1078) against the one-hot label, weight = bag has a valid instance
+    const float q = (c == label) ? 1.f : 0.f;
+    const float l1 = (bag - q) * (bag - q);
+    const float l2 = q * logf(bag + 1e-6f) + (1.f - q) * logf(1.f - bag + 1e-6f);
+    if (lane == 0 && any_valid) { part[0] += -(l1 * l2); if (c == 0) part[1] += 1.f; }
   }
-  if (sums != nullptr) block_accumulate(sums + S_POS, part, 2, red);
+  if (lane == 0) { red[warp * 2] = part[0]; red[warp * 2 + 1] = part[1]; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    if (sums != nullptr) {
+      float a = 0.f, b = 0.f;
+      for (int w = 0; w < SS_WARPS; w++) { a += red[w * 2]; b += red[w * 2 + 1]; }
+      atomicAdd(sums + S_POS, a);
+      atomicAdd(sums + S_NSAMPLE, b);
+    }
+    // replay of torch.topk(largest=True) on CPU over the flattened U1*U2 axis
+    cpu_topk_replay(sc, si, U, topk, /*largest=*/true);
+    float wsum = 0.f;
+    for (int t = 0; t < topk; t++) wsum += sc[t];
+    wsum += 1e-8f;
+    const int bd = rotated ? 5 : 4, rs = bd + 1;
+    float bx[5] = {0.f, 0.f, 0.f, 0.f, 0.f};
+    for (int t = 0; t < topk; t++) {
+      const float w = sc[t] / wsum;
+      const float* r = bag_rois + ((size_t)g * U + si[t]) * rs;
+      for (int j = 0; j < bd; j++) bx[j] += r[1 + j] * w;
+      sel_idx[(size_t)g * topk + t] = si[t];
+      sel_score[(size_t)g * topk + t] = sc[t];
+    }
+    int bi = (int)bag_rois[(size_t)g * U * rs];
+    bi = bi < 0 ? 0 : (bi >= B ? B - 1 : bi);
+    const float iw = img_wh[2 * bi], ih = img_wh[2 * bi + 1];
+    if (rotated) {
+      // rotated_fcos_head_p2rb_ts.py:1211-1212: (cx, cy) both clamped to [0, w] and then to [0, h]
+      bx[0] = fminf(fmaxf(fminf(fmaxf(bx[0], 0.f), iw), 0.f), ih);
+      bx[1] = fminf(fmaxf(fminf(fmaxf(bx[1], 0.f), iw), 0.f), ih);
+    } else {
+      bx[0] = fminf(fmaxf(bx[0], 0.f), iw); bx[2] = fminf(fmaxf(bx[2], 0.f), iw);
+      bx[1] = fminf(fmaxf(bx[1], 0.f), ih); bx[3] = fminf(fmaxf(bx[3], 0.f), ih);
+    }
+    if (pseudo != nullptr) {   // (1-beta)*box + beta*coarse   (fcos_head_p2b_ts.py:1109)
+      const float* pb = pseudo + (size_t)g * bd;
+      for (int j = 0; j < bd; j++) bx[j] = fadd(fmul(1.f - beta, bx[j]), fmul(beta, pb[j]));
+    }
+    for (int j = 0; j < bd; j++) merged[(size_t)g * bd + j] = bx[j];
+    if (merged_pts != nullptr) {  // refined points = box centres (fcos_p2b_teacher_student.py:465; OBB: box[:, :2])
+      merged_pts[(size_t)g * 2] = rotated ? bx[0] : fdiv(fadd(bx[0], bx[2]), 2.f);
+      merged_pts[(size_t)g * 2 + 1] = rotated ? bx[1] : fdiv(fadd(bx[1], bx[3]), 2.f);
+    }
+  }
 }
 
 // negatives: gfocal(sigmoid(neg_cls), 0, weight)   (fcos_head_p2b_ts.py:1169-1179)
@@ -548,12 +556,10 @@ extern "C" int pt_score_select(const float* cls, const float* ins, const unsigne
   if (G <= 0) return PT_OK;
   const int U = U1 * U2;
   if (topk < 1 || topk > 16 || topk > U) { set_error("pt_score_select: topk must be in [1, min(16, U)]"); return PT_ERR_ARG; }
-  const int warps = 4;
-  const size_t smem = ((size_t)warps * 2 * U + 2 * warps + 8) * sizeof(float);
-  if (smem > 200 * 1024) { set_error("pt_score_select: bag of %d instances does not fit shared memory", U); return PT_ERR_UNSUPPORTED; }
+  const size_t smem = ((size_t)2 * U * C + 2 * U + 2 * SS_WARPS) * sizeof(float) + ((U + 15) / 16) * 16;
+  if (smem > 200 * 1024) { set_error("pt_score_select: bag of %d instances x %d classes does not fit shared memory", U, C); return PT_ERR_UNSUPPORTED; }
   cudaFuncSetAttribute(score_select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  int grid = (G + warps - 1) / warps;
-  score_select_kernel<<<grid, warps * 32, smem, (cudaStream_t)stream>>>(cls, ins, valid, bag_rois, labels, pseudo,
+  score_select_kernel<<<G, SS_WARPS * 32, smem, (cudaStream_t)stream>>>(cls, ins, valid, bag_rois, labels, pseudo,
                                                                         img_wh, B, G, U1, U2, C, topk, beta, merged,
                                                                         merged_pts, sel_idx, sel_score, sums, rotated);
   return check_launch("score_select_kernel");

@@ -269,7 +269,7 @@ def reg_decode(H, Wreg, breg, bag_rois, valid, ref_boxes, real_boxes, U, max_wh,
     deltas = torch.empty((K, 4), dtype=_f32, device=dev) if want_deltas else None
     iou_t = torch.empty((K,), dtype=_f32, device=dev)
     deltas_in = None
-    if H.dtype == _bf16 and H.shape[1] % 64 == 0:          # H . Wreg^T on tensor cores; the kernel below only decodes
+    if H.dtype == _bf16 and H.shape[1] % 256 == 0:         # H . Wreg^T on tensor cores; the kernel below only decodes
         deltas_in = torch.empty((K, 4), dtype=_f32, device=dev)
         _lib.call("pt_small_heads_bf16", _p(H), H.shape[1], Wreg.shape[1], _p(Wreg), 4, _p(None), _p(None), 0, _p(None),
                   K, _p(deltas_in), _p(None), _stream())
@@ -286,7 +286,7 @@ def cls_ins_heads(H, Wcls, bcls, Wins, bins, M=None):
     C = Wcls.shape[0]
     cls = torch.empty((M, C), dtype=_f32, device=H.device)
     ins = torch.empty((M, C), dtype=_f32, device=H.device)
-    if H.dtype == _bf16 and H.shape[1] % 64 == 0 and 2 * C <= 32:       # tensor-core path (heads_mma.cu)
+    if H.dtype == _bf16 and H.shape[1] % 256 == 0 and 2 * C <= 32:       # tensor-core path (heads_mma.cu)
         _lib.call("pt_small_heads_bf16", _p(H), H.shape[1], Wcls.shape[1], _p(Wcls), C, _p(bcls), _p(Wins), C, _p(bins), M,
                   _p(cls), _p(ins), _stream())
         return cls, ins

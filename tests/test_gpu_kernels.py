@@ -229,7 +229,8 @@ def test_fc_gemm_vs_fp32_reference(cuda, M, N, K, relu, f32, split):
         tol = 1e-3 if f32 else 2e-2                      # fp32 out: accumulation-order noise only
         err = (out.float() - ref).abs().max().item()
         assert err <= tol * ref.abs().max().item(), (err, ref.abs().max().item())
-    assert torch.count_nonzero(ops.gemm_workspace(cuda)) == 0
+    # the split-K arrival / completion counters (head of the workspace) re-arm themselves
+    assert torch.count_nonzero(ops.gemm_workspace(cuda)[:4096]) == 0
 
 
 def test_fc_gemm_rejects_bad_shapes(cuda):
