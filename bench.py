@@ -284,6 +284,8 @@ def run_ours(args):
     # ---- training step: forward + hand-written backward + ONE all-reduce of the MIL-head gradients (NCCL over
     #      NVLink when N > 1).  Eager launches (the all-reduce is not graph-captured); reported beside the headline.
     train_ms = float("nan")
+    if args.precision != "bf16":
+        args.no_train = True                        # the hand-written backward runs in bf16 precision only
     if not args.no_train:
         from point_teacher_b200.train import Phase2Trainer
         trainer = Phase2Trainer(head, synth.HBB_FINE_CFG, synth.HBB_EXT_CFG, num_stages=1, cap=100)
