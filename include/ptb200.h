@@ -165,6 +165,17 @@ int pt_max_iou_assign(const float* gts, int ldg, int G, const float* anchors, in
                       int match_low_quality, const long long* gt_labels, long long* gt_inds, float* max_overlaps,
                       long long* labels, int* argmax_ws, unsigned* gt_ws, void* stream);
 
+/* ---- coarse pseudo boxes behind the FUSE assignment (section 8f rank 1) ------------------------------------
+ * pt_decode_ltrb: distance2bbox + bbox_xyxy_to_cxcywh (HBB_TOD/mmdet/core/bbox/transforms.py:134-166, 249-261).
+ * pt_pseudo_aggregate: _gnerate_pseudo_single (HBB_TOD/mmdet/models/dense_heads/fcos_head_p2b_ts.py:762-790):
+ *   per GT the sigmoid-score-weighted mean of the decoded boxes of its assigned points (8 x 8 box at the GT point
+ *   when none), mean score, assigned count, valid = assigned AND score >= filter, and the IoU-vs-GT sum / count. */
+int pt_decode_ltrb(const float* points, const float* ltrb, int P, float* xyxy, float* cxcywh, void* stream);
+int pt_pseudo_aggregate(const long long* gt_inds, const long long* labels, const float* cls, int C, const float* xyxy,
+                        int P, const float* gt_points, const float* gt_bboxes, int G, float filter_score, float* acc_ws,
+                        float* boxes, float* points, float* scores, long long* assign_nums, unsigned char* valid,
+                        float* iou_sum, void* stream);
+
 /* ---- phase-1 random region masking (row a16) --------------------------------------------------------------
  * The deterministic tail of generate_black_paper (HBB_TOD/mmdet/models/detectors/syn_images_generator_v2.py:664-690).
  * pt_nms_rotated: mmcv.ops.nms_rotated(dets [N, ld>=5], scores (stride lds), thr): order [N] int32 = box indices by

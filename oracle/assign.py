@@ -167,3 +167,37 @@ def max_iou_assign(overlaps, gt_labels=None, pos_iou_thr=0.5, neg_iou_thr=0.5, m
         p = gt_inds > 0
         lab[p] = gt_labels[gt_inds[p] - 1]
     return gt_inds, mx, lab
+
+
+# ------------------------------------------------------------------------------ coarse pseudo boxes (section 8f rank 1)
+def generate_pseudo_single(gt_points, gt_labels, gt_bboxes, cls_scores, bbox_preds, points, filter_scores, num_pre=5,
+                           topk=3):
+    """models/dense_heads/fcos_head_p2b_ts.py:736-794 with the FUSE assigner of the shipped config (5, 3)."""
+    from . import hbb
+    P, G = points.shape[0], gt_labels.shape[0]
+    act = cls_scores.detach().sigmoid()
+    dec = torch.stack([points[:, 0] - bbox_preds[:, 0], points[:, 1] - bbox_preds[:, 1], points[:, 0] + bbox_preds[:, 2],
+                       points[:, 1] + bbox_preds[:, 3]], -1)                                   # distance2bbox
+    gt_inds, lab = fuse_topk_assign(hbb.xyxy_to_cxcywh(dec), points, cls_scores, gt_points, gt_labels, num_pre, topk)
+    pos = (gt_inds != 0).nonzero().reshape(-1)
+    pos = pos[torch.sort(gt_inds[pos] - 1)[1]]
+    labels = torch.zeros(P, dtype=torch.long)
+    labels[pos] = lab[pos]
+    s = act[torch.arange(P), labels]
+    A, B, Cw = dec[pos], gt_inds[pos] - 1, s[pos]
+    nums = torch.bincount(B, minlength=G)
+    boxes = 8 * torch.ones_like(gt_bboxes)
+    boxes[:, :2] = gt_points
+    boxes = hbb.cxcywh_to_xyxy(boxes)
+    scores = torch.zeros(G)
+    pts = gt_points.clone()
+    onehot = torch.nn.functional.one_hot(B, num_classes=G).float()
+    bsum, ssum = onehot.t() @ (A * Cw[:, None]), onehot.t() @ Cw
+    has = (nums != 0).nonzero().reshape(-1)
+    boxes[has] = bsum[has] / ssum[has][:, None]
+    scores[has] = ssum[has] / nums[has]
+    pts[has] = hbb.xyxy_to_cxcywh(boxes[has])[:, :2]
+    miou = hbb.bbox_overlaps(boxes[has], gt_bboxes[has], "iou", True).mean()
+    valid = torch.zeros(G, dtype=torch.bool)
+    valid[has] = scores[has] >= filter_scores
+    return boxes, pts, gt_labels, miou, valid.nonzero().reshape(-1), scores, nums

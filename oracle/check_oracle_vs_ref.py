@@ -193,7 +193,34 @@ def check_mask():
     return ok
 
 
+def check_pseudo():
+    """Section 8f rank 1: the reference's own TS_P2BFCOSHead._gnerate_pseudo_single against oracle/assign.py."""
+    from oracle import assign
+    ns = ref_shim.install()
+    ok = True
+    for seed, G in ((0, 120), (1, 37), (2, 400)):
+        d = synth.pseudo_batch(seed, G=G)
+        head = ns.TS_P2BFCOSHead.__new__(ns.TS_P2BFCOSHead)
+        torch.nn.Module.__init__(head)
+        head.fuse_assigner = ns.FUSETopkAssigner(num_pre=5, topk=3, cls_cost=dict(type="FocalLossCost", weight=1.0),
+                                                 reg_cost=dict(type="PointCost", mode="L1", weight=1.0),
+                                                 location_cost=dict(type="InsiderCost", weight=1.0))
+        rb, rp, rl, rm, rv = head._gnerate_pseudo_single(d["gt_points"], d["labels"], d["gt_boxes"], d["logits"], d["ltrb"],
+                                                         None, None, None, 0.1, d["points"], None)
+        ob, op, ol, om, ov, _, _ = assign.generate_pseudo_single(d["gt_points"], d["labels"], d["gt_boxes"], d["logits"],
+                                                                 d["ltrb"], d["points"], 0.1)
+        ok &= _eq(ob, rb, f"pseudo boxes seed{seed}", 0.0)
+        ok &= _eq(op, rp, f"pseudo points seed{seed}", 0.0)
+        ok &= _eq(om, rm, f"mean iou seed{seed}", 0.0)
+        ok &= _eq(torch.sort(ov)[0], torch.sort(rv)[0], f"valid inds seed{seed} ({ov.numel()} of {G})", 0.0)
+    return ok
+
+
 if __name__ == "__main__":
+    if "--pseudo" in sys.argv:
+        good = check_pseudo()
+        print("ALL OK" if good else "MISMATCH")
+        sys.exit(0 if good else 1)
     if "--mask" in sys.argv:
         good = check_mask()
         print("ALL OK" if good else "MISMATCH")

@@ -135,6 +135,24 @@ def mask_case():
     print("wrote black_paper", [(o["kept"].shape[0], o["n_px"]) for o in out])
 
 
+def pseudo_case():
+    """Section 8f rank 1: outputs of the reference's own TS_P2BFCOSHead._gnerate_pseudo_single."""
+    ns = ref_shim.install()
+    out = []
+    for seed, G in ((0, 120), (2, 400)):
+        d = synth.pseudo_batch(seed, G=G)
+        head = ns.TS_P2BFCOSHead.__new__(ns.TS_P2BFCOSHead)
+        torch.nn.Module.__init__(head)
+        head.fuse_assigner = ns.FUSETopkAssigner(num_pre=5, topk=3, cls_cost=dict(type="FocalLossCost", weight=1.0),
+                                                 reg_cost=dict(type="PointCost", mode="L1", weight=1.0),
+                                                 location_cost=dict(type="InsiderCost", weight=1.0))
+        rb, rp, rl, rm, rv = head._gnerate_pseudo_single(d["gt_points"], d["labels"], d["gt_boxes"], d["logits"], d["ltrb"],
+                                                         None, None, None, 0.1, d["points"], None)
+        out.append(dict(seed=seed, G=G, boxes=rb, points=rp, mean_iou=rm, valid=torch.sort(rv)[0]))
+    torch.save(out, os.path.join(OUT, "pseudo_boxes.pt"))
+    print("wrote pseudo_boxes", [(o["G"], o["valid"].numel()) for o in out])
+
+
 def overlaps_case():
     ns = ref_shim.install()
     g = torch.Generator().manual_seed(7)
@@ -156,3 +174,4 @@ if __name__ == "__main__":
     obb_case(0, "s1_top3")
     assign_case()
     mask_case()
+    pseudo_case()

@@ -286,6 +286,73 @@ max_iou_pass2_kernel(const float* __restrict__ gts, int ldg, int G, const float*
   }
 }
 
+// ---- coarse pseudo-box aggregation behind the FUSE assignment
+//   _gnerate_pseudo_single   HBB_TOD/mmdet/models/dense_heads/fcos_head_p2b_ts.py:736-794
+// The reference builds an M x G one-hot matrix and two matmuls; here every assigned point adds its
+// score-weighted decoded box to its GT with six float atomics, and one thread per GT finishes.
+__global__ void decode_ltrb_kernel(const float* __restrict__ pts, const float* __restrict__ ltrb, int P,
+                                   float* __restrict__ xyxy, float* __restrict__ cxcywh) {
+  const int p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= P) return;
+  const float px = pts[2 * p], py = pts[2 * p + 1];
+  const float* d = ltrb + (size_t)p * 4;
+  const float x1 = fsub(px, d[0]), y1 = fsub(py, d[1]), x2 = fadd(px, d[2]), y2 = fadd(py, d[3]);   // distance2bbox
+  float* o = xyxy + (size_t)p * 4;
+  o[0] = x1; o[1] = y1; o[2] = x2; o[3] = y2;
+  float* c = cxcywh + (size_t)p * 4;                                                                  // bbox_xyxy_to_cxcywh
+  c[0] = fdiv(fadd(x1, x2), 2.f); c[1] = fdiv(fadd(y1, y2), 2.f); c[2] = fsub(x2, x1); c[3] = fsub(y2, y1);
+}
+
+__global__ void pseudo_accumulate_kernel(const long long* __restrict__ gt_inds, const long long* __restrict__ labels,
+                                         const float* __restrict__ cls, int C, const float* __restrict__ xyxy, int P,
+                                         float* __restrict__ acc /* [G][6]: sum(box*s) x4, sum(s), count */) {
+  const int p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= P) return;
+  const long long g1 = gt_inds[p];
+  if (g1 == 0) return;
+  const int g = (int)g1 - 1;
+  const float s = sigmoid_ref(cls[(size_t)p * C + (int)labels[p]]);
+  const float* b = xyxy + (size_t)p * 4;
+  float* a = acc + (size_t)g * 6;
+#pragma unroll
+  for (int j = 0; j < 4; j++) atomicAdd(a + j, fmul(b[j], s));
+  atomicAdd(a + 4, s);
+  atomicAdd(a + 5, 1.f);
+}
+
+__global__ void pseudo_finalize_kernel(const float* __restrict__ acc, const float* __restrict__ gt_points,
+                                       const float* __restrict__ gt_bboxes, int G, float filter_score,
+                                       float* __restrict__ boxes, float* __restrict__ points,
+                                       float* __restrict__ scores, long long* __restrict__ nums,
+                                       unsigned char* __restrict__ valid, float* __restrict__ iou_sum) {
+  const int g = blockIdx.x * blockDim.x + threadIdx.x;
+  float iou = 0.f, one = 0.f;
+  if (g < G) {
+    const float* a = acc + (size_t)g * 6;
+    const float gx = gt_points[2 * g], gy = gt_points[2 * g + 1];
+    float b[4] = {fsub(gx, 4.f), fsub(gy, 4.f), fadd(gx, 4.f), fadd(gy, 4.f)};   // bbox_cxcywh_to_xyxy of an 8 x 8 box
+    float px = gx, py = gy, sc = 0.f;
+    const bool has = a[5] > 0.f;
+    if (has) {
+#pragma unroll
+      for (int j = 0; j < 4; j++) b[j] = fdiv(a[j], a[4]);
+      sc = fdiv(a[4], a[5]);
+      px = fdiv(fadd(b[0], b[2]), 2.f); py = fdiv(fadd(b[1], b[3]), 2.f);
+      const float* t = gt_bboxes + (size_t)g * 4;
+      iou = pair_metric(0, METRIC_IOU, b[0], b[1], b[2], b[3], t[0], t[1], t[2], t[3], 1e-6f);
+      one = 1.f;
+    }
+#pragma unroll
+    for (int j = 0; j < 4; j++) boxes[(size_t)g * 4 + j] = b[j];
+    points[2 * g] = px; points[2 * g + 1] = py;
+    scores[g] = sc;
+    nums[g] = (long long)a[5];
+    valid[g] = (has && sc >= filter_score) ? 1 : 0;
+  }
+  iou = warp_sum(iou); one = warp_sum(one);
+  if ((threadIdx.x & 31) == 0 && one > 0.f) { atomicAdd(iou_sum, iou); atomicAdd(iou_sum + 1, one); }
+}
+
 }  // namespace ptb
 
 using namespace ptb;
@@ -380,4 +447,32 @@ extern "C" int pt_max_iou_assign(const float* gts, int ldg, int G, const float* 
                                               gt_argmax, pos_thr, neg_lo, neg_hi, min_pos, gt_max_assign_all,
                                               match_low_quality, gt_labels, gt_inds, labels);
   return check_launch("max_iou_pass2_kernel");
+}
+
+// distance2bbox + bbox_xyxy_to_cxcywh (HBB_TOD/mmdet/core/bbox/transforms.py:134-166, 249-261)
+extern "C" int pt_decode_ltrb(const float* points, const float* ltrb, int P, float* xyxy, float* cxcywh, void* stream) {
+  if (P <= 0) return PT_OK;
+  decode_ltrb_kernel<<<(P + 255) / 256, 256, 0, (cudaStream_t)stream>>>(points, ltrb, P, xyxy, cxcywh);
+  return check_launch("decode_ltrb_kernel");
+}
+
+// _gnerate_pseudo_single aggregation (fcos_head_p2b_ts.py:762-790).  acc_ws [G*6] + iou_sum [2] are scratch (zeroed
+// here); outputs: boxes [G,4], points [G,2], scores [G], assign_nums [G] int64, valid [G] uint8 (assigned AND
+// score >= filter), iou_sum = (sum of IoU(pseudo, gt) over assigned GTs, their count).
+extern "C" int pt_pseudo_aggregate(const long long* gt_inds, const long long* labels, const float* cls, int C,
+                                   const float* xyxy, int P, const float* gt_points, const float* gt_bboxes, int G,
+                                   float filter_score, float* acc_ws, float* boxes, float* points, float* scores,
+                                   long long* assign_nums, unsigned char* valid, float* iou_sum, void* stream) {
+  cudaStream_t s = (cudaStream_t)stream;
+  if (G <= 0) return PT_OK;
+  cudaMemsetAsync(acc_ws, 0, (size_t)G * 6 * sizeof(float), s);
+  cudaMemsetAsync(iou_sum, 0, 2 * sizeof(float), s);
+  if (P > 0) {
+    pseudo_accumulate_kernel<<<(P + 255) / 256, 256, 0, s>>>(gt_inds, labels, cls, C, xyxy, P, acc_ws);
+    int rc = check_launch("pseudo_accumulate_kernel");
+    if (rc != PT_OK) return rc;
+  }
+  pseudo_finalize_kernel<<<(G + 127) / 128, 128, 0, s>>>(acc_ws, gt_points, gt_bboxes, G, filter_score, boxes, points,
+                                                          scores, assign_nums, valid, iou_sum);
+  return check_launch("pseudo_finalize_kernel");
 }

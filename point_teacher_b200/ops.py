@@ -582,3 +582,35 @@ def roi_align_backward(dA, rois, feat_shape_nhwc, spatial_scale, sampling_ratio=
     _lib.call("pt_roi_align_backward", _p(dA), dA.shape[1], _p(rois), K, B, C, H, W, float(spatial_scale),
               int(sampling_ratio), int(aligned), _p(dfeat), _stream())
     return dfeat
+
+
+# ------------------------------------------------------------------------------ coarse pseudo boxes (section 8f rank 1)
+def decode_ltrb(points, ltrb):
+    """distance2bbox + bbox_xyxy_to_cxcywh: -> (xyxy (P,4), cxcywh (P,4))."""
+    _chk(points, "points", _f32, 2, 2)
+    _chk(ltrb, "bbox_preds", _f32, 2, 4)
+    P = points.shape[0]
+    xyxy = torch.empty((P, 4), dtype=_f32, device=points.device)
+    cxcywh = torch.empty((P, 4), dtype=_f32, device=points.device)
+    _lib.call("pt_decode_ltrb", _p(points), _p(ltrb), P, _p(xyxy), _p(cxcywh), _stream())
+    return xyxy, cxcywh
+
+
+def pseudo_aggregate(gt_inds, labels, cls_scores, xyxy, gt_points, gt_bboxes, filter_score):
+    _chk(gt_inds, "gt_inds", _i64, 1)
+    _chk(labels, "labels", _i64, 1)
+    _chk(cls_scores, "cls_scores", _f32, 2)
+    _chk(gt_points, "gt_points", _f32, 2, 2)
+    _chk(gt_bboxes, "gt_bboxes", _f32, 2, 4)
+    G, P, dev = gt_points.shape[0], gt_inds.shape[0], gt_inds.device
+    ws = torch.empty((G * 6,), dtype=_f32, device=dev)
+    boxes = torch.empty((G, 4), dtype=_f32, device=dev)
+    pts = torch.empty((G, 2), dtype=_f32, device=dev)
+    scores = torch.empty((G,), dtype=_f32, device=dev)
+    nums = torch.empty((G,), dtype=_i64, device=dev)
+    valid = torch.empty((G,), dtype=_u8, device=dev)
+    iou = torch.empty((2,), dtype=_f32, device=dev)
+    _lib.call("pt_pseudo_aggregate", _p(gt_inds), _p(labels), _p(cls_scores), cls_scores.shape[1], _p(xyxy), P,
+              _p(gt_points), _p(gt_bboxes), G, float(filter_score), _p(ws), _p(boxes), _p(pts), _p(scores), _p(nums),
+              _p(valid), _p(iou), _stream())
+    return boxes, pts, scores, nums, valid, iou

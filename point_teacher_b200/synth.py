@@ -150,3 +150,18 @@ def mask_batch(seed, imgsize=800, n_gt=(150, 300), n_shapes=5):
     cls = torch.randint(0, n_shapes, (n, 1), generator=g).float()
     bb = torch.cat([cxcywh, torch.zeros(n, 1), torch.ones(n, 1), cls], 1)
     return dict(img=img, bb_occupied=bb, imgsize=imgsize)
+
+
+def pseudo_batch(seed, P_hw=(100, 100), G=120, C=8, stride=8):
+    """Inputs of the coarse pseudo-box step: grid points, FCOS-style (l, t, r, b) distances and logits, GT points
+    (integer valued: L1 ties), GT boxes (xyxy) and labels."""
+    d = assign_batch(seed, P_hw=P_hw, G=G, C=C, stride=stride, ties=True)
+    g = torch.Generator().manual_seed(5000 + seed)
+    P = d["points"].shape[0]
+    ltrb = (torch.randn(P, 4, generator=g) * 0.5 + 2.0).exp()
+    ctr, wh = d["gt"][:, :2], d["gt"][:, 2:]
+    gt_boxes = torch.cat([ctr - wh / 2, ctr + wh / 2], 1)
+    logits = d["logits"].clone()
+    logits[torch.randperm(P, generator=g)[:P // 3]] += 3.0          # some confident points: scores above the filter
+    return dict(points=d["points"], ltrb=ltrb, logits=logits, gt_points=ctr.clone(), gt_boxes=gt_boxes,
+                labels=d["labels"])

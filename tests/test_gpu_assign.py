@@ -143,3 +143,31 @@ def test_max_iou_assign_vs_oracle_dense(cuda, calc, mode, G, A):
     m = Amod.BboxOverlaps2D()(gts.to(cuda), anchors.to(cuda), mode) if calc == "BboxOverlaps2D" else \
         Amod.BboxDistanceMetric()(gts.to(cuda), anchors.to(cuda), mode)
     assert torch.equal(m.cpu(), ov)
+
+
+def test_coarse_pseudo_boxes_vs_reference_golden_and_oracle(cuda, golden_dir):
+    """Section 8f rank 1 (_gnerate_pseudo_single): FUSE assignment + score-weighted box aggregation."""
+    from point_teacher_b200 import coarse
+    fuse = _mk_fuse(5, 3)
+    for c in torch.load(os.path.join(golden_dir, "pseudo_boxes.pt")):
+        d = synth.pseudo_batch(c["seed"], G=c["G"])
+        dc = {k: v.to(cuda) for k, v in d.items()}
+        b, p, lab, miou, valid = coarse.generate_pseudo_single(fuse, dc["gt_points"], dc["labels"], dc["gt_boxes"],
+                                                               dc["logits"], dc["ltrb"], None, None, None, 0.1,
+                                                               dc["points"], None)
+        # sums of <= 5 score-weighted boxes per GT: fp32 summation order is the only difference
+        assert (b.cpu() - c["boxes"]).abs().max() <= 1e-5 * c["boxes"].abs().max()
+        assert (p.cpu() - c["points"]).abs().max() <= 1e-5 * c["points"].abs().max()
+        assert abs(float(miou) - float(c["mean_iou"])) < 1e-5
+        assert torch.equal(valid.cpu(), c["valid"])
+        assert torch.equal(lab, dc["labels"])
+    # no GT: the reference's empty return
+    b, p, lab, miou, valid = coarse.generate_pseudo_single(fuse, dc["gt_points"][:0], dc["labels"][:0], dc["gt_boxes"][:0],
+                                                           dc["logits"], dc["ltrb"], None, None, None, 0.1, dc["points"])
+    assert b.shape == (0, 4) and p.shape == (0, 2) and valid is None and miou == 0.0
+    # a GT far away from every point keeps the 8 x 8 box at its point and is never valid
+    d = synth.pseudo_batch(3, G=10)
+    dc = {k: v.to(cuda) for k, v in d.items()}
+    b, p, _, _, valid = coarse.generate_pseudo_single(fuse, dc["gt_points"], dc["labels"], dc["gt_boxes"], dc["logits"],
+                                                      dc["ltrb"], None, None, None, 2.0, dc["points"])
+    assert valid.numel() == 0                                   # score filter above any sigmoid

@@ -254,3 +254,13 @@ def test_black_paper_oracle_reproduces_reference_golden(golden_dir):
         assert int(m.sum()) == c["n_px"]
         _, _, _, _, m2 = M.black_paper_from_candidates(d["img"].clone(), allb, d["imgsize"], use_cv2=False)
         assert np.array_equal(m, m2)
+
+
+def test_pseudo_box_oracle_reproduces_reference_golden(golden_dir):
+    from oracle import assign
+    for c in torch.load(os.path.join(golden_dir, "pseudo_boxes.pt")):
+        d = synth.pseudo_batch(c["seed"], G=c["G"])
+        b, p, _, m, v, _, _ = assign.generate_pseudo_single(d["gt_points"], d["labels"], d["gt_boxes"], d["logits"],
+                                                            d["ltrb"], d["points"], 0.1)
+        assert torch.equal(b, c["boxes"]) and torch.equal(p, c["points"])
+        assert torch.equal(m, c["mean_iou"]) and torch.equal(torch.sort(v)[0], c["valid"])
