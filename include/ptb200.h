@@ -176,6 +176,11 @@ int pt_pseudo_aggregate(const long long* gt_inds, const long long* labels, const
                         float* boxes, float* points, float* scores, long long* assign_nums, unsigned char* valid,
                         float* iou_sum, void* stream);
 
+/* pt_ltrb_targets (section 8f rank 2): _get_target_pseudo_single's regression targets + centerness_target
+ * (fcos_head_p2b_ts.py:657-708, 1019-1038) without the (P, G, 4) broadcast. */
+int pt_ltrb_targets(const float* points, const float* boxes, const long long* gt_inds, const long long* assigned_labels,
+                    int P, int num_classes, float* targets, long long* labels, float* centerness, void* stream);
+
 /* ---- phase-1 random region masking (row a16) --------------------------------------------------------------
  * The deterministic tail of generate_black_paper (HBB_TOD/mmdet/models/detectors/syn_images_generator_v2.py:664-690).
  * pt_nms_rotated: mmcv.ops.nms_rotated(dets [N, ld>=5], scores (stride lds), thr): order [N] int32 = box indices by

@@ -201,3 +201,26 @@ def generate_pseudo_single(gt_points, gt_labels, gt_bboxes, cls_scores, bbox_pre
     valid = torch.zeros(G, dtype=torch.bool)
     valid[has] = scores[has] >= filter_scores
     return boxes, pts, gt_labels, miou, valid.nonzero().reshape(-1), scores, nums
+
+
+def get_target_pseudo_single(points, cls_scores, gt_points, gt_labels, pseudo_bboxes, pseudo_labels, num_classes,
+                             a=(1, 1), pa=(3, 3)):
+    """models/dense_heads/fcos_head_p2b_ts.py:657-708 with the shipped assigners (1,1) / (3,3)."""
+    from . import hbb
+    P = points.shape[0]
+    gi, lb = topk_assign(points, cls_scores, gt_points, gt_labels, *a)
+    labels = torch.full((P,), num_classes, dtype=torch.long)
+    labels[gi != 0] = lb[gi != 0]
+    gi2, lb2 = topk_assign(points, cls_scores, hbb.xyxy_to_cxcywh(pseudo_bboxes), pseudo_labels, *pa)
+    labels_reg = torch.full((P,), num_classes, dtype=torch.long)
+    labels_reg[gi2 != 0] = lb2[gi2 != 0]
+    idx = torch.where(gi2 != 0, gi2 - 1, torch.zeros_like(gi2))
+    b = pseudo_bboxes[idx]
+    t = torch.stack([points[:, 0] - b[:, 0], points[:, 1] - b[:, 1], b[:, 2] - points[:, 0], b[:, 3] - points[:, 1]], -1)
+    return labels_reg, t, labels, torch.ones(P)
+
+
+def centerness_target(t):
+    """models/dense_heads/fcos_head_p2b_ts.py:1019-1038."""
+    lr, tb = t[:, [0, 2]], t[:, [1, 3]]
+    return torch.sqrt((lr.min(-1)[0].clamp(min=0.01) / lr.max(-1)[0]) * (tb.min(-1)[0].clamp(min=0.01) / tb.max(-1)[0]))

@@ -213,6 +213,19 @@ def check_pseudo():
         ok &= _eq(op, rp, f"pseudo points seed{seed}", 0.0)
         ok &= _eq(om, rm, f"mean iou seed{seed}", 0.0)
         ok &= _eq(torch.sort(ov)[0], torch.sort(rv)[0], f"valid inds seed{seed} ({ov.numel()} of {G})", 0.0)
+        # rank 2: the consumer of the refined boxes
+        head.num_classes = 8
+        head.assigner = ns.TopkAssigner(num_pre=1, topk=1, cls_cost=dict(type="FocalLossCost", weight=1.0),
+                                        reg_cost=dict(type="PointCost", mode="L1", weight=1.0))
+        head.pseudo_assigner = ns.TopkAssigner(num_pre=3, topk=3, cls_cost=dict(type="FocalLossCost", weight=1.0),
+                                               reg_cost=dict(type="PointCost", mode="L1", weight=1.0))
+        r = head._get_target_pseudo_single(d["gt_points"], d["labels"], rp, d["labels"], rb, d["logits"], d["ltrb"], None,
+                                           dict(ori_filename="x"), None, None, d["points"], None, False)
+        o = assign.get_target_pseudo_single(d["points"], d["logits"], d["gt_points"], d["labels"], rb, d["labels"], 8)
+        for nm, a_, b_ in zip(("labels_reg", "bbox_targets", "labels", "weights"), o, r):
+            ok &= _eq(a_, b_, f"get_target_pseudo {nm} seed{seed}", 0.0)
+        pos = (r[0] != 8).nonzero().reshape(-1)
+        ok &= _eq(assign.centerness_target(o[1][pos]), head.centerness_target(r[1][pos]), f"centerness seed{seed}", 0.0)
     return ok
 
 

@@ -148,7 +148,18 @@ def pseudo_case():
                                                  location_cost=dict(type="InsiderCost", weight=1.0))
         rb, rp, rl, rm, rv = head._gnerate_pseudo_single(d["gt_points"], d["labels"], d["gt_boxes"], d["logits"], d["ltrb"],
                                                          None, None, None, 0.1, d["points"], None)
-        out.append(dict(seed=seed, G=G, boxes=rb, points=rp, mean_iou=rm, valid=torch.sort(rv)[0]))
+        head.num_classes = 8
+        head.assigner = ns.TopkAssigner(num_pre=1, topk=1, cls_cost=dict(type="FocalLossCost", weight=1.0),
+                                        reg_cost=dict(type="PointCost", mode="L1", weight=1.0))
+        head.pseudo_assigner = ns.TopkAssigner(num_pre=3, topk=3, cls_cost=dict(type="FocalLossCost", weight=1.0),
+                                               reg_cost=dict(type="PointCost", mode="L1", weight=1.0))
+        t = head._get_target_pseudo_single(d["gt_points"], d["labels"], rp, d["labels"], rb, d["logits"], d["ltrb"], None,
+                                           dict(ori_filename="x"), None, None, d["points"], None, False)
+        pos = (t[0] != 8).nonzero().reshape(-1)
+        out.append(dict(seed=seed, G=G, boxes=rb, points=rp, mean_iou=rm, valid=torch.sort(rv)[0],
+                        labels_reg=t[0].to(torch.int16), bbox_targets_pos=t[1][pos], pos=pos.to(torch.int32),
+                        labels=t[2].to(torch.int16), centerness_pos=head.centerness_target(t[1][pos]),
+                        targets_checksum=t[1].double().sum()))
     torch.save(out, os.path.join(OUT, "pseudo_boxes.pt"))
     print("wrote pseudo_boxes", [(o["G"], o["valid"].numel()) for o in out])
 

@@ -58,6 +58,8 @@ SIGNATURES = {
     "pt_pseudo_aggregate": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_int, c_void_p, c_void_p, c_int,
                                     c_float, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                                     c_void_p]),
+    "pt_ltrb_targets": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p,
+                                c_void_p]),
     "pt_nms_rotated_workspace_bytes": (c_ll, [c_int]),
     "pt_nms_rotated": (c_int, [c_void_p, c_int, c_void_p, c_int, c_int, c_float, c_void_p, c_void_p, c_void_p, c_ll,
                                c_void_p]),

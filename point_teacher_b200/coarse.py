@@ -28,3 +28,35 @@ def generate_pseudo_single(fuse_assigner, gt_points, gt_labels, gt_bboxes, cls_s
     mean_iou = iou[0] / iou[1]                       # nan when nothing was assigned, like .mean() of an empty tensor
     valid_inds = valid.nonzero().reshape(-1)
     return boxes, ppts, gt_labels, mean_iou, valid_inds
+
+
+def get_target_pseudo_single(assigner, pseudo_assigner, num_classes, gt_points, gt_labels, pseudo_points, pseudo_labels,
+                             pseudo_bboxes, cls_scores, bbox_preds, centernesses, img_metas, img_list,
+                             gt_augument_ignore, points, num_points_per_lvl=None, burn_in_step1=False):
+    """``TS_P2BFCOSHead._get_target_pseudo_single`` (fcos_head_p2b_ts.py:657-708), the
+    consumer of the refined boxes: classification labels from ``assigner`` on the GT points, regression labels and
+    (l, t, r, b) targets from ``pseudo_assigner`` on the refined boxes.  Returns (labels_reg, bbox_targets, labels,
+    weights) like the reference; background = ``num_classes``; background points are measured against box 0."""
+    pts = points.detach().float().contiguous()
+    cls = cls_scores.detach().float().contiguous()
+    n = pts.size(0)
+    res = assigner.assign(pts, cls, gt_points, gt_labels, gt_bboxes_ignore=None)
+    labels = torch.where(res.gt_inds != 0, res.labels, torch.full_like(res.labels, num_classes))
+    weights = torch.ones_like(labels).float()
+    if len(pseudo_bboxes) == 0:
+        return gt_labels.new_full((n,), num_classes), pseudo_bboxes.new_zeros((n, 4)), labels, weights
+    pb = pseudo_bboxes.detach().float().contiguous()
+    cxcywh = torch.cat([(pb[:, :2] + pb[:, 2:]) / 2, pb[:, 2:] - pb[:, :2]], 1)          # bbox_xyxy_to_cxcywh
+    res2 = pseudo_assigner.assign(pts, cls, cxcywh, pseudo_labels, gt_bboxes_ignore=None)
+    targets, labels_reg, _ = ops.ltrb_targets(pts, pb, res2.gt_inds, res2.labels, num_classes)
+    return labels_reg, targets, labels, weights
+
+
+def centerness_target(pos_bbox_targets):
+    """fcos_head_p2b_ts.py:1019-1038 (elementwise; evaluated inside ``ops.ltrb_targets`` when asked for all points)."""
+    t = pos_bbox_targets
+    if t.shape[0] == 0:
+        return t[:, 0]
+    lr_min, lr_max = torch.minimum(t[:, 0], t[:, 2]), torch.maximum(t[:, 0], t[:, 2])
+    tb_min, tb_max = torch.minimum(t[:, 1], t[:, 3]), torch.maximum(t[:, 1], t[:, 3])
+    return torch.sqrt((lr_min.clamp(min=0.01) / lr_max) * (tb_min.clamp(min=0.01) / tb_max))

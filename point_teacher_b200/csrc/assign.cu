@@ -353,6 +353,31 @@ __global__ void pseudo_finalize_kernel(const float* __restrict__ acc, const floa
   if ((threadIdx.x & 31) == 0 && one > 0.f) { atomicAdd(iou_sum, iou); atomicAdd(iou_sum + 1, one); }
 }
 
+// ---- dense regression targets after the refinement
+//   _get_target_pseudo_single   HBB_TOD/mmdet/models/dense_heads/fcos_head_p2b_ts.py:657-708
+//   centerness_target           HBB_TOD/mmdet/models/dense_heads/fcos_head_p2b_ts.py:1019-1038
+// The reference broadcasts a (P, G, 4) ltrb tensor and gathers one column; here each point reads its own box.
+__global__ void ltrb_targets_kernel(const float* __restrict__ pts, const float* __restrict__ boxes,
+                                    const long long* __restrict__ gt_inds, const long long* __restrict__ asg_labels,
+                                    int P, int num_classes, float* __restrict__ targets, long long* __restrict__ labels,
+                                    float* __restrict__ centerness) {
+  const int p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= P) return;
+  const long long g1 = gt_inds[p];
+  const int g = g1 != 0 ? (int)g1 - 1 : 0;          // background points are measured against box 0 (reference quirk)
+  const float x = pts[2 * p], y = pts[2 * p + 1];
+  const float* b = boxes + (size_t)g * 4;
+  const float l = fsub(x, b[0]), t = fsub(y, b[1]), r = fsub(b[2], x), bt = fsub(b[3], y);
+  float* o = targets + (size_t)p * 4;
+  o[0] = l; o[1] = t; o[2] = r; o[3] = bt;
+  labels[p] = g1 != 0 ? asg_labels[p] : (long long)num_classes;
+  if (centerness != nullptr) {
+    const float lr = fdiv(fmaxf(fminf(l, r), 0.01f), fmaxf(l, r));
+    const float tb = fdiv(fmaxf(fminf(t, bt), 0.01f), fmaxf(t, bt));
+    centerness[p] = sqrtf(fmul(lr, tb));
+  }
+}
+
 }  // namespace ptb
 
 using namespace ptb;
@@ -475,4 +500,15 @@ extern "C" int pt_pseudo_aggregate(const long long* gt_inds, const long long* la
   pseudo_finalize_kernel<<<(G + 127) / 128, 128, 0, s>>>(acc_ws, gt_points, gt_bboxes, G, filter_score, boxes, points,
                                                           scores, assign_nums, valid, iou_sum);
   return check_launch("pseudo_finalize_kernel");
+}
+
+// targets [P,4] = (l, t, r, b) of every point against its assigned pseudo box (box 0 for background), labels [P]
+// (num_classes for background), optional centerness [P] = centerness_target(targets).
+extern "C" int pt_ltrb_targets(const float* points, const float* boxes, const long long* gt_inds,
+                               const long long* assigned_labels, int P, int num_classes, float* targets,
+                               long long* labels, float* centerness, void* stream) {
+  if (P <= 0) return PT_OK;
+  ltrb_targets_kernel<<<(P + 255) / 256, 256, 0, (cudaStream_t)stream>>>(points, boxes, gt_inds, assigned_labels, P,
+                                                                        num_classes, targets, labels, centerness);
+  return check_launch("ltrb_targets_kernel");
 }

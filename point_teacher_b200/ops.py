@@ -614,3 +614,18 @@ def pseudo_aggregate(gt_inds, labels, cls_scores, xyxy, gt_points, gt_bboxes, fi
               _p(gt_points), _p(gt_bboxes), G, float(filter_score), _p(ws), _p(boxes), _p(pts), _p(scores), _p(nums),
               _p(valid), _p(iou), _stream())
     return boxes, pts, scores, nums, valid, iou
+
+
+def ltrb_targets(points, boxes, gt_inds, assigned_labels, num_classes, want_centerness=False):
+    """-> (targets (P,4), labels (P,) int64 with num_classes = background, centerness (P,) | None)."""
+    _chk(points, "points", _f32, 2, 2)
+    _chk(boxes, "pseudo_bboxes", _f32, 2, 4)
+    _chk(gt_inds, "gt_inds", _i64, 1)
+    _chk(assigned_labels, "labels", _i64, 1)
+    P, dev = points.shape[0], points.device
+    t = torch.empty((P, 4), dtype=_f32, device=dev)
+    lab = torch.empty((P,), dtype=_i64, device=dev)
+    cen = torch.empty((P,), dtype=_f32, device=dev) if want_centerness else None
+    _lib.call("pt_ltrb_targets", _p(points), _p(boxes), _p(gt_inds), _p(assigned_labels), P, int(num_classes), _p(t),
+              _p(lab), _p(cen), _stream())
+    return t, lab, cen

@@ -171,3 +171,32 @@ def test_coarse_pseudo_boxes_vs_reference_golden_and_oracle(cuda, golden_dir):
     b, p, _, _, valid = coarse.generate_pseudo_single(fuse, dc["gt_points"], dc["labels"], dc["gt_boxes"], dc["logits"],
                                                       dc["ltrb"], None, None, None, 2.0, dc["points"])
     assert valid.numel() == 0                                   # score filter above any sigmoid
+
+
+def test_target_pseudo_vs_reference_golden(cuda, golden_dir):
+    """Section 8f rank 2 (_get_target_pseudo_single + centerness_target): labels bit-exact, ltrb targets bit-exact."""
+    from point_teacher_b200 import coarse, ops
+    a, pa = _mk_topk(1, 1), _mk_topk(3, 3)
+    for c in torch.load(os.path.join(golden_dir, "pseudo_boxes.pt")):
+        d = {k: v.to(cuda) for k, v in synth.pseudo_batch(c["seed"], G=c["G"]).items()}
+        boxes = c["boxes"].to(cuda)
+        lr, t, lb, w = coarse.get_target_pseudo_single(a, pa, 8, d["gt_points"], d["labels"], c["points"].to(cuda),
+                                                       d["labels"], boxes, d["logits"], d["ltrb"], None, None, None, None,
+                                                       d["points"])
+        pos = c["pos"].long()
+        assert torch.equal(lr.cpu(), c["labels_reg"].long()) and torch.equal(lb.cpu(), c["labels"].long())
+        assert torch.equal(t.cpu()[pos], c["bbox_targets_pos"])
+        assert float(t.cpu().double().sum()) == float(c["targets_checksum"])
+        assert (w == 1).all()
+        cen = coarse.centerness_target(t[pos.to(cuda)])
+        assert (cen.cpu() - c["centerness_pos"]).abs().max() < 1e-6
+        # fused variant: centerness for every point from the same kernel
+        res = pa.assign(d["points"], d["logits"], torch.cat([(boxes[:, :2] + boxes[:, 2:]) / 2, boxes[:, 2:] - boxes[:, :2]], 1),
+                        d["labels"])
+        _, _, cen_all = ops.ltrb_targets(d["points"], boxes, res.gt_inds, res.labels, 8, want_centerness=True)
+        assert (cen_all.cpu()[pos] - c["centerness_pos"]).abs().max() < 1e-6
+    # no pseudo boxes: the reference's early return
+    lr, t, lb, w = coarse.get_target_pseudo_single(a, pa, 8, d["gt_points"], d["labels"], d["gt_points"][:0],
+                                                   d["labels"][:0], boxes[:0], d["logits"], d["ltrb"], None, None, None,
+                                                   None, d["points"])
+    assert (lr == 8).all() and torch.count_nonzero(t) == 0

@@ -264,3 +264,15 @@ def test_pseudo_box_oracle_reproduces_reference_golden(golden_dir):
                                                             d["ltrb"], d["points"], 0.1)
         assert torch.equal(b, c["boxes"]) and torch.equal(p, c["points"])
         assert torch.equal(m, c["mean_iou"]) and torch.equal(torch.sort(v)[0], c["valid"])
+
+
+def test_target_pseudo_oracle_reproduces_reference_golden(golden_dir):
+    from oracle import assign
+    for c in torch.load(os.path.join(golden_dir, "pseudo_boxes.pt")):
+        d = synth.pseudo_batch(c["seed"], G=c["G"])
+        lr, t, lb, w = assign.get_target_pseudo_single(d["points"], d["logits"], d["gt_points"], d["labels"], c["boxes"],
+                                                       d["labels"], 8)
+        pos = c["pos"].long()
+        assert torch.equal(lr, c["labels_reg"].long()) and torch.equal(lb, c["labels"].long())
+        assert torch.equal(t[pos], c["bbox_targets_pos"]) and float(t.double().sum()) == float(c["targets_checksum"])
+        assert torch.equal(assign.centerness_target(t[pos]), c["centerness_pos"])
