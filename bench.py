@@ -138,6 +138,34 @@ def run_reference(args):
         "e2e": {"value": val, "unit": "imgs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
 
 
+def _bind_to_gpu_numa_node(local):
+    """Pin this rank's host threads (and therefore its first-touch pinned buffers) to the NUMA node of its GPU, so
+    that the per-step H2D copies of N ranks do not all stream through one socket's memory controllers."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+        phys = int(vis.split(",")[local]) if vis and all(v.strip().isdigit() for v in vis.split(",")) else local
+        bus = pynvml.nvmlDeviceGetPciInfo(pynvml.nvmlDeviceGetHandleByIndex(phys)).busId
+        bus = (bus.decode() if isinstance(bus, bytes) else bus).lower()
+        if len(bus.split(":")[0]) == 8:
+            bus = bus[4:]
+        node = int(open(f"/sys/bus/pci/devices/{bus}/numa_node").read())
+        if node < 0:
+            return None
+        cpus = set()
+        for part in open(f"/sys/devices/system/node/node{node}/cpulist").read().strip().split(","):
+            a, _, b = part.partition("-")
+            cpus.update(range(int(a), int(b or a) + 1))
+        cpus &= os.sched_getaffinity(0)
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+            return node
+    except Exception:
+        pass
+    return None
+
+
 def _traffic(kernel_key):
     """Per-launch DRAM bytes of a kernel from the committed ncu --set full capture (profiles/traffic.json)."""
     p = os.path.join(ROOT, "profiles", "traffic.json")
@@ -156,6 +184,7 @@ def run_ours(args):
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
+    numa = _bind_to_gpu_numa_node(local) if world > 1 else None
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
@@ -353,7 +382,8 @@ def run_ours(args):
                        "roi_feature_map": f"NHWC {feat_dt}"},
             "e2e": {"value": total_imgs / (e2e_ms * 1e-3), "unit": "imgs/s", "h2d_bytes_per_step": h2d_bytes,
                     "d2h_bytes_per_step": d2h_bytes, "ms_per_step": e2e_ms,
-                    "api": "point_teacher_b200.refine.Phase2Pipeline.submit/result (double-buffered H2D)"},
+                    "api": "point_teacher_b200.refine.Phase2Pipeline.submit/result (double-buffered H2D)",
+                    "host_numa_node_rank0": numa},
             "gpu_launches": launches_per_step * args.steps,
             "clocks": clocks,
             "roofline": {"kernel": "fc_gemm_kernel (FC1, M=5000/5400 N=1024 K=12544)", "bound": "tensor",

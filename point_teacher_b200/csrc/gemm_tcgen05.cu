@@ -15,17 +15,30 @@
 // partials of a tile are parked in private fp32 workspace slots and reduced all-to-all (each CTA finalises 1/S of
 // the rows), which is deterministic and free of same-address atomics.
 #include <cuda.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 
 namespace ptb {
 namespace gemm {
 
-constexpr int BM = 128, BN = 256, BK = 64, UMMA_K = 16, STAGES = 4, ACC_STAGES = 2;
-constexpr int A_BYTES = BM * BK * 2, B_BYTES = BN * BK * 2, STAGE_BYTES = A_BYTES + B_BYTES;
+constexpr int BM = 128, BN = 256, BK = 64, UMMA_K = 16, ACC_STAGES = 2;
+constexpr int A_BYTES = BM * BK * 2;
 constexpr int NUM_THREADS = 192;
 constexpr int TMEM_COLS = ACC_STAGES * BN;  // 512
-constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 256 + 1024;
+// TWO = false: one CTA per tile (128 x 256), B tile 256 rows, 4 stages of 48 KB.
+// TWO = true : CTA pair (cluster of 2, tcgen05 cta_group::2) per 256 x 256 tile: every CTA stages its own 128 A rows
+//              and HALF of the B tile (128 rows), 6 stages of 32 KB.  The single-CTA mainloop moves 96 KB through
+//              shared memory per k-block (48 KB written by TMA + 48 KB read by the MMA) in the ~0.28 us the tensor
+//              pipe needs -- more than the 128 B/clk the SM's shared memory delivers; pairing cuts that to 64 KB.
+template <bool TWO> struct Cfg {
+  static constexpr int STAGES = TWO ? 6 : 4;
+  static constexpr int B_ROWS = TWO ? BN / 2 : BN;
+  static constexpr int B_BYTES = B_ROWS * BK * 2;
+  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 256 + 1024;
+};
+constexpr uint32_t PEER_BIT_MASK = 0xFEFFFFFFu;   // shared::cluster address of the same offset in CTA 0 of the pair
 
 struct Params {
   const float* bias;  // [N] or nullptr
@@ -44,8 +57,9 @@ struct Unit {
   int m_blk, n_blk, kb0, kb1, tail_idx;  // tail_idx >= 0: split unit
 };
 
-__device__ __forceinline__ bool get_unit(const Params& p, int it, Unit& u) {
-  const int G = gridDim.x, c = blockIdx.x;
+// G / c: number and index of the scheduling units (CTAs, or CTA pairs); rank: CTA inside the pair (0 when unpaired).
+// Paired: a "tile" is 256 x 256 and this CTA owns rows [128 * (2 m + rank), +128) of it.
+__device__ __forceinline__ bool get_unit(const Params& p, int it, Unit& u, int G, int c, int pair, int rank) {
   const int kb_total = p.K / BK;
   int tile;
   if (it < p.full_rounds) {
@@ -71,7 +85,45 @@ __device__ __forceinline__ bool get_unit(const Params& p, int it, Unit& u) {
   }
   u.m_blk = tile / p.tiles_n;  // n fastest: the N-tiles of one M-tile run concurrently -> A read from HBM once
   u.n_blk = tile % p.tiles_n;
+  if (pair) {
+    u.m_blk = u.m_blk * 2 + rank;
+    if (u.tail_idx >= 0) u.tail_idx = u.tail_idx * 2 + rank;
+  }
   return true;
+}
+
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tma_load_2d_pair(void* smem_dst, const void* desc, uint64_t* bar, int c0, int c1) {
+  // executed by both CTAs of the pair; the transaction bytes update CTA 0's barrier
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(smem_u32(smem_dst)), "l"(desc), "r"(smem_u32(bar) & PEER_BIT_MASK), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tc_mma_bf16_pair(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                                 uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void tc_commit_pair(uint64_t* bar) {   // arrives on the same barrier offset in both CTAs
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+               ::"r"(smem_u32(bar)), "h"((uint16_t)3)
+               : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_cta0(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(smem_u32(bar) & PEER_BIT_MASK) : "memory");
 }
 
 __device__ __forceinline__ uint64_t make_desc(uint32_t saddr) {
@@ -85,6 +137,8 @@ constexpr uint32_t IDESC = (1u << 4)      // D format: fp32
                            | (1u << 7)    // A format: bf16
                            | (1u << 10)   // B format: bf16
                            | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);  // K-major A and B
+constexpr uint32_t IDESC_PAIR = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) |
+                                ((uint32_t)((2 * BM) >> 4) << 24);                        // M = 256 across the pair
 
 __device__ __forceinline__ void store_chunk(const Params& p, int row, int col0, const uint32_t* r, bool row_ok) {
   // r: 32 fp32 accumulators of columns col0..col0+31 of this thread's row
@@ -131,11 +185,16 @@ __device__ __forceinline__ void store_chunk(const Params& p, int row, int col0, 
   }
 }
 
+template <bool TWO>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 fc_gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b,
                const Params p) {
+  constexpr int STAGES = Cfg<TWO>::STAGES, STAGE_BYTES = Cfg<TWO>::STAGE_BYTES, B_ROWS = Cfg<TWO>::B_ROWS;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  const int rank = TWO ? (int)cluster_ctarank() : 0;
+  const int sched_G = TWO ? (int)(gridDim.x >> 1) : (int)gridDim.x;
+  const int sched_c = TWO ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES);
   uint64_t* empty_bar = full_bar + STAGES;
   uint64_t* tfull_bar = empty_bar + STAGES;
@@ -149,15 +208,23 @@ fc_gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
     tma_prefetch_desc(&tma_a);
     tma_prefetch_desc(&tma_b);
     for (int i = 0; i < STAGES; i++) { mbar_init(full_bar + i, 1); mbar_init(empty_bar + i, 1); }
-    for (int i = 0; i < ACC_STAGES; i++) { mbar_init(tfull_bar + i, 1); mbar_init(tempty_bar + i, 4); }
+    for (int i = 0; i < ACC_STAGES; i++) { mbar_init(tfull_bar + i, 1); mbar_init(tempty_bar + i, TWO ? 8 : 4); }
     fence_barrier_init();
   }
+  if (TWO) cluster_sync_all();          // the peer's barriers exist before anything can signal them
   if (warp == 1) {
-    tmem_alloc(tmem_ptr, TMEM_COLS);
-    tmem_relinquish();
+    if (TWO) {
+      asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_ptr)),
+                   "r"((uint32_t)TMEM_COLS) : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    } else {
+      tmem_alloc(tmem_ptr, TMEM_COLS);
+      tmem_relinquish();
+    }
   }
   tc_fence_before();
   __syncthreads();
+  if (TWO) cluster_sync_all();          // both CTAs own their accumulator columns before the first paired MMA
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
 
@@ -166,51 +233,62 @@ fc_gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
     if (lane == 0) {
       int stage = 0; uint32_t phase = 0;
       Unit u;
-      for (int it = 0; get_unit(p, it, u); it++) {
+      for (int it = 0; get_unit(p, it, u, sched_G, sched_c, TWO, rank); it++) {
         for (int kb = u.kb0; kb < u.kb1; kb++) {
           mbar_wait(empty_bar + stage, phase ^ 1);
           uint8_t* sa = smem + stage * STAGE_BYTES;
-          mbar_expect_tx(full_bar + stage, STAGE_BYTES);
-          tma_load_2d(sa, &tma_a, full_bar + stage, kb * BK, u.m_blk * BM);
-          tma_load_2d(sa + A_BYTES, &tma_b, full_bar + stage, kb * BK, u.n_blk * BN);
+          if (TWO) {
+            // CTA 0's barrier collects the bytes of both CTAs' loads (its own arrive arms 2 x STAGE_BYTES)
+            if (rank == 0) mbar_expect_tx(full_bar + stage, 2 * STAGE_BYTES);
+            tma_load_2d_pair(sa, &tma_a, full_bar + stage, kb * BK, u.m_blk * BM);
+            tma_load_2d_pair(sa + A_BYTES, &tma_b, full_bar + stage, kb * BK, u.n_blk * BN + rank * B_ROWS);
+          } else {
+            mbar_expect_tx(full_bar + stage, STAGE_BYTES);
+            tma_load_2d(sa, &tma_a, full_bar + stage, kb * BK, u.m_blk * BM);
+            tma_load_2d(sa + A_BYTES, &tma_b, full_bar + stage, kb * BK, u.n_blk * BN);
+          }
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
       }
     }
   } else if (warp == 1) {
-    // ------------------------------------------------------------------ MMA issuer
-    int stage = 0; uint32_t phase = 0;
-    int acc = 0; uint32_t acc_phase = 0;
-    Unit u;
-    for (int it = 0; get_unit(p, it, u); it++) {
-      mbar_wait(tempty_bar + acc, acc_phase ^ 1);
-      tc_fence_after();
-      const uint32_t tmem_d = tmem_base + acc * BN;
-      for (int kb = u.kb0; kb < u.kb1; kb++) {
-        mbar_wait(full_bar + stage, phase);
+    // ------------------------------------------------------------------ MMA issuer (paired: CTA 0 only)
+    if (!TWO || rank == 0) {
+      int stage = 0; uint32_t phase = 0;
+      int acc = 0; uint32_t acc_phase = 0;
+      Unit u;
+      for (int it = 0; get_unit(p, it, u, sched_G, sched_c, TWO, rank); it++) {
+        mbar_wait(tempty_bar + acc, acc_phase ^ 1);
         tc_fence_after();
-        if (lane == 0) {
-          const uint32_t sa = smem_u32(smem + stage * STAGE_BYTES);
-          const uint64_t adesc = make_desc(sa), bdesc = make_desc(sa + A_BYTES);
+        const uint32_t tmem_d = tmem_base + acc * BN;
+        for (int kb = u.kb0; kb < u.kb1; kb++) {
+          mbar_wait(full_bar + stage, phase);
+          tc_fence_after();
+          if (lane == 0) {
+            const uint32_t sa = smem_u32(smem + stage * STAGE_BYTES);
+            const uint64_t adesc = make_desc(sa), bdesc = make_desc(sa + A_BYTES);
 #pragma unroll
-          for (int k = 0; k < BK / UMMA_K; k++) {
-            // advance 16 bf16 = 32 B along K inside the 128 B swizzle row: +2 in 16 B units
-            tc_mma_bf16(tmem_d, adesc + 2 * k, bdesc + 2 * k, IDESC, (kb > u.kb0 || k > 0) ? 1u : 0u);
+            for (int k = 0; k < BK / UMMA_K; k++) {
+              // advance 16 bf16 = 32 B along K inside the 128 B swizzle row: +2 in 16 B units
+              if (TWO) tc_mma_bf16_pair(tmem_d, adesc + 2 * k, bdesc + 2 * k, IDESC_PAIR, (kb > u.kb0 || k > 0) ? 1u : 0u);
+              else tc_mma_bf16(tmem_d, adesc + 2 * k, bdesc + 2 * k, IDESC, (kb > u.kb0 || k > 0) ? 1u : 0u);
+            }
+            // frees the smem slot (in both CTAs when paired) when these MMAs retire
+            if (TWO) tc_commit_pair(empty_bar + stage); else tc_commit(empty_bar + stage);
+            if (kb == u.kb1 - 1) { if (TWO) tc_commit_pair(tfull_bar + acc); else tc_commit(tfull_bar + acc); }
           }
-          tc_commit(empty_bar + stage);  // frees the smem slot when these MMAs retire
-          if (kb == u.kb1 - 1) tc_commit(tfull_bar + acc);
+          __syncwarp();
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
-        __syncwarp();
-        if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        if (++acc == ACC_STAGES) { acc = 0; acc_phase ^= 1; }
       }
-      if (++acc == ACC_STAGES) { acc = 0; acc_phase ^= 1; }
     }
   } else {
     // ------------------------------------------------------------------ epilogue (warps 2..5)
     const int q = warp & 3;  // TMEM lane quarter this warp may touch
     int acc = 0; uint32_t acc_phase = 0;
     Unit u;
-    for (int it = 0; get_unit(p, it, u); it++) {
+    for (int it = 0; get_unit(p, it, u, sched_G, sched_c, TWO, rank); it++) {
       mbar_wait(tfull_bar + acc, acc_phase);
       tc_fence_after();
       const int row = u.m_blk * BM + q * 32 + lane;
@@ -226,13 +304,13 @@ fc_gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
         }
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(tempty_bar + acc);
+        if (lane == 0) { if (TWO) mbar_arrive_cta0(tempty_bar + acc); else mbar_arrive(tempty_bar + acc); }
       } else {
         // split-K partial (tail wave): the S CTAs of a tile each park their fp32 partial in a private workspace
         // slot (plain 16-byte stores), meet at a counter, and then each CTA reduces and finalises 1/S of the tile's
         // rows from all S slots -- a deterministic all-to-all reduction, 2 x 128 KB of L2 traffic per CTA.  (The
         // earlier red.global.add version serialised S-way on every address and cost ~25 us per FC1 launch.)
-        const int s_idx = blockIdx.x % p.split;
+        const int s_idx = sched_c % p.split;
         float* slot = p.ws + ((size_t)u.tail_idx * p.split + s_idx) * (BM * BN);
         float* wrow = slot + (size_t)(q * 32 + lane) * BN;
 #pragma unroll 1
@@ -248,7 +326,7 @@ fc_gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
         }
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(tempty_bar + acc);
+        if (lane == 0) { if (TWO) mbar_arrive_cta0(tempty_bar + acc); else mbar_arrive(tempty_bar + acc); }
         __threadfence();
         asm volatile("bar.sync 1, 128;" ::: "memory");  // the 4 epilogue warps
         int* cnt = p.counters + 2 * u.tail_idx;
@@ -313,9 +391,11 @@ fc_gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
 
   tc_fence_before();
   __syncthreads();
+  if (TWO) cluster_sync_all();          // the peer may still be reading accumulators the pair allocated together
   if (warp == 1) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, TMEM_COLS);
+    if (TWO) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)TMEM_COLS) : "memory");
+    else tmem_dealloc(tmem_base, TMEM_COLS);
   }
 }
 
@@ -333,6 +413,16 @@ static EncodeTiledFn get_encode() {
     fn = reinterpret_cast<EncodeTiledFn>(ptr);
   }
   return fn;
+}
+
+// PTB200_GEMM_PAIR=1 selects the paired (cta_group::2) kernel for the long contractions.  Measured on B200
+// (tools/bench_gemm_ab.py): wave-exact 18944x1024x12544 1490 vs 1467 TFLOP/s, 5000 rows 105 vs 111 us alone, but no
+// gain inside the captured step (0.495 vs 0.494 ms) -- the single-CTA mainloop already runs at ~90 % of the measured
+// cuBLAS peak and the FC1 launches are bound by wave quantisation, so the simpler kernel stays the default.
+static bool pair_enabled() {
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("PTB200_GEMM_PAIR"); v = (e != nullptr && e[0] == '1') ? 1 : 0; }
+  return v == 1;
 }
 
 static int make_map(CUtensorMap* map, const void* base, long long rows, long long cols, long long ld, int box_rows) {
@@ -394,31 +484,36 @@ extern "C" int pt_fc_gemm_bf16_ex(const void* A, long long lda, const void* B, l
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
   }
+  // paired (cta_group::2) kernel for the long contractions; single-CTA kernel otherwise
+  const bool two = (K >= 4096) && (num_sms % 2 == 0) && (M > 2 * BM) && pair_enabled();
   CUtensorMap ma, mb;
   int rc = make_map(&ma, A, M, K, lda, BM);
   if (rc != PT_OK) return rc;
-  rc = make_map(&mb, B, N, K, ldb, BN);
+  rc = make_map(&mb, B, N, K, ldb, two ? BN / 2 : BN);
   if (rc != PT_OK) return rc;
 
   Params p;
   p.mask = reinterpret_cast<const __nv_bfloat16*>(mask); p.ldmask = (int)ldmask;
   p.bias = bias; p.C = C; p.M = M; p.N = N; p.K = K; p.ldc = (int)ldc; p.relu = relu; p.out_f32 = out_f32;
   p.tiles_n = N / BN;
-  const int tiles_m = (M + BM - 1) / BM;
+  const int tile_rows = two ? 2 * BM : BM;                 // rows of one scheduling tile
+  const int tiles_m = (M + tile_rows - 1) / tile_rows;
   p.tiles_total = tiles_m * p.tiles_n;
-  int grid = p.tiles_total < num_sms ? p.tiles_total : num_sms;
-  p.full_rounds = p.tiles_total / grid;
-  const int tail = p.tiles_total - p.full_rounds * grid;
+  const int units = two ? num_sms / 2 : num_sms;           // scheduling units: CTA pairs or CTAs
+  int grid_u = p.tiles_total < units ? p.tiles_total : units;
+  p.full_rounds = p.tiles_total / grid_u;
+  const int tail = p.tiles_total - p.full_rounds * grid_u;
+  const int sub = two ? 2 : 1;                             // 128-row output sub-tiles per scheduling tile
   p.split = 0;
   p.ws = nullptr; p.counters = nullptr;
-  if (allow_split && tail > 0 && tail * 8 <= 4096 && workspace != nullptr) {
-    int S = grid / tail;
+  if (allow_split && tail > 0 && tail * sub * 8 <= 4096 && workspace != nullptr) {
+    int S = grid_u / tail;
     const int kb_total = K / BK;
     // every split must keep >= 8 k-blocks of MMA work, otherwise the fp32 reduction costs more than it saves; short
     // contractions (K < 4096: FC2, measured 43 us split vs 27 us unsplit at 5000x1024x1024) are never split
     if (S > kb_total / 8) S = kb_total / 8;
     if (kb_total < 64) S = 0;
-    const long long need = (long long)tail * S * BM * BN * 4 + 4096;
+    const long long need = (long long)tail * sub * S * BM * BN * 4 + 4096;
     if (S >= 2 && need <= workspace_bytes) {
       p.split = S;
       // counters first (they must stay zero between launches; the partial slots need no initialisation)
@@ -428,10 +523,24 @@ extern "C" int pt_fc_gemm_bf16_ex(const void* A, long long lda, const void* B, l
   }
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(fc_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+    cudaError_t e = cudaFuncSetAttribute(fc_gemm_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<false>::SMEM_BYTES);
+    if (e == cudaSuccess)
+      e = cudaFuncSetAttribute(fc_gemm_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<true>::SMEM_BYTES);
     if (e != cudaSuccess) { set_error("cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return PT_ERR_CUDA; }
     attr_set = true;
   }
-  fc_gemm_kernel<<<grid, NUM_THREADS, SMEM_BYTES, (cudaStream_t)stream>>>(ma, mb, p);
+  if (two) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(2 * grid_u); cfg.blockDim = dim3(NUM_THREADS);
+    cfg.dynamicSmemBytes = Cfg<true>::SMEM_BYTES; cfg.stream = (cudaStream_t)stream;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+    cfg.attrs = at; cfg.numAttrs = 1;
+    cudaError_t e = cudaLaunchKernelEx(&cfg, fc_gemm_kernel<true>, ma, mb, p);
+    if (e != cudaSuccess) { set_error("fc_gemm_kernel<pair>: launch failed: %s", cudaGetErrorString(e)); return PT_ERR_CUDA; }
+    return check_launch("fc_gemm_kernel<pair>");
+  }
+  fc_gemm_kernel<false><<<grid_u, NUM_THREADS, Cfg<false>::SMEM_BYTES, (cudaStream_t)stream>>>(ma, mb, p);
   return check_launch("fc_gemm_kernel");
 }

@@ -233,6 +233,32 @@ def test_fc_gemm_vs_fp32_reference(cuda, M, N, K, relu, f32, split):
     assert torch.count_nonzero(ops.gemm_workspace(cuda)[:4096]) == 0
 
 
+def test_fc_gemm_paired_cta_group2_variant(cuda):
+    """The opt-in cta_group::2 kernel (PTB200_GEMM_PAIR=1) in a fresh process: same numerics as the fp32 reference,
+    including the tail-wave split-K reduction at pair granularity."""
+    import subprocess
+    import sys
+    code = (
+        "import torch\n"
+        "from point_teacher_b200 import ops\n"
+        "g = torch.Generator().manual_seed(1)\n"
+        "for M, N, K in [(5400, 1024, 12544), (5000, 1024, 4096), (700, 512, 8192)]:\n"
+        "    A = torch.randn(M, K, generator=g).to(torch.bfloat16).cuda()\n"
+        "    B = (torch.randn(N, K, generator=g) * 0.05).to(torch.bfloat16).cuda()\n"
+        "    bias = torch.randn(N, generator=g).cuda()\n"
+        "    ref = (A.float() @ B.float().t() + bias).relu()\n"
+        "    for _ in range(2):\n"
+        "        out = ops.fc_gemm(A, B, bias, relu=True, out_dtype=torch.float32)\n"
+        "        err = (out - ref).abs().max().item() / ref.abs().max().item()\n"
+        "        assert err < 1e-3, (M, N, K, err)\n"
+        "torch.cuda.synchronize()\n"
+        "print('paired ok')\n")
+    env = dict(os.environ, PTB200_GEMM_PAIR="1")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, "-c", code], cwd=root, env=env, capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0 and "paired ok" in r.stdout, r.stderr[-2000:]
+
+
 def test_fc_gemm_rejects_bad_shapes(cuda):
     from point_teacher_b200 import ops
     from point_teacher_b200._lib import PTB200Error
