@@ -49,7 +49,14 @@ def phase2_refine(head, x_ori, img_metas, pseudo_bboxes, pseudo_points, pseudo_l
             for c in counts:
                 o.append(o[-1] + c * U1)
             offs = const_tensor(o, torch.int32, dev)
-        if train:      # the two MIL losses carry a grad_fn (feature map + head parameters), see train.py
+        if train == "manual":     # forward only, intermediates kept for an explicit backward (train.Phase2Trainer)
+            keep = {}
+            head._wcache.clear()
+            pb_new, pts, mil_loss = head.mil_stage_packed(x_ori, img_metas, img_wh, base_rois, U1, pb, gb, negs, neg_idx,
+                                                          offs, labels, pb, fine_proposal_extensive_cfg[stage], stage,
+                                                          loss_scales=alpha, keep=keep)
+            head._train_keeps = getattr(head, "_train_keeps", []) + [keep]
+        elif train:    # the two MIL losses carry a grad_fn (feature map + head parameters), see train.py
             from .train import mil_stage_train
             pb_new, pts, mil_loss = mil_stage_train(head, x_ori, img_metas, img_wh, base_rois, U1, pb, gb, negs, neg_idx,
                                                     offs, labels, pb, fine_proposal_extensive_cfg[stage], stage,

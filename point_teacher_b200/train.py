@@ -134,17 +134,77 @@ class Phase2Trainer:
         self.bucket = MILGradBucket(head)
 
     def step(self, x, img_metas, pseudo_bboxes, pseudo_points, pseudo_labels, gt_bboxes, neg_boxes=None,
-             reduce_logs=True):
+             reduce_logs=True, use_autograd=False):
         """x: tuple with the (B,C,H,W) fp32 feature map (``requires_grad`` decides whether its gradient is produced).
         Returns (refined boxes, refined points, losses dict); parameter gradients are left in ``param.grad``
-        (already averaged over ranks), the feature gradient in ``x[0].grad``."""
+        (already averaged over ranks), the feature gradient in ``x[0].grad``.
+
+        By default the backward kernels are driven directly (every loss has upstream gradient 1, as when
+        ``_parse_losses`` sums the dict) -- no autograd engine, hence capturable in a CUDA graph without
+        AccumulateGrad stream bookkeeping.  ``use_autograd=True`` goes through ``loss.backward()`` instead."""
         from .dist import reduce_mean_losses
         from .refine import phase2_refine
+        head = self.head
         for _, p in self.bucket.named:
             p.grad = None
-        boxes, pts, losses = phase2_refine(self.head, x, img_metas, pseudo_bboxes, pseudo_points, pseudo_labels,
-                                           gt_bboxes, neg_boxes=neg_boxes, train=True, **self.kw)
-        total = sum(v for k, v in losses.items() if "loss" in k)       # BaseDetector._parse_losses
-        total.backward()
+        if use_autograd:
+            boxes, pts, losses = phase2_refine(head, x, img_metas, pseudo_bboxes, pseudo_points, pseudo_labels,
+                                               gt_bboxes, neg_boxes=neg_boxes, train=True, **self.kw)
+            total = sum(v for k, v in losses.items() if "loss" in k)       # BaseDetector._parse_losses
+            total.backward()
+        else:
+            head._train_keeps = []
+            with torch.no_grad():
+                boxes, pts, losses = phase2_refine(head, (x[0].detach(),), img_metas, pseudo_bboxes, pseudo_points,
+                                                   pseudo_labels, gt_bboxes, neg_boxes=neg_boxes, train="manual",
+                                                   **self.kw)
+                one = torch.ones((1,), dtype=torch.float32, device=x[0].device)
+                need_x = x[0].requires_grad
+                dx = None
+                for keep in head._train_keeps:
+                    dfeat, grads = mil_stage_backward(head, keep, x[0], one, one, need_x)
+                    for p, g in zip(stage_params(head, keep["stage"]), grads):
+                        p.grad = g if p.grad is None else p.grad + g
+                    if need_x:
+                        dx = dfeat if dx is None else dx + dfeat
+                head._train_keeps = []
+                if need_x:
+                    x[0].grad = dx if x[0].grad is None else x[0].grad + dx
         self.bucket.all_reduce_()
         return boxes, pts, (reduce_mean_losses(losses) if reduce_logs else losses)
+
+
+class CapturedTrainStep:
+    """``Phase2Trainer.step`` (forward + backward + gradient all-reduce) captured once into a CUDA graph: the
+    training step is ~90 launches of mostly short kernels, so eager Python launch overhead is larger than the device
+    time.  Static inputs live in ``self.inputs`` (copy new data in, ``replay()``); results in ``self.outputs``
+    (boxes, points, losses), parameter gradients in ``param.grad`` and the feature gradient in ``self.x.grad`` --
+    all at fixed addresses that every replay overwrites."""
+
+    def __init__(self, head, inputs, img_metas, fine_cfg, ext_cfg, num_stages=1, cap=100, alpha=(0.01, 0.25),
+                 warmup=3, feat_grad=True):
+        self.trainer = Phase2Trainer(head, fine_cfg, ext_cfg, num_stages, cap, alpha)
+        self.inputs, self.img_metas = inputs, img_metas
+        self.x = inputs["feat"].detach().requires_grad_(feat_grad)
+        s = torch.cuda.Stream()
+        s.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(s):
+            for _ in range(warmup):
+                self._step()
+        torch.cuda.current_stream().wait_stream(s)
+        torch.cuda.synchronize()
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph):
+            self.outputs = self._step()
+
+    def _step(self):
+        i = self.inputs
+        self.x.grad = None
+        for layer in self.trainer.head.bbox_roi_extractor.roi_layers:
+            layer._cache.clear()
+        return self.trainer.step((self.x,), self.img_metas, i["pseudo_boxes"], i["pseudo_points"], i["pseudo_labels"],
+                                 i["gt_boxes"], neg_boxes=i.get("neg_boxes"), reduce_logs=False)
+
+    def replay(self):
+        self.graph.replay()
+        return self.outputs

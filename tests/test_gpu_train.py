@@ -187,7 +187,15 @@ def test_phase2_trainer_single_process(cuda):
     negs = [to(n) for n in d["neg_boxes"]]
     x = d["feat"].to(cuda).requires_grad_(True)
     tr = Phase2Trainer(head, synth.HBB_FINE_CFG, synth.HBB_EXT_CFG, num_stages=2)
-    boxes, pts, losses = tr.step((x,), *args, neg_boxes=negs)
+    boxes, pts, losses = tr.step((x,), *args, neg_boxes=negs, use_autograd=True)
+    ga = {n: p.grad.clone() for n, p in head.named_parameters() if p.grad is not None}
+    gxa = x.grad.clone()
+    x.grad = None
+    boxes, pts, losses = tr.step((x,), *args, neg_boxes=negs)            # direct (engine-free) backward: same gradients
+    for n, p in head.named_parameters():
+        if p.grad is not None:
+            assert torch.allclose(p.grad, ga[n], rtol=0, atol=1e-5 * float(ga[n].abs().max()) + 1e-9), n
+    assert torch.allclose(x.grad, gxa, rtol=0, atol=1e-5 * float(gxa.abs().max()))
     g1 = {n: p.grad.clone() for n, p in head.named_parameters() if p.grad is not None}
     gx1 = x.grad.clone()
     assert set(k.split(".")[0] for k in g1) == {"shared_fcs_reg", "shared_fcs_bag", "fc_cls", "fc_ins", "fc_reg"}
@@ -209,3 +217,35 @@ def test_phase2_trainer_single_process(cuda):
     for a, b in zip(boxes, b3):
         assert torch.equal(a, b)
     assert all(torch.isfinite(v).all() for v in losses.values())
+
+
+def test_captured_train_step_matches_eager(cuda):
+    from point_teacher_b200.mil_head import MILHead
+    from point_teacher_b200.train import CapturedTrainStep, Phase2Trainer
+    d = synth.hbb_batch(seed=6, **SMALL)
+    torch.manual_seed(1)
+    head = MILHead(num_classes=8, num_stages=1, top_k=1, precision="bf16").to(cuda)
+    to = lambda l: [t.to(cuda) for t in l]  # noqa: E731
+    inputs = dict(feat=d["feat"].to(cuda), pseudo_boxes=to(d["pseudo_boxes"]), pseudo_points=to(d["pseudo_points"]),
+                  pseudo_labels=to(d["pseudo_labels"]), gt_boxes=to(d["gt_boxes"]), neg_boxes=[to(d["neg_boxes"][0])])
+    x = inputs["feat"].clone().requires_grad_(True)
+    tr = Phase2Trainer(head, synth.HBB_FINE_CFG, synth.HBB_EXT_CFG)
+    eb, ep, el = tr.step((x,), d["img_metas"], inputs["pseudo_boxes"], inputs["pseudo_points"], inputs["pseudo_labels"],
+                         inputs["gt_boxes"], neg_boxes=inputs["neg_boxes"])
+    g_eager = {n: p.grad.clone() for n, p in tr.bucket.named}
+    gx_eager = x.grad.clone()
+    cap = CapturedTrainStep(head, inputs, d["img_metas"], synth.HBB_FINE_CFG, synth.HBB_EXT_CFG)
+    for _ in range(2):
+        boxes, pts, losses = cap.replay()
+    torch.cuda.synchronize()
+    for a, b in zip(eb, boxes):
+        assert torch.equal(a, b)
+    for n, p in tr.bucket.named:
+        pg = dict(head.named_parameters())[n].grad
+        assert torch.allclose(pg, g_eager[n], rtol=0, atol=1e-5 * float(g_eager[n].abs().max()) + 1e-9), n
+    assert torch.allclose(cap.x.grad, gx_eager, rtol=0, atol=1e-5 * float(gx_eager.abs().max()))
+    # new data through the static buffers changes the gradients
+    inputs["feat"].mul_(0.5)
+    cap.replay()
+    torch.cuda.synchronize()
+    assert not torch.allclose(cap.x.grad, gx_eager, rtol=0, atol=1e-5 * float(gx_eager.abs().max()))
