@@ -86,7 +86,7 @@ int pt_roi_rescale(const float* rois, int K, int rotated, float factor_h, float 
  * nn.Linear (+ReLU) of shared_fcs_reg / shared_fcs_bag,
  *   HBB_TOD/mmdet/models/dense_heads/fcos_head_p2b_ts.py:1205-1206, 1246-1247, 1271-1272.
  * C[M,N] = act(A[M,K] * B[N,K]^T + bias); A, B bf16 row-major (K contiguous); C bf16 or fp32.
- * N % 256 == 0, K % 64 == 0.  workspace: pt_fc_gemm_workspace_bytes(), ZERO-filled once by the
+ * N % 256 == 0; a ragged K is zero-filled by TMA.  workspace: pt_fc_gemm_workspace_bytes(), ZERO-filled once by the
  * caller (the kernel leaves it zeroed); may be NULL (no split-K tail balancing). */
 long long pt_fc_gemm_workspace_bytes(int num_sms);
 int pt_fc_gemm_bf16(const void* A, long long lda, const void* B, long long ldb, const float* bias, void* C,
@@ -212,9 +212,26 @@ int pt_fill_polys(const int* polys, const int* count, int max_polys, float* img,
 int pt_fc_gemm_bf16_ex(const void* A, long long lda, const void* B, long long ldb, const float* bias, void* C,
                        long long ldc, int M, int N, int K, int relu, int out_f32, const void* mask, long long ldmask,
                        void* workspace, long long workspace_bytes, int num_sms, int allow_split, void* stream);
+/* pt_fc_gemm_bf16_mn: the same GEMM with operands that may be stored contraction-index-major (a_mn: A as [K, M],
+ *   b_mn: B as [K, N]; ld = elements per stored row) and are fed to tcgen05 as MN-major shared-memory tiles: the
+ *   autograd of nn.Linear (dW = dY^T X, dX = dY W) without materialising a transposed copy. */
+int pt_fc_gemm_bf16_mn(const void* A, long long lda, int a_mn, const void* B, long long ldb, int b_mn, const float* bias,
+                       void* C, long long ldc, int M, int N, int K, int relu, int out_f32, const void* mask,
+                       long long ldmask, void* workspace, long long workspace_bytes, int num_sms, int allow_split,
+                       void* stream);
 int pt_reg_loss_grad(const float* deltas, const float* bag_rois, const unsigned char* valid, const float* ref_boxes,
                      int U, int K, float max_w, float max_h, float wh_ratio_clip, float hyper, float eps,
                      const float* sums, const float* gscale, float scale, float* g, void* stream);
+/* OBB twin (rotated = 1): bag_rois [K,6] (b,cx,cy,w,h,theta), ref_boxes [G,5]; horizontal DN-DIoU on the (cx,cy,w,h)
+ *   parts, OBB_TOD/mmrotate/models/dense_heads/rotated_fcos_head_p2rb_ts.py:1314-1322. */
+int pt_reg_loss_grad_ex(const float* deltas, const float* bag_rois, const unsigned char* valid, const float* ref_boxes,
+                        int U, int K, float max_w, float max_h, float wh_ratio_clip, float hyper, float eps,
+                        const float* sums, const float* gscale, float scale, float* g, int rotated, void* stream);
+/* mmcv RoIAlignRotated backward (call site OBB_TOD/mmrotate/models/roi_heads/roi_extractors/
+ *   rotate_single_level_roi_extractor.py:90-167): rois [K,6]; dfeat NHWC fp32 (zeroed by the caller) += scatter. */
+int pt_roi_align_rotated_backward(const void* dA_bf16, long long ld, const float* rois, int K, int B, int C, int H,
+                                  int W, float spatial_scale, int sampling_ratio, int aligned, int clockwise,
+                                  float* dfeat, void* stream);
 int pt_bag_loss_grad(const float* cls, const float* ins, const unsigned char* valid, const long long* labels, int G,
                      int U1, int U2, int C, const unsigned char* neg_weight, int n_neg, const float* sums,
                      const float* gscale, float pos_scale, float neg_scale, float* g, void* stream);

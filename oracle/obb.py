@@ -78,11 +78,16 @@ def gen_negative_proposals(points, cfg, pos_bags, img_metas, injected=None, gene
     return negs, ws
 
 
+DIFFERENTIABLE_ROI = False      # tests that need torch autograd through the extraction flip this
+
+
 def rotated_roi_extract(feats, rois, strides, out_size=7, sampling_ratio=2, clockwise=True):
     """models/roi_heads/roi_extractors/rotate_single_level_roi_extractor.py:90-148, single level."""
     assert len(feats) == 1
     if rois.shape[0] == 0:
         return feats[0].new_zeros(0, feats[0].shape[1], out_size, out_size)
+    if DIFFERENTIABLE_ROI:
+        return rotated.roi_align_rotated_torch(feats[0], rois, out_size, 1 / strides[0], sampling_ratio, True, clockwise)
     return rotated.roi_align_rotated(feats[0], rois, out_size, 1 / strides[0], sampling_ratio, True, clockwise)
 
 

@@ -93,6 +93,51 @@ def roi_align_rotated(x, rois, out_size, spatial_scale, sampling_ratio, aligned,
     return torch.from_numpy(out).to(x.device)
 
 
+def roi_align_rotated_torch(x, rois, out_size, spatial_scale, sampling_ratio, aligned, clockwise):
+    """Differentiable (w.r.t. ``x``) PyTorch twin of ``roi_align_rotated`` for a fixed sampling grid
+    (``sampling_ratio > 0``), same formulae in the same fp32 order (Appendix A.2); used only where a test needs
+    torch autograd through the extraction.  Checked against the C restatement in tests/test_oracle.py."""
+    assert sampling_ratio > 0
+    K, P, g = rois.shape[0], out_size, sampling_ratio
+    B, C, H, W = x.shape
+    off = 0.5 if aligned else 0.0
+    b = rois[:, 0].long()
+    cx, cy = rois[:, 1] * spatial_scale - off, rois[:, 2] * spatial_scale - off
+    rw, rh = rois[:, 3] * spatial_scale, rois[:, 4] * spatial_scale
+    th = -rois[:, 5] if clockwise else rois[:, 5]
+    if not aligned:
+        rw, rh = rw.clamp(min=1.0), rh.clamp(min=1.0)
+    bh, bw = rh / P, rw / P
+    sh, sw = -rh / 2.0, -rw / 2.0
+    ct, st = torch.cos(th), torch.sin(th)
+    pi = torch.arange(P, dtype=torch.float32)
+    si = torch.arange(g, dtype=torch.float32) + 0.5
+    # yy[k, ph, iy], xx[k, pw, ix]
+    yy = (sh[:, None, None] + pi[None, :, None] * bh[:, None, None]) + si[None, None, :] * bh[:, None, None] / g
+    xx = (sw[:, None, None] + pi[None, :, None] * bw[:, None, None]) + si[None, None, :] * bw[:, None, None] / g
+    yy = yy[:, :, None, :, None]                                     # (K, P, 1, g, 1)
+    xx = xx[:, None, :, None, :]                                     # (K, 1, P, 1, g)
+    c4, s4 = ct[:, None, None, None, None], st[:, None, None, None, None]
+    y = (yy * c4 - xx * s4) + cy[:, None, None, None, None]
+    xs = (yy * s4 + xx * c4) + cx[:, None, None, None, None]
+    ok = ~((y < -1.0) | (y > H) | (xs < -1.0) | (xs > W))
+    y, xs = y.clamp(min=0.0), xs.clamp(min=0.0)
+    yl, xl = y.floor().long(), xs.floor().long()
+    ycap, xcap = yl >= H - 1, xl >= W - 1
+    yl, xl = torch.where(ycap, torch.full_like(yl, H - 1), yl), torch.where(xcap, torch.full_like(xl, W - 1), xl)
+    yh, xh = torch.where(ycap, yl, yl + 1), torch.where(xcap, xl, xl + 1)
+    y, xs = torch.where(ycap, yl.float(), y), torch.where(xcap, xl.float(), xs)
+    ly, lx = y - yl.float(), xs - xl.float()
+    hy, hx = 1.0 - ly, 1.0 - lx
+    xn = x.permute(0, 2, 3, 1)                                        # (B, H, W, C)
+    bb = b[:, None, None, None, None].expand_as(yl)
+    okf = ok.float()
+    val = ((hy * hx * okf)[..., None] * xn[bb, yl, xl] + (hy * lx * okf)[..., None] * xn[bb, yl, xh]
+           + (ly * hx * okf)[..., None] * xn[bb, yh, xl] + (ly * lx * okf)[..., None] * xn[bb, yh, xh])
+    out = val.sum(dim=(3, 4)) / float(max(g * g, 1))                  # (K, P, P, C)
+    return out.permute(0, 3, 1, 2).contiguous()
+
+
 def roi_align(x, rois, out_size, spatial_scale, sampling_ratio, aligned):
     """Horizontal RoIAlign (Appendix A.1), C restatement; pinned against
     torchvision.ops.roi_align in tests/test_oracle.py."""

@@ -68,8 +68,14 @@ SIGNATURES = {
     "pt_fill_polys": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_int, c_int, c_int, c_float, c_void_p]),
     "pt_fc_gemm_bf16_ex": (c_int, [c_void_p, c_ll, c_void_p, c_ll, c_void_p, c_void_p, c_ll, c_int, c_int, c_int, c_int,
                                    c_int, c_void_p, c_ll, c_void_p, c_ll, c_int, c_int, c_void_p]),
+    "pt_fc_gemm_bf16_mn": (c_int, [c_void_p, c_ll, c_int, c_void_p, c_ll, c_int, c_void_p, c_void_p, c_ll, c_int, c_int,
+                                   c_int, c_int, c_int, c_void_p, c_ll, c_void_p, c_ll, c_int, c_int, c_void_p]),
     "pt_reg_loss_grad": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_float, c_float, c_float,
                                  c_float, c_float, c_void_p, c_void_p, c_float, c_void_p, c_void_p]),
+    "pt_reg_loss_grad_ex": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_float, c_float, c_float,
+                                    c_float, c_float, c_void_p, c_void_p, c_float, c_void_p, c_int, c_void_p]),
+    "pt_roi_align_rotated_backward": (c_int, [c_void_p, c_ll, c_void_p, c_int, c_int, c_int, c_int, c_int, c_float, c_int,
+                                              c_int, c_int, c_void_p, c_void_p]),
     "pt_bag_loss_grad": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_int,
                                  c_void_p, c_void_p, c_float, c_float, c_void_p, c_void_p]),
     "pt_head_bwd": (c_int, [c_void_p, c_int, c_void_p, c_ll, c_int, c_void_p, c_int, c_void_p, c_ll, c_void_p, c_void_p,

@@ -63,12 +63,18 @@ __global__ void reg_loss_grad_kernel(const float* __restrict__ deltas, const flo
                                      const uint8_t* __restrict__ valid, const float* __restrict__ ref_boxes, int U,
                                      int K, float max_w, float max_h, float max_ratio, float hyper, float eps,
                                      const float* __restrict__ sums, const float* __restrict__ gscale, float scale,
-                                     float* __restrict__ g) {
+                                     float* __restrict__ g, int rotated) {
   const int k = blockIdx.x * blockDim.x + threadIdx.x;
   if (k >= K) return;
-  const float* r = bag_rois + (size_t)k * 5;
+  const float* r = bag_rois + (size_t)k * (rotated ? 6 : 5);
   const float* dl = deltas + (size_t)k * 4;
-  const float px = (r[1] + r[3]) * 0.5f, py = (r[2] + r[4]) * 0.5f, pw = r[3] - r[1], ph = r[4] - r[2];
+  // rotated (rotated_fcos_head_p2rb_ts.py:1314-1320): the decode runs on cxcywh_to_xyxy(bag[:, :4])
+  float rx1 = r[1], ry1 = r[2], rx2 = r[3], ry2 = r[4];
+  if (rotated) {
+    rx1 = fsub(r[1], fmul(0.5f, r[3])); ry1 = fsub(r[2], fmul(0.5f, r[4]));
+    rx2 = fadd(r[1], fmul(0.5f, r[3])); ry2 = fadd(r[2], fmul(0.5f, r[4]));
+  }
+  const float px = (rx1 + rx2) * 0.5f, py = (ry1 + ry2) * 0.5f, pw = rx2 - rx1, ph = ry2 - ry1;
   const D4 dx = dvar(dl[0], 0), dy = dvar(dl[1], 1);
   D4 dw = dvar(dl[2], 2), dh = dvar(dl[3], 3);
   // clamp(min=-mr, max=mr): zero gradient outside
@@ -86,7 +92,12 @@ __global__ void reg_loss_grad_kernel(const float* __restrict__ deltas, const flo
     if (b[i].v < 0.f) b[i] = dconst(0.f);
     if (b[i].v > hi[i]) b[i] = dconst(hi[i]);
   }
-  const float* ref = ref_boxes + (size_t)(k / U) * 4;
+  const float* refp = ref_boxes + (size_t)(k / U) * (rotated ? 5 : 4);
+  float ref[4] = {refp[0], refp[1], refp[2], refp[3]};
+  if (rotated) {
+    ref[0] = fsub(refp[0], fmul(0.5f, refp[2])); ref[1] = fsub(refp[1], fmul(0.5f, refp[3]));
+    ref[2] = fadd(refp[0], fmul(0.5f, refp[2])); ref[3] = fadd(refp[1], fmul(0.5f, refp[3]));
+  }
   const D4 base = diou_dual(b, ref, eps);
   const float anx = hyper / 2.f, tw = ref[2] - ref[0], th = ref[3] - ref[1];
   D4 best = dconst(3.0e38f);
@@ -222,9 +233,9 @@ head_bwd_kernel(const float* __restrict__ g, const __nv_bfloat16* __restrict__ H
       *reinterpret_cast<uint2*>(dZ + (size_t)r * ldz + c0) = make_uint2(pack_bf16(dz[0], dz[1]), pack_bf16(dz[2], dz[3]));
     }
 #pragma unroll
-    for (int o = 0; o < NOUT; o++)
-#pragma unroll
-      for (int j = 0; j < 4; j++) atomicAdd(dW + (size_t)o * D + c0 + j, acc[o][j]);
+    for (int o = 0; o < NOUT; o++)     // one 16-byte reduction per output row instead of four scalar atomics
+      asm volatile("red.relaxed.gpu.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dW + (size_t)o * D + c0),
+                   "f"(acc[o][0]), "f"(acc[o][1]), "f"(acc[o][2]), "f"(acc[o][3]) : "memory");
   }
   if (threadIdx.x < NOUT) {
     float s = 0.f;
@@ -252,33 +263,57 @@ transpose_pad_bf16_kernel(const __nv_bfloat16* __restrict__ in, long long ldin, 
   }
 }
 
-// dW1 (bin-major columns bin*C + c, fp32 [N, C*bins]) -> the parameter's order c*bins + bin, accumulated into grad
+// dW1 (bin-major columns bin*C + c, fp32 [N, C*bins]) -> the parameter's order c*bins + bin, accumulated into grad.
+// Block = (row n, slab of UNP_CH channels): reads `bins` segments of UNP_CH floats, writes UNP_CH*bins contiguous floats.
+constexpr int UNP_CH = 64;
 __global__ void __launch_bounds__(256)
 unpermute_dw1_kernel(const float* __restrict__ dwp, int C, int bins, float* __restrict__ grad, int accumulate) {
-  extern __shared__ float row[];
-  const int n = blockIdx.x, K = C * bins;
-  const float* src = dwp + (size_t)n * K;
-  for (int i = threadIdx.x; i < K; i += blockDim.x) row[i] = src[i];
+  extern __shared__ float slab[];                       // [bins][UNP_CH + 1]
+  const int n = blockIdx.x, c0 = blockIdx.y * UNP_CH;
+  const int nc = min(UNP_CH, C - c0);
+  const float* src = dwp + (size_t)n * C * bins + c0;
+  for (int i = threadIdx.x; i < bins * UNP_CH; i += blockDim.x) {
+    const int b = i / UNP_CH, c = i - b * UNP_CH;
+    if (c < nc) slab[b * (UNP_CH + 1) + c] = src[(size_t)b * C + c];
+  }
   __syncthreads();
-  float* dst = grad + (size_t)n * K;
-  for (int k = threadIdx.x; k < K; k += blockDim.x) {
+  float* dst = grad + (size_t)n * C * bins + (size_t)c0 * bins;
+  for (int k = threadIdx.x; k < nc * bins; k += blockDim.x) {
     const int c = k / bins, b = k - c * bins;
-    const float v = row[b * C + c];
+    const float v = slab[b * (UNP_CH + 1) + c];
     dst[k] = accumulate ? dst[k] + v : v;
   }
 }
 
-// db[n] (+)= sum_m dZ[m][n], dZ bf16 [M, ld]
+// db[n] (+)= sum_m dZ[m][n], dZ bf16 [M, ld].  Block = 32 column groups (8 columns = one 16-byte load each) x 8 row
+// lanes; a block covers 256 columns and a contiguous slab of rows; partials meet in shared memory, one atomic per column.
 __global__ void __launch_bounds__(256)
 colsum_bf16_kernel(const __nv_bfloat16* __restrict__ dZ, long long ld, int M, int N, float* __restrict__ db) {
-  const int n = blockIdx.x * 64 + (threadIdx.x & 63);
-  const int part = threadIdx.x >> 6;                           // 4 row groups per block
-  const int rows_per = (M + gridDim.y * 4 - 1) / (gridDim.y * 4);
-  const int r0 = (blockIdx.y * 4 + part) * rows_per, r1 = min(M, r0 + rows_per);
-  if (n >= N) return;
-  float s = 0.f;
-  for (int r = r0; r < r1; r++) s += __bfloat162float(dZ[(size_t)r * ld + n]);
-  atomicAdd(db + n, s);
+  __shared__ float part[8][256 + 8];
+  const int cg = threadIdx.x & 31, rl = threadIdx.x >> 5;
+  const int n0 = blockIdx.x * 256 + cg * 8;
+  const int rows_per = (M + gridDim.y - 1) / gridDim.y;
+  const int r0 = blockIdx.y * rows_per, r1 = min(M, r0 + rows_per);
+  float s[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  if (n0 < N) {
+#pragma unroll 4
+    for (int r = r0 + rl; r < r1; r += 8) {
+      const uint4 u = __ldg(reinterpret_cast<const uint4*>(dZ + (size_t)r * ld + n0));
+      const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+      for (int q = 0; q < 4; q++) { s[2 * q] += __uint_as_float(w[q] << 16); s[2 * q + 1] += __uint_as_float(w[q] & 0xffff0000u); }
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < 8; j++) part[rl][cg * 8 + j] = s[j];
+  __syncthreads();
+  const int n = blockIdx.x * 256 + threadIdx.x;
+  if (n < N) {
+    float t = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; i++) t += part[i][threadIdx.x];
+    atomicAdd(db + n, t);
+  }
 }
 
 __global__ void __launch_bounds__(256)
@@ -390,13 +425,18 @@ roi_align_bwd_kernel(const __nv_bfloat16* __restrict__ dA, long long ld, const f
 #pragma unroll
             for (int q = 0; q < 4; q++) wyv[q] = wy[(cy - ymin + q) * 8 + ph] * inv_count;
             if (wyv[0] == 0.f && wyv[1] == 0.f && wyv[2] == 0.f && wyv[3] == 0.f) continue;
+            // the 7 bins of this output row are fetched together (7 x 16 B in flight per lane) before any is used
+            uint4 u7[7];
+#pragma unroll
+            for (int pw = 0; pw < 7; pw++)
+              u7[pw] = __ldg(reinterpret_cast<const uint4*>(drow + (size_t)(ph * 7 + pw) * C + c0));
+#pragma unroll
             for (int pw = 0; pw < 7; pw++) {
               float wxv[4];
 #pragma unroll
               for (int q = 0; q < 4; q++) wxv[q] = wx[(cx - xmin + q) * 8 + pw];
               if (wxv[0] == 0.f && wxv[1] == 0.f && wxv[2] == 0.f && wxv[3] == 0.f) continue;
-              const uint4 u = __ldg(reinterpret_cast<const uint4*>(drow + (size_t)(ph * 7 + pw) * C + c0));
-              const uint32_t wv[4] = {u.x, u.y, u.z, u.w};
+              const uint32_t wv[4] = {u7[pw].x, u7[pw].y, u7[pw].z, u7[pw].w};
               float d[8];
 #pragma unroll
               for (int q = 0; q < 4; q++) { d[2 * q] = __uint_as_float(wv[q] << 16); d[2 * q + 1] = __uint_as_float(wv[q] & 0xffff0000u); }
@@ -405,6 +445,7 @@ roi_align_bwd_kernel(const __nv_bfloat16* __restrict__ dA, long long ld, const f
 #pragma unroll
                 for (int px = 0; px < 4; px++) {
                   const float wgt = wyv[py] * wxv[px];
+                  if (wgt == 0.f) continue;      // warp-uniform: a bin of a tiny RoI touches 2x2 of the 4x4 pixels
 #pragma unroll
                   for (int j = 0; j < 8; j++) acc[py * 4 + px][j] = fmaf(wgt, d[j], acc[py * 4 + px][j]);
                 }
@@ -430,18 +471,172 @@ roi_align_bwd_kernel(const __nv_bfloat16* __restrict__ dA, long long ld, const f
   }
 }
 
+// ---------------------------------------------------------------------------------------- RoIAlignRotated backward
+// One warp per RoI, lane = 8 channels.  The samples of a (tiny) rotated RoI fall in a small pixel patch: per 4x4-pixel
+// chunk the warp first builds Wmat[bin][pixel] (sum of the bilinear tap weights of that bin's sampling grid that land
+// on the pixel; lane b owns bins b, b+32 -> no conflicts) in shared memory with the forward's exact coordinate
+// arithmetic (roi_align.cu: roi_align_rotated_fwd_kernel), then accumulates dP[pixel] = sum_bins Wmat[bin][pixel] dA[bin]
+// in registers and adds it to the NHWC fp32 map with 16-byte reductions.
+__global__ void __launch_bounds__(RB_WARPS * 32)
+roi_align_rotated_bwd_kernel(const __nv_bfloat16* __restrict__ dA, long long ld, const float* __restrict__ rois, int K,
+                             int B, int C, int H, int W, float scale, int sampling_ratio, int aligned, int clockwise,
+                             float* __restrict__ dfeat) {
+  __shared__ __align__(16) float wmat_all[RB_WARPS][49 * 16];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  float* wmat = wmat_all[warp];
+  const float off = aligned ? 0.5f : 0.f;
+  for (int roi = blockIdx.x * RB_WARPS + warp; roi < K; roi += gridDim.x * RB_WARPS) {
+    const float* r = rois + (size_t)roi * 6;
+    const int b = (int)__ldg(r);
+    if (b < 0 || b >= B) continue;
+    const float cx = fsub(fmul(__ldg(r + 1), scale), off), cy = fsub(fmul(__ldg(r + 2), scale), off);
+    float rw = fmul(__ldg(r + 3), scale), rh = fmul(__ldg(r + 4), scale);
+    float theta = __ldg(r + 5);
+    if (clockwise) theta = -theta;
+    if (!aligned) { rw = fmaxf(rw, 1.f); rh = fmaxf(rh, 1.f); }
+    const float bh = fdiv(rh, 7.f), bw = fdiv(rw, 7.f);
+    const int gh = sampling_ratio > 0 ? sampling_ratio : (int)ceilf(bh);
+    const int gw = sampling_ratio > 0 ? sampling_ratio : (int)ceilf(bw);
+    const float sh = fdiv(-rh, 2.0f), sw = fdiv(-rw, 2.0f);
+    const float ct = cosf(theta), st = sinf(theta);
+    const int cnt = gh * gw > 1 ? gh * gw : 1;
+    const float inv_count = 1.0f / (float)cnt;
+    // pixel bounding box of all taps: the sample coordinates are affine in (yy, xx), extremes at the four corner samples
+    float xlo = 3.0e38f, xhi = -3.0e38f, ylo = 3.0e38f, yhi = -3.0e38f;
+#pragma unroll
+    for (int q = 0; q < 4; q++) {
+      const int ph = (q & 1) ? 6 : 0, iy = (q & 1) ? gh - 1 : 0, pw = (q & 2) ? 6 : 0, ix = (q & 2) ? gw - 1 : 0;
+      const float yy = fadd(fadd(sh, fmul((float)ph, bh)), fdiv(fmul((float)iy + .5f, bh), (float)gh));
+      const float xx = fadd(fadd(sw, fmul((float)pw, bw)), fdiv(fmul((float)ix + .5f, bw), (float)gw));
+      const float y = fadd(fsub(fmul(yy, ct), fmul(xx, st)), cy);
+      const float x = fadd(fadd(fmul(yy, st), fmul(xx, ct)), cx);
+      xlo = fminf(xlo, x); xhi = fmaxf(xhi, x); ylo = fminf(ylo, y); yhi = fmaxf(yhi, y);
+    }
+    // one pixel of slack on each side absorbs the rounding of the interior samples relative to the corners
+    const int xmin = max(0, (int)floorf(xlo) - 1), xmax = min(W - 1, (int)floorf(xhi) + 2);
+    const int ymin = max(0, (int)floorf(ylo) - 1), ymax = min(H - 1, (int)floorf(yhi) + 2);
+    if (xmax < xmin || ymax < ymin || gh <= 0 || gw <= 0) continue;
+    const __nv_bfloat16* drow = dA + (size_t)roi * ld;
+    float* fb = dfeat + (size_t)b * H * W * C;
+    for (int cy0 = ymin; cy0 <= ymax; cy0 += 4) {
+      for (int cx0 = xmin; cx0 <= xmax; cx0 += 4) {
+        __syncwarp();
+        int any = 0;
+        for (int bin = lane; bin < 49; bin += 32) {
+          float wr[16];
+#pragma unroll
+          for (int i = 0; i < 16; i++) wr[i] = 0.f;
+          const int ph = bin / 7, pw = bin - ph * 7;
+          const float xb = fadd(sw, fmul((float)pw, bw));
+          for (int iy = 0; iy < gh; iy++) {
+            const float yy = fadd(fadd(sh, fmul((float)ph, bh)), fdiv(fmul((float)iy + .5f, bh), (float)gh));
+            for (int ix = 0; ix < gw; ix++) {
+              const float xx = fadd(xb, fdiv(fmul((float)ix + .5f, bw), (float)gw));
+              const float y = fadd(fsub(fmul(yy, ct), fmul(xx, st)), cy);
+              const float x = fadd(fadd(fmul(yy, st), fmul(xx, ct)), cx);
+              int yl, yh, xl, xh; float ly, hy, lx, hx;
+              if (y < -1.0f || y > (float)H || x < -1.0f || x > (float)W) continue;
+              axis_setup_b(y, H, yl, yh, ly, hy);
+              axis_setup_b(x, W, xl, xh, lx, hx);
+              const int ty[2] = {yl - cy0, yh - cy0}, tx[2] = {xl - cx0, xh - cx0};
+              const float wyv[2] = {hy, ly}, wxv[2] = {hx, lx};
+#pragma unroll
+              for (int a = 0; a < 2; a++)
+#pragma unroll
+                for (int c = 0; c < 2; c++) {
+                  if ((unsigned)ty[a] < 4u && (unsigned)tx[c] < 4u) {
+                    const int idx = ty[a] * 4 + tx[c];
+                    const float wv = wyv[a] * wxv[c] * inv_count;
+#pragma unroll
+                    for (int i = 0; i < 16; i++) wr[i] += (i == idx) ? wv : 0.f;
+                    any = 1;
+                  }
+                }
+            }
+          }
+#pragma unroll
+          for (int i = 0; i < 4; i++)
+            *reinterpret_cast<float4*>(wmat + bin * 16 + i * 4) = make_float4(wr[4 * i], wr[4 * i + 1], wr[4 * i + 2], wr[4 * i + 3]);
+        }
+        any = __any_sync(0xffffffffu, any);
+        __syncwarp();
+        if (!any) continue;
+        for (int c0 = lane * 8; c0 < C; c0 += 256) {
+          float acc[16][8];
+#pragma unroll
+          for (int p = 0; p < 16; p++)
+#pragma unroll
+            for (int j = 0; j < 8; j++) acc[p][j] = 0.f;
+          for (int ph = 0; ph < 7; ph++) {
+            uint4 u7[7];
+#pragma unroll
+            for (int pw = 0; pw < 7; pw++)
+              u7[pw] = __ldg(reinterpret_cast<const uint4*>(drow + (size_t)(ph * 7 + pw) * C + c0));
+#pragma unroll
+            for (int pw = 0; pw < 7; pw++) {
+              const uint32_t wv[4] = {u7[pw].x, u7[pw].y, u7[pw].z, u7[pw].w};
+              float d[8];
+#pragma unroll
+              for (int q = 0; q < 4; q++) { d[2 * q] = __uint_as_float(wv[q] << 16); d[2 * q + 1] = __uint_as_float(wv[q] & 0xffff0000u); }
+#pragma unroll
+              for (int q4 = 0; q4 < 4; q4++) {
+                const float4 w4 = *reinterpret_cast<const float4*>(wmat + (ph * 7 + pw) * 16 + q4 * 4);
+                const float wq[4] = {w4.x, w4.y, w4.z, w4.w};
+#pragma unroll
+                for (int e = 0; e < 4; e++) {
+                  if (wq[e] == 0.f) continue;                 // warp-uniform
+#pragma unroll
+                  for (int j = 0; j < 8; j++) acc[q4 * 4 + e][j] = fmaf(wq[e], d[j], acc[q4 * 4 + e][j]);
+                }
+              }
+            }
+          }
+#pragma unroll
+          for (int py = 0; py < 4; py++)
+#pragma unroll
+            for (int px = 0; px < 4; px++) {
+              const int yy = cy0 + py, xx = cx0 + px;
+              if (yy > ymax || xx > xmax) continue;
+              float* dst = fb + ((size_t)yy * W + xx) * C + c0;
+              const float* a = acc[py * 4 + px];
+              asm volatile("red.relaxed.gpu.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst), "f"(a[0]), "f"(a[1]),
+                           "f"(a[2]), "f"(a[3]) : "memory");
+              asm volatile("red.relaxed.gpu.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst + 4), "f"(a[4]), "f"(a[5]),
+                           "f"(a[6]), "f"(a[7]) : "memory");
+            }
+        }
+      }
+    }
+  }
+}
+
 }  // namespace ptb
 
 using namespace ptb;
+
+extern "C" int pt_reg_loss_grad_ex(const float* deltas, const float* bag_rois, const unsigned char* valid,
+                                   const float* ref_boxes, int U, int K, float max_w, float max_h, float wh_ratio_clip,
+                                   float hyper, float eps, const float* sums, const float* gscale, float scale, float* g,
+                                   int rotated, void* stream);
 
 extern "C" int pt_reg_loss_grad(const float* deltas, const float* bag_rois, const unsigned char* valid,
                                 const float* ref_boxes, int U, int K, float max_w, float max_h, float wh_ratio_clip,
                                 float hyper, float eps, const float* sums, const float* gscale, float scale, float* g,
                                 void* stream) {
+  return pt_reg_loss_grad_ex(deltas, bag_rois, valid, ref_boxes, U, K, max_w, max_h, wh_ratio_clip, hyper, eps, sums,
+                             gscale, scale, g, 0, stream);
+}
+
+// rotated = 1: bag_rois [K,6] (b,cx,cy,w,h,theta), ref_boxes [G,5]; the loss itself is the horizontal DN-DIoU on the
+// (cx,cy,w,h) parts (OBB_TOD/mmrotate/models/dense_heads/rotated_fcos_head_p2rb_ts.py:1314-1322)
+extern "C" int pt_reg_loss_grad_ex(const float* deltas, const float* bag_rois, const unsigned char* valid,
+                                   const float* ref_boxes, int U, int K, float max_w, float max_h, float wh_ratio_clip,
+                                   float hyper, float eps, const float* sums, const float* gscale, float scale, float* g,
+                                   int rotated, void* stream) {
   if (K <= 0) return PT_OK;
   reg_loss_grad_kernel<<<(K + 127) / 128, 128, 0, (cudaStream_t)stream>>>(deltas, bag_rois, valid, ref_boxes, U, K, max_w,
                                                                          max_h, fabsf(logf(wh_ratio_clip)), hyper, eps,
-                                                                         sums, gscale, scale, g);
+                                                                         sums, gscale, scale, g, rotated);
   return check_launch("reg_loss_grad_kernel");
 }
 
@@ -473,7 +668,7 @@ extern "C" int pt_head_bwd(const float* g, int nout, const void* H_bf16, long lo
   if (M <= 0) return PT_OK;
   if (D % 4 != 0 || (ldh % 4) || (ldz % 4)) { set_error("pt_head_bwd: D / leading dimensions must be multiples of 4"); return PT_ERR_ARG; }
   cudaStream_t s = (cudaStream_t)stream;
-  const int grid = M < 592 ? M : 592;
+  const int grid = M < 296 ? M : 296;     // 2 CTAs per SM: the dW reductions (grid x nout x D / 4) stay cheap
   const __nv_bfloat16* H = reinterpret_cast<const __nv_bfloat16*>(H_bf16);
   __nv_bfloat16* dZ = reinterpret_cast<__nv_bfloat16*>(dZ_bf16);
   switch (nout) {
@@ -498,17 +693,20 @@ extern "C" int pt_transpose_pad_bf16(const void* in, long long ldin, int R, int 
 extern "C" int pt_unpermute_dw1(const float* dw_binmajor, int N, int C, int bins, float* grad, int accumulate,
                                 void* stream) {
   if (N <= 0) return PT_OK;
-  const size_t smem = (size_t)C * bins * sizeof(float);
-  if (smem > 200 * 1024) { set_error("pt_unpermute_dw1: row of %d floats exceeds shared memory", C * bins); return PT_ERR_UNSUPPORTED; }
-  cudaError_t e = cudaFuncSetAttribute(unpermute_dw1_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  if (e != cudaSuccess) { set_error("cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return PT_ERR_CUDA; }
-  unpermute_dw1_kernel<<<N, 256, smem, (cudaStream_t)stream>>>(dw_binmajor, C, bins, grad, accumulate);
+  const size_t smem = (size_t)(UNP_CH + 1) * bins * sizeof(float);
+  if (smem > 48 * 1024) { set_error("pt_unpermute_dw1: %d bins exceed shared memory", bins); return PT_ERR_UNSUPPORTED; }
+  dim3 grid(N, (C + UNP_CH - 1) / UNP_CH);
+  unpermute_dw1_kernel<<<grid, 256, smem, (cudaStream_t)stream>>>(dw_binmajor, C, bins, grad, accumulate);
   return check_launch("unpermute_dw1_kernel");
 }
 
 extern "C" int pt_colsum_bf16(const void* dZ, long long ld, int M, int N, float* db, void* stream) {
   if (M <= 0 || N <= 0) return PT_OK;
-  dim3 grid((N + 63) / 64, 16);
+  if ((N % 8) || (ld % 8) || ((uintptr_t)dZ & 15)) { set_error("pt_colsum_bf16: N / ld must be multiples of 8, 16-byte aligned"); return PT_ERR_ARG; }
+  const int col_blocks = (N + 255) / 256;
+  int row_blocks = (M + 31) / 32;
+  if (row_blocks * col_blocks > 592) row_blocks = (592 + col_blocks - 1) / col_blocks;
+  dim3 grid(col_blocks, row_blocks);
   colsum_bf16_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<const __nv_bfloat16*>(dZ), ld, M, N, db);
   return check_launch("colsum_bf16_kernel");
 }
@@ -536,4 +734,17 @@ extern "C" int pt_roi_align_backward(const void* dA_bf16, long long ld, const fl
       reinterpret_cast<const __nv_bfloat16*>(dA_bf16), ld, rois, K, B, C, H, W, spatial_scale, sampling_ratio, aligned,
       dfeat);
   return check_launch("roi_align_bwd_kernel");
+}
+
+// RoIAlignRotated backward (mmcv roi_align_rotated, fixed or adaptive sampling grid): rois [K,6] (b,cx,cy,w,h,theta).
+extern "C" int pt_roi_align_rotated_backward(const void* dA_bf16, long long ld, const float* rois, int K, int B, int C,
+                                             int H, int W, float spatial_scale, int sampling_ratio, int aligned,
+                                             int clockwise, float* dfeat, void* stream) {
+  if (K <= 0) return PT_OK;
+  if (C % 8 != 0) { set_error("pt_roi_align_rotated_backward: C must be a multiple of 8"); return PT_ERR_ARG; }
+  const int blocks = (K + RB_WARPS - 1) / RB_WARPS;
+  roi_align_rotated_bwd_kernel<<<blocks < 148 * 8 ? blocks : 148 * 8, RB_WARPS * 32, 0, (cudaStream_t)stream>>>(
+      reinterpret_cast<const __nv_bfloat16*>(dA_bf16), ld, rois, K, B, C, H, W, spatial_scale, sampling_ratio, aligned,
+      clockwise, dfeat);
+  return check_launch("roi_align_rotated_bwd_kernel");
 }

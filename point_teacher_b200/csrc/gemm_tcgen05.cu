@@ -51,6 +51,7 @@ struct Params {
   int ldmask;
   int tiles_n, tiles_total, split;  // split = S (>=2) when the tail wave is K-split, else 0
   int full_rounds;
+  int a_mn, b_mn;                   // operand stored [K, M] / [K, N] (MN-major): wgrad / dgrad without a transposed copy
 };
 
 struct Unit {
@@ -60,7 +61,7 @@ struct Unit {
 // G / c: number and index of the scheduling units (CTAs, or CTA pairs); rank: CTA inside the pair (0 when unpaired).
 // Paired: a "tile" is 256 x 256 and this CTA owns rows [128 * (2 m + rank), +128) of it.
 __device__ __forceinline__ bool get_unit(const Params& p, int it, Unit& u, int G, int c, int pair, int rank) {
-  const int kb_total = p.K / BK;
+  const int kb_total = (p.K + BK - 1) / BK;   // a ragged last k-block is zero-filled by TMA (out-of-bounds rows / columns)
   int tile;
   if (it < p.full_rounds) {
     tile = it * G + c;
@@ -130,6 +131,14 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t saddr) {
   // K-major, SWIZZLE_128B canonical layout: LBO = 1 (16 B units, ignored), SBO = 8 rows * 128 B = 1024 B,
   // version = 1 (Blackwell), layout_type = 2 (SWIZZLE_128B).
   return (uint64_t)((saddr & 0x3FFFF) >> 4) | ((uint64_t)1 << 16) | ((uint64_t)(1024 >> 4) << 32) |
+         ((uint64_t)1 << 46) | ((uint64_t)2 << 61);
+}
+
+__device__ __forceinline__ uint64_t make_desc_mn(uint32_t saddr) {
+  // MN-major, SWIZZLE_128B canonical layout ((64 mn, n_atoms), (8 k, k_groups)): one TMA box = 64 k-rows of 128 B
+  // (64 MN elements); SBO = 8 k-rows * 128 B = 1024 B between k-groups, LBO = 64 k-rows * 128 B = 8192 B between
+  // 64-element MN atoms (consecutive TMA boxes).
+  return (uint64_t)((saddr & 0x3FFFF) >> 4) | ((uint64_t)(8192 >> 4) << 16) | ((uint64_t)(1024 >> 4) << 32) |
          ((uint64_t)1 << 46) | ((uint64_t)2 << 61);
 }
 
@@ -244,8 +253,20 @@ fc_gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
             tma_load_2d_pair(sa + A_BYTES, &tma_b, full_bar + stage, kb * BK, u.n_blk * BN + rank * B_ROWS);
           } else {
             mbar_expect_tx(full_bar + stage, STAGE_BYTES);
-            tma_load_2d(sa, &tma_a, full_bar + stage, kb * BK, u.m_blk * BM);
-            tma_load_2d(sa + A_BYTES, &tma_b, full_bar + stage, kb * BK, u.n_blk * BN);
+            if (p.a_mn) {
+#pragma unroll
+              for (int j = 0; j < BM / 64; j++)
+                tma_load_2d(sa + j * (64 * BK * 2), &tma_a, full_bar + stage, u.m_blk * BM + j * 64, kb * BK);
+            } else {
+              tma_load_2d(sa, &tma_a, full_bar + stage, kb * BK, u.m_blk * BM);
+            }
+            if (p.b_mn) {
+#pragma unroll
+              for (int j = 0; j < BN / 64; j++)
+                tma_load_2d(sa + A_BYTES + j * (64 * BK * 2), &tma_b, full_bar + stage, u.n_blk * BN + j * 64, kb * BK);
+            } else {
+              tma_load_2d(sa + A_BYTES, &tma_b, full_bar + stage, kb * BK, u.n_blk * BN);
+            }
           }
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
@@ -266,12 +287,17 @@ fc_gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
           tc_fence_after();
           if (lane == 0) {
             const uint32_t sa = smem_u32(smem + stage * STAGE_BYTES);
-            const uint64_t adesc = make_desc(sa), bdesc = make_desc(sa + A_BYTES);
+            const bool amn = !TWO && p.a_mn, bmn = !TWO && p.b_mn;
+            const uint64_t adesc = amn ? make_desc_mn(sa) : make_desc(sa);
+            const uint64_t bdesc = bmn ? make_desc_mn(sa + A_BYTES) : make_desc(sa + A_BYTES);
+            // K-major: advance 16 bf16 = 32 B along K inside the 128 B swizzle row: +2 in 16 B units;
+            // MN-major: 16 k-rows of 128 B = 2048 B: +128
+            const uint32_t astep = amn ? 128u : 2u, bstep = bmn ? 128u : 2u;
+            const uint32_t idesc = IDESC | (amn ? (1u << 15) : 0u) | (bmn ? (1u << 16) : 0u);
 #pragma unroll
             for (int k = 0; k < BK / UMMA_K; k++) {
-              // advance 16 bf16 = 32 B along K inside the 128 B swizzle row: +2 in 16 B units
               if (TWO) tc_mma_bf16_pair(tmem_d, adesc + 2 * k, bdesc + 2 * k, IDESC_PAIR, (kb > u.kb0 || k > 0) ? 1u : 0u);
-              else tc_mma_bf16(tmem_d, adesc + 2 * k, bdesc + 2 * k, IDESC, (kb > u.kb0 || k > 0) ? 1u : 0u);
+              else tc_mma_bf16(tmem_d, adesc + astep * k, bdesc + bstep * k, idesc, (kb > u.kb0 || k > 0) ? 1u : 0u);
             }
             // frees the smem slot (in both CTAs when paired) when these MMAs retire
             if (TWO) tc_commit_pair(empty_bar + stage); else tc_commit(empty_bar + stage);
@@ -439,6 +465,21 @@ static int make_map(CUtensorMap* map, const void* base, long long rows, long lon
   return PT_OK;
 }
 
+// MN-major operand stored [kdim rows, mndim columns] (ld elements per row): boxes of 64 columns (128 B) x BK rows.
+static int make_map_mn(CUtensorMap* map, const void* base, long long kdim, long long mndim, long long ld) {
+  EncodeTiledFn enc = get_encode();
+  if (enc == nullptr) { set_error("cuTensorMapEncodeTiled entry point not found"); return PT_ERR_DRIVER; }
+  cuuint64_t dims[2] = {(cuuint64_t)mndim, (cuuint64_t)kdim};
+  cuuint64_t strides[1] = {(cuuint64_t)ld * 2};
+  cuuint32_t box[2] = {64u, (cuuint32_t)BK};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled (MN-major) failed: CUresult %d", (int)r); return PT_ERR_DRIVER; }
+  return PT_OK;
+}
+
 }  // namespace gemm
 }  // namespace ptb
 
@@ -453,6 +494,10 @@ extern "C" int pt_fc_gemm_bf16_ex(const void* A, long long lda, const void* B, l
                                   void* C, long long ldc, int M, int N, int K, int relu, int out_f32, const void* mask,
                                   long long ldmask, void* workspace, long long workspace_bytes, int num_sms,
                                   int allow_split, void* stream);
+extern "C" int pt_fc_gemm_bf16_mn(const void* A, long long lda, int a_mn, const void* B, long long ldb, int b_mn,
+                                  const float* bias, void* C, long long ldc, int M, int N, int K, int relu, int out_f32,
+                                  const void* mask, long long ldmask, void* workspace, long long workspace_bytes,
+                                  int num_sms, int allow_split, void* stream);
 
 extern "C" int pt_fc_gemm_bf16(const void* A, long long lda, const void* B, long long ldb, const float* bias,
                                void* C, long long ldc, int M, int N, int K, int relu, int out_f32, void* workspace,
@@ -465,14 +510,25 @@ extern "C" int pt_fc_gemm_bf16_ex(const void* A, long long lda, const void* B, l
                                   void* C, long long ldc, int M, int N, int K, int relu, int out_f32, const void* mask,
                                   long long ldmask, void* workspace, long long workspace_bytes, int num_sms,
                                   int allow_split, void* stream) {
+  return pt_fc_gemm_bf16_mn(A, lda, 0, B, ldb, 0, bias, C, ldc, M, N, K, relu, out_f32, mask, ldmask, workspace,
+                            workspace_bytes, num_sms, allow_split, stream);
+}
+
+// a_mn / b_mn = 1: the operand is stored with the contraction index as its ROW index (A as [K, M], B as [K, N], ld =
+// elements per row) -- the layouts wgrad (dW = dY^T X) and dgrad (dX = dY W) meet -- and is fed to the tensor core as
+// an MN-major shared-memory tile, so no transposed copy is ever materialised.  K may then be ragged (TMA zero-fills).
+extern "C" int pt_fc_gemm_bf16_mn(const void* A, long long lda, int a_mn, const void* B, long long ldb, int b_mn,
+                                  const float* bias, void* C, long long ldc, int M, int N, int K, int relu, int out_f32,
+                                  const void* mask, long long ldmask, void* workspace, long long workspace_bytes,
+                                  int num_sms, int allow_split, void* stream) {
   using namespace gemm;
   if (mask != nullptr && (((uintptr_t)mask & 15) || (ldmask % 8))) {
     set_error("pt_fc_gemm_bf16_ex: mask must be 16-byte aligned with ldmask a multiple of 8");
     return PT_ERR_ARG;
   }
   if (M <= 0) return PT_OK;
-  if (N % BN != 0 || K % BK != 0 || K <= 0) {
-    set_error("pt_fc_gemm_bf16: N must be a multiple of %d and K of %d (got N=%d K=%d)", BN, BK, N, K);
+  if (N % BN != 0 || K <= 0) {   // a ragged K is fine: the tensor maps carry the true extents and TMA zero-fills
+    set_error("pt_fc_gemm_bf16: N must be a multiple of %d and K positive (got N=%d K=%d)", BN, N, K);
     return PT_ERR_ARG;
   }
   if (((uintptr_t)A & 15) || ((uintptr_t)B & 15) || ((uintptr_t)C & 15) || (lda % 8) || (ldb % 8) || (ldc % 8)) {
@@ -485,15 +541,16 @@ extern "C" int pt_fc_gemm_bf16_ex(const void* A, long long lda, const void* B, l
     cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
   }
   // paired (cta_group::2) kernel for the long contractions; single-CTA kernel otherwise
-  const bool two = (K >= 4096) && (num_sms % 2 == 0) && (M > 2 * BM) && pair_enabled();
+  const bool two = (K >= 4096) && (num_sms % 2 == 0) && (M > 2 * BM) && pair_enabled() && !a_mn && !b_mn;
   CUtensorMap ma, mb;
-  int rc = make_map(&ma, A, M, K, lda, BM);
+  int rc = a_mn ? make_map_mn(&ma, A, K, M, lda) : make_map(&ma, A, M, K, lda, BM);
   if (rc != PT_OK) return rc;
-  rc = make_map(&mb, B, N, K, ldb, two ? BN / 2 : BN);
+  rc = b_mn ? make_map_mn(&mb, B, K, N, ldb) : make_map(&mb, B, N, K, ldb, two ? BN / 2 : BN);
   if (rc != PT_OK) return rc;
 
   Params p;
   p.mask = reinterpret_cast<const __nv_bfloat16*>(mask); p.ldmask = (int)ldmask;
+  p.a_mn = a_mn ? 1 : 0; p.b_mn = b_mn ? 1 : 0;
   p.bias = bias; p.C = C; p.M = M; p.N = N; p.K = K; p.ldc = (int)ldc; p.relu = relu; p.out_f32 = out_f32;
   p.tiles_n = N / BN;
   const int tile_rows = two ? 2 * BM : BM;                 // rows of one scheduling tile
@@ -508,7 +565,7 @@ extern "C" int pt_fc_gemm_bf16_ex(const void* A, long long lda, const void* B, l
   p.ws = nullptr; p.counters = nullptr;
   if (allow_split && tail > 0 && tail * sub * 8 <= 4096 && workspace != nullptr) {
     int S = grid_u / tail;
-    const int kb_total = K / BK;
+    const int kb_total = (K + BK - 1) / BK;
     // every split must keep >= 8 k-blocks of MMA work, otherwise the fp32 reduction costs more than it saves; short
     // contractions (K < 4096: FC2, measured 43 us split vs 27 us unsplit at 5000x1024x1024) are never split
     if (S > kb_total / 8) S = kb_total / 8;

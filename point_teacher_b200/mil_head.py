@@ -262,8 +262,6 @@ class MILHeadMixin:
                   f"stage{stage}_coarse_bags_iou": out[2], f"stage{stage}_refine_bags_iou": out[3]}
         self.last_losses = losses
         if keep is not None:
-            if rot:
-                raise NotImplementedError("the backward is built for the HBB head")
             keep.update(reg=kreg, bag=kbag, deltas=deltas, ebags=ebags, evalid=evalid, ref=ref, rois2=rois2, cls=cls,
                         ins=ins, neg_w=neg_w, n_neg=n_neg, labels=labels, sums=sums, K=K, G=G, U1=U1, U2=U2,
                         max_wh=(w0, h0), stage=stage, loss_scales=loss_scales)

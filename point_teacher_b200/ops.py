@@ -503,15 +503,45 @@ def fc_gemm_masked(A, B, mask, out_dtype=_bf16, M=None, allow_split=True):
     return out
 
 
+def fc_gemm_mn(A, B, a_mn=False, b_mn=False, mask=None, out_dtype=_bf16, M=None, K=None, allow_split=True):
+    """C[M,N] = A' @ B'^T with operands as they are stored: ``a_mn`` -> A is [K, M] (else [M, K]); ``b_mn`` -> B is
+    [K, N] (else [N, K]).  ``M`` / ``K`` restrict to the leading rows of padded buffers.  Optional ReLU-backward
+    ``mask`` [>=M, N] bf16.  nn.Linear autograd (dW = dY^T X, dX = dY W) with no transposed copies."""
+    _chk(A, "A", _bf16, 2)
+    _chk(B, "B", _bf16, 2)
+    Ka, Ma = (A.shape[0], A.shape[1]) if a_mn else (A.shape[1], A.shape[0])
+    Kb, N = (B.shape[0], B.shape[1]) if b_mn else (B.shape[1], B.shape[0])
+    if a_mn:
+        K = min(Ka, Kb) if K is None else K
+        M = Ma if M is None else M
+    else:
+        M = Ma if M is None else M
+        K = Ka if K is None else K
+    if K > Ka or K > Kb or M > Ma:
+        raise ValueError(f"fc_gemm_mn: M={M} K={K} exceed the operands A {tuple(A.shape)} B {tuple(B.shape)}")
+    rows_out = M if a_mn else A.shape[0]
+    if mask is not None:
+        _chk(mask, "mask", _bf16, 2)
+        if mask.shape[1] != N or mask.shape[0] < M:
+            raise ValueError("fc_gemm_mn: mask shape mismatch")
+    out = torch.empty((rows_out, N), dtype=out_dtype, device=A.device)
+    ws = gemm_workspace(A.device)
+    _lib.call("pt_fc_gemm_bf16_mn", _p(A), A.shape[1], int(a_mn), _p(B), B.shape[1], int(b_mn), _p(None), _p(out),
+              out.shape[1], M, N, K, 0, int(out.dtype == _f32), _p(mask), 0 if mask is None else mask.shape[1], _p(ws),
+              ws.numel(), num_sms(), int(allow_split), _stream())
+    return out
+
+
 def reg_loss_grad(deltas, bag_rois, valid, ref_boxes, U, max_wh, sums, gscale, scale, hyper=0.2, eps=1e-6,
-                  wh_ratio_clip=16 / 1000):
+                  wh_ratio_clip=16 / 1000, rotated=False):
     _chk(deltas, "deltas", _f32, 2, 4)
-    _chk(bag_rois, "bag_rois", _f32, 2, 5)
+    _chk(bag_rois, "bag_rois", _f32, 2, 6 if rotated else 5)
+    _chk(ref_boxes, "ref_boxes", _f32, 2, 5 if rotated else 4)
     K = deltas.shape[0]
     g = torch.empty((K, 4), dtype=_f32, device=deltas.device)
-    _lib.call("pt_reg_loss_grad", _p(deltas), _p(bag_rois), _p(valid), _p(ref_boxes), int(U), K, float(max_wh[0]),
+    _lib.call("pt_reg_loss_grad_ex", _p(deltas), _p(bag_rois), _p(valid), _p(ref_boxes), int(U), K, float(max_wh[0]),
               float(max_wh[1]), float(wh_ratio_clip), float(hyper), float(eps), _p(sums), _p(gscale), float(scale), _p(g),
-              _stream())
+              int(rotated), _stream())
     return g
 
 
@@ -571,14 +601,20 @@ def nhwc_to_nchw_f32(x, out=None, accumulate=False):
     return out
 
 
-def roi_align_backward(dA, rois, feat_shape_nhwc, spatial_scale, sampling_ratio=0, aligned=True, dfeat=None, K=None):
-    """dA bf16 [K, 49*C] bin-major -> dfeat NHWC fp32 (accumulated into ``dfeat`` when given, else zero-initialised)."""
+def roi_align_backward(dA, rois, feat_shape_nhwc, spatial_scale, sampling_ratio=0, aligned=True, dfeat=None, K=None,
+                       rotated=False, clockwise=True):
+    """dA bf16 [K, 49*C] bin-major -> dfeat NHWC fp32 (accumulated into ``dfeat`` when given, else zero-initialised).
+    ``rotated``: rois (K,6) [b,cx,cy,w,h,theta], RoIAlignRotated semantics."""
     _chk(dA, "dA", _bf16, 2)
-    _chk(rois, "rois", _f32, 2, 5)
+    _chk(rois, "rois", _f32, 2, 6 if rotated else 5)
     B, H, W, C = feat_shape_nhwc
     if dfeat is None:
         dfeat = torch.zeros((B, H, W, C), dtype=_f32, device=dA.device)
     K = rois.shape[0] if K is None else K
+    if rotated:
+        _lib.call("pt_roi_align_rotated_backward", _p(dA), dA.shape[1], _p(rois), K, B, C, H, W, float(spatial_scale),
+                  int(sampling_ratio), int(aligned), int(clockwise), _p(dfeat), _stream())
+        return dfeat
     _lib.call("pt_roi_align_backward", _p(dA), dA.shape[1], _p(rois), K, B, C, H, W, float(spatial_scale),
               int(sampling_ratio), int(aligned), _p(dfeat), _stream())
     return dfeat

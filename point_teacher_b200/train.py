@@ -29,21 +29,17 @@ def _fc_branch_backward(head, k, dZ2, need_dA):
     dW2, db2, dA | None)."""
     M, dev = k["M"], dZ2.device
     N1 = k["W1"].shape[0]
-    w2t = ops.transpose_pad(k["W2"])                                   # [in, out]: dgrad operand
-    dZ1 = ops.fc_gemm_masked(dZ2, w2t, k["H1"], M=M)                   # (dZ2 @ W2) * (H1 > 0)
-    dZ2t, H1t = ops.transpose_pad(dZ2, rows=M), ops.transpose_pad(k["H1"], rows=M)
-    dW2 = ops.fc_gemm(dZ2t, H1t, None, relu=False, out_dtype=torch.float32)
+    # every operand is consumed in the layout the forward left it in (MN-major tcgen05 tiles): no transposed copies
+    dZ1 = ops.fc_gemm_mn(dZ2, k["W2"], b_mn=True, mask=k["H1"], M=M)                                # (dZ2 @ W2) * (H1 > 0)
+    dW2 = ops.fc_gemm_mn(dZ2, k["H1"], a_mn=True, b_mn=True, out_dtype=torch.float32, K=M)          # dZ2^T @ H1
     db2 = ops.colsum_bf16(dZ2, torch.zeros((dZ2.shape[1],), dtype=torch.float32, device=dev), M=M)
-    dZ1t, At = ops.transpose_pad(dZ1, rows=M), ops.transpose_pad(k["A"], rows=M)
-    dW1p = ops.fc_gemm(dZ1t, At, None, relu=False, out_dtype=torch.float32)      # [N1, 49*C] bin-major columns
-    del At
+    dW1p = ops.fc_gemm_mn(dZ1, k["A"], a_mn=True, b_mn=True, out_dtype=torch.float32, K=M)          # [N1, 49*C] bin-major
     dW1 = torch.empty_like(dW1p)
     ops.unpermute_dw1(dW1p, head.in_channels, head.roi_feat_area, dW1, accumulate=False)
     db1 = ops.colsum_bf16(dZ1, torch.zeros((N1,), dtype=torch.float32, device=dev), M=M)
     dA = None
     if need_dA:
-        w1t = ops.transpose_pad(k["W1"])                               # [49*C, N1]
-        dA = ops.fc_gemm(dZ1, w1t, None, relu=False, out_dtype=torch.bfloat16, M=M)
+        dA = ops.fc_gemm_mn(dZ1, k["W1"], b_mn=True, out_dtype=torch.bfloat16, M=M)                 # dZ1 @ W1
     return dW1, db1, dW2, db2, dA
 
 
@@ -57,8 +53,9 @@ def mil_stage_backward(head, keep, x, g_bbox, g_bags, need_feat_grad=True):
     C = fc.weight.shape[0]
     layer = head.bbox_roi_extractor.roi_layers[0]
     # ---- regression branch: DN-DIoU -> delta2bbox -> fc_reg -> FC2 -> FC1 -> RoIAlign
+    rot = head.bbox_roi_extractor.rotated
     g4 = ops.reg_loss_grad(keep["deltas"], keep["ebags"], keep["evalid"], keep["ref"], U1 * U2, keep["max_wh"],
-                           keep["sums"], g_bbox, s_bbox, hyper=head.loss_bbox_denosing_hyper)
+                           keep["sums"], g_bbox, s_bbox, hyper=head.loss_bbox_denosing_hyper, rotated=rot)
     dWreg, dbreg = torch.zeros_like(fr.weight), torch.zeros_like(fr.bias)
     dZ2 = ops.head_bwd(g4, keep["reg"]["H2"], fr.weight.detach(), dWreg, dbreg, M=K)
     r = _fc_branch_backward(head, keep["reg"], dZ2, need_feat_grad)
@@ -73,9 +70,11 @@ def mil_stage_backward(head, keep, x, g_bbox, g_bags, need_feat_grad=True):
     if need_feat_grad:
         Bn, _, H, W = x.shape
         shape = (Bn, H, W, x.shape[1])
-        dn = ops.roi_align_backward(r[4], keep["ebags"], shape, layer.spatial_scale, layer.sampling_ratio, layer.aligned, K=K)
+        rk = dict(rotated=rot, clockwise=getattr(layer, "clockwise", True))
+        dn = ops.roi_align_backward(r[4], keep["ebags"], shape, layer.spatial_scale, layer.sampling_ratio, layer.aligned,
+                                    K=K, **rk)
         ops.roi_align_backward(b[4], keep["rois2"], shape, layer.spatial_scale, layer.sampling_ratio, layer.aligned,
-                               dfeat=dn, K=K + n_neg)
+                               dfeat=dn, K=K + n_neg, **rk)
         dfeat = ops.nhwc_to_nchw_f32(dn)
     grads = [r[0], r[1], r[2], r[3], b[0], b[1], b[2], b[3], dWreg, dbreg, dWci[:C], dbci[:C], dWci[C:], dbci[C:]]
     return dfeat, grads

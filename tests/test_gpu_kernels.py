@@ -259,6 +259,31 @@ def test_fc_gemm_paired_cta_group2_variant(cuda):
     assert r.returncode == 0 and "paired ok" in r.stdout, r.stderr[-2000:]
 
 
+@pytest.mark.parametrize("a_mn,b_mn,M,N,K", [
+    (False, True, 700, 1024, 1024),      # dgrad dX = dY W           (W stored [out, in] = [K, N])
+    (True, True, 1024, 1024, 5000),      # wgrad dW = dY^T X          (ragged K = RoIs: TMA zero-fill)
+    (True, True, 1000, 12544, 777),      # FC1 wgrad shape class, ragged M and K, split-K tail
+    (True, False, 296, 256, 192),        # mixed
+    (False, True, 5000, 12544, 1024)])   # FC1 dgrad
+def test_fc_gemm_mn_major_operands(cuda, a_mn, b_mn, M, N, K):
+    """Operands stored contraction-index-major ([K, M] / [K, N]) feed tcgen05 as MN-major tiles: same result as the
+    fp32 reference of the transposed-copy formulation, with padded trailing rows ignored."""
+    from point_teacher_b200 import ops
+    g = torch.Generator().manual_seed(M + 3 * N + K)
+    A = torch.randn(M, K, generator=g).to(torch.bfloat16)
+    B = (torch.randn(N, K, generator=g) * 0.05).to(torch.bfloat16)
+    ref = A.float().to(cuda) @ B.float().to(cuda).t()
+    junk = lambda r, c: torch.full((r, c), float("nan"), dtype=torch.bfloat16)  # noqa: E731
+    As = torch.cat([A.t().contiguous(), junk(13, M)], 0) if a_mn else torch.cat([A, junk(5, K)], 0)
+    Bs = torch.cat([B.t().contiguous(), junk(9, N)], 0) if b_mn else B
+    for split in (True, False):
+        out = ops.fc_gemm_mn(As.to(cuda), Bs.to(cuda), a_mn=a_mn, b_mn=b_mn, out_dtype=torch.float32, M=M, K=K,
+                             allow_split=split)
+        err = (out[:M] - ref).abs().max().item()
+        assert err <= 1e-3 * ref.abs().max().item(), (err, ref.abs().max().item())
+    assert torch.count_nonzero(ops.gemm_workspace(cuda)[:4096]) == 0
+
+
 def test_fc_gemm_rejects_bad_shapes(cuda):
     from point_teacher_b200 import ops
     from point_teacher_b200._lib import PTB200Error

@@ -249,3 +249,74 @@ def test_captured_train_step_matches_eager(cuda):
     cap.replay()
     torch.cuda.synchronize()
     assert not torch.allclose(cap.x.grad, gx_eager, rtol=0, atol=1e-5 * float(gx_eager.abs().max()))
+
+
+# ------------------------------------------------------------------------------ OBB twin
+def test_roi_align_rotated_backward_vs_autograd(cuda):
+    import math
+    from oracle import rotated
+    from point_teacher_b200 import ops
+    g = torch.Generator().manual_seed(7)
+    K = 240
+    x = torch.randn(2, 256, 40, 40, generator=g, requires_grad=True)
+    rois = torch.stack([torch.randint(0, 2, (K,), generator=g).float(), torch.rand(K, generator=g) * 340 - 10,
+                        torch.rand(K, generator=g) * 340 - 10, torch.rand(K, generator=g) * 40 + 2,
+                        torch.rand(K, generator=g) * 40 + 2, torch.rand(K, generator=g) * math.pi - math.pi / 2], 1)
+    rois[0, 3:5] = torch.tensor([300., 200.])                     # large RoI: many 4x4-pixel chunks
+    rois[1, 1:3] = torch.tensor([-40., -40.])                     # entirely outside: no gradient
+    for cw in (True, False):
+        x.grad = None
+        out = rotated.roi_align_rotated_torch(x, rois, 7, 0.125, 2, True, cw)
+        gout = torch.randn(out.shape, generator=g).to(torch.bfloat16).float()
+        out.backward(gout)
+        dA = gout.permute(0, 2, 3, 1).reshape(K, -1).to(torch.bfloat16)
+        dfeat = ops.roi_align_backward(dA.to(cuda), rois.to(cuda), (2, 40, 40, 256), 0.125, sampling_ratio=2,
+                                       rotated=True, clockwise=cw)
+        assert _rel(ops.nhwc_to_nchw_f32(dfeat), x.grad) < 1e-4
+
+
+@pytest.mark.parametrize("seed,alpha", [(0, (1.0, 1.0)), (3, (0.01, 0.25))])
+def test_obb_training_step_gradients_vs_oracle(cuda, seed, alpha):
+    """OBB twin of the training step (rotated bags, RoIAlignRotated backward, 0.25/0.75 bag loss) against torch
+    autograd through oracle/obb.py with the differentiable RoIAlignRotated twin."""
+    from oracle import obb
+    from point_teacher_b200.mil_head import RotatedMILHead
+    from point_teacher_b200.train import Phase2Trainer
+    d = synth.obb_batch(seed=seed, **SMALL)
+    P = hbb.MilHeadParams(num_classes=9, num_stages=1, seed=seed).requires_grad_(True)
+    feat = d["feat"].clone().requires_grad_(True)
+    obb.DIFFERENTIABLE_ROI = True
+    try:
+        ob, op, ol, aux = obb.phase2_refine(P, (feat,), [d["stride"]], d["img_metas"], d["pseudo_boxes"],
+                                            d["pseudo_points"], d["pseudo_labels"], d["gt_boxes"], synth.OBB_FINE_CFG,
+                                            synth.OBB_EXT_CFG, alpha=alpha, injected_negs=d["neg_boxes"])
+    finally:
+        obb.DIFFERENTIABLE_ROI = False
+    (ol["stage0_loss_mil_bbox"] + ol["stage0_loss_mil_bags"]).backward()
+    ref = {k: v.grad for k, v in P.state_dict().items()}
+    head = RotatedMILHead(num_classes=9, num_stages=1, top_k=3, precision="bf16").to(cuda)
+    head.load_state_dict({k: v.detach() for k, v in P.state_dict().items()}, strict=False)
+    x = d["feat"].to(cuda).requires_grad_(True)
+    to = lambda l: [t.to(cuda) for t in l]  # noqa: E731
+    tr = Phase2Trainer(head, synth.OBB_FINE_CFG, synth.OBB_EXT_CFG, num_stages=1, alpha=alpha)
+    gb, gp, gl = tr.step((x,), d["img_metas"], to(d["pseudo_boxes"]), to(d["pseudo_points"]), to(d["pseudo_labels"]),
+                         to(d["gt_boxes"]), neg_boxes=[to(d["neg_boxes"][0])])
+    for k in ("stage0_loss_mil_bbox", "stage0_loss_mil_bags"):
+        assert abs(float(gl[k]) - float(ol[k].detach())) <= 2e-2 * max(abs(float(ol[k].detach())), 1e-3), k
+    got = dict(head.named_parameters())
+
+    def close(a, b, name):
+        a, b = a.double().cpu().flatten(), b.double().flatten()
+        if b.abs().max() < 1e-9:
+            assert a.abs().max() < 1e-6, name
+            return
+        cos = F.cosine_similarity(a, b, 0).item()
+        fro = ((a - b).norm() / b.norm()).item()
+        assert cos >= 0.998 and fro <= 8e-2, (name, cos, fro)
+
+    for k, r in ref.items():
+        assert got[k].grad is not None, k
+        close(got[k].grad, r, k)
+    close(x.grad, feat.grad, "feature map")
+    for a, b in zip(gb, ob):
+        assert a.shape[1] == 5 and _rel(a.detach(), b.detach()) < 2e-2

@@ -96,6 +96,21 @@ def test_rotated_roi_align_theta0_equals_horizontal():
     assert torch.allclose(out, ref, atol=2e-5)
 
 
+def test_rotated_roi_align_torch_twin_matches_c_restatement():
+    """The autograd-capable PyTorch twin (used for the OBB gradient tests) == the C restatement, incl. RoIs that
+    leave the map and both rotation directions."""
+    g = torch.Generator().manual_seed(0)
+    x = torch.randn(2, 16, 32, 32, generator=g)
+    K = 300
+    rois = torch.stack([torch.randint(0, 2, (K,), generator=g).float(), torch.rand(K, generator=g) * 280 - 10,
+                        torch.rand(K, generator=g) * 280 - 10, torch.rand(K, generator=g) * 60 + 1,
+                        torch.rand(K, generator=g) * 60 + 1, torch.rand(K, generator=g) * math.pi - math.pi / 2], 1)
+    for cw in (True, False):
+        a = rotated.roi_align_rotated(x, rois, 7, 0.125, 2, True, cw)
+        b = rotated.roi_align_rotated_torch(x, rois, 7, 0.125, 2, True, cw)
+        assert torch.allclose(a, b, atol=2e-5)
+
+
 def test_rotated_roi_align_orientation_kat():
     # SURVEY Appendix A.2: square RoI, theta=+pi/2, clockwise=True == theta=0 transposed and flipped
     g = torch.Generator().manual_seed(5)
