@@ -244,6 +244,25 @@ int pt_nhwc_to_nchw_f32(const float* in, float* out, int B, int C, int H, int W,
 int pt_roi_align_backward(const void* dA_bf16, long long ld, const float* rois, int K, int B, int C, int H, int W,
                           float spatial_scale, int sampling_ratio, int aligned, float* dfeat, void* stream);
 
+/* ---- strong_augmentation ---------------------------------------------------------
+ * Replaces HBB_TOD/mmdet/models/detectors/syn_images_generator_v2.py:24-132 and
+ * OBB_TOD/mmrotate/models/detectors/syn_images_generator_v2.py:223-357.
+ * params: fp32 [B, pt_augment_param_stride()], one block per image:
+ *   [0] flip x  [1] flip y  [2] rotate flag  [3..6] r00 r01 r10 r11 (affine sampling grid theta^T / (w/2, h/2))
+ *   [7] scale_H [8] scale_W [9] start_y [10] start_x [11] zero-pad flag (scale < 1)  [12] scale factor
+ *   [13] cos(-angle) [14] sin(-angle) [15] blank_w [16] blank_h.
+ * pt_augment_image: flip -> (rotate nearest, fill 0) -> bilinear resize (align_corners = false) -> crop / pad ->
+ *   round, one pass, [B,C,H,W] fp32 -> [B,C,H,W] fp32.
+ * pt_augment_coords: the same transform on the packed GT-point / pseudo-point / pseudo-box lists (int32 offsets
+ *   [B+1]) with the reference's in-image filters and a stable compaction; box_dim 4 = xyxy, 5 = (cx,cy,w,h,theta)
+ *   le90 via obb2poly / poly2obb; counts int32 [B,2] = kept (GT points, pseudo entries) per image. */
+int pt_augment_param_stride(void);
+int pt_augment_image(const float* img, float* out, const float* params, int B, int C, int H, int W, void* stream);
+int pt_augment_coords(const float* gt_pts, const long long* gt_lab, const int* gt_off, const float* ps_pts,
+                      const long long* ps_lab, const float* ps_box, const int* ps_off, int box_dim, const float* params,
+                      int B, int H, int W, float* o_gt_pts, long long* o_gt_lab, float* o_ps_pts, long long* o_ps_lab,
+                      float* o_ps_box, int* counts, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -229,7 +229,58 @@ def check_pseudo():
     return ok
 
 
+def _aug_args(d):
+    return [d["img"].clone()] + [[t.clone() for t in d[k]] for k in
+                                 ("gt_points", "gt_labels", "pseudo_points", "pseudo_labels", "pseudo_bboxes")]
+
+
+def check_augment():
+    """Section 8f rank 3: the reference's own strong_augmentation (HBB and OBB, seeded ``random`` + ``np.random``)
+    against oracle/augment.py fed with the replayed draws; plus the explicit-arithmetic resamplers against the
+    library calls they restate."""
+    import random
+
+    import numpy as np
+    import torch.nn.functional as F
+    import torchvision.transforms.functional as TF
+    from oracle import augment
+    ns = ref_shim.install()
+    o = ref_shim.install_obb()
+    ok = True
+    names = ("images", "image list", "gt points", "gt labels", "pseudo points", "pseudo labels", "pseudo boxes")
+    for rot in (False, True):
+        for seed in range(8):
+            d = synth.augment_batch(seed, rotated=rot)
+            random.seed(seed)
+            np.random.seed(seed)
+            ref = o.syn.strong_augmentation(*_aug_args(d), "le90") if rot else ns.syn.strong_augmentation(*_aug_args(d))
+            random.seed(seed)
+            np.random.seed(seed)
+            ch = augment.draw_choices(2, rotated=rot)
+            fn = augment.strong_augmentation_obb if rot else augment.strong_augmentation_hbb
+            got = fn(*_aug_args(d), ch)
+            for nm, a_, b_ in zip(names, got, ref):
+                if torch.is_tensor(a_):
+                    ok &= _eq(a_, b_, f"augment {'obb' if rot else 'hbb'} {nm} seed{seed} {ch}", 0.0)
+                else:
+                    ok &= len(a_) == len(b_)
+                    for x_, y_ in zip(a_, b_):
+                        ok &= _eq(x_, y_, f"augment {'obb' if rot else 'hbb'} {nm} seed{seed}", 0.0)
+    img = synth.augment_batch(0, img_hw=(200, 168))["img"][0]
+    for sf in (0.8, 0.9, 1.1, 1.2):
+        oh, ow = int(200 * sf), int(168 * sf)
+        ok &= _eq(augment.bilinear_resize_exact(img, oh, ow),
+                  F.interpolate(img[None], size=(oh, ow), mode="bilinear", align_corners=False)[0], f"bilinear x{sf}", 0.0)
+    for ang in (1, 7, 19):
+        ok &= _eq(augment.rotate_nearest_exact(img, ang), TF.rotate(img, ang, fill=0), f"rotate {ang} deg", 0.0)
+    return ok
+
+
 if __name__ == "__main__":
+    if "--augment" in sys.argv:
+        good = check_augment()
+        print("ALL OK" if good else "MISMATCH")
+        sys.exit(0 if good else 1)
     if "--pseudo" in sys.argv:
         good = check_pseudo()
         print("ALL OK" if good else "MISMATCH")

@@ -164,6 +164,33 @@ def pseudo_case():
     print("wrote pseudo_boxes", [(o["G"], o["valid"].numel()) for o in out])
 
 
+def augment_case():
+    """Section 8f rank 3: outputs of the reference's own strong_augmentation (HBB and OBB) with seeded
+    ``random`` / ``np.random``; images stored as uint8 (the reference rounds them)."""
+    import random
+
+    import numpy as np
+    from oracle import augment
+    ns = ref_shim.install()
+    o = ref_shim.install_obb()
+    out = []
+    for rot, seed in ((False, 1), (False, 5), (True, 1), (True, 6)):
+        d = synth.augment_batch(seed, rotated=rot)
+        args = [d["img"].clone()] + [[t.clone() for t in d[k]] for k in
+                                     ("gt_points", "gt_labels", "pseudo_points", "pseudo_labels", "pseudo_bboxes")]
+        random.seed(seed)
+        np.random.seed(seed)
+        choices = augment.draw_choices(2, rotated=rot)
+        random.seed(seed)
+        np.random.seed(seed)
+        r = o.syn.strong_augmentation(*args, "le90") if rot else ns.syn.strong_augmentation(*args)
+        assert r[0].min() >= 0 and r[0].max() <= 255 and torch.equal(r[0], r[0].round())
+        out.append(dict(rotated=rot, seed=seed, choices=choices, images=r[0].to(torch.uint8), gt_points=r[2],
+                        gt_labels=r[3], pseudo_points=r[4], pseudo_labels=r[5], pseudo_bboxes=r[6]))
+    torch.save(out, os.path.join(OUT, "augment.pt"))
+    print("wrote augment", [(c["rotated"], c["choices"], [len(x) for x in c["gt_points"]]) for c in out])
+
+
 def overlaps_case():
     ns = ref_shim.install()
     g = torch.Generator().manual_seed(7)

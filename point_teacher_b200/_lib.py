@@ -86,6 +86,11 @@ SIGNATURES = {
     "pt_nhwc_to_nchw_f32": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p]),
     "pt_roi_align_backward": (c_int, [c_void_p, c_ll, c_void_p, c_int, c_int, c_int, c_int, c_int, c_float, c_int, c_int,
                                       c_void_p, c_void_p]),
+    "pt_augment_param_stride": (c_int, []),
+    "pt_augment_image": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
+    "pt_augment_coords": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p,
+                                  c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+                                  c_void_p]),
     "pt_aligned_iou_mean": (c_int, [c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p]),
 }
 
@@ -116,7 +121,7 @@ def load():
 
 LAUNCHES = {"count": 0}   # kernels enqueued through the C-ABI (every launching entry point = one kernel)
 _NO_KERNEL = {"pt_last_error", "pt_abi_version", "pt_build_arch", "pt_fc_gemm_workspace_bytes",
-              "pt_nms_rotated_workspace_bytes"}
+              "pt_nms_rotated_workspace_bytes", "pt_augment_param_stride"}
 
 
 def call(name, *args):

@@ -165,3 +165,22 @@ def pseudo_batch(seed, P_hw=(100, 100), G=120, C=8, stride=8):
     logits[torch.randperm(P, generator=g)[:P // 3]] += 3.0          # some confident points: scores above the filter
     return dict(points=d["points"], ltrb=ltrb, logits=logits, gt_points=ctr.clone(), gt_boxes=gt_boxes,
                 labels=d["labels"])
+
+
+def augment_batch(seed=0, batch=2, img_hw=(160, 176), n=30, rotated=False, num_classes=8):
+    """Inputs of ``strong_augmentation`` (section 8f rank 3): uint8-valued fp32 images, GT points, pseudo points /
+    labels / boxes (xyxy, or (cx,cy,w,h,theta) when ``rotated``), a few of them outside the image."""
+    g = torch.Generator().manual_seed(seed)
+    h, w = img_hw
+    img = torch.randint(0, 256, (batch, 3, h, w), generator=g).float()
+    wh_t = torch.tensor([w, h], dtype=torch.float32)
+    gtp = [torch.rand(n, 2, generator=g) * wh_t for _ in range(batch)]
+    gtl = [torch.randint(0, num_classes, (n,), generator=g) for _ in range(batch)]
+    pp = [p + torch.randn(n, 2, generator=g) * 2 for p in gtp]
+    pl = [l.clone() for l in gtl]
+    sz = [torch.rand(n, 2, generator=g) * 30 + 4 for _ in range(batch)]
+    if rotated:
+        pb = [torch.cat([p, s, torch.rand(n, 1, generator=g) * math.pi - math.pi / 2], 1) for p, s in zip(pp, sz)]
+    else:
+        pb = [torch.cat([p - s / 2, p + s / 2], 1) for p, s in zip(pp, sz)]
+    return dict(img=img, gt_points=gtp, gt_labels=gtl, pseudo_points=pp, pseudo_labels=pl, pseudo_bboxes=pb)

@@ -291,3 +291,44 @@ def test_target_pseudo_oracle_reproduces_reference_golden(golden_dir):
         assert torch.equal(lr, c["labels_reg"].long()) and torch.equal(lb, c["labels"].long())
         assert torch.equal(t[pos], c["bbox_targets_pos"]) and float(t.double().sum()) == float(c["targets_checksum"])
         assert torch.equal(assign.centerness_target(t[pos]), c["centerness_pos"])
+
+
+# ------------------------------------------------------------------------------ strong_augmentation (8f rank 3)
+def _aug_args(d):
+    return [d["img"].clone()] + [[t.clone() for t in d[k]] for k in
+                                 ("gt_points", "gt_labels", "pseudo_points", "pseudo_labels", "pseudo_bboxes")]
+
+
+def test_augment_oracle_reproduces_reference_golden(golden_dir):
+    """Outputs of the reference's own strong_augmentation (HBB and OBB) from the injected draws: kept sets, labels
+    and coordinates bit-exact; the rounded image bit-exact (same ATen / torchvision CPU kernels)."""
+    import random
+    from oracle import augment
+    for c in torch.load(os.path.join(golden_dir, "augment.pt")):
+        d = synth.augment_batch(c["seed"], rotated=c["rotated"])
+        random.seed(c["seed"])
+        np.random.seed(c["seed"])
+        assert augment.draw_choices(2, rotated=c["rotated"]) == [tuple(x) for x in c["choices"]]     # RNG call order
+        fn = augment.strong_augmentation_obb if c["rotated"] else augment.strong_augmentation_hbb
+        out = fn(*_aug_args(d), c["choices"])
+        assert torch.equal(out[0], c["images"].float())
+        for key, got in zip(("gt_points", "gt_labels", "pseudo_points", "pseudo_labels", "pseudo_bboxes"), out[2:]):
+            for a, b in zip(got, c[key]):
+                assert a.shape == b.shape and torch.equal(a, b), key
+
+
+def test_augment_explicit_resamplers_match_library_kernels():
+    """The explicit fp32 formulae the device kernel replays == F.interpolate / torchvision rotate on this CPU
+    (the generic ATen upsample kernel is the one used for H + W > 128 with more than one thread)."""
+    import torch.nn.functional as F
+    import torchvision.transforms.functional as TF
+    from oracle import augment
+    if torch.get_num_threads() == 1:
+        pytest.skip("single-threaded ATen takes the other (vectorised) bilinear kernel for 3-channel images")
+    img = synth.augment_batch(0, img_hw=(200, 168))["img"][0]
+    for sf in (0.8, 0.9, 1.0, 1.1, 1.2):
+        oh, ow = int(200 * sf), int(168 * sf)
+        ref = F.interpolate(img[None], size=(oh, ow), mode="bilinear", align_corners=False)[0]
+        assert torch.equal(augment.bilinear_resize_exact(img, oh, ow), ref), sf
+    for ang in (1, 7, 19):
+        assert torch.equal(augment.rotate_nearest_exact(img, ang), TF.rotate(img, ang, fill=0)), ang
