@@ -263,6 +263,19 @@ int pt_augment_coords(const float* gt_pts, const long long* gt_lab, const int* g
                       int B, int H, int W, float* o_gt_pts, long long* o_gt_lab, float* o_ps_pts, long long* o_ps_lab,
                       float* o_ps_box, int* counts, void* stream);
 
+/* ---- student-branch losses that are mmcv-native in the reference -----------------
+ * pt_sigmoid_focal_loss: HBB_TOD/mmdet/models/losses/focal_loss.py:11-100 (mmcv.ops.sigmoid_focal_loss).
+ *   pred [N,C] logits, target [N] int64 in [0,C] (C = background); weight_mode 0 none | 1 [N] | 2 [N*C];
+ *   loss_elem / grad_elem [N,C] (either may be NULL): weighted element loss and its derivative w.r.t. pred;
+ *   sum (may be NULL): += total weighted loss.
+ * pt_rotated_iou_loss: OBB_TOD/mmrotate/models/losses/rotated_iou_loss.py:17-147 on mmcv.ops.diff_iou_rotated_2d.
+ *   pred / target [n,5] (cx,cy,w,h,theta); mode 0 log | 1 linear | 2 square; dn = 1: DN_iou_loss with `hyper`;
+ *   loss [n] element losses, grad [n,5] (may be NULL) = d loss / d pred. */
+int pt_sigmoid_focal_loss(const float* pred, const long long* target, const float* weight, int weight_mode, float gamma,
+                          float alpha, int N, int C, float* loss_elem, float* grad_elem, float* sum, void* stream);
+int pt_rotated_iou_loss(const float* pred, const float* target, int n, int mode, float eps, int dn, float hyper,
+                        float* loss, float* grad, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -276,7 +276,43 @@ def check_augment():
     return ok
 
 
+def check_losses():
+    """Section 8f rank 4: the reference's own FocalLoss (CPU branch) and RotatedIoULoss / DN_IoULoss wrappers (with
+    the restated diff_iou_rotated_2d bound into mmcv.ops) against oracle/losses.py."""
+    import math
+    from oracle import losses as L
+    o = ref_shim.install_obb()
+    ok = True
+    g = torch.Generator().manual_seed(0)
+    n = 300
+    c = torch.rand(n, 2, generator=g) * 200 + 20
+    wh = torch.rand(n, 2, generator=g) * 40 + 2
+    b1 = torch.cat([c, wh, torch.rand(n, 1, generator=g) * math.pi - math.pi / 2], 1)
+    b2 = b1.clone()
+    b2[:, :2] += torch.randn(n, 2, generator=g) * 6
+    b2[:, 2:4] *= torch.exp(torch.randn(n, 2, generator=g) * 0.3)
+    b2[:, 4] += torch.randn(n, generator=g) * 0.5
+    w = (torch.rand(n, generator=g) > 0.3).float()
+    for mode in ("log", "linear", "square"):
+        ref = o.riou_loss.RotatedIoULoss(mode=mode, loss_weight=1.5)(b1, b2, weight=w, avg_factor=77.0)
+        got = L.rotated_loss_forward(L.rotated_iou_loss_elem, b1, b2, weight=w, avg_factor=77.0, loss_weight=1.5, mode=mode)
+        ok &= _eq(got, ref, f"RotatedIoULoss {mode}", 0.0)
+        ref = o.riou_loss.DN_IoULoss(mode=mode, hyper=0.3)(b1, b2, weight=w, avg_factor=77.0)
+        got = L.rotated_loss_forward(L.dn_iou_loss_elem, b1, b2, weight=w, avg_factor=77.0, hyper=0.3, mode=mode)
+        ok &= _eq(got, ref, f"DN_IoULoss {mode}", 0.0)
+    P, t, ww = torch.randn(500, 8, generator=g) * 2, torch.randint(0, 9, (500,), generator=g), torch.rand(500, generator=g)
+    fl = o.focal.FocalLoss(gamma=2.0, alpha=0.25, loss_weight=1.0)
+    ok &= _eq(L.sigmoid_focal_loss(P, t, ww, avg_factor=33.0), fl(P, t, ww, avg_factor=33.0), "FocalLoss weighted", 0.0)
+    ok &= _eq(L.sigmoid_focal_loss(P, t), fl(P, t), "FocalLoss mean", 0.0)
+    ok &= _eq(L.sigmoid_focal_loss(P, t, reduction="none"), fl(P, t, reduction_override="none"), "FocalLoss none", 0.0)
+    return ok
+
+
 if __name__ == "__main__":
+    if "--losses" in sys.argv:
+        good = check_losses()
+        print("ALL OK" if good else "MISMATCH")
+        sys.exit(0 if good else 1)
     if "--augment" in sys.argv:
         good = check_augment()
         print("ALL OK" if good else "MISMATCH")

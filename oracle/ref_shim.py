@@ -375,7 +375,20 @@ def install_obb():
     # returns a 3-tuple; HBB_TOD's vendored 2.13 version is wrapped to that signature.
     _old = head._expand_onehot_labels
     head._expand_onehot_labels = lambda labels, w, ch, ignore_index=None: _old(labels, w, ch) + (None,)
+    # section 8f rank 4: the rotated IoU losses; their mmcv kernel (diff_iou_rotated_2d) is un-vendored and is bound to
+    # the restatement in oracle/losses.py (PARITY UNPINNED for that kernel; the wrappers are the reference's own)
+    from . import losses as _losses
+    _mk("mmrotate.models.losses", p("models", "losses"))
+    sys.modules["mmcv.ops"].diff_iou_rotated_2d = _losses.diff_iou_rotated_2d
+    riou_loss = _imp("mmrotate.models.losses.rotated_iou_loss")
+    focal = None
+    try:
+        sys.modules["mmcv.ops"].sigmoid_focal_loss = None      # only the CUDA branch uses it
+        focal = _imp("mmdet.models.losses.focal_loss")
+    except Exception:  # pragma: no cover
+        pass
     _OBB = types.SimpleNamespace(hbb=ns, rbbox_overlaps=riou.rbbox_overlaps, transforms=tr, syn=syn,
+                                 riou_loss=riou_loss, focal=focal,
                                  RotatedSingleRoIExtractor=rext.RotatedSingleRoIExtractor, head_mod=head,
                                  TS_P2RBRotatedFCOSHead=head.TS_P2RBRotatedFCOSHead)
     return _OBB

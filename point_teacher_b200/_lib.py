@@ -91,6 +91,10 @@ SIGNATURES = {
     "pt_augment_coords": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p,
                                   c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                                   c_void_p]),
+    "pt_sigmoid_focal_loss": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_float, c_float, c_int, c_int, c_void_p,
+                                      c_void_p, c_void_p, c_void_p]),
+    "pt_rotated_iou_loss": (c_int, [c_void_p, c_void_p, c_int, c_int, c_float, c_int, c_float, c_void_p, c_void_p,
+                                    c_void_p]),
     "pt_aligned_iou_mean": (c_int, [c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p]),
 }
 

@@ -55,8 +55,9 @@ def _try_import_registries():
         regs.update(HEADS=HEADS, ROI_EXTRACTORS=ROI_EXTRACTORS, LOSSES=LOSSES, BBOX_ASSIGNERS=BBOX_ASSIGNERS,
                     BBOX_CODERS=BBOX_CODERS, IOU_CALCULATORS=IOU_CALCULATORS, MATCH_COST=MATCH_COST)
         try:
-            from mmrotate.models.builder import ROTATED_ROI_EXTRACTORS, ROTATED_HEADS
-            regs.update(ROTATED_ROI_EXTRACTORS=ROTATED_ROI_EXTRACTORS, ROTATED_HEADS=ROTATED_HEADS)
+            from mmrotate.models.builder import ROTATED_ROI_EXTRACTORS, ROTATED_HEADS, ROTATED_LOSSES
+            regs.update(ROTATED_ROI_EXTRACTORS=ROTATED_ROI_EXTRACTORS, ROTATED_HEADS=ROTATED_HEADS,
+                        ROTATED_LOSSES=ROTATED_LOSSES)
         except Exception:
             pass
     except Exception:
@@ -77,6 +78,7 @@ ROI_EXTRACTORS = _get("ROI_EXTRACTORS")
 ROTATED_ROI_EXTRACTORS = _EXTERNAL.get("ROTATED_ROI_EXTRACTORS") or ROI_EXTRACTORS
 ROTATED_HEADS = _EXTERNAL.get("ROTATED_HEADS") or HEADS
 LOSSES = _get("LOSSES")
+ROTATED_LOSSES = _EXTERNAL.get("ROTATED_LOSSES") or LOSSES
 BBOX_ASSIGNERS = _get("BBOX_ASSIGNERS")
 BBOX_CODERS = _get("BBOX_CODERS")
 IOU_CALCULATORS = _get("IOU_CALCULATORS")

@@ -332,3 +332,37 @@ def test_augment_explicit_resamplers_match_library_kernels():
         assert torch.equal(augment.bilinear_resize_exact(img, oh, ow), ref), sf
     for ang in (1, 7, 19):
         assert torch.equal(augment.rotate_nearest_exact(img, ang), TF.rotate(img, ang, fill=0)), ang
+
+
+# ------------------------------------------------------------------------------ losses (8f rank 4)
+def test_diff_iou_rotated_restatement_cross_checks():
+    """mmcv's diff_iou_rotated_2d is un-vendored (parity unpinned): the restatement agrees with the polygon-clipping
+    IoU (a different algorithm, oracle/rotated.py) and, at theta = 0, with the axis-aligned IoU."""
+    from oracle import losses as L
+    g = torch.Generator().manual_seed(0)
+    n = 400
+    c = torch.rand(n, 2, generator=g) * 200 + 20
+    wh = torch.rand(n, 2, generator=g) * 40 + 2
+    a = torch.rand(n, 1, generator=g) * math.pi - math.pi / 2
+    b1 = torch.cat([c, wh, a], 1)
+    b2 = b1.clone()
+    b2[:, :2] += torch.randn(n, 2, generator=g) * 6
+    b2[:, 2:4] *= torch.exp(torch.randn(n, 2, generator=g) * 0.3)
+    b2[:, 4] += torch.randn(n, generator=g) * 0.5
+    iou = L.diff_iou_rotated_2d(b1[None], b2[None])[0]
+    assert (iou - rotated.box_iou_rotated(b1, b2, aligned=True)).abs().max().item() < 2e-4
+    b1[:, 4] = 0
+    b2[:, 4] = 0
+    ref = hbb.bbox_overlaps(hbb.cxcywh_to_xyxy(b1[:, :4]), hbb.cxcywh_to_xyxy(b2[:, :4]), is_aligned=True)
+    assert (L.diff_iou_rotated_2d(b1[None], b2[None])[0] - ref).abs().max().item() < 2e-4
+
+
+def test_focal_loss_matches_binary_cross_entropy_limit():
+    """gamma = 0, alpha = 0.5 reduces the focal loss to half the BCE-with-logits (focal_loss.py:11-57)."""
+    import torch.nn.functional as F
+    from oracle import losses as L
+    g = torch.Generator().manual_seed(1)
+    p, t = torch.randn(50, 6, generator=g), torch.randint(0, 7, (50,), generator=g)
+    oh = F.one_hot(t, 7)[:, :6].float()
+    assert torch.allclose(L.sigmoid_focal_loss(p, t, gamma=0.0, alpha=0.5, reduction="sum"),
+                          0.5 * F.binary_cross_entropy_with_logits(p, oh, reduction="sum"), rtol=1e-6)
