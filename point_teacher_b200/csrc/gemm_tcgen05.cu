@@ -194,7 +194,8 @@ __device__ __forceinline__ void store_chunk(const Params& p, int row, int col0, 
   }
 }
 
-template <bool TWO>
+// AMN / BMN: operand staged as an MN-major tile (compile-time, so the K-major forward kernel is unchanged)
+template <bool TWO, bool AMN = false, bool BMN = false>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 fc_gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b,
                const Params p) {
@@ -253,14 +254,14 @@ fc_gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
             tma_load_2d_pair(sa + A_BYTES, &tma_b, full_bar + stage, kb * BK, u.n_blk * BN + rank * B_ROWS);
           } else {
             mbar_expect_tx(full_bar + stage, STAGE_BYTES);
-            if (p.a_mn) {
+            if (AMN) {
 #pragma unroll
               for (int j = 0; j < BM / 64; j++)
                 tma_load_2d(sa + j * (64 * BK * 2), &tma_a, full_bar + stage, u.m_blk * BM + j * 64, kb * BK);
             } else {
               tma_load_2d(sa, &tma_a, full_bar + stage, kb * BK, u.m_blk * BM);
             }
-            if (p.b_mn) {
+            if (BMN) {
 #pragma unroll
               for (int j = 0; j < BN / 64; j++)
                 tma_load_2d(sa + A_BYTES + j * (64 * BK * 2), &tma_b, full_bar + stage, u.n_blk * BN + j * 64, kb * BK);
@@ -287,13 +288,13 @@ fc_gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
           tc_fence_after();
           if (lane == 0) {
             const uint32_t sa = smem_u32(smem + stage * STAGE_BYTES);
-            const bool amn = !TWO && p.a_mn, bmn = !TWO && p.b_mn;
+            constexpr bool amn = !TWO && AMN, bmn = !TWO && BMN;
             const uint64_t adesc = amn ? make_desc_mn(sa) : make_desc(sa);
             const uint64_t bdesc = bmn ? make_desc_mn(sa + A_BYTES) : make_desc(sa + A_BYTES);
             // K-major: advance 16 bf16 = 32 B along K inside the 128 B swizzle row: +2 in 16 B units;
             // MN-major: 16 k-rows of 128 B = 2048 B: +128
-            const uint32_t astep = amn ? 128u : 2u, bstep = bmn ? 128u : 2u;
-            const uint32_t idesc = IDESC | (amn ? (1u << 15) : 0u) | (bmn ? (1u << 16) : 0u);
+            constexpr uint32_t astep = amn ? 128u : 2u, bstep = bmn ? 128u : 2u;
+            constexpr uint32_t idesc = IDESC | (amn ? (1u << 15) : 0u) | (bmn ? (1u << 16) : 0u);
 #pragma unroll
             for (int k = 0; k < BK / UMMA_K; k++) {
               if (TWO) tc_mma_bf16_pair(tmem_d, adesc + 2 * k, bdesc + 2 * k, IDESC_PAIR, (kb > u.kb0 || k > 0) ? 1u : 0u);
@@ -583,6 +584,12 @@ extern "C" int pt_fc_gemm_bf16_mn(const void* A, long long lda, int a_mn, const 
     cudaError_t e = cudaFuncSetAttribute(fc_gemm_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<false>::SMEM_BYTES);
     if (e == cudaSuccess)
       e = cudaFuncSetAttribute(fc_gemm_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<true>::SMEM_BYTES);
+    if (e == cudaSuccess)
+      e = cudaFuncSetAttribute(fc_gemm_kernel<false, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<false>::SMEM_BYTES);
+    if (e == cudaSuccess)
+      e = cudaFuncSetAttribute(fc_gemm_kernel<false, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<false>::SMEM_BYTES);
+    if (e == cudaSuccess)
+      e = cudaFuncSetAttribute(fc_gemm_kernel<false, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<false>::SMEM_BYTES);
     if (e != cudaSuccess) { set_error("cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return PT_ERR_CUDA; }
     attr_set = true;
   }
@@ -598,6 +605,11 @@ extern "C" int pt_fc_gemm_bf16_mn(const void* A, long long lda, int a_mn, const 
     if (e != cudaSuccess) { set_error("fc_gemm_kernel<pair>: launch failed: %s", cudaGetErrorString(e)); return PT_ERR_CUDA; }
     return check_launch("fc_gemm_kernel<pair>");
   }
-  fc_gemm_kernel<false><<<grid_u, NUM_THREADS, Cfg<false>::SMEM_BYTES, (cudaStream_t)stream>>>(ma, mb, p);
+  const size_t sm = Cfg<false>::SMEM_BYTES;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (a_mn && b_mn) fc_gemm_kernel<false, true, true><<<grid_u, NUM_THREADS, sm, st>>>(ma, mb, p);
+  else if (a_mn) fc_gemm_kernel<false, true, false><<<grid_u, NUM_THREADS, sm, st>>>(ma, mb, p);
+  else if (b_mn) fc_gemm_kernel<false, false, true><<<grid_u, NUM_THREADS, sm, st>>>(ma, mb, p);
+  else fc_gemm_kernel<false><<<grid_u, NUM_THREADS, sm, st>>>(ma, mb, p);
   return check_launch("fc_gemm_kernel");
 }
