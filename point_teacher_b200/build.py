@@ -12,7 +12,7 @@ OUT_DIR = os.path.join(HERE, "_C")
 SO = os.path.join(OUT_DIR, "libptb200.so")
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
-         "-Xcompiler", "-fPIC", "--use_fast_math=false" if False else "-Xcompiler", "-O2",
+         "-Xcompiler", "-fPIC", "-Xcompiler", "-O2",
          "--expt-relaxed-constexpr"]
 
 

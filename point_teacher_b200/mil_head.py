@@ -79,6 +79,30 @@ class MILHeadMixin:
             hit = self._wcache[key]
         return hit[1]
 
+    def _side_work(self, stage, between=None):
+        """Fork/join: work that the data path does not need until later runs on a side stream -- the fp32 -> bf16
+        rebuild of both FC stacks' operands when they are stale (training: every step; 2 x 77 MB weight streams that
+        now overlap bag generation and the first RoIAlign instead of sitting in front of the GEMMs) and
+        ``between()`` (the negatives' RoIs and weights).  Returns (event after the first stack's weights, event
+        after everything); the caller joins with ``wait_event``.  Works the same inside a CUDA-graph capture (the
+        side stream is forked from, and joined back into, the capturing stream)."""
+        main = torch.cuda.current_stream()
+        side = getattr(self, "_side_stream", None)
+        if side is None or side.device != main.device:
+            side = self._side_stream = torch.cuda.Stream(device=main.device)
+        side.wait_stream(main)
+        evs = []
+        with torch.cuda.stream(side):
+            for i, fcs in enumerate((self.shared_fcs_reg[stage], self.shared_fcs_bag[stage])):
+                if i == 1 and between is not None:
+                    between()
+                self._weight(fcs[0], True)
+                self._weight(fcs[1], False)
+                ev = torch.cuda.Event()
+                ev.record(side)
+                evs.append(ev)
+        return evs
+
     def _fc_stack(self, A, fcs, M, keep=None):
         w1, w2 = self._weight(fcs[0], True), self._weight(fcs[1], False)
         b1, b2 = fcs[0].bias.detach(), fcs[1].bias.detach()
@@ -227,26 +251,33 @@ class MILHeadMixin:
         dev = x[0].device
         rot = self.bbox_roi_extractor.rotated
         rs = 6 if rot else 5
+        n_neg = 0 if neg_boxes is None else neg_boxes.shape[0]
+        U2 = len(cfg["base_ratios"]) ** 2 * (1 + 4 * len(cfg["shake_ratio"] or []))
+        K, G = base_rois.shape[0] * U2, pseudo.shape[0]
+        rois2 = torch.empty((K + n_neg, rs), dtype=torch.float32, device=dev)
+        side = {}
+
+        def negatives():
+            if n_neg:
+                ops.make_rois(neg_boxes, neg_img_idx, out=rois2[K:])
+                side["neg_w"] = ops.neg_weight(rois2[K:], base_rois, bag_offsets, rot)
+        ev_reg, ev_all = self._side_work(stage, negatives)
+        neg_w = side.get("neg_w")
         ebags, evalid = ops.bag_gen(base_rois, img_wh, cfg["base_ratios"], cfg["shake_ratio"], cfg["min_scale"], rot)
-        K, G = ebags.shape[0], pseudo.shape[0]
-        U2 = K // max(base_rois.shape[0], 1)
+        assert ebags.shape[0] == K
         sums = torch.zeros((8,), dtype=torch.float32, device=dev)
         kreg = {} if keep is not None else None
         kbag = {} if keep is not None else None
         A = self._roi_operand(x, ebags)
+        torch.cuda.current_stream().wait_event(ev_reg)
         H = self._fc_stack(A, self.shared_fcs_reg[stage], K, kreg)
-        n_neg = 0 if neg_boxes is None else neg_boxes.shape[0]
-        rois2 = torch.empty((K + n_neg, rs), dtype=torch.float32, device=dev)
-        neg_w = None
-        if n_neg:
-            ops.make_rois(neg_boxes, neg_img_idx, out=rois2[K:])
-            neg_w = ops.neg_weight(rois2[K:], base_rois, bag_offsets, rot)
         h0, w0, _ = img_metas[0]["img_shape"]
         fr = self.fc_reg[stage]
         _, deltas, iou_t = ops.reg_decode(H, fr.weight.detach(), fr.bias.detach(), ebags, evalid, ref, real, U1 * U2,
                                           (w0, h0), sums, K=K, hyper=self.loss_bbox_denosing_hyper, out_rois=rois2,
                                           rotated=rot, want_deltas=keep is not None)
         del A, H
+        torch.cuda.current_stream().wait_event(ev_all)      # negatives' RoIs + the bag stack's operands
         A2 = self._roi_operand(x, rois2)
         H2 = self._fc_stack(A2, self.shared_fcs_bag[stage], K + n_neg, kbag)
         fc, fi = self.fc_cls[stage], self.fc_ins[stage]
