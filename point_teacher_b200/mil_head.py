@@ -80,12 +80,13 @@ class MILHeadMixin:
         return hit[1]
 
     def _side_work(self, stage, between=None):
-        """Fork/join: work that the data path does not need until later runs on a side stream -- the fp32 -> bf16
+        """Fork/join: work that the data path does not need immediately runs on a side stream -- the fp32 -> bf16
         rebuild of both FC stacks' operands when they are stale (training: every step; 2 x 77 MB weight streams that
-        now overlap bag generation and the first RoIAlign instead of sitting in front of the GEMMs) and
-        ``between()`` (the negatives' RoIs and weights).  Returns (event after the first stack's weights, event
-        after everything); the caller joins with ``wait_event``.  Works the same inside a CUDA-graph capture (the
-        side stream is forked from, and joined back into, the capturing stream)."""
+        overlap bag generation and the first RoIAlign instead of sitting in front of the GEMMs) and ``between()``
+        (the negatives' RoIs and weights).  Returns the events (first stack's weights ready, everything done); the
+        caller joins with ``wait_event``.  Works the same inside a CUDA-graph capture (the side stream is forked
+        from, and joined back into, the capturing stream).  (Measured: moving the NCHW -> NHWC transpose here as
+        well gains nothing -- it then competes with the weight stream for HBM in front of the first RoIAlign.)"""
         main = torch.cuda.current_stream()
         side = getattr(self, "_side_stream", None)
         if side is None or side.device != main.device:
@@ -283,10 +284,13 @@ class MILHeadMixin:
         fc, fi = self.fc_cls[stage], self.fc_ins[stage]
         cls, ins = ops.cls_ins_heads(H2, fc.weight.detach(), fc.bias.detach(), fi.weight.detach(),
                                      fi.bias.detach(), M=K + n_neg)
+        if n_neg:
+            with ops.fork() as fneg:                      # beside score_select (both reduce into ``sums``)
+                ops.neg_loss(cls[K:], neg_w, sums)
         merged, pts, idx, sc = ops.score_select(cls, ins, evalid, rois2, labels, pseudo, img_wh, G, U1, U2,
                                                 self.topk, self.beta, sums, rot)
         if n_neg:
-            ops.neg_loss(cls[K:], neg_w, sums)
+            fneg.join()
         out = ops.finalize_losses(sums, K, bool(n_neg), loss_scales[0], loss_scales[1], self.bag_loss_pos_scale,
                                   self.bag_loss_neg_scale)
         losses = {f"stage{stage}_loss_mil_bbox": out[0], f"stage{stage}_loss_mil_bags": out[1],

@@ -42,6 +42,34 @@ def _farr(vals):
     return (ctypes.c_float * max(len(vals), 1))(*vals), len(vals)
 
 
+_SIDE = {}
+
+
+class fork:
+    """``with ops.fork() as f: <launches>`` runs the launches on a side stream forked from the current stream;
+    ``f.join()`` makes the current stream wait for them.  Used for work that is off the critical path of the step
+    (logged IoU means); graph-capture safe as long as every fork is joined before the capture ends."""
+
+    def __enter__(self):
+        main = torch.cuda.current_stream()
+        key = (main.device.index, 1)
+        if key not in _SIDE:
+            _SIDE[key] = torch.cuda.Stream(device=main.device)
+        self.side = _SIDE[key]
+        self.side.wait_stream(main)
+        self.ctx = torch.cuda.stream(self.side)
+        self.ctx.__enter__()
+        return self
+
+    def __exit__(self, *exc):
+        self.event = torch.cuda.Event()
+        self.event.record(self.side)
+        return self.ctx.__exit__(*exc)
+
+    def join(self):
+        torch.cuda.current_stream().wait_event(self.event)
+
+
 def num_sms():
     return torch.cuda.get_device_properties(torch.cuda.current_device()).multi_processor_count
 

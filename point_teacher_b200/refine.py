@@ -31,7 +31,10 @@ def phase2_refine(head, x_ori, img_metas, pseudo_bboxes, pseudo_points, pseudo_l
     labels = torch.cat([l[:cap] for l in pseudo_labels]).long().contiguous()
     img_idx = const_tensor([i for i, c in enumerate(counts) for _ in range(c)], torch.int32, dev)
     img_wh = img_wh_tensor(img_metas, dev)
-    losses = {"coarse_bboxes_iou": ops.aligned_iou_mean(pb, gb, rot)}
+    forks = []
+    with ops.fork() as f:                       # logged scalars run beside the data path
+        losses = {"coarse_bboxes_iou": ops.aligned_iou_mean(pb, gb, rot)}
+    forks.append(f)
     pts = None
     for stage in range(num_stages):
         cfg = fine_proposal_cfg[stage]
@@ -66,7 +69,9 @@ def phase2_refine(head, x_ori, img_metas, pseudo_bboxes, pseudo_points, pseudo_l
                                                           offs, labels, pb, fine_proposal_extensive_cfg[stage], stage,
                                                           loss_scales=alpha)
         pb = pb_new
-        losses[f"stage{stage}_refine_bboxes_iou"] = ops.aligned_iou_mean(pb, gb, rot)
+        with ops.fork() as f:
+            losses[f"stage{stage}_refine_bboxes_iou"] = ops.aligned_iou_mean(pb, gb, rot)
+        forks.append(f)
         losses.update(mil_loss)
     # write-back (:463-465): refined head + untouched tail, one concat for boxes and one for points
     mb, mp = torch.split(pb, counts), torch.split(pts, counts)
@@ -77,6 +82,8 @@ def phase2_refine(head, x_ori, img_metas, pseudo_bboxes, pseudo_points, pseudo_l
         pt_parts += [mp[i].to(pseudo_points[i].dtype), pseudo_points[i][cap:, :]]
     refined_b = list(torch.split(torch.cat(box_parts), sizes))
     refined_p = list(torch.split(torch.cat(pt_parts), sizes))
+    for f in forks:
+        f.join()
     return refined_b, refined_p, losses
 
 
