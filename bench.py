@@ -443,6 +443,267 @@ def run_ours(args):
         dist.destroy_process_group()
 
 
+# ---------------------------------------------------------------------------------------------------------------
+# Secondary configurations (BASELINE.json configs[2..3] and SURVEY section 8 rows a13-a16): ``--config obb|assign|
+# mask`` prints ONE JSON line of the same shape for that workload.  They are parity-test cases first; these lines
+# put a measured number and the CPU oracle's time beside each.
+def _events_ms(fn, iters, flush, warm=3):
+    import torch
+    for _ in range(warm):
+        fn()
+    ts = []
+    for _ in range(iters):
+        if flush is not None:
+            flush.zero_()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(); fn(); e1.record()
+        torch.cuda.synchronize()
+        ts.append(e0.elapsed_time(e1))
+    ts.sort()
+    return ts[len(ts) // 2]
+
+
+def _cpu_ms(fn, n):
+    fn()
+    t0 = time.perf_counter()
+    for _ in range(n):
+        fn()
+    return (time.perf_counter() - t0) / n * 1e3
+
+
+def run_config_obb(args):
+    """Config #3: OBB (SODA-A shaped) phase-2 refinement: rotated bags, RoIAlignRotated, rotated IoU, top-3 merge."""
+    import torch
+    from point_teacher_b200 import _lib, ops, synth
+    from point_teacher_b200.mil_head import RotatedMILHead
+    from point_teacher_b200.refine import CapturedPhase2, Phase2Pipeline
+    dev = torch.device("cuda", 0)
+    _lib.load()
+    d = synth.obb_batch(seed=0)
+    torch.manual_seed(0)
+    head = RotatedMILHead(num_classes=9, num_stages=1, top_k=3, precision=args.precision).to(dev)
+    to = lambda l: [t.to(dev) for t in l]  # noqa: E731
+    pin = lambda l: [t.pin_memory() for t in l]  # noqa: E731
+    inputs = dict(feat=d["feat"].to(dev), pseudo_boxes=to(d["pseudo_boxes"]), pseudo_points=to(d["pseudo_points"]),
+                  pseudo_labels=to(d["pseudo_labels"]), gt_boxes=to(d["gt_boxes"]), neg_boxes=[to(d["neg_boxes"][0])])
+    host = dict(feat=d["feat"].pin_memory(), pseudo_boxes=pin(d["pseudo_boxes"]), pseudo_points=pin(d["pseudo_points"]),
+                pseudo_labels=pin(d["pseudo_labels"]), gt_boxes=pin(d["gt_boxes"]), neg_boxes=[pin(d["neg_boxes"][0])])
+    W = max(args.warmup, 3)
+    cap = CapturedPhase2(head, inputs, d["img_metas"], synth.OBB_FINE_CFG, synth.OBB_EXT_CFG, num_stages=1, cap=100,
+                         refresh_weights=True, warmup=W)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    c0 = _lib.LAUNCHES["count"]
+    with torch.no_grad():
+        cap._step()
+    torch.cuda.synchronize()
+    launches = _lib.LAUNCHES["count"] - c0
+    sampler = ClockSampler(0)
+    sampler.start()
+    sampler.region(True)
+    dev_ms = _events_ms(cap.replay, args.steps, flush, warm=W)
+    pipe = Phase2Pipeline(head, inputs, d["img_metas"], synth.OBB_FINE_CFG, synth.OBB_EXT_CFG, num_stages=1, cap=100,
+                          depth=2)
+    for _ in range(W):
+        t = pipe.submit(host)
+    pipe.result(t)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        t = pipe.submit(host)
+    pipe.result(t)
+    e1.record()
+    torch.cuda.synchronize()
+    sampler.region(False)
+    e2e_ms = e0.elapsed_time(e1) / args.steps
+    ops.PROFILE["on"], ops.PROFILE["events"] = True, []
+    with torch.no_grad():
+        for _ in range(5):
+            flush.zero_()
+            torch.cuda._sleep(int(6e-3 * 1.9e9))
+            cap._step()
+    torch.cuda.synchronize()
+    ops.PROFILE["on"] = False
+    hbm_peak, tf_peak, peak_src = _peaks()
+    roi = [(a.elapsed_time(b), by) for tag, a, b, by, shp in ops.PROFILE["events"] if tag == "roi_align"]
+    roi_ms = sum(t for t, _ in roi) / max(len(roi), 1)
+    roi_bytes = sum(b for _, b in roi) / max(len(roi), 1)
+    cpu = None
+    if not args.no_cpu_baseline:
+        from oracle import hbb, obb                 # the checker, timed as the reported CPU baseline only
+        torch.set_num_threads(os.cpu_count() or 1)
+        P = hbb.MilHeadParams(num_classes=9, num_stages=1, seed=0)
+
+        def cstep():
+            with torch.no_grad():
+                obb.phase2_refine(P, (d["feat"],), [d["stride"]], d["img_metas"], d["pseudo_boxes"], d["pseudo_points"],
+                                  d["pseudo_labels"], d["gt_boxes"], synth.OBB_FINE_CFG, synth.OBB_EXT_CFG,
+                                  injected_negs=d["neg_boxes"])
+        cms = _cpu_ms(cstep, 3)
+        cpu = {"value": 2e3 / cms, "unit": "imgs/s", "cores": torch.get_num_threads(), "kind": "port",
+               "sample": "3 full steps (2 images each) after 1 warm-up; oracle/obb.py (PyTorch fp32 + the C restatement "
+                         "of mmcv RoIAlignRotated / box_iou_rotated)"}
+    print(json.dumps({
+        "metric": METRIC, "value": 2e3 / dev_ms, "unit": "imgs/s", "n_gpus": 1, "steps": args.steps, "warmup": W,
+        "ms_per_step": dev_ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "bf16 (fp32 accumulate; fp32 box/score math)" if args.precision == "bf16" else "bf16x3 (fp32 emulation)",
+        "data": "synthetic",
+        "config": {"workload": "OBB cfg#3: phase-2 MIL refinement forward, 2 imgs 1024x1024 (SODA-A shaped), 5-d boxes, "
+                               "RoIAlignRotated(sampling_ratio=2, clockwise), rotated IoU, 9 classes, top-3 merge, "
+                               "K=5000 RoIs x2 passes + 400 negatives",
+                   "launch": "cuda_graph", "l2": "flushed between steps (256 MiB write, untimed)"},
+        "e2e": {"value": 2e3 / e2e_ms, "unit": "imgs/s", "h2d_bytes_per_step": pipe.h2d_bytes,
+                "d2h_bytes_per_step": pipe.d2h_bytes, "ms_per_step": e2e_ms},
+        "gpu_launches": launches * args.steps, "clocks": sampler.summary(),
+        "roofline": {"kernel": "roi_align_rotated_fwd_kernel (bf16 bin-major out)", "bound": "hbm",
+                     "achieved": roi_bytes / (roi_ms * 1e-3) / 1e9 if roi else 0.0, "peak": hbm_peak, "unit": "GB/s",
+                     "frac": (roi_bytes / (roi_ms * 1e-3) / 1e9 / hbm_peak) if roi else 0.0, "traffic": None,
+                     "avg_launch_ms": roi_ms, "algorithmic_bytes": roi_bytes, "peak_source": peak_src},
+        "cpu_baseline": cpu}))
+
+
+def run_config_assign(args):
+    """Config #4 (assignment half) / rows a13-a15: TopK / FUSE / MaxIoU assignment and the IoU / NWD matrix on the
+    800x800 stride-8 grid (P = 10^4 points) for G = 100 / 500 / 1500 GTs."""
+    import torch
+    from point_teacher_b200 import _lib, assigners as A, synth
+    dev = torch.device("cuda", 0)
+    _lib.load()
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    hbm_peak, _, peak_src = _peaks()
+    kw = dict(cls_cost=dict(type="FocalLossCost", weight=1.0), reg_cost=dict(type="PointCost", mode="L1", weight=1.0))
+    topk = A.TopkAssigner(num_pre=3, topk=3, **kw)
+    fuse = A.FUSETopkAssigner(num_pre=5, topk=3, location_cost=dict(type="InsiderCost", weight=1.0), **kw)
+    maxiou = A.MaxIoUAssigner(pos_iou_thr=0.5, neg_iou_thr=0.4, min_pos_iou=0.2)
+    iou, nwd = A.BboxOverlaps2D(), A.BboxDistanceMetric()
+    sweep, launches = [], 0
+    sampler = ClockSampler(0)
+    sampler.start()
+    for G in (100, 500, 1500):
+        d = synth.assign_batch(7, P_hw=(100, 100), G=G, ties=True)
+        c = {k: v.to(dev) for k, v in d.items()}
+        P = d["points"].shape[0]
+        C = d["logits"].shape[1]
+        to_xyxy = lambda b: torch.cat([b[:, :2] - b[:, 2:] / 2, b[:, :2] + b[:, 2:] / 2], 1).contiguous()  # noqa: E731
+        gx, px = to_xyxy(c["gt"]), to_xyxy(c["pred"])
+        fns = {"topk(3,3)": lambda: topk.assign(c["pred"], c["logits"], c["gt"], c["labels"]),
+               "fuse(5,3)": lambda: fuse.assign(c["pred"], c["points"], c["logits"], None, c["gt"], c["labels"]),
+               "max_iou": lambda: maxiou.assign(px, gx, gt_labels=c["labels"]),
+               "iou_matrix": lambda: iou(gx, px, "iou"), "nwd_matrix": lambda: nwd(gx, px, "wd")}
+        row = {"G": G, "P": P}
+        sampler.region(True)
+        for name, fn in fns.items():
+            c0 = _lib.LAUNCHES["count"]
+            fn()
+            launches += (_lib.LAUNCHES["count"] - c0) * (args.steps + 3)
+            ms = _events_ms(fn, args.steps, flush)
+            alg = P * G * 4 if name.endswith("matrix") else P * (8 + 4 * C + 16) + G * 24 + P * 16
+            row[name] = {"ms": ms, "algorithmic_GBps": alg / ms / 1e6, "matrix_equivalent_GBps": P * G * 4 / ms / 1e6}
+        sampler.region(False)
+        if not args.no_cpu_baseline:
+            from oracle import assign, hbb             # the checker, timed as the reported CPU baseline only
+            torch.set_num_threads(os.cpu_count() or 1)
+            gx_c, px_c = to_xyxy(d["gt"]), to_xyxy(d["pred"])
+            cf = {"topk(3,3)": lambda: assign.topk_assign(d["pred"], d["logits"], d["gt"], d["labels"], 3, 3),
+                  "fuse(5,3)": lambda: assign.fuse_topk_assign(d["pred"], d["points"], d["logits"], d["gt"], d["labels"], 5, 3),
+                  "max_iou": lambda: assign.max_iou_assign(hbb.bbox_overlaps(gx_c, px_c, "iou"), d["labels"], pos_iou_thr=0.5,
+                                                           neg_iou_thr=0.4, min_pos_iou=0.2),
+                  "iou_matrix": lambda: hbb.bbox_overlaps(gx_c, px_c, "iou"),
+                  "nwd_matrix": lambda: assign.bbox_metric(gx_c, px_c, "wd")}
+            for name, fn in cf.items():
+                row[name]["cpu_ms"] = _cpu_ms(fn, 2)
+        sweep.append(row)
+    head_row = sweep[-1]["fuse(5,3)"]
+    Pn, Gn = sweep[-1]["P"], sweep[-1]["G"]
+    mat = sweep[-1]["iou_matrix"]
+    cpu = None
+    if "cpu_ms" in head_row:
+        cpu = {"value": Pn / head_row["cpu_ms"] * 1e3, "unit": "points/s", "cores": os.cpu_count(), "kind": "port",
+               "sample": "2 calls after 1 warm-up of oracle/assign.py fuse_topk_assign on the same inputs (P=10^4, G=1500)"}
+    print(json.dumps({
+        "metric": "dense-head label assignment points/s (FUSETopkAssigner num_pre=5 topk=3, P=10^4, G=1500)",
+        "value": Pn / head_row["ms"] * 1e3, "unit": "points/s", "n_gpus": 1, "steps": args.steps, "warmup": 3,
+        "ms_per_step": head_row["ms"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32 costs -> int64 indices",
+        "data": "synthetic",
+        "config": {"workload": "cfg#4 assignment sweep: 800x800 stride-8 grid (P=10^4), G in {100,500,1500}, tie-heavy integer "
+                               "GT points; TopK(3,3), FUSE(5,3), MaxIoU(0.5/0.4/0.2), IoU and NWD matrices",
+                   "l2": "flushed between calls (256 MiB write, untimed)", "launch": "eager through the registry classes"},
+        "e2e": None, "gpu_launches": launches, "clocks": sampler.summary(),
+        "roofline": {"kernel": "bbox_overlaps_kernel (G x A IoU matrix, the one assignment product whose output IS the "
+                               "matrix), G=1500 A=10^4", "bound": "hbm", "achieved": mat["algorithmic_GBps"],
+                     "peak": hbm_peak, "unit": "GB/s", "frac": mat["algorithmic_GBps"] / hbm_peak, "traffic": None,
+                     "avg_launch_ms": mat["ms"], "peak_source": peak_src,
+                     "note": "the assigners never materialise P x G; their algorithmic bytes are P*(8+4C+16)+G*24+P*16 "
+                             "and they are latency-bound (see sweep)"},
+        "sweep": sweep, "cpu_baseline": cpu}))
+
+
+def run_config_mask(args):
+    """Row a16: phase-1 random region masking (rotated NMS + filters + obb2poly + fillPoly) on an 800x800 image."""
+    import numpy as np
+    import torch
+    from point_teacher_b200 import _lib, masking, synth
+    dev = torch.device("cuda", 0)
+    _lib.load()
+    d = synth.mask_batch(0)
+    _, prior = masking.load_basic_shape(synth.SHAPE_LIST)
+    torch.manual_seed(0)
+    np.random.seed(0)
+    allb = masking.sample_black_paper_candidates(d["bb_occupied"], prior, range(2), d["imgsize"])
+    img0 = d["img"].to(dev)
+    allb_d = allb.to(dev)
+    img = img0.clone()
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+
+    def step():
+        img.copy_(img0)
+        return masking.black_paper_from_candidates(img, allb_d, d["imgsize"])
+    c0 = _lib.LAUNCHES["count"]
+    _, kept = step()
+    launches = _lib.LAUNCHES["count"] - c0
+    sampler = ClockSampler(0)
+    sampler.start()
+    sampler.region(True)
+    ms = _events_ms(step, args.steps, flush)
+    # end to end: candidates + image from pinned host memory, masked image and kept boxes back
+    himg, hb = d["img"].pin_memory(), allb.pin_memory()
+    out_img = torch.empty_like(himg).pin_memory()
+
+    def e2e_step():
+        img.copy_(himg, non_blocking=True)
+        _, k = masking.black_paper_from_candidates(img, hb.to(dev, non_blocking=True), d["imgsize"])
+        out_img.copy_(img, non_blocking=True)
+        return k.cpu()
+    e2e_ms = _events_ms(e2e_step, args.steps, None)
+    sampler.region(False)
+    hbm_peak, _, peak_src = _peaks()
+    alg = allb.numel() * 4 + kept.numel() * 4 + 2 * img.numel() * 4      # boxes in/out + image read-modify-write bound
+    cpu = None
+    if not args.no_cpu_baseline:
+        from oracle import mask as M                # the checker, timed as the reported CPU baseline only
+        torch.set_num_threads(os.cpu_count() or 1)
+        cms = _cpu_ms(lambda: M.black_paper_from_candidates(d["img"].clone(), allb, d["imgsize"]), 3)
+        cpu = {"value": 1e3 / cms, "unit": "imgs/s", "cores": torch.get_num_threads(), "kind": "port",
+               "sample": "3 calls after 1 warm-up of oracle/mask.py black_paper_from_candidates (C nms_rotated + cv2.fillPoly)"}
+    print(json.dumps({
+        "metric": "phase-1 region masking imgs/s (generate_black_paper tail, injected candidates)",
+        "value": 1e3 / ms, "unit": "imgs/s", "n_gpus": 1, "steps": args.steps, "warmup": 3, "ms_per_step": ms,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32 boxes -> int32 polygons -> u8 mask",
+        "data": "synthetic",
+        "config": {"workload": f"row a16: one 3x800x800 fp32 image, {d['bb_occupied'].shape[0]} GT points + "
+                               f"{allb.shape[0] - d['bb_occupied'].shape[0]} candidates, nms_rotated(0.05), {kept.shape[0]} regions filled",
+                   "l2": "flushed between calls", "launch": "eager; one host read of the survivor count per call"},
+        "e2e": {"value": 1e3 / e2e_ms, "unit": "imgs/s", "h2d_bytes_per_step": himg.numel() * 4 + hb.numel() * 4,
+                "d2h_bytes_per_step": himg.numel() * 4 + kept.numel() * 4, "ms_per_step": e2e_ms},
+        "gpu_launches": launches * args.steps, "clocks": sampler.summary(),
+        "roofline": {"kernel": "whole call (nms bit-matrix + greedy scan + select + fill)", "bound": "hbm",
+                     "achieved": alg / ms / 1e6, "peak": hbm_peak, "unit": "GB/s", "frac": alg / ms / 1e6 / hbm_peak,
+                     "traffic": None, "peak_source": peak_src,
+                     "note": "latency-bound: ~6 dependent small launches and one host sync; bytes are an upper bound"},
+        "cpu_baseline": cpu}))
+
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -450,6 +711,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
+    ap.add_argument("--config", default="hbb", choices=["hbb", "obb", "assign", "mask"],
+                    help="hbb = the headline workload; the others print one line for a secondary configuration")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="eager launches (for ncu passes)")
     ap.add_argument("--no-stress", action="store_true", help="skip the 96k-RoI RoIAlign roofline measurement")
@@ -457,6 +720,9 @@ def main():
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
+    elif args.config != "hbb":
+        if int(os.environ.get("RANK", "0")) == 0:
+            {"obb": run_config_obb, "assign": run_config_assign, "mask": run_config_mask}[args.config](args)
     else:
         run_ours(args)
 

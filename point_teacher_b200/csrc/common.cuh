@@ -15,6 +15,10 @@ namespace ptb {
 void set_error(const char* fmt, ...);
 int check_launch(const char* what);
 
+// RoIAlignRotated, bf16 operand path: RoIs whose longer side exceeds this many FEATURE pixels go to the direct
+// gather kernel (roi_align.cu), the rest to the TMA + mma.sync kernel (roi_align_mma.cu); both apply the same test.
+constexpr float ROT_BIG_THRESHOLD = 8.0f;
+
 // ---------------------------------------------------------------- exact fp32 (never contracted)
 // Coordinate / box geometry must match the reference's CPU arithmetic bit for bit, so every
 // multiply-add on that path is spelled with the round-to-nearest intrinsics (nvcc never fuses

@@ -20,10 +20,10 @@
 namespace ptb {
 
 namespace ramma {   // roi_align_mma.cu: TMA + mma.sync bf16 throughput path
-bool supported(int C, int H, int W);
+bool supported(int C, int H, int W, bool rot, int sampling_ratio);
 int launch(const void* feat_nhwc, int feat_f16, const float* rois, void* out, long long ld_out, int K, int B, int C,
            int H, int W, float scale, int sampling_ratio, int aligned, const int* roi_level, int level,
-           cudaStream_t stream);
+           bool rot, int clockwise, cudaStream_t stream);
 }  // namespace ramma
 
 constexpr int P7 = 7;
@@ -379,7 +379,7 @@ __global__ void __launch_bounds__(P7 * 32, 2)
 roi_align_rotated_fwd_kernel(const TIn* __restrict__ feat, const float* __restrict__ rois, void* __restrict__ out,
                              long long ld_out, int K, int B, int C, int H, int W, float scale,
                              int sampling_ratio, int aligned, int clockwise,
-                             const int* __restrict__ roi_level, int level) {
+                             const int* __restrict__ roi_level, int level, float only_larger_than) {
   extern __shared__ float stage[];
   const int ph = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const float off = aligned ? 0.5f : 0.f;
@@ -392,6 +392,8 @@ roi_align_rotated_fwd_kernel(const TIn* __restrict__ feat, const float* __restri
     float theta = __ldg(r + 5);
     if (clockwise) theta = -theta;
     if (!aligned) { rw = fmaxf(rw, 1.f); rh = fmaxf(rh, 1.f); }
+    // second half of the tensor-core path (roi_align_mma.cu): only the RoIs that kernel leaves out
+    if (only_larger_than >= 0.f && !(fmaxf(rw, rh) > only_larger_than)) continue;
     const float bh = fdiv(rh, (float)P7), bw = fdiv(rw, (float)P7);
     const int gh = sampling_ratio > 0 ? sampling_ratio : (int)ceilf(bh);
     const int gw = sampling_ratio > 0 ? sampling_ratio : (int)ceilf(bw);
@@ -473,7 +475,7 @@ __global__ void roi_rescale_kernel(const float* __restrict__ rois, int K, int ro
 template <typename TIn, int MODE>
 static int launch_fwd(bool rotated, const void* feat, const float* rois, void* out, long long ld_out, int K, int B,
                       int C, int H, int W, float scale, int sampling_ratio, int aligned, int clockwise,
-                      const int* roi_level, int level, cudaStream_t stream) {
+                      const int* roi_level, int level, cudaStream_t stream, float only_larger_than = -1.f) {
   const size_t stage_bytes = MODE == OUT_F32_NCHW ? (size_t)P7 * P7 * (C + 1) * sizeof(float) : 0;
   const size_t tab_bytes = rotated ? 0 : 2 * ((size_t)(W + 4) * 8 + (size_t)(H + 1) * 8) * sizeof(float);
   size_t smem = stage_bytes + tab_bytes;
@@ -486,7 +488,7 @@ static int launch_fwd(bool rotated, const void* feat, const float* rois, void* o
     auto kern = roi_align_rotated_fwd_kernel<TIn, MODE>;
     if (smem > 48 * 1024) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     kern<<<grid, P7 * 32, smem, stream>>>(reinterpret_cast<const TIn*>(feat), rois, out, ld_out, K, B, C, H, W,
-                                           scale, sampling_ratio, aligned, clockwise, roi_level, level);
+                                           scale, sampling_ratio, aligned, clockwise, roi_level, level, only_larger_than);
   } else {
     auto kern = roi_align_fwd_kernel<TIn, MODE>;
     if (smem > 48 * 1024) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -530,9 +532,19 @@ extern "C" int pt_roi_align_forward(const void* feat, int feat_bf16, const float
   }
   cudaStream_t s = (cudaStream_t)stream;
   const bool rot = rotated != 0;
-  if (feat_bf16 && !rot && out_mode == OUT_BF16_BINMAJOR && ramma::supported(C, H, W))
-    return ramma::launch(feat, feat_bf16 == 2, rois, out, ld_out, K, B, C, H, W, spatial_scale, sampling_ratio, aligned,
-                         roi_level, level, s);
+  if (feat_bf16 && out_mode == OUT_BF16_BINMAJOR && ramma::supported(C, H, W, rot, sampling_ratio)) {
+    const int rc = ramma::launch(feat, feat_bf16 == 2, rois, out, ld_out, K, B, C, H, W, spatial_scale, sampling_ratio,
+                                 aligned, roi_level, level, rot, clockwise, s);
+    if (!rot || rc != PT_OK) return rc;
+    // rotated: RoIs larger than ROT_BIG_THRESHOLD feature pixels were left out above (sparse in the chunked
+    // formulation); the direct gather kernel fills exactly those rows
+    if (feat_bf16 == 2)
+      return launch_fwd<__half, OUT_BF16_BINMAJOR>(true, feat, rois, out, ld_out, K, B, C, H, W, spatial_scale, sampling_ratio,
+                                                   aligned, clockwise, roi_level, level, s, ROT_BIG_THRESHOLD);
+    return launch_fwd<__nv_bfloat16, OUT_BF16_BINMAJOR>(true, feat, rois, out, ld_out, K, B, C, H, W, spatial_scale,
+                                                        sampling_ratio, aligned, clockwise, roi_level, level, s,
+                                                        ROT_BIG_THRESHOLD);
+  }
 #define PT_DISPATCH(T, M) return launch_fwd<T, M>(rot, feat, rois, out, ld_out, K, B, C, H, W, spatial_scale, sampling_ratio, aligned, clockwise, roi_level, level, s)
   if (feat_bf16 == 2) {
     if (out_mode == OUT_BF16_BINMAJOR) PT_DISPATCH(__half, OUT_BF16_BINMAJOR);

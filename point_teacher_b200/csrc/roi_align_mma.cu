@@ -23,6 +23,13 @@
 //             chunk: bf16 pack -> stmatrix into a warp-private SWIZZLE_64B staging -> one TMA tensor store of the
 //             warp's 49 bins x 32 channels (no CTA-wide barrier in the steady state; the output never touches
 //             the LSU pipe, which the ncu captures showed to be the limiter of the LDS+STG copy-out).
+//
+// Rotated twin (ROT = true; mmcv.ops.RoIAlignRotated(sampling_ratio = 1|2, clockwise) reached through
+//   OBB_TOD/mmrotate/models/roi_heads/roi_extractors/rotate_single_level_roi_extractor.py:90-167):
+// the sample grid is not axis-separable, so the builder warp first writes one 16-byte record per sample
+// (x_low|x_high, y_low|y_high, lx, ly -- the reference's exact coordinate arithmetic and border rule) into shared
+// memory, then builds each 4x4-pixel chunk's Wmat fragment by summing the <= 4 samples of every bin it owns.  The
+// MMA / store side is unchanged: only the weights differ.
 #include <cuda.h>
 #include <cuda_fp16.h>
 
@@ -42,6 +49,10 @@ constexpr int AFRAG_BYTES = 4 * 32 * 16;          // 4 m-tiles x 32 lanes x uint
 // (16 B chunk index ^= (row >> 1) & 3), which also makes the stmatrix writes bank-conflict free
 constexpr int STG_ROW_BYTES = 64;
 constexpr int STG_BYTES = ((NBIN * STG_ROW_BYTES + 511) / 512) * 512;   // per MMA warp and buffer
+constexpr int ROT_SAMPLES = 4;                                          // rotated: sampling_ratio^2 <= 4 samples per bin
+constexpr float ROT_BIG_FPX = ROT_BIG_THRESHOLD;                         // feature pixels (roi_align.cu shares it)
+constexpr int ROT_MAP_WORDS = 128;                                      // occupancy bitmap: up to 4096 chunks per RoI
+constexpr int ROT_TAB_FLOATS = NBIN * ROT_SAMPLES * 4 + ROT_MAP_WORDS;  // one 16-byte record per sample + bitmap
 enum { F_LAST = 2, F_ZERO = 4, F_SKIP = 8 };
 
 __device__ __forceinline__ void tma_load_5d(uint32_t dst, const void* desc, uint32_t bar, int c0, int c1, int c2,
@@ -124,12 +135,12 @@ __device__ __forceinline__ bool axis_setup(float v, int size, int& lo, int& hi, 
 
 // F16: the feature map (and therefore the interpolation weights) are fp16 instead of bf16 -- 3 more mantissa
 // bits on both mma operands, so the interpolation itself adds no visible error on top of the bf16 output.
-template <bool F16>
+template <bool F16, bool ROT>
 __global__ void __launch_bounds__(THREADS, 2)
 roi_align_mma_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ CUtensorMap omap,
                      const float* __restrict__ rois, int K, int B, int C, int H, int W,
                      float scale, int sampling_ratio, int aligned, const int* __restrict__ roi_level, int level,
-                     int stg_bufs) {
+                     int stg_bufs, int clockwise) {
   extern __shared__ uint8_t smem_raw[];
   // shared-window byte addresses (explicit .shared accesses below; generic pointers would cost LD/ST.E)
   const uint32_t sbase = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -137,7 +148,7 @@ roi_align_mma_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_cons
   const uint32_t s_afrag = s_patch + STAGES * PATCH_BYTES;           // [STAGES][AFRAG_BYTES]
   const uint32_t s_stg = s_afrag + STAGES * AFRAG_BYTES;             // [MMA_WARPS][2][STG_BYTES]
   const uint32_t s_tab = s_stg + MMA_WARPS * stg_bufs * STG_BYTES;                      // [BUILDERS][(W+4)*8 + (H+4)*8] floats
-  const int tab_floats = (W + 4) * 8 + (H + 4) * 8;
+  const int tab_floats = ROT ? ROT_TAB_FLOATS : (W + 4) * 8 + (H + 4) * 8;
   const uint32_t s_full = s_tab + BUILDERS * tab_floats * 4;         // [STAGES] mbarriers
   const uint32_t s_empty = s_full + STAGES * 8;
   const uint32_t s_meta = s_empty + STAGES * 8;                      // [STAGES] {roi, flags}
@@ -159,6 +170,164 @@ roi_align_mma_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_cons
   if (warp >= MMA_WARPS) {
     // ---------------------------------------------------------------------------------- builder warps
     const int bw_id = warp - MMA_WARPS;                 // RoIs bw_id, bw_id + BUILDERS, ... of this CTA
+    if constexpr (ROT) {
+      const uint32_t s_samp = s_tab + (uint32_t)(bw_id * tab_floats) * 4u;   // [NBIN][ROT_SAMPLES] 16-byte records
+      // chunk-occupancy bitmap: a large rotated RoI (the 200-px negatives) spans hundreds of 4x4-pixel chunks but
+      // its 196 samples touch only a few of them; only occupied chunks are loaded and multiplied
+      const uint32_t s_map = s_samp + NBIN * ROT_SAMPLES * 16;
+      unsigned int* map_g = reinterpret_cast<unsigned int*>(gen + (s_map - sbase));
+      const float off = aligned ? 0.5f : 0.f;
+      const uint32_t tx_bytes = (uint32_t)(C / 64) * QUARTER_BYTES;
+      const int gs = sampling_ratio, cnt = gs * gs;        // host guarantees 1 <= sampling_ratio <= 2
+      const float inv_count = 1.0f / (float)cnt;
+      int slot = 0; uint32_t phase = 0;
+      float rnext = 0.f;
+      if (bw_id < n_iter && lane < 6) rnext = __ldg(rois + (size_t)(blockIdx.x + bw_id * gridDim.x) * 6 + lane);
+      for (int it = bw_id; it < n_iter; it += BUILDERS) {
+        const int roi = blockIdx.x + it * gridDim.x;
+        const float rcur = rnext;
+        if (it + BUILDERS < n_iter && lane < 6)
+          rnext = __ldg(rois + (size_t)(blockIdx.x + (it + BUILDERS) * gridDim.x) * 6 + lane);
+        bool skip = roi_level != nullptr && roi_level[roi] != level;
+        const int b = (int)__shfl_sync(0xffffffffu, rcur, 0);
+        const float cxr = fsub(fmul(__shfl_sync(0xffffffffu, rcur, 1), scale), off);
+        const float cyr = fsub(fmul(__shfl_sync(0xffffffffu, rcur, 2), scale), off);
+        float rw = fmul(__shfl_sync(0xffffffffu, rcur, 3), scale), rh = fmul(__shfl_sync(0xffffffffu, rcur, 4), scale);
+        float theta = __shfl_sync(0xffffffffu, rcur, 5);
+        if (clockwise) theta = -theta;
+        if (!aligned) { rw = fmaxf(rw, 1.f); rh = fmaxf(rh, 1.f); }
+        // large RoIs (the 200-px random negatives) are sparse in this formulation -- 196 samples scattered over
+        // hundreds of chunks; they are left to roi_align.cu's direct gather kernel, launched right after this one
+        // with the same test
+        if (fmaxf(rw, rh) > ROT_BIG_FPX) skip = true;
+        const float bh = fdiv(rh, (float)P7), bw = fdiv(rw, (float)P7);
+        const float sh = fdiv(-rh, 2.0f), sw = fdiv(-rw, 2.0f);
+        const float ct = cosf(theta), st = sinf(theta);
+        const bool b_ok = b >= 0 && b < B && !skip;
+        int xlo = 1 << 30, xhi = -1, ylo = 1 << 30, yhi = -1;
+        __syncwarp();   // the previous RoI's fragment builds are done reading the sample table
+        for (int sidx = lane; sidx < NBIN * ROT_SAMPLES; sidx += 32) {
+          const int bin = sidx >> 2, sub = sidx & 3;
+          uint4 rec = make_uint4(0x7fff7fffu, 0x7fff7fffu, 0u, 0u);     // never matches a pixel coordinate
+          if (b_ok && sub < cnt) {
+            const int iy = sub / gs, ix = sub - iy * gs;
+            const int ph = bin / P7, pw = bin - ph * P7;
+            const float yy = fadd(fadd(sh, fmul((float)ph, bh)), fdiv(fmul((float)iy + .5f, bh), (float)gs));
+            const float xx = fadd(fadd(sw, fmul((float)pw, bw)), fdiv(fmul((float)ix + .5f, bw), (float)gs));
+            const float y = fadd(fsub(fmul(yy, ct), fmul(xx, st)), cyr);
+            const float x = fadd(fadd(fmul(yy, st), fmul(xx, ct)), cxr);
+            if (!(y < -1.0f || y > (float)H || x < -1.0f || x > (float)W)) {
+              int yl, yh, xl, xh; float ly, hy, lx, hx;
+              axis_setup(y, H, yl, yh, ly, hy);
+              axis_setup(x, W, xl, xh, lx, hx);
+              rec = make_uint4((uint32_t)xl | ((uint32_t)xh << 16), (uint32_t)yl | ((uint32_t)yh << 16),
+                               __float_as_uint(lx), __float_as_uint(ly));
+              xlo = min(xlo, xl); xhi = max(xhi, xh); ylo = min(ylo, yl); yhi = max(yhi, yh);
+            }
+          }
+          sts128(s_samp + sidx * 16, rec);
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+          xlo = min(xlo, __shfl_xor_sync(0xffffffffu, xlo, o)); xhi = max(xhi, __shfl_xor_sync(0xffffffffu, xhi, o));
+          ylo = min(ylo, __shfl_xor_sync(0xffffffffu, ylo, o)); yhi = max(yhi, __shfl_xor_sync(0xffffffffu, yhi, o));
+        }
+        __syncwarp();
+        const bool empty = !b_ok || xhi < xlo || yhi < ylo;
+        const int ncx = empty ? 1 : (xhi - xlo) / 4 + 1, ncy = empty ? 1 : (yhi - ylo) / 4 + 1;
+        const int nch = ncx * ncy;
+        const bool use_map = !empty && nch <= ROT_MAP_WORDS * 32;
+        const int nwords = (nch + 31) >> 5;
+        int total = nch;
+        if (use_map) {
+          for (int w = lane; w < nwords; w += 32) map_g[w] = 0u;
+          __syncwarp();
+          for (int sidx = lane; sidx < NBIN * ROT_SAMPLES; sidx += 32) {
+            const uint4 r = lds128(s_samp + sidx * 16);
+            if (r.x != 0x7fff7fffu) {
+              const int cxl = ((int)(r.x & 0xffffu) - xlo) >> 2, cxh = ((int)(r.x >> 16) - xlo) >> 2;
+              const int cyl = ((int)(r.y & 0xffffu) - ylo) >> 2, cyh = ((int)(r.y >> 16) - ylo) >> 2;
+              int ch = cyl * ncx + cxl;
+              atomicOr(map_g + (ch >> 5), 1u << (ch & 31));
+              if (cxh != cxl) { ch = cyl * ncx + cxh; atomicOr(map_g + (ch >> 5), 1u << (ch & 31)); }
+              if (cyh != cyl) {
+                ch = cyh * ncx + cxl; atomicOr(map_g + (ch >> 5), 1u << (ch & 31));
+                if (cxh != cxl) { ch = cyh * ncx + cxh; atomicOr(map_g + (ch >> 5), 1u << (ch & 31)); }
+              }
+            }
+          }
+          __syncwarp();
+          int pc = 0;
+          for (int w = lane; w < nwords; w += 32) pc += __popc(map_g[w]);
+#pragma unroll
+          for (int o = 16; o > 0; o >>= 1) pc += __shfl_xor_sync(0xffffffffu, pc, o);
+          total = pc;
+        }
+        int done = 0;
+        for (int w = 0; w < nwords; w++) {
+          uint32_t bits = use_map ? map_g[w] : 0xffffffffu;
+          while (bits != 0u) {
+            const int chn = w * 32 + __ffs((int)bits) - 1;
+            bits &= bits - 1u;
+            if (chn >= nch) break;
+            const int cy = chn / ncx, cx = chn - cy * ncx;
+            done++;
+            const int stage = bw_id * DEPTH + slot;
+            mbar_wait(empty_bar + stage, phase ^ 1);
+            int flags = (done == total ? F_LAST : 0);
+            if (empty) {
+              flags |= skip ? F_SKIP : F_ZERO;
+            } else {
+              // this lane's pixels of the chunk: rows ra, ra + 2, columns ca, ca + 1 (k = 2t, 2t+1, 2t+8, 2t+9)
+              const uint32_t ra = (uint32_t)(ylo + cy * 4 + (t >> 1)), rb = ra + 2;
+              const uint32_t ca = (uint32_t)(xlo + cx * 4 + 2 * (t & 1)), cb = ca + 1;
+              const uint32_t dst = s_afrag + stage * AFRAG_BYTES + lane * 16;
+#pragma unroll
+              for (int mt = 0; mt < 4; mt++) {
+                uint32_t a[4];
+#pragma unroll
+                for (int hl = 0; hl < 2; hl++) {
+                  const int bin = mt * 16 + g + hl * 8;
+                  float w00 = 0.f, w01 = 0.f, w10 = 0.f, w11 = 0.f;
+                  if (bin < NBIN) {
+#pragma unroll
+                    for (int sub = 0; sub < ROT_SAMPLES; sub++) {
+                      if (sub < cnt) {
+                        const uint4 r = lds128(s_samp + (bin * ROT_SAMPLES + sub) * 16);
+                        const uint32_t xl = r.x & 0xffffu, xh = r.x >> 16, yl = r.y & 0xffffu, yh = r.y >> 16;
+                        const float lx = __uint_as_float(r.z), ly = __uint_as_float(r.w);
+                        const float hx = fsub(1.0f, lx), hy = fsub(1.0f, ly);
+                        const float wya = (ra == yl ? hy : 0.f) + (ra == yh ? ly : 0.f);
+                        const float wyb = (rb == yl ? hy : 0.f) + (rb == yh ? ly : 0.f);
+                        const float wxa = (ca == xl ? hx : 0.f) + (ca == xh ? lx : 0.f);
+                        const float wxb = (cb == xl ? hx : 0.f) + (cb == xh ? lx : 0.f);
+                        w00 += wya * wxa; w01 += wya * wxb; w10 += wyb * wxa; w11 += wyb * wxb;
+                      }
+                    }
+                  }
+                  w00 *= inv_count; w01 *= inv_count; w10 *= inv_count; w11 *= inv_count;
+                  a[hl] = F16 ? pack_f16(w00, w01) : pack_bf16(w00, w01);            // k = 2t, 2t+1
+                  a[2 + hl] = F16 ? pack_f16(w10, w11) : pack_bf16(w10, w11);        // k = 2t+8, 2t+9
+                }
+                sts128(dst + mt * 512, make_uint4(a[0], a[1], a[2], a[3]));
+              }
+            }
+            if (lane == 0) asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(s_meta + stage * 8), "r"(roi), "r"(flags) : "memory");
+            __syncwarp();
+            if (lane == 0) {
+              if (empty) {
+                mbar_arrive(full_bar + stage);
+              } else {
+                mbar_expect_tx(full_bar + stage, tx_bytes);
+                tma_load_5d(s_patch + stage * PATCH_BYTES, &tmap, s_full + stage * 8, 0, xlo + cx * 4, ylo + cy * 4, b, 0);
+              }
+            }
+            if (++slot == DEPTH) { slot = 0; phase ^= 1; }
+          }
+        }
+      }
+      return;
+    }
     float* wx = reinterpret_cast<float*>(gen + (s_tab - sbase)) + bw_id * tab_floats;   // wx[col - xmin][pw]
     float* wy = wx + (W + 4) * 8;                                                        // wy[row - ymin][ph]
     const float off = aligned ? 0.5f : 0.f;
@@ -426,18 +595,22 @@ static EncodeTiledFn get_encode() {
 
 constexpr size_t SMEM_LIMIT = 113 * 1024;   // two CTAs per SM
 
-size_t smem_bytes(int H, int W, int stg_bufs) {
+size_t smem_bytes(int H, int W, int stg_bufs, bool rot) {
+  const size_t tab = rot ? (size_t)ROT_TAB_FLOATS : (size_t)(W + 4) * 8 + (size_t)(H + 4) * 8;
   return 1024 + (size_t)STAGES * (PATCH_BYTES + AFRAG_BYTES) + MMA_WARPS * stg_bufs * (size_t)STG_BYTES +
-         BUILDERS * ((size_t)(W + 4) * 8 + (size_t)(H + 4) * 8) * sizeof(float) + 3 * STAGES * 8 + 64;
+         BUILDERS * tab * sizeof(float) + 3 * STAGES * 8 + 64;
 }
 
-bool supported(int C, int H, int W) {
-  return C % 64 == 0 && C >= 64 && C <= 256 && smem_bytes(H, W, 1) <= SMEM_LIMIT;
+// rotated: fixed sampling grids of 1 or 2 samples per axis (the shipped sampling_ratio = 2); the adaptive grid
+// (sampling_ratio = 0) stays on roi_align.cu's direct kernel.  Coordinates are packed into 16 bits.
+bool supported(int C, int H, int W, bool rot, int sampling_ratio) {
+  if (rot && (sampling_ratio < 1 || sampling_ratio * sampling_ratio > ROT_SAMPLES || H > 32000 || W > 32000)) return false;
+  return C % 64 == 0 && C >= 64 && C <= 256 && smem_bytes(H, W, 1, rot) <= SMEM_LIMIT;
 }
 
 int launch(const void* feat_bf16_nhwc, int feat_f16, const float* rois, void* out, long long ld_out, int K, int B, int C,
            int H, int W, float scale, int sampling_ratio, int aligned, const int* roi_level, int level,
-           cudaStream_t stream) {
+           bool rot, int clockwise, cudaStream_t stream) {
   EncodeTiledFn enc = get_encode();
   if (enc == nullptr) { set_error("cuTensorMapEncodeTiled entry point not found"); return PT_ERR_DRIVER; }
   if ((uintptr_t)feat_bf16_nhwc & 15) { set_error("roi_align_mma: feature map must be 16-byte aligned"); return PT_ERR_ARG; }
@@ -464,22 +637,18 @@ int launch(const void* feat_bf16_nhwc, int feat_f16, const float* rois, void* ou
             CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) { set_error("roi_align_mma: output cuTensorMapEncodeTiled failed: CUresult %d", (int)r); return PT_ERR_DRIVER; }
   }
-  const int stg_bufs = smem_bytes(H, W, 2) <= SMEM_LIMIT ? 2 : 1;   // large maps: single-buffered staging
-  const size_t smem = smem_bytes(H, W, stg_bufs);
-  cudaError_t e = feat_f16
-      ? cudaFuncSetAttribute(roi_align_mma_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)
-      : cudaFuncSetAttribute(roi_align_mma_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  const int stg_bufs = smem_bytes(H, W, 2, rot) <= SMEM_LIMIT ? 2 : 1;   // large maps: single-buffered staging
+  const size_t smem = smem_bytes(H, W, stg_bufs, rot);
+  auto kern = feat_f16 ? (rot ? roi_align_mma_kernel<true, true> : roi_align_mma_kernel<true, false>)
+                       : (rot ? roi_align_mma_kernel<false, true> : roi_align_mma_kernel<false, false>);
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) { set_error("cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return PT_ERR_CUDA; }
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   const int grid = K < 2 * sms ? K : 2 * sms;
-  if (feat_f16)
-    roi_align_mma_kernel<true><<<grid, THREADS, smem, stream>>>(map, omap, rois, K, B, C, H, W, scale, sampling_ratio,
-                                                                aligned, roi_level, level, stg_bufs);
-  else
-    roi_align_mma_kernel<false><<<grid, THREADS, smem, stream>>>(map, omap, rois, K, B, C, H, W, scale, sampling_ratio,
-                                                                 aligned, roi_level, level, stg_bufs);
+  kern<<<grid, THREADS, smem, stream>>>(map, omap, rois, K, B, C, H, W, scale, sampling_ratio, aligned, roi_level, level,
+                                        stg_bufs, clockwise);
   return check_launch("roi_align_mma_kernel");
 }
 

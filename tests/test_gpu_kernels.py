@@ -191,6 +191,49 @@ def test_roi_align_rotated_vs_oracle(cuda):
     assert _rel(got, ref) < 1e-3
 
 
+@pytest.mark.parametrize("fdt", [torch.bfloat16, torch.float16])
+@pytest.mark.parametrize("sr,clockwise,C,hw", [(2, True, 256, (512, 512)), (1, False, 128, (256, 384)), (2, False, 64, (1024, 1024))])
+def test_roi_align_rotated_mma_path_vs_oracle(cuda, sr, clockwise, C, hw, fdt):
+    """Rotated twin of the TMA + mma.sync RoIAlign (bf16 / fp16 NHWC in, bf16 bin-major out): tiny, large (many 4x4
+    chunks), border-straddling, fully-outside and zero-size rotated RoIs; 1 and 2 samples per axis; both angle
+    conventions; multi-level skip mask."""
+    from point_teacher_b200 import ops
+    g = torch.Generator().manual_seed(77 + sr + C)
+    n = 300
+    x = torch.randn(2, C, hw[0] // 8, hw[1] // 8, generator=g)
+    boxes = synth.make_boxes(g, n, hw, median=16, hi=90)
+    boxes[20:50] = synth.make_boxes(g, 30, hw, median=150, sigma=0.6, lo=60, hi=min(hw) * 0.8)
+    c = hbb.xyxy_to_cxcywh(boxes)
+    th = torch.rand(n, 1, generator=g) * math.pi - math.pi / 2
+    th[50:60] = 0.0
+    th[60:65] = math.pi / 2
+    rois = torch.cat([torch.randint(0, 2, (n, 1), generator=g).float(), c, th], 1)
+    rois[:3, 1:3] = torch.tensor([[2., 2.], [hw[1] - 2., 5.], [hw[1] / 2, hw[0] - 1.]])     # straddling the border
+    rois[3, 1:3] = torch.tensor([-400., -400.])                                                # fully outside
+    rois[4, 3:5] = 0.0                                                                         # zero size: one point
+    rois[5, 1:5] = torch.tensor([hw[1] + 3.0, hw[0] + 3.0, 30.0, 30.0])                      # beyond the far corner
+    ref = rotated.roi_align_rotated(x, rois, 7, 0.125, sr, True, clockwise).permute(0, 2, 3, 1).reshape(n, -1)
+    feat = ops.nchw_to_nhwc(x.to(cuda), fdt)
+    got = ops.roi_align_forward(feat, rois.to(cuda), ops.OUT_BF16_BINMAJOR, 0.125, sampling_ratio=sr, rotated=True,
+                                clockwise=clockwise).float().cpu()
+    err = (got - ref).abs()
+    assert torch.isfinite(got).all()
+    assert err.max() <= 2e-2 * ref.abs().max(), err.max()
+    assert err.mean() <= (4e-3 if fdt == torch.bfloat16 else 2e-3) * ref.abs().mean() + 1e-6
+    assert torch.count_nonzero(got[3]) == 0
+    # agrees with the direct (fp32-exact) rotated kernel on the same bf16/fp16 feature map to output rounding
+    direct = ops.roi_align_forward(feat, rois.to(cuda), ops.OUT_F32_NCHW, 0.125, sampling_ratio=sr, rotated=True,
+                                   clockwise=clockwise).permute(0, 2, 3, 1).reshape(n, -1).cpu()
+    assert (got - direct).abs().max() <= 1.2e-2 * direct.abs().max()
+    lv = (torch.arange(n) % 3 == 0).int()
+    out = torch.full((n, 49 * C), 7.0, dtype=torch.bfloat16, device=cuda)
+    ops.roi_align_forward(feat, rois.to(cuda), ops.OUT_BF16_BINMAJOR, 0.125, sampling_ratio=sr, rotated=True,
+                          clockwise=clockwise, out=out, roi_level=lv.to(cuda), level=1)
+    o = out.float().cpu()
+    assert torch.equal(o[lv == 0], torch.full_like(o[lv == 0], 7.0))
+    assert torch.equal(o[lv == 1], got[lv == 1])
+
+
 def test_multi_level_extractor_matches_oracle(cuda):
     from point_teacher_b200.roi_extractors import SingleRoIExtractor
     g = torch.Generator().manual_seed(15)
