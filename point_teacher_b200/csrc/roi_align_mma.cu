@@ -42,6 +42,10 @@ constexpr int P7 = 7, NBIN = 49;
 constexpr int BUILDERS = 2, DEPTH = 2, STAGES = BUILDERS * DEPTH;   // every builder warp owns a DEPTH-deep ring
 constexpr int MMA_WARPS = 8;
 constexpr int THREADS = (MMA_WARPS + BUILDERS) * 32;
+// Rotated variant: the builder does ~4x the work per RoI (non-separable weights), so it runs ONE CTA per SM with 6
+// builder warps (12 stages, ~208 KB of shared memory) instead of two CTAs with 2 builders each.  The ncu source view
+// of the 2-builder variant showed the 8 MMA warps spinning on the full barriers 80 % of the time.
+constexpr int ROT_BUILDERS = 6;
 constexpr int QUARTER_BYTES = 16 * 128;           // 16 pixels x 64 channels bf16
 constexpr int PATCH_BYTES = 4 * QUARTER_BYTES;    // 8 KB
 constexpr int AFRAG_BYTES = 4 * 32 * 16;          // 4 m-tiles x 32 lanes x uint4
@@ -50,9 +54,9 @@ constexpr int AFRAG_BYTES = 4 * 32 * 16;          // 4 m-tiles x 32 lanes x uint
 constexpr int STG_ROW_BYTES = 64;
 constexpr int STG_BYTES = ((NBIN * STG_ROW_BYTES + 511) / 512) * 512;   // per MMA warp and buffer
 constexpr int ROT_SAMPLES = 4;                                          // rotated: sampling_ratio^2 <= 4 samples per bin
-constexpr float ROT_BIG_FPX = ROT_BIG_THRESHOLD;                         // feature pixels (roi_align.cu shares it)
 constexpr int ROT_MAP_WORDS = 128;                                      // occupancy bitmap: up to 4096 chunks per RoI
-constexpr int ROT_TAB_FLOATS = NBIN * ROT_SAMPLES * 4 + ROT_MAP_WORDS;  // one 16-byte record per sample + bitmap
+constexpr int ROT_W_STRIDE = 20;                                        // floats per W row (16 pixels, 80-byte pitch)
+constexpr int ROT_TAB_FLOATS = NBIN * ROT_W_STRIDE + ROT_MAP_WORDS;     // per builder warp: W[49][20] + bitmap
 enum { F_LAST = 2, F_ZERO = 4, F_SKIP = 8 };
 
 __device__ __forceinline__ void tma_load_5d(uint32_t dst, const void* desc, uint32_t bar, int c0, int c1, int c2,
@@ -136,22 +140,24 @@ __device__ __forceinline__ bool axis_setup(float v, int size, int& lo, int& hi, 
 // F16: the feature map (and therefore the interpolation weights) are fp16 instead of bf16 -- 3 more mantissa
 // bits on both mma operands, so the interpolation itself adds no visible error on top of the bf16 output.
 template <bool F16, bool ROT>
-__global__ void __launch_bounds__(THREADS, 2)
+__global__ void __launch_bounds__((MMA_WARPS + (ROT ? ROT_BUILDERS : BUILDERS)) * 32, ROT ? 1 : 2)
 roi_align_mma_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ CUtensorMap omap,
                      const float* __restrict__ rois, int K, int B, int C, int H, int W,
                      float scale, int sampling_ratio, int aligned, const int* __restrict__ roi_level, int level,
                      int stg_bufs, int clockwise) {
   extern __shared__ uint8_t smem_raw[];
+  constexpr int NB = ROT ? ROT_BUILDERS : BUILDERS;     // builder warps
+  constexpr int NSTAGES = NB * DEPTH;
   // shared-window byte addresses (explicit .shared accesses below; generic pointers would cost LD/ST.E)
   const uint32_t sbase = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t s_patch = sbase;                                    // [STAGES][PATCH_BYTES], 1 KB aligned
-  const uint32_t s_afrag = s_patch + STAGES * PATCH_BYTES;           // [STAGES][AFRAG_BYTES]
-  const uint32_t s_stg = s_afrag + STAGES * AFRAG_BYTES;             // [MMA_WARPS][2][STG_BYTES]
+  const uint32_t s_afrag = s_patch + NSTAGES * PATCH_BYTES;          // [STAGES][AFRAG_BYTES]
+  const uint32_t s_stg = s_afrag + NSTAGES * AFRAG_BYTES;            // [MMA_WARPS][2][STG_BYTES]
   const uint32_t s_tab = s_stg + MMA_WARPS * stg_bufs * STG_BYTES;                      // [BUILDERS][(W+4)*8 + (H+4)*8] floats
   const int tab_floats = ROT ? ROT_TAB_FLOATS : (W + 4) * 8 + (H + 4) * 8;
-  const uint32_t s_full = s_tab + BUILDERS * tab_floats * 4;         // [STAGES] mbarriers
-  const uint32_t s_empty = s_full + STAGES * 8;
-  const uint32_t s_meta = s_empty + STAGES * 8;                      // [STAGES] {roi, flags}
+  const uint32_t s_full = s_tab + NB * tab_floats * 4;               // [STAGES] mbarriers
+  const uint32_t s_empty = s_full + NSTAGES * 8;
+  const uint32_t s_meta = s_empty + NSTAGES * 8;                     // [STAGES] {roi, flags}
   uint8_t* gen = smem_raw + (sbase - smem_u32(smem_raw));            // generic view of the same window
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(gen + (s_full - sbase));
   uint64_t* empty_bar = reinterpret_cast<uint64_t*>(gen + (s_empty - sbase));
@@ -160,7 +166,7 @@ roi_align_mma_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_cons
   if (threadIdx.x == 0) {
     tma_prefetch_desc(&tmap);
     tma_prefetch_desc(&omap);
-    for (int i = 0; i < STAGES; i++) { mbar_init(full_bar + i, 1); mbar_init(empty_bar + i, MMA_WARPS); }
+    for (int i = 0; i < NSTAGES; i++) { mbar_init(full_bar + i, 1); mbar_init(empty_bar + i, MMA_WARPS); }
     fence_barrier_init();
   }
   __syncthreads();
@@ -171,11 +177,13 @@ roi_align_mma_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_cons
     // ---------------------------------------------------------------------------------- builder warps
     const int bw_id = warp - MMA_WARPS;                 // RoIs bw_id, bw_id + BUILDERS, ... of this CTA
     if constexpr (ROT) {
-      const uint32_t s_samp = s_tab + (uint32_t)(bw_id * tab_floats) * 4u;   // [NBIN][ROT_SAMPLES] 16-byte records
-      // chunk-occupancy bitmap: a large rotated RoI (the 200-px negatives) spans hundreds of 4x4-pixel chunks but
-      // its 196 samples touch only a few of them; only occupied chunks are loaded and multiplied
-      const uint32_t s_map = s_samp + NBIN * ROT_SAMPLES * 16;
-      unsigned int* map_g = reinterpret_cast<unsigned int*>(gen + (s_map - sbase));
+      // Lane-owned bins: lane owns bins `lane` and `lane + 32` (< 49).  Its <= 8 sample records live in registers;
+      // per occupied 4x4-pixel chunk the lane accumulates the 16 pixel weights of each owned bin in registers
+      // (row weights x column weights, fully unrolled: no shared-memory latency in the chain), writes the two rows
+      // into a small shared W[bin][16] table, and the warp re-reads that table in mma fragment order.
+      const uint32_t s_w = s_tab + (uint32_t)(bw_id * tab_floats) * 4u;            // [NBIN][ROT_W_STRIDE] floats
+      // chunk-occupancy bitmap: a rotated RoI's bounding box may span many chunks that no sample touches
+      unsigned int* map_g = reinterpret_cast<unsigned int*>(gen + (s_w + NBIN * ROT_W_STRIDE * 4 - sbase));
       const float off = aligned ? 0.5f : 0.f;
       const uint32_t tx_bytes = (uint32_t)(C / 64) * QUARTER_BYTES;
       const int gs = sampling_ratio, cnt = gs * gs;        // host guarantees 1 <= sampling_ratio <= 2
@@ -183,11 +191,11 @@ roi_align_mma_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_cons
       int slot = 0; uint32_t phase = 0;
       float rnext = 0.f;
       if (bw_id < n_iter && lane < 6) rnext = __ldg(rois + (size_t)(blockIdx.x + bw_id * gridDim.x) * 6 + lane);
-      for (int it = bw_id; it < n_iter; it += BUILDERS) {
+      for (int it = bw_id; it < n_iter; it += NB) {
         const int roi = blockIdx.x + it * gridDim.x;
         const float rcur = rnext;
-        if (it + BUILDERS < n_iter && lane < 6)
-          rnext = __ldg(rois + (size_t)(blockIdx.x + (it + BUILDERS) * gridDim.x) * 6 + lane);
+        if (it + NB < n_iter && lane < 6)
+          rnext = __ldg(rois + (size_t)(blockIdx.x + (it + NB) * gridDim.x) * 6 + lane);
         bool skip = roi_level != nullptr && roi_level[roi] != level;
         const int b = (int)__shfl_sync(0xffffffffu, rcur, 0);
         const float cxr = fsub(fmul(__shfl_sync(0xffffffffu, rcur, 1), scale), off);
@@ -199,51 +207,61 @@ roi_align_mma_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_cons
         // large RoIs (the 200-px random negatives) are sparse in this formulation -- 196 samples scattered over
         // hundreds of chunks; they are left to roi_align.cu's direct gather kernel, launched right after this one
         // with the same test
-        if (fmaxf(rw, rh) > ROT_BIG_FPX) skip = true;
+        if (fmaxf(rw, rh) > ROT_BIG_THRESHOLD) skip = true;
         const float bh = fdiv(rh, (float)P7), bw = fdiv(rw, (float)P7);
         const float sh = fdiv(-rh, 2.0f), sw = fdiv(-rw, 2.0f);
         const float ct = cosf(theta), st = sinf(theta);
         const bool b_ok = b >= 0 && b < B && !skip;
+        // (i + .5) * bin / gs for i = 0, 1: the same values the per-sample expression of the reference produces
+        const float ys0 = fdiv(fmul(.5f, bh), (float)gs), ys1 = fdiv(fmul(1.5f, bh), (float)gs);
+        const float xs0 = fdiv(fmul(.5f, bw), (float)gs), xs1 = fdiv(fmul(1.5f, bw), (float)gs);
         int xlo = 1 << 30, xhi = -1, ylo = 1 << 30, yhi = -1;
-        __syncwarp();   // the previous RoI's fragment builds are done reading the sample table
-        for (int sidx = lane; sidx < NBIN * ROT_SAMPLES; sidx += 32) {
-          const int bin = sidx >> 2, sub = sidx & 3;
-          uint4 rec = make_uint4(0x7fff7fffu, 0x7fff7fffu, 0u, 0u);     // never matches a pixel coordinate
-          if (b_ok && sub < cnt) {
-            const int iy = sub / gs, ix = sub - iy * gs;
-            const int ph = bin / P7, pw = bin - ph * P7;
-            const float yy = fadd(fadd(sh, fmul((float)ph, bh)), fdiv(fmul((float)iy + .5f, bh), (float)gs));
-            const float xx = fadd(fadd(sw, fmul((float)pw, bw)), fdiv(fmul((float)ix + .5f, bw), (float)gs));
-            const float y = fadd(fsub(fmul(yy, ct), fmul(xx, st)), cyr);
-            const float x = fadd(fadd(fmul(yy, st), fmul(xx, ct)), cxr);
-            if (!(y < -1.0f || y > (float)H || x < -1.0f || x > (float)W)) {
-              int yl, yh, xl, xh; float ly, hy, lx, hx;
-              axis_setup(y, H, yl, yh, ly, hy);
-              axis_setup(x, W, xl, xh, lx, hx);
-              rec = make_uint4((uint32_t)xl | ((uint32_t)xh << 16), (uint32_t)yl | ((uint32_t)yh << 16),
+        // records: (x_low | x_high << 16, y_low | y_high << 16, lx, ly); 0x7fff never matches a pixel coordinate
+        uint4 rec[2 * ROT_SAMPLES];
+#pragma unroll
+        for (int j = 0; j < 2; j++) {
+          const int bin = lane + 32 * j;
+          const int ph = bin / P7, pw = bin - ph * P7;
+          const float yb = fadd(sh, fmul((float)ph, bh)), xb = fadd(sw, fmul((float)pw, bw));
+#pragma unroll
+          for (int sub = 0; sub < ROT_SAMPLES; sub++) {
+            uint4 r = make_uint4(0x7fff7fffu, 0x7fff7fffu, 0u, 0u);
+            if (b_ok && bin < NBIN && sub < cnt) {
+              const int iy = gs == 2 ? (sub >> 1) : 0, ix = gs == 2 ? (sub & 1) : 0;
+              const float yy = fadd(yb, iy ? ys1 : ys0);
+              const float xx = fadd(xb, ix ? xs1 : xs0);
+              const float y = fadd(fsub(fmul(yy, ct), fmul(xx, st)), cyr);
+              const float x = fadd(fadd(fmul(yy, st), fmul(xx, ct)), cxr);
+              if (!(y < -1.0f || y > (float)H || x < -1.0f || x > (float)W)) {
+                int yl, yh, xl, xh; float ly, hy, lx, hx;
+                axis_setup(y, H, yl, yh, ly, hy);
+                axis_setup(x, W, xl, xh, lx, hx);
+                r = make_uint4((uint32_t)xl | ((uint32_t)xh << 16), (uint32_t)yl | ((uint32_t)yh << 16),
                                __float_as_uint(lx), __float_as_uint(ly));
-              xlo = min(xlo, xl); xhi = max(xhi, xh); ylo = min(ylo, yl); yhi = max(yhi, yh);
+                xlo = min(xlo, xl); xhi = max(xhi, xh); ylo = min(ylo, yl); yhi = max(yhi, yh);
+              }
             }
+            rec[j * ROT_SAMPLES + sub] = r;
           }
-          sts128(s_samp + sidx * 16, rec);
         }
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) {
           xlo = min(xlo, __shfl_xor_sync(0xffffffffu, xlo, o)); xhi = max(xhi, __shfl_xor_sync(0xffffffffu, xhi, o));
           ylo = min(ylo, __shfl_xor_sync(0xffffffffu, ylo, o)); yhi = max(yhi, __shfl_xor_sync(0xffffffffu, yhi, o));
         }
-        __syncwarp();
         const bool empty = !b_ok || xhi < xlo || yhi < ylo;
         const int ncx = empty ? 1 : (xhi - xlo) / 4 + 1, ncy = empty ? 1 : (yhi - ylo) / 4 + 1;
         const int nch = ncx * ncy;
-        const bool use_map = !empty && nch <= ROT_MAP_WORDS * 32;
+        const bool use_map = !empty && nch > 1 && nch <= ROT_MAP_WORDS * 32;
         const int nwords = (nch + 31) >> 5;
         int total = nch;
         if (use_map) {
+          __syncwarp();   // the previous RoI's chunk walk is done reading the bitmap
           for (int w = lane; w < nwords; w += 32) map_g[w] = 0u;
           __syncwarp();
-          for (int sidx = lane; sidx < NBIN * ROT_SAMPLES; sidx += 32) {
-            const uint4 r = lds128(s_samp + sidx * 16);
+#pragma unroll
+          for (int q = 0; q < 2 * ROT_SAMPLES; q++) {
+            const uint4 r = rec[q];
             if (r.x != 0x7fff7fffu) {
               const int cxl = ((int)(r.x & 0xffffu) - xlo) >> 2, cxh = ((int)(r.x >> 16) - xlo) >> 2;
               const int cyl = ((int)(r.y & 0xffffu) - ylo) >> 2, cyh = ((int)(r.y >> 16) - ylo) >> 2;
@@ -272,42 +290,67 @@ roi_align_mma_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_cons
             if (chn >= nch) break;
             const int cy = chn / ncx, cx = chn - cy * ncx;
             done++;
-            const int stage = bw_id * DEPTH + slot;
-            mbar_wait(empty_bar + stage, phase ^ 1);
             int flags = (done == total ? F_LAST : 0);
             if (empty) {
               flags |= skip ? F_SKIP : F_ZERO;
             } else {
-              // this lane's pixels of the chunk: rows ra, ra + 2, columns ca, ca + 1 (k = 2t, 2t+1, 2t+8, 2t+9)
-              const uint32_t ra = (uint32_t)(ylo + cy * 4 + (t >> 1)), rb = ra + 2;
-              const uint32_t ca = (uint32_t)(xlo + cx * 4 + 2 * (t & 1)), cb = ca + 1;
+              const int x0 = xlo + cx * 4, y0 = ylo + cy * 4;
+              __syncwarp();   // the previous chunk's fragment gather is done reading W
+#pragma unroll
+              for (int j = 0; j < 2; j++) {
+                const int bin = lane + 32 * j;
+                if (bin < NBIN) {
+                  float wv[16];
+#pragma unroll
+                  for (int i = 0; i < 16; i++) wv[i] = 0.f;
+#pragma unroll
+                  for (int sub = 0; sub < ROT_SAMPLES; sub++) {
+                    const uint4 r = rec[j * ROT_SAMPLES + sub];
+                    const int dxl = (int)(r.x & 0xffffu) - x0, dxh = (int)(r.x >> 16) - x0;
+                    const int dyl = (int)(r.y & 0xffffu) - y0, dyh = (int)(r.y >> 16) - y0;
+                    const float lx = __uint_as_float(r.z), ly = __uint_as_float(r.w);
+                    const float hx = fsub(1.0f, lx), hy = fsub(1.0f, ly);
+                    float cw[4], rwt[4];
+#pragma unroll
+                    for (int c = 0; c < 4; c++) {
+                      cw[c] = (dxl == c ? hx : 0.f) + (dxh == c ? lx : 0.f);
+                      rwt[c] = (dyl == c ? hy : 0.f) + (dyh == c ? ly : 0.f);
+                    }
+#pragma unroll
+                    for (int rr = 0; rr < 4; rr++)
+#pragma unroll
+                      for (int c = 0; c < 4; c++) wv[rr * 4 + c] += rwt[rr] * cw[c];
+                  }
+                  const uint32_t wrow = s_w + (uint32_t)bin * (ROT_W_STRIDE * 4);
+#pragma unroll
+                  for (int i = 0; i < 4; i++)
+                    sts128(wrow + i * 16, make_uint4(__float_as_uint(wv[4 * i] * inv_count), __float_as_uint(wv[4 * i + 1] * inv_count),
+                                                     __float_as_uint(wv[4 * i + 2] * inv_count), __float_as_uint(wv[4 * i + 3] * inv_count)));
+                }
+              }
+              __syncwarp();
+            }
+            const int stage = bw_id * DEPTH + slot;
+            mbar_wait(empty_bar + stage, phase ^ 1);
+            if (!empty) {
+              // fragment order: rows g / g + 8 of m-tile mt, pixels k = 2t, 2t+1 (chunk row t>>1) and 2t+8, 2t+9 (row +2)
               const uint32_t dst = s_afrag + stage * AFRAG_BYTES + lane * 16;
+              const uint32_t pix = (uint32_t)(((t >> 1) * 4 + 2 * (t & 1)) * 4);
 #pragma unroll
               for (int mt = 0; mt < 4; mt++) {
                 uint32_t a[4];
 #pragma unroll
                 for (int hl = 0; hl < 2; hl++) {
                   const int bin = mt * 16 + g + hl * 8;
-                  float w00 = 0.f, w01 = 0.f, w10 = 0.f, w11 = 0.f;
+                  float2 lo = make_float2(0.f, 0.f), hi = make_float2(0.f, 0.f);
                   if (bin < NBIN) {
-#pragma unroll
-                    for (int sub = 0; sub < ROT_SAMPLES; sub++) {
-                      if (sub < cnt) {
-                        const uint4 r = lds128(s_samp + (bin * ROT_SAMPLES + sub) * 16);
-                        const uint32_t xl = r.x & 0xffffu, xh = r.x >> 16, yl = r.y & 0xffffu, yh = r.y >> 16;
-                        const float lx = __uint_as_float(r.z), ly = __uint_as_float(r.w);
-                        const float hx = fsub(1.0f, lx), hy = fsub(1.0f, ly);
-                        const float wya = (ra == yl ? hy : 0.f) + (ra == yh ? ly : 0.f);
-                        const float wyb = (rb == yl ? hy : 0.f) + (rb == yh ? ly : 0.f);
-                        const float wxa = (ca == xl ? hx : 0.f) + (ca == xh ? lx : 0.f);
-                        const float wxb = (cb == xl ? hx : 0.f) + (cb == xh ? lx : 0.f);
-                        w00 += wya * wxa; w01 += wya * wxb; w10 += wyb * wxa; w11 += wyb * wxb;
-                      }
-                    }
+                    const uint2 u0 = lds64(s_w + (uint32_t)bin * (ROT_W_STRIDE * 4) + pix);
+                    const uint2 u1 = lds64(s_w + (uint32_t)bin * (ROT_W_STRIDE * 4) + pix + 32);
+                    lo = make_float2(__uint_as_float(u0.x), __uint_as_float(u0.y));
+                    hi = make_float2(__uint_as_float(u1.x), __uint_as_float(u1.y));
                   }
-                  w00 *= inv_count; w01 *= inv_count; w10 *= inv_count; w11 *= inv_count;
-                  a[hl] = F16 ? pack_f16(w00, w01) : pack_bf16(w00, w01);            // k = 2t, 2t+1
-                  a[2 + hl] = F16 ? pack_f16(w10, w11) : pack_bf16(w10, w11);        // k = 2t+8, 2t+9
+                  a[hl] = F16 ? pack_f16(lo.x, lo.y) : pack_bf16(lo.x, lo.y);
+                  a[2 + hl] = F16 ? pack_f16(hi.x, hi.y) : pack_bf16(hi.x, hi.y);
                 }
                 sts128(dst + mt * 512, make_uint4(a[0], a[1], a[2], a[3]));
               }
@@ -483,7 +526,7 @@ roi_align_mma_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_cons
 
   uint32_t slotbits = 0, phasebits = 0;          // per-builder ring position / parity (bit = builder id)
   for (int it = 0; it < n_iter; it++) {
-    const int bw_id = it % BUILDERS;
+    const int bw_id = it % NB;
     int roi, flags;
     bool first = true;
     do {
@@ -593,19 +636,21 @@ static EncodeTiledFn get_encode() {
   return fn;
 }
 
-constexpr size_t SMEM_LIMIT = 113 * 1024;   // two CTAs per SM
+constexpr size_t SMEM_LIMIT = 113 * 1024;       // two CTAs per SM
+constexpr size_t SMEM_LIMIT_ROT = 226 * 1024;   // rotated: one CTA per SM
 
 size_t smem_bytes(int H, int W, int stg_bufs, bool rot) {
   const size_t tab = rot ? (size_t)ROT_TAB_FLOATS : (size_t)(W + 4) * 8 + (size_t)(H + 4) * 8;
-  return 1024 + (size_t)STAGES * (PATCH_BYTES + AFRAG_BYTES) + MMA_WARPS * stg_bufs * (size_t)STG_BYTES +
-         BUILDERS * tab * sizeof(float) + 3 * STAGES * 8 + 64;
+  const size_t nb = rot ? ROT_BUILDERS : BUILDERS, stages = nb * DEPTH;
+  return 1024 + stages * (PATCH_BYTES + AFRAG_BYTES) + MMA_WARPS * stg_bufs * (size_t)STG_BYTES +
+         nb * tab * sizeof(float) + 3 * stages * 8 + 64;
 }
 
 // rotated: fixed sampling grids of 1 or 2 samples per axis (the shipped sampling_ratio = 2); the adaptive grid
 // (sampling_ratio = 0) stays on roi_align.cu's direct kernel.  Coordinates are packed into 16 bits.
 bool supported(int C, int H, int W, bool rot, int sampling_ratio) {
   if (rot && (sampling_ratio < 1 || sampling_ratio * sampling_ratio > ROT_SAMPLES || H > 32000 || W > 32000)) return false;
-  return C % 64 == 0 && C >= 64 && C <= 256 && smem_bytes(H, W, 1, rot) <= SMEM_LIMIT;
+  return C % 64 == 0 && C >= 64 && C <= 256 && smem_bytes(H, W, 1, rot) <= (rot ? SMEM_LIMIT_ROT : SMEM_LIMIT);
 }
 
 int launch(const void* feat_bf16_nhwc, int feat_f16, const float* rois, void* out, long long ld_out, int K, int B, int C,
@@ -637,7 +682,7 @@ int launch(const void* feat_bf16_nhwc, int feat_f16, const float* rois, void* ou
             CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) { set_error("roi_align_mma: output cuTensorMapEncodeTiled failed: CUresult %d", (int)r); return PT_ERR_DRIVER; }
   }
-  const int stg_bufs = smem_bytes(H, W, 2, rot) <= SMEM_LIMIT ? 2 : 1;   // large maps: single-buffered staging
+  const int stg_bufs = smem_bytes(H, W, 2, rot) <= (rot ? SMEM_LIMIT_ROT : SMEM_LIMIT) ? 2 : 1;   // large maps: single-buffered staging
   const size_t smem = smem_bytes(H, W, stg_bufs, rot);
   auto kern = feat_f16 ? (rot ? roi_align_mma_kernel<true, true> : roi_align_mma_kernel<true, false>)
                        : (rot ? roi_align_mma_kernel<false, true> : roi_align_mma_kernel<false, false>);
@@ -646,8 +691,9 @@ int launch(const void* feat_bf16_nhwc, int feat_f16, const float* rois, void* ou
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-  const int grid = K < 2 * sms ? K : 2 * sms;
-  kern<<<grid, THREADS, smem, stream>>>(map, omap, rois, K, B, C, H, W, scale, sampling_ratio, aligned, roi_level, level,
+  const int per_sm = rot ? 1 : 2;
+  const int grid = K < per_sm * sms ? K : per_sm * sms;
+  kern<<<grid, (MMA_WARPS + (rot ? ROT_BUILDERS : BUILDERS)) * 32, smem, stream>>>(map, omap, rois, K, B, C, H, W, scale, sampling_ratio, aligned, roi_level, level,
                                         stg_bufs, clockwise);
   return check_launch("roi_align_mma_kernel");
 }
