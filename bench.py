@@ -456,7 +456,8 @@ def _events_ms(fn, iters, flush, warm=3):
         if flush is not None:
             flush.zero_()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record(); fn(); e1.record()
+        torch.cuda._sleep(400000)      # ~0.2 ms on the device: the host enqueues fn() meanwhile, so the events
+        e0.record(); fn(); e1.record()  # bracket device time and not the host's launch latency
         torch.cuda.synchronize()
         ts.append(e0.elapsed_time(e1))
     ts.sort()

@@ -172,6 +172,53 @@ __global__ void bbox_metric_kernel(const float* __restrict__ a, int lda, const f
   }
 }
 
+// Tiled variant: the matrix is a pure 4 B/element output stream (60 MB at G = 1500, A = 10^4), so the kernel is
+// organised around the store: a thread owns 4 consecutive columns (its 4 boxes stay in registers) and walks 8 rows
+// whose box is a broadcast load; one 16-byte streaming store per row.  The element arithmetic is pair_metric()
+// unchanged, so every entry is bit-identical to the one-thread-per-element kernel.
+constexpr int MM_ROWS = 8, MM_THREADS = 256;
+__global__ void __launch_bounds__(MM_THREADS)
+metric_matrix_kernel(const float* __restrict__ a, int lda, const float* __restrict__ b, int ldb, int M, int N, int calc,
+                     int mode, float eps, float* __restrict__ out, int vec_ok) {
+  const int j0 = (blockIdx.x * MM_THREADS + threadIdx.x) * 4;
+  if (j0 >= N) return;
+  float bx[4][4];
+#pragma unroll
+  for (int q = 0; q < 4; q++) {
+    const float* p = b + (size_t)min(j0 + q, N - 1) * ldb;
+    bx[q][0] = __ldg(p); bx[q][1] = __ldg(p + 1); bx[q][2] = __ldg(p + 2); bx[q][3] = __ldg(p + 3);
+  }
+  const int i0 = blockIdx.y * MM_ROWS;
+#pragma unroll 2
+  for (int r = 0; r < MM_ROWS; r++) {
+    const int i = i0 + r;
+    if (i >= M) break;
+    const float* pa = a + (size_t)i * lda;
+    const float a0 = __ldg(pa), a1 = __ldg(pa + 1), a2 = __ldg(pa + 2), a3 = __ldg(pa + 3);
+    float v[4];
+#pragma unroll
+    for (int q = 0; q < 4; q++) v[q] = pair_metric(calc, mode, a0, a1, a2, a3, bx[q][0], bx[q][1], bx[q][2], bx[q][3], eps);
+    float* o = out + (size_t)i * N + j0;
+    if (vec_ok && j0 + 3 < N) {
+      __stcs(reinterpret_cast<float4*>(o), make_float4(v[0], v[1], v[2], v[3]));
+    } else {
+#pragma unroll
+      for (int q = 0; q < 4; q++)
+        if (j0 + q < N) o[q] = v[q];
+    }
+  }
+}
+
+int launch_metric_matrix(const float* a, int lda, const float* b, int ldb, long long M, long long N, int calc, int mode,
+                         float eps, float* out, cudaStream_t stream) {
+  const long long gy = (M + MM_ROWS - 1) / MM_ROWS, gx = (N + MM_THREADS * 4 - 1) / (MM_THREADS * 4);
+  if (gy > 65535 || gx > 2147483647LL || M > 2147483647LL || N > 2147483647LL) return PT_ERR_UNSUPPORTED;
+  const int vec_ok = (N % 4 == 0) && (((uintptr_t)out & 15) == 0);
+  metric_matrix_kernel<<<dim3((unsigned)gx, (unsigned)gy), MM_THREADS, 0, stream>>>(a, lda, b, ldb, (int)M, (int)N, calc, mode,
+                                                                                    eps, out, vec_ok);
+  return check_launch("metric_matrix_kernel");
+}
+
 // ---- MaxIoUAssigner without the G x A matrix
 // order-preserving float <-> uint32 so that atomicMax works on signed floats (GIoU is negative)
 __device__ __forceinline__ unsigned enc_f(float f) {
@@ -184,40 +231,42 @@ __device__ __forceinline__ float dec_f(unsigned e) {
 
 constexpr int GT_TILE = 256;
 
-// pass 1: per anchor max / first argmax over the GTs; per GT max over the anchors (atomicMax)
+// The G x A work is tiled over BOTH axes (grid = anchor blocks x GT tiles): at G = 1500, A = 10^4 an anchors-only grid
+// is 40 CTAs with a 1500-iteration serial loop per thread (0.72 ms); the 2-D grid runs 240 CTAs of 256 iterations.
+// Cross-tile reductions are order-independent integer atomics, so the result does not depend on scheduling:
+//   per anchor (max, FIRST argmax)  -> 64-bit atomicMax of  enc(v) << 32 | ~g       (key buffer = the gt_inds output)
+//   per GT max over anchors         -> 32-bit atomicMax of  enc(v)
+//   low-quality matches (last GT wins) -> 32-bit atomicMax of g + 1                 (buffer = argmax_ws, re-used)
+
+// pass 1: per anchor max / first argmax over this GT tile; per GT max over this anchor block
 __global__ void __launch_bounds__(256)
 max_iou_pass1_kernel(const float* __restrict__ gts, int ldg, int G, const float* __restrict__ anchors, int lda, int A,
-                     int calc, int mode, float eps, float* __restrict__ max_ov, int* __restrict__ argmax,
-                     unsigned* __restrict__ gt_max) {
+                     int calc, int mode, float eps, unsigned long long* __restrict__ key, unsigned* __restrict__ gt_max) {
   __shared__ float4 sg[GT_TILE];
   __shared__ unsigned smax[GT_TILE];
   const int a = blockIdx.x * blockDim.x + threadIdx.x;
+  const int g0 = blockIdx.y * GT_TILE, n = min(GT_TILE, G - g0);
   float4 bx = make_float4(0.f, 0.f, 0.f, 0.f);
   if (a < A) { const float* p = anchors + (size_t)a * lda; bx = make_float4(p[0], p[1], p[2], p[3]); }
-  float best = 0.f; int bi = 0; bool has = false;
-  for (int g0 = 0; g0 < G; g0 += GT_TILE) {
-    const int n = min(GT_TILE, G - g0);
-    __syncthreads();
-    if (threadIdx.x < n) {
-      const float* p = gts + (size_t)(g0 + threadIdx.x) * ldg;
-      sg[threadIdx.x] = make_float4(p[0], p[1], p[2], p[3]);
-      smax[threadIdx.x] = 0u;   // below enc_f of every float
-    }
-    __syncthreads();
-    if (a < A) {
-      for (int j = 0; j < n; j++) {
-        const float4 gb = sg[j];
-        const float v = pair_metric(calc, mode, gb.x, gb.y, gb.z, gb.w, bx.x, bx.y, bx.z, bx.w, eps);
-        if (!has || v > best) { best = v; bi = g0 + j; has = true; }     // first index among equal maxima
-        // the running maximum settles after a few anchors: a broadcast read filters almost every atomic
-        const unsigned e = enc_f(v);
-        if (e > smax[j]) atomicMax(&smax[j], e);
-      }
-    }
-    __syncthreads();
-    if (threadIdx.x < n && smax[threadIdx.x] != 0u) atomicMax(gt_max + g0 + threadIdx.x, smax[threadIdx.x]);
+  if (threadIdx.x < n) {
+    const float* p = gts + (size_t)(g0 + threadIdx.x) * ldg;
+    sg[threadIdx.x] = make_float4(p[0], p[1], p[2], p[3]);
+    smax[threadIdx.x] = 0u;   // below enc_f of every float
   }
-  if (a < A) { max_ov[a] = best; argmax[a] = bi; }
+  __syncthreads();
+  if (a < A) {
+    unsigned best = 0u; int bi = 0;
+    for (int j = 0; j < n; j++) {
+      const float4 gb = sg[j];
+      const unsigned e = enc_f(pair_metric(calc, mode, gb.x, gb.y, gb.z, gb.w, bx.x, bx.y, bx.z, bx.w, eps));
+      if (e > best) { best = e; bi = g0 + j; }                          // first index among equal maxima
+      // the running maximum settles after a few anchors: a broadcast read filters almost every atomic
+      if (e > smax[j]) atomicMax(&smax[j], e);
+    }
+    atomicMax(key + a, ((unsigned long long)best << 32) | (unsigned long long)(0xffffffffu - (unsigned)bi));
+  }
+  __syncthreads();
+  if (threadIdx.x < n && smax[threadIdx.x] != 0u) atomicMax(gt_max + g0 + threadIdx.x, smax[threadIdx.x]);
 }
 
 // pass 1b (gt_max_assign_all == False): first anchor index achieving each GT's max
@@ -228,62 +277,72 @@ max_iou_argmax_kernel(const float* __restrict__ gts, int ldg, int G, const float
   const int a = blockIdx.x * blockDim.x + threadIdx.x;
   if (a >= A) return;
   const float* p = anchors + (size_t)a * lda;
-  for (int g = 0; g < G; g++) {
+  const int g0 = blockIdx.y * GT_TILE, g1 = min(G, g0 + GT_TILE);
+  for (int g = g0; g < g1; g++) {
     const float* q = gts + (size_t)g * ldg;
     const float v = pair_metric(calc, mode, q[0], q[1], q[2], q[3], p[0], p[1], p[2], p[3], eps);
     if (v == dec_f(gt_max[g])) atomicMin(gt_argmax + g, a);
   }
 }
 
-// pass 2: thresholds + low-quality matching (sequential "for i in range(num_gts)" == largest i wins)
+// between the passes: decode the key, apply the thresholds; the key buffer becomes gt_inds, lowq is cleared
+__global__ void max_iou_mid_kernel(int A, float pos_thr, float neg_lo, float neg_hi, long long* __restrict__ gt_inds,
+                                   float* __restrict__ max_ov, int* __restrict__ lowq) {
+  const int a = blockIdx.x * blockDim.x + threadIdx.x;
+  if (a >= A) return;
+  const unsigned long long k = reinterpret_cast<const unsigned long long*>(gt_inds)[a];
+  const float m = dec_f((unsigned)(k >> 32));
+  const int bi = (int)(0xffffffffu - (unsigned)(k & 0xffffffffull));
+  long long asg = -1;
+  if (m >= neg_lo && m < neg_hi) asg = 0;
+  if (m >= pos_thr) asg = bi + 1;
+  max_ov[a] = m;
+  gt_inds[a] = asg;
+  lowq[a] = 0;
+}
+
+// pass 2: low-quality matching (sequential "for i in range(num_gts)" == largest matching i wins)
 __global__ void __launch_bounds__(256)
 max_iou_pass2_kernel(const float* __restrict__ gts, int ldg, int G, const float* __restrict__ anchors, int lda, int A,
-                     int calc, int mode, float eps, const float* __restrict__ max_ov, const int* __restrict__ argmax,
-                     const unsigned* __restrict__ gt_max, const int* __restrict__ gt_argmax, float pos_thr,
-                     float neg_lo, float neg_hi, float min_pos, int assign_all, int low_quality,
-                     const long long* __restrict__ gt_labels, long long* __restrict__ gt_inds,
-                     long long* __restrict__ labels) {
+                     int calc, int mode, float eps, const unsigned* __restrict__ gt_max,
+                     const int* __restrict__ gt_argmax, float min_pos, int assign_all, int* __restrict__ lowq) {
   __shared__ float4 sg[GT_TILE];
   __shared__ float sm[GT_TILE];
   const int a = blockIdx.x * blockDim.x + threadIdx.x;
-  float4 bx = make_float4(0.f, 0.f, 0.f, 0.f);
-  long long asg = -1;
-  if (a < A) {
-    const float* p = anchors + (size_t)a * lda;
-    bx = make_float4(p[0], p[1], p[2], p[3]);
-    const float m = max_ov[a];
-    if (m >= neg_lo && m < neg_hi) asg = 0;
-    if (m >= pos_thr) asg = argmax[a] + 1;
+  const int g0 = blockIdx.y * GT_TILE, n = min(GT_TILE, G - g0);
+  if (threadIdx.x < n) {
+    const float* p = gts + (size_t)(g0 + threadIdx.x) * ldg;
+    sg[threadIdx.x] = make_float4(p[0], p[1], p[2], p[3]);
+    sm[threadIdx.x] = dec_f(gt_max[g0 + threadIdx.x]);
   }
-  if (low_quality) {
-    for (int g0 = 0; g0 < G; g0 += GT_TILE) {
-      const int n = min(GT_TILE, G - g0);
-      __syncthreads();
-      if (threadIdx.x < n) {
-        const float* p = gts + (size_t)(g0 + threadIdx.x) * ldg;
-        sg[threadIdx.x] = make_float4(p[0], p[1], p[2], p[3]);
-        sm[threadIdx.x] = dec_f(gt_max[g0 + threadIdx.x]);
-      }
-      __syncthreads();
-      if (a < A) {
-        for (int j = 0; j < n; j++) {
-          const float gm = sm[j];
-          if (!(gm >= min_pos)) continue;
-          if (assign_all) {
-            const float4 gb = sg[j];
-            const float v = pair_metric(calc, mode, gb.x, gb.y, gb.z, gb.w, bx.x, bx.y, bx.z, bx.w, eps);
-            if (v == gm) asg = g0 + j + 1;
-          } else if (gt_argmax[g0 + j] == a) {
-            asg = g0 + j + 1;
-          }
-        }
-      }
+  __syncthreads();
+  if (a >= A) return;
+  const float* p = anchors + (size_t)a * lda;
+  const float4 bx = make_float4(p[0], p[1], p[2], p[3]);
+  int hit = 0;
+  for (int j = 0; j < n; j++) {
+    const float gm = sm[j];
+    if (!(gm >= min_pos)) continue;
+    if (assign_all) {
+      const float4 gb = sg[j];
+      const float v = pair_metric(calc, mode, gb.x, gb.y, gb.z, gb.w, bx.x, bx.y, bx.z, bx.w, eps);
+      if (v == gm) hit = g0 + j + 1;
+    } else if (gt_argmax[g0 + j] == a) {
+      hit = g0 + j + 1;
     }
   }
-  if (a < A) {
-    gt_inds[a] = asg;
-    if (labels != nullptr) labels[a] = asg > 0 ? gt_labels[asg - 1] : -1;
-  }
+  if (hit > 0) atomicMax(lowq + a, hit);
+}
+
+__global__ void max_iou_final_kernel(int A, int low_quality, const int* __restrict__ lowq,
+                                     const long long* __restrict__ gt_labels, long long* __restrict__ gt_inds,
+                                     long long* __restrict__ labels) {
+  const int a = blockIdx.x * blockDim.x + threadIdx.x;
+  if (a >= A) return;
+  long long asg = gt_inds[a];
+  if (low_quality && lowq[a] > 0) asg = lowq[a];
+  gt_inds[a] = asg;
+  if (labels != nullptr) labels[a] = asg > 0 ? gt_labels[asg - 1] : -1;
 }
 
 // ---- coarse pseudo-box aggregation behind the FUSE assignment
@@ -437,7 +496,9 @@ extern "C" int pt_bbox_metric(const float* a, int lda, const float* b, int ldb, 
     set_error("pt_bbox_metric: unsupported calculator %d / mode %d", calc, mode);
     return PT_ERR_ARG;
   }
-  const long long total = M * N;
+  const int rc = launch_metric_matrix(a, lda, b, ldb, M, N, calc, mode, eps, out, (cudaStream_t)stream);
+  if (rc != PT_ERR_UNSUPPORTED) return rc;
+  const long long total = M * N;                      // > 524 280 rows: one thread per element
   const int blocks = (int)((total + 255) / 256 < 148LL * 32 ? (total + 255) / 256 : 148LL * 32);
   bbox_metric_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(a, lda, b, ldb, M, N, calc, mode, eps, out);
   return check_launch("bbox_metric_kernel");
@@ -459,19 +520,28 @@ extern "C" int pt_max_iou_assign(const float* gts, int ldg, int G, const float* 
   int* gt_argmax = reinterpret_cast<int*>(gt_ws + G);
   cudaMemsetAsync(gt_ws, 0, (size_t)G * sizeof(unsigned), s);
   cudaMemsetAsync(gt_argmax, 0x7f, (size_t)G * sizeof(int), s);
+  cudaMemsetAsync(gt_inds, 0, (size_t)A * sizeof(long long), s);       // the per-anchor (max, argmax) keys
   const int blocks = (A + 255) / 256;
-  max_iou_pass1_kernel<<<blocks, 256, 0, s>>>(gts, ldg, G, anchors, lda, A, calc, mode, eps, max_overlaps, argmax_ws, gt_ws);
+  const dim3 grid2(blocks, (G + GT_TILE - 1) / GT_TILE);
+  if (grid2.y > 65535) { set_error("pt_max_iou_assign: more than 16 M GTs"); return PT_ERR_UNSUPPORTED; }
+  max_iou_pass1_kernel<<<grid2, 256, 0, s>>>(gts, ldg, G, anchors, lda, A, calc, mode, eps,
+                                             reinterpret_cast<unsigned long long*>(gt_inds), gt_ws);
   int rc = check_launch("max_iou_pass1_kernel");
   if (rc != PT_OK) return rc;
   if (match_low_quality && !gt_max_assign_all) {
-    max_iou_argmax_kernel<<<blocks, 256, 0, s>>>(gts, ldg, G, anchors, lda, A, calc, mode, eps, gt_ws, gt_argmax);
+    max_iou_argmax_kernel<<<grid2, 256, 0, s>>>(gts, ldg, G, anchors, lda, A, calc, mode, eps, gt_ws, gt_argmax);
     rc = check_launch("max_iou_argmax_kernel");
     if (rc != PT_OK) return rc;
   }
-  max_iou_pass2_kernel<<<blocks, 256, 0, s>>>(gts, ldg, G, anchors, lda, A, calc, mode, eps, max_overlaps, argmax_ws, gt_ws,
-                                              gt_argmax, pos_thr, neg_lo, neg_hi, min_pos, gt_max_assign_all,
-                                              match_low_quality, gt_labels, gt_inds, labels);
-  return check_launch("max_iou_pass2_kernel");
+  max_iou_mid_kernel<<<blocks, 256, 0, s>>>(A, pos_thr, neg_lo, neg_hi, gt_inds, max_overlaps, argmax_ws);
+  if (match_low_quality) {
+    max_iou_pass2_kernel<<<grid2, 256, 0, s>>>(gts, ldg, G, anchors, lda, A, calc, mode, eps, gt_ws, gt_argmax, min_pos,
+                                               gt_max_assign_all, argmax_ws);
+    rc = check_launch("max_iou_pass2_kernel");
+    if (rc != PT_OK) return rc;
+  }
+  max_iou_final_kernel<<<blocks, 256, 0, s>>>(A, match_low_quality, argmax_ws, gt_labels, gt_inds, labels);
+  return check_launch("max_iou_final_kernel");
 }
 
 // distance2bbox + bbox_xyxy_to_cxcywh (HBB_TOD/mmdet/core/bbox/transforms.py:134-166, 249-261)

@@ -9,6 +9,7 @@
 //   bbox_overlaps                HBB_TOD/mmdet/core/bbox/iou_calculators/iou2d_calculator.py:74-260
 // Bit-exact contract: every fp32 operation is issued in the reference's order with non-contracted intrinsics.
 #include "common.cuh"
+#include "overlap_metric.cuh"
 #include "rotated_iou.cuh"
 
 namespace ptb {
@@ -239,6 +240,10 @@ extern "C" int pt_bbox_overlaps(const float* a, int lda, const float* b, int ldb
   if (aligned && M != N) { set_error("pt_bbox_overlaps: aligned needs M == N"); return PT_ERR_ARG; }
   const long long total = aligned ? M : M * N;
   if (total <= 0) return PT_OK;
+  if (!aligned) {   // the M x N matrix: tiled kernel of assign.cu (same element arithmetic, calc 0)
+    const int rc = launch_metric_matrix(a, lda, b, ldb, M, N, 0, mode, eps, out, (cudaStream_t)stream);
+    if (rc != PT_ERR_UNSUPPORTED) return rc;
+  }
   const int threads = 256;
   long long blocks = (total + threads - 1) / threads;
   if (blocks > 148LL * 32) blocks = 148LL * 32;

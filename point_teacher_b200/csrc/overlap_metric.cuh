@@ -65,4 +65,9 @@ __device__ __forceinline__ float pair_metric(int calc, int mode, float ax1, floa
   return expf(fdiv(-kl, 10.f));
 }
 
+// Tiled G x A matrix of pair_metric (assign.cu): 8 rows x 4 columns per thread, 16-byte streaming stores, no 64-bit
+// index division.  Returns PT_OK or a negative code; falls back to nothing -- callers keep their aligned kernels.
+int launch_metric_matrix(const float* a, int lda, const float* b, int ldb, long long M, long long N, int calc, int mode,
+                         float eps, float* out, cudaStream_t stream);
+
 }  // namespace ptb

@@ -225,22 +225,27 @@ roi_align_mma_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_cons
           const float yb = fadd(sh, fmul((float)ph, bh)), xb = fadd(sw, fmul((float)pw, bw));
 #pragma unroll
           for (int sub = 0; sub < ROT_SAMPLES; sub++) {
-            uint4 r = make_uint4(0x7fff7fffu, 0x7fff7fffu, 0u, 0u);
-            if (b_ok && bin < NBIN && sub < cnt) {
-              const int iy = gs == 2 ? (sub >> 1) : 0, ix = gs == 2 ? (sub & 1) : 0;
-              const float yy = fadd(yb, iy ? ys1 : ys0);
-              const float xx = fadd(xb, ix ? xs1 : xs0);
-              const float y = fadd(fsub(fmul(yy, ct), fmul(xx, st)), cyr);
-              const float x = fadd(fadd(fmul(yy, st), fmul(xx, ct)), cxr);
-              if (!(y < -1.0f || y > (float)H || x < -1.0f || x > (float)W)) {
-                int yl, yh, xl, xh; float ly, hy, lx, hx;
-                axis_setup(y, H, yl, yh, ly, hy);
-                axis_setup(x, W, xl, xh, lx, hx);
-                r = make_uint4((uint32_t)xl | ((uint32_t)xh << 16), (uint32_t)yl | ((uint32_t)yh << 16),
-                               __float_as_uint(lx), __float_as_uint(ly));
-                xlo = min(xlo, xl); xhi = max(xhi, xh); ylo = min(ylo, yl); yhi = max(yhi, yh);
-              }
-            }
+            // branch-free (selects only) so that the 8 unrolled samples of a lane interleave: the builder is a single
+            // warp and lives on instruction-level parallelism.  Same arithmetic and border rule as axis_setup().
+            const int iy = gs == 2 ? (sub >> 1) : 0, ix = gs == 2 ? (sub & 1) : 0;
+            const float yy = fadd(yb, iy ? ys1 : ys0);
+            const float xx = fadd(xb, ix ? xs1 : xs0);
+            const float y = fadd(fsub(fmul(yy, ct), fmul(xx, st)), cyr);
+            const float x = fadd(fadd(fmul(yy, st), fmul(xx, ct)), cxr);
+            const bool ok = b_ok && bin < NBIN && sub < cnt && !(y < -1.0f || y > (float)H || x < -1.0f || x > (float)W);
+            float yc = y <= 0.f ? 0.f : y, xc = x <= 0.f ? 0.f : x;
+            int yl = (int)yc, xl = (int)xc;
+            const bool ytop = yl >= H - 1, xtop = xl >= W - 1;
+            yl = ytop ? H - 1 : yl; xl = xtop ? W - 1 : xl;
+            const int yh = ytop ? yl : yl + 1, xh = xtop ? xl : xl + 1;
+            yc = ytop ? (float)yl : yc; xc = xtop ? (float)xl : xc;
+            const float ly = fsub(yc, (float)yl), lx = fsub(xc, (float)xl);
+            uint4 r;
+            r.x = ok ? ((uint32_t)xl | ((uint32_t)xh << 16)) : 0x7fff7fffu;      // 0x7fff never matches a pixel coordinate
+            r.y = ok ? ((uint32_t)yl | ((uint32_t)yh << 16)) : 0x7fff7fffu;
+            r.z = __float_as_uint(lx); r.w = __float_as_uint(ly);
+            xlo = ok ? min(xlo, xl) : xlo; xhi = ok ? max(xhi, xh) : xhi;
+            ylo = ok ? min(ylo, yl) : ylo; yhi = ok ? max(yhi, yh) : yhi;
             rec[j * ROT_SAMPLES + sub] = r;
           }
         }
@@ -252,7 +257,8 @@ roi_align_mma_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_cons
         const bool empty = !b_ok || xhi < xlo || yhi < ylo;
         const int ncx = empty ? 1 : (xhi - xlo) / 4 + 1, ncy = empty ? 1 : (yhi - ylo) / 4 + 1;
         const int nch = ncx * ncy;
-        const bool use_map = !empty && nch > 1 && nch <= ROT_MAP_WORDS * 32;
+        // few chunks (the common case): walk them all -- an untouched chunk only costs a zero-weight pass
+        const bool use_map = !empty && nch > 6 && nch <= ROT_MAP_WORDS * 32;
         const int nwords = (nch + 31) >> 5;
         int total = nch;
         if (use_map) {
