@@ -438,9 +438,21 @@ def run_ours(args):
                         "(average) of the 27.8 M MIL-head gradients" + (" over NCCL" if world > 1 else " (single rank: no-op)")},
             "cpu_baseline": cpu,
         }
-        print(json.dumps(line))
+        print(json.dumps(line), flush=True)
     if world > 1:
-        dist.destroy_process_group()
+        # Tear-down order matters: the captured training step holds NCCL kernels inside a CUDA graph, and destroying
+        # the communicator while such a graph is alive blocks forever (observed at N=2: the line above was printed and
+        # the job then hung in destroy_process_group until the launcher's timeout).  Drop every graph first, meet at a
+        # barrier, and leave without NCCL's blocking finalizer.
+        cap = pipe = ctrain = trainer = train_once = None  # noqa: F841
+        import gc
+        gc.collect()
+        torch.cuda.synchronize()
+        dist.barrier()
+        torch.cuda.synchronize()
+        sys.stdout.flush()
+        sys.stderr.flush()
+        os._exit(0)
 
 
 # ---------------------------------------------------------------------------------------------------------------

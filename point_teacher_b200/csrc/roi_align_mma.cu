@@ -42,10 +42,11 @@ constexpr int P7 = 7, NBIN = 49;
 constexpr int BUILDERS = 2, DEPTH = 2, STAGES = BUILDERS * DEPTH;   // every builder warp owns a DEPTH-deep ring
 constexpr int MMA_WARPS = 8;
 constexpr int THREADS = (MMA_WARPS + BUILDERS) * 32;
-// Rotated variant: the builder does ~4x the work per RoI (non-separable weights), so it runs ONE CTA per SM with 6
-// builder warps (12 stages, ~208 KB of shared memory) instead of two CTAs with 2 builders each.  The ncu source view
-// of the 2-builder variant showed the 8 MMA warps spinning on the full barriers 80 % of the time.
-constexpr int ROT_BUILDERS = 6;
+// Rotated variant: the builder does ~4x the work per RoI (non-separable weights), so it runs ONE CTA per SM with 8
+// builder warps (16 stages, ~221 KB of shared memory, single-buffered output staging, 16 warps x 128 registers = the
+// whole register file) instead of two CTAs with 2 builders each.  The ncu source view of the 2-builder variant showed
+// the 8 MMA warps spinning on the full barriers 80 % of the time.
+constexpr int ROT_BUILDERS = 8;
 constexpr int QUARTER_BYTES = 16 * 128;           // 16 pixels x 64 channels bf16
 constexpr int PATCH_BYTES = 4 * QUARTER_BYTES;    // 8 KB
 constexpr int AFRAG_BYTES = 4 * 32 * 16;          // 4 m-tiles x 32 lanes x uint4
@@ -54,7 +55,7 @@ constexpr int AFRAG_BYTES = 4 * 32 * 16;          // 4 m-tiles x 32 lanes x uint
 constexpr int STG_ROW_BYTES = 64;
 constexpr int STG_BYTES = ((NBIN * STG_ROW_BYTES + 511) / 512) * 512;   // per MMA warp and buffer
 constexpr int ROT_SAMPLES = 4;                                          // rotated: sampling_ratio^2 <= 4 samples per bin
-constexpr int ROT_MAP_WORDS = 128;                                      // occupancy bitmap: up to 4096 chunks per RoI
+constexpr int ROT_MAP_WORDS = 32;                                       // occupancy bitmap: up to 1024 chunks per RoI
 constexpr int ROT_W_STRIDE = 20;                                        // floats per W row (16 pixels, 80-byte pitch)
 constexpr int ROT_TAB_FLOATS = NBIN * ROT_W_STRIDE + ROT_MAP_WORDS;     // per builder warp: W[49][20] + bitmap
 enum { F_LAST = 2, F_ZERO = 4, F_SKIP = 8 };
