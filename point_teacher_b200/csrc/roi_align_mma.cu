@@ -42,11 +42,11 @@ constexpr int P7 = 7, NBIN = 49;
 constexpr int BUILDERS = 2, DEPTH = 2, STAGES = BUILDERS * DEPTH;   // every builder warp owns a DEPTH-deep ring
 constexpr int MMA_WARPS = 8;
 constexpr int THREADS = (MMA_WARPS + BUILDERS) * 32;
-// Rotated variant: the builder does ~4x the work per RoI (non-separable weights), so it runs ONE CTA per SM with 8
-// builder warps (16 stages, ~221 KB of shared memory, single-buffered output staging, 16 warps x 128 registers = the
-// whole register file) instead of two CTAs with 2 builders each.  The ncu source view of the 2-builder variant showed
-// the 8 MMA warps spinning on the full barriers 80 % of the time.
-constexpr int ROT_BUILDERS = 8;
+// Rotated variant: the builder does ~4x the work per RoI (non-separable weights), so it runs ONE CTA per SM with 6
+// builder warps (12 stages, ~208 KB of shared memory) instead of two CTAs with 2 builders each.  The ncu source view
+// of the 2-builder variant showed the 8 MMA warps spinning on the full barriers 80 % of the time.  (8 builders with
+// single-buffered output staging measured the same step time: beyond 6 the builders are no longer the limiter.)
+constexpr int ROT_BUILDERS = 6;
 constexpr int QUARTER_BYTES = 16 * 128;           // 16 pixels x 64 channels bf16
 constexpr int PATCH_BYTES = 4 * QUARTER_BYTES;    // 8 KB
 constexpr int AFRAG_BYTES = 4 * 32 * 16;          // 4 m-tiles x 32 lanes x uint4
