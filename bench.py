@@ -568,9 +568,11 @@ def run_config_obb(args):
         "e2e": {"value": 2e3 / e2e_ms, "unit": "imgs/s", "h2d_bytes_per_step": pipe.h2d_bytes,
                 "d2h_bytes_per_step": pipe.d2h_bytes, "ms_per_step": e2e_ms},
         "gpu_launches": launches * args.steps, "clocks": sampler.summary(),
-        "roofline": {"kernel": "roi_align_rotated_fwd_kernel (bf16 bin-major out)", "bound": "hbm",
+        "roofline": {"kernel": "roi_align_mma_kernel<ROT> (TMA + mma.sync, RoIs <= 8 feature px) + roi_align_rotated_fwd_kernel "
+                               "(direct gathers, larger RoIs), timed as one pair", "bound": "hbm",
                      "achieved": roi_bytes / (roi_ms * 1e-3) / 1e9 if roi else 0.0, "peak": hbm_peak, "unit": "GB/s",
-                     "frac": (roi_bytes / (roi_ms * 1e-3) / 1e9 / hbm_peak) if roi else 0.0, "traffic": None,
+                     "frac": (roi_bytes / (roi_ms * 1e-3) / 1e9 / hbm_peak) if roi else 0.0,
+                     "traffic": _traffic("roi_align_mma_kernel_rot@5000"),
                      "avg_launch_ms": roi_ms, "algorithmic_bytes": roi_bytes, "peak_source": peak_src},
         "cpu_baseline": cpu}))
 

@@ -42,8 +42,11 @@ def to_bytes(v, unit):
     return f * {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}.get(unit, 1)
 
 
-def launches_md():
-    rows = [r for r in csv.reader(open(os.path.join(G, "launches.csv"))) if len(r) > 5]
+def launches_md(src="launches.csv", dst="r01_launches.md", title="phase-2 step (current kernels)",
+                cmd="python bench.py --steps 2 --warmup 1 --no-graph --no-cpu-baseline --no-stress --no-train"):
+    if not os.path.exists(os.path.join(G, src)):
+        return
+    rows = [r for r in csv.reader(open(os.path.join(G, src))) if len(r) > 5]
     hdr = rows[0]
     i_name, i_val = hdr.index("Kernel Name"), hdr.index("Metric Value")
     agg = collections.OrderedDict()
@@ -56,14 +59,13 @@ def launches_md():
         a[0] += 1
         a[1] += v
     tot = sum(a[1] for a in agg.values())
-    lines = ["# Round 1 - ncu launch list of the phase-2 step (current kernels)", "",
-             "Command: `ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv python bench.py --steps 2 "
-             "--warmup 1 --no-graph --no-cpu-baseline --no-stress --no-train` (cold-cache, serialised launches: compare SHARES, "
-             "not absolutes; the capture spans ~8 eager steps).", "",
+    lines = [f"# Round 1 - ncu launch list of the {title}", "",
+             f"Command: `ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv {cmd}` (cold-cache, "
+             "serialised launches: compare SHARES, not absolutes; the capture spans several eager steps).", "",
              "| kernel | launches | total ns | avg ns | share |", "|---|---:|---:|---:|---:|"]
     for k, a in sorted(agg.items(), key=lambda kv: -kv[1][1]):
         lines.append(f"| `{k}` | {a[0]} | {a[1]:.0f} | {a[1] / a[0]:.0f} | {100 * a[1] / tot:.1f}% |")
-    open(os.path.join(P, "r01_launches.md"), "w").write("\n".join(lines) + "\n")
+    open(os.path.join(P, dst), "w").write("\n".join(lines) + "\n")
 
 
 def kernels_md():
@@ -73,7 +75,8 @@ def kernels_md():
              "`bench.py --no-graph` (K = 5000 / 5400 RoIs), the stress capture from `tools/prof_roi.py` "
              "(96 000 RoIs = config #4, one image).", ""]
     for title, rep, keys in [("In-step kernels (bench workload)", "prof_step.ncu-rep", None),
-                             ("RoIAlign at the stress shape (96 000 RoIs, 2.4 GB bf16 out)", "prof_roi_stress.ncu-rep", None)]:
+                             ("RoIAlign at the stress shape (96 000 RoIs, 2.4 GB bf16 out)", "prof_roi_stress.ncu-rep", None),
+                             ("RoIAlignRotated on the TMA + mma path (OBB config #3, 5000 / 5400 RoIs)", "prof_obb_roi.ncu-rep", None)]:
         path = os.path.join(G, rep)
         if not os.path.exists(path):
             continue
@@ -90,7 +93,9 @@ def kernels_md():
             dur = float(d["gpu__time_duration.sum"][0].replace(",", ""))
             if "fc_gemm" in nm and dur > 80:
                 traffic.setdefault("fc_gemm_kernel@fc1", rd + wr)
-            if "roi_align_mma" in nm:
+            if "roi_align_mma" in nm and "obb" in rep:
+                traffic.setdefault("roi_align_mma_kernel_rot@5000", rd + wr)
+            elif "roi_align_mma" in nm:
                 traffic.setdefault("roi_align_mma_kernel@96000" if "stress" in rep else "roi_align_mma_kernel@5000", rd + wr)
     open(os.path.join(P, "r01_kernels.md"), "w").write("\n".join(lines) + "\n")
     json.dump(traffic, open(os.path.join(P, "traffic.json"), "w"), indent=1)
@@ -100,4 +105,7 @@ def kernels_md():
 if __name__ == "__main__":
     os.makedirs(P, exist_ok=True)
     launches_md()
+    launches_md("obb_launches.csv", "r01_launches_obb.md", "OBB (config #3) phase-2 step", "python tools/prof_obb.py 3")
+    launches_md("train_launches.csv", "r01_launches_train.md", "HBB training step (forward + backward)",
+                "python tools/prof_train.py 3")
     print(kernels_md())
