@@ -135,6 +135,27 @@ __device__ __forceinline__ F8 load8(const __half* p) {
   return r;
 }
 
+// raw 8-channel loads of the 16-bit feature maps (kept unconverted while a batch of gathers is in flight)
+__device__ __forceinline__ uint4 raw8(const __nv_bfloat16* p) { return __ldg(reinterpret_cast<const uint4*>(p)); }
+__device__ __forceinline__ uint4 raw8(const __half* p) { return __ldg(reinterpret_cast<const uint4*>(p)); }
+__device__ __forceinline__ F8 cvt8(const uint4& u, const __nv_bfloat16*) {
+  F8 r;
+  const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+  for (int i = 0; i < 4; i++) { r.v[2 * i] = __uint_as_float(w[i] << 16); r.v[2 * i + 1] = __uint_as_float(w[i] & 0xffff0000u); }
+  return r;
+}
+__device__ __forceinline__ F8 cvt8(const uint4& u, const __half*) {
+  F8 r;
+  const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+  for (int i = 0; i < 4; i++) {
+    const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&w[i]));
+    r.v[2 * i] = f.x; r.v[2 * i + 1] = f.y;
+  }
+  return r;
+}
+
 enum { OUT_BF16_BINMAJOR = 0, OUT_F32_NCHW = 1, OUT_BF16X3_BINMAJOR = 2 };
 
 template <int MODE>
@@ -441,6 +462,97 @@ roi_align_rotated_fwd_kernel(const TIn* __restrict__ feat, const float* __restri
   }
 }
 
+// "Large RoIs only" pass behind the tensor-core kernel (roi_align_mma.cu leaves out every rotated RoI whose longer
+// side exceeds ROT_BIG_THRESHOLD feature pixels; sampling_ratio is 1 or 2 there).  Few RoIs, so the kernel is
+// organised for LATENCY:
+//   * CTA (block b, column pw): the 32 lanes of every warp test 32 RoIs at once (b, b + NB, b + 2 NB, ...: strided,
+//     so that the 400 consecutive negatives spread over all blocks) -- one L2 round trip to find the large ones;
+//   * one work item = one output column (pw) of one large RoI, a warp per output row: the <= 4 samples of the bin are
+//     set up first and their 16 gathers issued back to back.
+// Same per-sample arithmetic and accumulation order (iy outer, ix inner) as roi_align_rotated_fwd_kernel.
+// __launch_bounds__(224, 3): <= 96 registers, three CTAs per SM (at 162 registers / one CTA per SM the 8 waves of this
+// grid ran back to back: 54 us for the 480 large RoIs of the classification pass).
+template <typename TIn>
+__global__ void __launch_bounds__(P7 * 32, 3)
+roi_align_rotated_big_kernel(const TIn* __restrict__ feat, const float* __restrict__ rois, __nv_bfloat16* __restrict__ out,
+                             long long ld_out, int K, int B, int C, int H, int W, float scale, int gs, int aligned,
+                             int clockwise, const int* __restrict__ roi_level, int level, float only_larger_than, int NB) {
+  const int ph = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int blk = blockIdx.x / P7, pw = blockIdx.x - blk * P7;
+  const float off = aligned ? 0.5f : 0.f;
+  const int cand = blk + lane * NB;
+  bool big = false;
+  if (cand < K && (roi_level == nullptr || roi_level[cand] == level)) {
+    float rw = fmul(__ldg(rois + (size_t)cand * 6 + 3), scale), rh = fmul(__ldg(rois + (size_t)cand * 6 + 4), scale);
+    if (!aligned) { rw = fmaxf(rw, 1.f); rh = fmaxf(rh, 1.f); }
+    big = fmaxf(rw, rh) > only_larger_than;
+  }
+  unsigned todo = __ballot_sync(0xffffffffu, big);
+  const int cnt = gs * gs;
+  const float inv_count = 1.0f / (float)cnt;
+  while (todo != 0u) {
+    const int roi = blk + (__ffs((int)todo) - 1) * NB;
+    todo &= todo - 1u;
+    const float* r = rois + (size_t)roi * 6;
+    const int b = (int)__ldg(r);
+    const float cx = fsub(fmul(__ldg(r + 1), scale), off), cy = fsub(fmul(__ldg(r + 2), scale), off);
+    float rw = fmul(__ldg(r + 3), scale), rh = fmul(__ldg(r + 4), scale);
+    float theta = __ldg(r + 5);
+    if (clockwise) theta = -theta;
+    if (!aligned) { rw = fmaxf(rw, 1.f); rh = fmaxf(rh, 1.f); }
+    const float bh = fdiv(rh, (float)P7), bw = fdiv(rw, (float)P7);
+    const float sh = fdiv(-rh, 2.0f), sw = fdiv(-rw, 2.0f);
+    const float ct = cosf(theta), st = sinf(theta);
+    const bool b_ok = b >= 0 && b < B;
+    const TIn* fb = feat + (size_t)(b_ok ? b : 0) * H * W * C;
+    const float yb = fadd(sh, fmul((float)ph, bh)), xb = fadd(sw, fmul((float)pw, bw));
+    float wt[4][4];
+    uint32_t po[4][4];                             // element offsets inside this image's map (H * W * C < 2^32)
+    bool ok[4];
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+      const int iy = gs == 2 ? (k >> 1) : 0, ix = gs == 2 ? (k & 1) : 0;
+      const float yy = fadd(yb, fdiv(fmul((float)iy + .5f, bh), (float)gs));
+      const float xx = fadd(xb, fdiv(fmul((float)ix + .5f, bw), (float)gs));
+      const float y = fadd(fsub(fmul(yy, ct), fmul(xx, st)), cy);
+      const float x = fadd(fadd(fmul(yy, st), fmul(xx, ct)), cx);
+      ok[k] = b_ok && k < cnt && !(y < -1.0f || y > (float)H || x < -1.0f || x > (float)W);
+      int yl = 0, yh = 0, xl = 0, xh = 0; float ly = 0.f, hy = 0.f, lx = 0.f, hx = 0.f;
+      if (ok[k]) { axis_setup(y, H, yl, yh, ly, hy); axis_setup(x, W, xl, xh, lx, hx); }
+      wt[k][0] = hy * hx; wt[k][1] = hy * lx; wt[k][2] = ly * hx; wt[k][3] = ly * lx;
+      po[k][0] = (uint32_t)((yl * W + xl) * C); po[k][1] = (uint32_t)((yl * W + xh) * C);
+      po[k][2] = (uint32_t)((yh * W + xl) * C); po[k][3] = (uint32_t)((yh * W + xh) * C);
+    }
+    for (int c0 = lane * 8; c0 < C; c0 += 256) {
+      float acc[8];
+#pragma unroll
+      for (int j = 0; j < 8; j++) acc[j] = 0.f;
+#pragma unroll
+      for (int k0 = 0; k0 < 4; k0 += 2) {          // two samples = 8 gathers in flight per lane
+        uint4 raw[2][4];
+#pragma unroll
+        for (int k = 0; k < 2; k++)
+#pragma unroll
+          for (int q = 0; q < 4; q++) raw[k][q] = raw8(fb + po[k0 + k][q] + c0);   // invalid samples read pixel (0, 0): harmless
+#pragma unroll
+        for (int k = 0; k < 2; k++) {
+          if (ok[k0 + k]) {
+            const F8 f1 = cvt8(raw[k][0], fb), f2 = cvt8(raw[k][1], fb), f3 = cvt8(raw[k][2], fb), f4 = cvt8(raw[k][3], fb);
+#pragma unroll
+            for (int j = 0; j < 8; j++)
+              acc[j] += wt[k0 + k][0] * f1.v[j] + wt[k0 + k][1] * f2.v[j] + wt[k0 + k][2] * f3.v[j] + wt[k0 + k][3] * f4.v[j];
+          }
+        }
+      }
+      float v[8];
+#pragma unroll
+      for (int j = 0; j < 8; j++) v[j] = acc[j] * inv_count;
+      *reinterpret_cast<uint4*>(out + (size_t)roi * ld_out + (size_t)(ph * P7 + pw) * C + c0) =
+          make_uint4(pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]), pack_bf16(v[4], v[5]), pack_bf16(v[6], v[7]));
+    }
+  }
+}
+
 // FPN level of each RoI: clamp(floor(log2(sqrt(w*h)/finest + 1e-6)), 0, L-1)
 // (single_level_roi_extractor.py:35-54; rotated: sqrt(w*h) of columns 3,4, rotate_single_level_roi_extractor.py:84)
 __global__ void map_roi_levels_kernel(const float* __restrict__ rois, int K, int rotated, float finest, int L,
@@ -538,12 +650,16 @@ extern "C" int pt_roi_align_forward(const void* feat, int feat_bf16, const float
     if (!rot || rc != PT_OK) return rc;
     // rotated: RoIs larger than ROT_BIG_THRESHOLD feature pixels were left out above (sparse in the chunked
     // formulation); the direct gather kernel fills exactly those rows
+    const int NB = (K + 31) / 32;
     if (feat_bf16 == 2)
-      return launch_fwd<__half, OUT_BF16_BINMAJOR>(true, feat, rois, out, ld_out, K, B, C, H, W, spatial_scale, sampling_ratio,
-                                                   aligned, clockwise, roi_level, level, s, ROT_BIG_THRESHOLD);
-    return launch_fwd<__nv_bfloat16, OUT_BF16_BINMAJOR>(true, feat, rois, out, ld_out, K, B, C, H, W, spatial_scale,
-                                                        sampling_ratio, aligned, clockwise, roi_level, level, s,
-                                                        ROT_BIG_THRESHOLD);
+      roi_align_rotated_big_kernel<__half><<<NB * P7, P7 * 32, 0, s>>>(
+          reinterpret_cast<const __half*>(feat), rois, reinterpret_cast<__nv_bfloat16*>(out), ld_out, K, B, C, H, W,
+          spatial_scale, sampling_ratio, aligned, clockwise, roi_level, level, ROT_BIG_THRESHOLD, NB);
+    else
+      roi_align_rotated_big_kernel<__nv_bfloat16><<<NB * P7, P7 * 32, 0, s>>>(
+          reinterpret_cast<const __nv_bfloat16*>(feat), rois, reinterpret_cast<__nv_bfloat16*>(out), ld_out, K, B, C, H, W,
+          spatial_scale, sampling_ratio, aligned, clockwise, roi_level, level, ROT_BIG_THRESHOLD, NB);
+    return check_launch("roi_align_rotated_big_kernel");
   }
 #define PT_DISPATCH(T, M) return launch_fwd<T, M>(rot, feat, rois, out, ld_out, K, B, C, H, W, spatial_scale, sampling_ratio, aligned, clockwise, roi_level, level, s)
   if (feat_bf16 == 2) {
