@@ -39,10 +39,10 @@ def main():
     d = synth.hbb_batch(seed=0)
     res = {}
     if a.what in ("roi", "all"):
-        from oracle import hbb
-        props, _ = hbb.fine_proposals([b[:100] for b in d["pseudo_boxes"]], synth.HBB_EXT_CFG[0], d["img_metas"])
-        rois = hbb.bbox2roi(props).to(dev)
-        negs = hbb.bbox2roi(d["neg_boxes"][0]).to(dev)
+        from point_teacher_b200.proposals import boxes_to_rois, fine_proposals_from_cfg
+        props, _ = fine_proposals_from_cfg([b[:100].to(dev) for b in d["pseudo_boxes"]], synth.HBB_EXT_CFG[0], d["img_metas"])
+        rois = boxes_to_rois(props)
+        negs = boxes_to_rois([n.to(dev) for n in d["neg_boxes"][0]])
         rois_all = torch.cat([rois, negs]).contiguous()
         x = d["feat"].to(dev)
         f32, b16 = ops.nchw_to_nhwc(x), ops.nchw_to_nhwc(x, torch.bfloat16)
