@@ -400,7 +400,7 @@ __global__ void __launch_bounds__(P7 * 32, 2)
 roi_align_rotated_fwd_kernel(const TIn* __restrict__ feat, const float* __restrict__ rois, void* __restrict__ out,
                              long long ld_out, int K, int B, int C, int H, int W, float scale,
                              int sampling_ratio, int aligned, int clockwise,
-                             const int* __restrict__ roi_level, int level, float only_larger_than) {
+                             const int* __restrict__ roi_level, int level) {
   extern __shared__ float stage[];
   const int ph = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const float off = aligned ? 0.5f : 0.f;
@@ -413,8 +413,6 @@ roi_align_rotated_fwd_kernel(const TIn* __restrict__ feat, const float* __restri
     float theta = __ldg(r + 5);
     if (clockwise) theta = -theta;
     if (!aligned) { rw = fmaxf(rw, 1.f); rh = fmaxf(rh, 1.f); }
-    // second half of the tensor-core path (roi_align_mma.cu): only the RoIs that kernel leaves out
-    if (only_larger_than >= 0.f && !(fmaxf(rw, rh) > only_larger_than)) continue;
     const float bh = fdiv(rh, (float)P7), bw = fdiv(rw, (float)P7);
     const int gh = sampling_ratio > 0 ? sampling_ratio : (int)ceilf(bh);
     const int gw = sampling_ratio > 0 ? sampling_ratio : (int)ceilf(bw);
@@ -587,7 +585,7 @@ __global__ void roi_rescale_kernel(const float* __restrict__ rois, int K, int ro
 template <typename TIn, int MODE>
 static int launch_fwd(bool rotated, const void* feat, const float* rois, void* out, long long ld_out, int K, int B,
                       int C, int H, int W, float scale, int sampling_ratio, int aligned, int clockwise,
-                      const int* roi_level, int level, cudaStream_t stream, float only_larger_than = -1.f) {
+                      const int* roi_level, int level, cudaStream_t stream) {
   const size_t stage_bytes = MODE == OUT_F32_NCHW ? (size_t)P7 * P7 * (C + 1) * sizeof(float) : 0;
   const size_t tab_bytes = rotated ? 0 : 2 * ((size_t)(W + 4) * 8 + (size_t)(H + 1) * 8) * sizeof(float);
   size_t smem = stage_bytes + tab_bytes;
@@ -600,7 +598,7 @@ static int launch_fwd(bool rotated, const void* feat, const float* rois, void* o
     auto kern = roi_align_rotated_fwd_kernel<TIn, MODE>;
     if (smem > 48 * 1024) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     kern<<<grid, P7 * 32, smem, stream>>>(reinterpret_cast<const TIn*>(feat), rois, out, ld_out, K, B, C, H, W,
-                                           scale, sampling_ratio, aligned, clockwise, roi_level, level, only_larger_than);
+                                           scale, sampling_ratio, aligned, clockwise, roi_level, level);
   } else {
     auto kern = roi_align_fwd_kernel<TIn, MODE>;
     if (smem > 48 * 1024) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
