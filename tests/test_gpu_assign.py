@@ -145,6 +145,30 @@ def test_max_iou_assign_vs_oracle_dense(cuda, calc, mode, G, A):
     assert torch.equal(m.cpu(), ov)
 
 
+@pytest.mark.parametrize("assign_all", [True, False])
+def test_max_iou_ties_across_gt_tiles(cuda, assign_all):
+    """The device path tiles the GTs by 256 and merges tiles with integer atomics: duplicated GTs in DIFFERENT tiles
+    must still resolve like the reference (per-anchor argmax = FIRST index among equal maxima; low-quality matching =
+    LAST matching GT wins), and anchors equal to a GT give exact-equality maxima."""
+    g = torch.Generator().manual_seed(91)
+    G, A = 700, 3000
+    gts = synth.make_boxes(g, G, (800, 800))
+    gts[300:340] = gts[10:50]                    # duplicates one tile later
+    gts[600:620] = gts[10:30]                    # and two tiles later
+    anchors = torch.cat([synth.jitter_boxes(g, gts.repeat(4, 1), 2.0, 0.3), synth.make_boxes(g, A - 4 * G, (800, 800))])
+    anchors[:60] = gts[:60]                      # IoU == 1 with three different GT indices
+    labels = torch.randint(0, 8, (G,), generator=g)
+    for calc, mode in (("BboxOverlaps2D", "iou"), ("BboxOverlaps2D", "giou"), ("BboxDistanceMetric", "wd")):
+        ov = hbb.bbox_overlaps(gts, anchors, mode) if calc == "BboxOverlaps2D" else assign.bbox_metric(gts, anchors, mode)
+        kw = dict(pos_iou_thr=0.5, neg_iou_thr=0.4, min_pos_iou=0.0, gt_max_assign_all=assign_all)
+        gi, mx, lb = assign.max_iou_assign(ov, labels, **kw)
+        r = _assigners().MaxIoUAssigner(iou_calculator=dict(type=calc), **kw).assign(
+            anchors.to(cuda), gts.to(cuda), gt_labels=labels.to(cuda), mode=mode)
+        assert torch.equal(r.gt_inds.cpu(), gi), (calc, mode)
+        assert torch.equal(r.max_overlaps.cpu(), mx)
+        assert torch.equal(r.labels.cpu(), lb)
+
+
 def test_coarse_pseudo_boxes_vs_reference_golden_and_oracle(cuda, golden_dir):
     """Section 8f rank 1 (_gnerate_pseudo_single): FUSE assignment + score-weighted box aggregation."""
     from point_teacher_b200 import coarse
