@@ -188,10 +188,18 @@ def run_ours(args):
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
-        # NCCL_DEBUG=VERSION prints "NCCL version ..." on STDOUT, in front of the one JSON line this script owes
-        if os.environ.get("NCCL_DEBUG", "").upper() == "VERSION":
-            os.environ["NCCL_DEBUG"] = "WARN"
-        dist.init_process_group("nccl", device_id=dev)
+        # NCCL prints its "NCCL version ..." banner on STDOUT (C-level) while the communicator is created, in front of
+        # the one JSON line this script owes: point fd 1 at stderr for the duration of the (eager) initialisation
+        sys.stdout.flush()
+        saved_fd = os.dup(1)
+        os.dup2(2, 1)
+        try:
+            dist.init_process_group("nccl", device_id=dev)
+            dist.barrier()
+            torch.cuda.synchronize()
+        finally:
+            os.dup2(saved_fd, 1)
+            os.close(saved_fd)
     _lib.load()                                # raises when the CUDA extension is missing: no fallback
 
     d = make_inputs(rank)                      # per-image sharding: every rank owns its own 2 images
