@@ -104,3 +104,22 @@ def test_gen_num_neg_zero_returns_none_pair():
     import torch
     from point_teacher_b200.proposals import gen_negative_proposals
     assert gen_negative_proposals([torch.zeros(1, 2)], dict(gen_num_neg=0), None, None) == (None, None)
+
+
+def test_bench_reference_arm_prints_one_contract_line():
+    """``bench.py --impl reference`` (the CPU arm the driver runs beside ours): exactly one JSON line on stdout with
+    the contract's keys; needs no GPU."""
+    import json
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--steps", "1",
+                          "--warmup", "0"], capture_output=True, text=True, timeout=600, cwd=root)
+    assert out.returncode == 0, out.stderr[-2000:]
+    lines = [l for l in out.stdout.splitlines() if l.strip()]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["unit"] == "imgs/s" and d["higher_is_better"] is True and d["value"] > 0
+    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1 and d["cpu_baseline"]["sample"]
+    assert d["e2e"] == {"value": d["value"], "unit": "imgs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    assert d["config"]["workload"].startswith("HBB cfg#1") and d["vs_baseline"] is None
