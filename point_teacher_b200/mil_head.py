@@ -242,6 +242,25 @@ class MILHeadMixin:
         self.last_results = R
         return losses, tuple(torch.split(merged, per_img))
 
+    def inference_mil_head(self, x, img_metas, proposals_list, proposals_valid_list, proposals_reference_list,
+                           proposals_real_list, pseudo_bboxes, pseudo_labels, fine_proposal_cfg, stage):
+        """:1346-1390: refinement without losses (no negatives) -> (list of merged (G_i, 4|5) boxes, IoU logs).  No
+        detector of the reference calls it; kept so that the head's MIL surface is complete.  Its
+        ``fine_proposal_cfg is None`` branch calls ``self.fc_cls(...)`` on a ModuleList in the reference (:1373) and
+        cannot run there either."""
+        if fine_proposal_cfg is None:
+            raise NotImplementedError("inference_mil_head(fine_proposal_cfg=None): the reference branch calls a "
+                                      "ModuleList (fcos_head_p2b_ts.py:1373) and never runs")
+        num_gt = sum(p.shape[0] for p in pseudo_bboxes)
+        per_img = [p.shape[0] for p in pseudo_bboxes]
+        R = self.forward_mil_head(num_gt, per_img, x, proposals_list, proposals_valid_list, proposals_reference_list,
+                                  proposals_real_list, img_metas, fine_proposal_cfg, stage)
+        losses = {f"stage{stage}_coarse_bags_iou": R["coarse_bags_iou"],
+                  f"stage{stage}_refine_bags_iou": R["refine_bags_iou"]}
+        merged = self.mil_bag_selection(R, img_metas, pseudo_bboxes, pseudo_labels)
+        self.last_results = R
+        return list(merged), losses
+
     def mil_stage_packed(self, x, img_metas, img_wh, base_rois, U1, ref, real, neg_boxes, neg_img_idx, bag_offsets,
                          labels, pseudo, cfg, stage, loss_scales=(1.0, 1.0), keep=None):
         """One MIL stage on packed tensors (the fast path behind ``phase2_refine``): no per-image lists, no

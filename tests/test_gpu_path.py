@@ -237,6 +237,32 @@ def test_list_api_equals_packed_fast_path(cuda):
         assert torch.equal(b[7:].cpu(), d["pseudo_boxes"][i][7:])
 
 
+def test_inference_mil_head_matches_training_entry(cuda):
+    """``inference_mil_head`` (fcos_head_p2b_ts.py:1346-1390) = the stage without negatives and without loss terms:
+    same merged boxes and bag-IoU logs as ``MIL_head_burn_in_step2`` fed no negatives."""
+    from point_teacher_b200.proposals import MIL_gen_proposals_from_cfg
+    d = synth.hbb_batch(seed=5, **SMALL)
+    P = hbb.MilHeadParams(num_stages=1, seed=5)
+    head = _make_head(cuda, P, 1, 1, "fp32")
+    to = lambda l: [t.to(cuda) for t in l]  # noqa: E731
+    x = (d["feat"].to(cuda),)
+    pb, pp, pl, gb = to(d["pseudo_boxes"]), to(d["pseudo_points"]), to(d["pseudo_labels"]), to(d["gt_boxes"])
+    with torch.no_grad():
+        props, valids, refs, reals = MIL_gen_proposals_from_cfg(pp, pb, synth.HBB_FINE_CFG[0], gb, d["img_metas"])
+        merged, logs = head.inference_mil_head(x, d["img_metas"], props, valids, refs, reals, pb, pl,
+                                               synth.HBB_EXT_CFG[0], 0)
+        losses, merged2 = head.MIL_head_burn_in_step2(x, d["img_metas"], props, valids, refs, reals, None, None, pb, pl,
+                                                      synth.HBB_EXT_CFG[0], 0)
+    assert isinstance(merged, list) and len(merged) == len(pb)
+    for a, b in zip(merged, merged2):
+        assert torch.equal(a, b)
+    assert set(logs) == {"stage0_coarse_bags_iou", "stage0_refine_bags_iou"}
+    for k in logs:
+        assert abs(float(logs[k]) - float(losses[k])) < 1e-6
+    with pytest.raises(NotImplementedError):
+        head.inference_mil_head(x, d["img_metas"], props, valids, refs, reals, pb, pl, None, 0)
+
+
 def test_captured_graph_replay_matches_eager(cuda):
     from point_teacher_b200.refine import CapturedPhase2, phase2_refine
     d = synth.hbb_batch(seed=4, **SMALL)
