@@ -141,6 +141,9 @@ class MILHeadMixin:
                          proposals_reference_list, proposals_real_list, img_metas, fine_proposal_cfg, stage,
                          neg_proposal_list=None, neg_weight_list=None):
         """:1259-1277 (= mil_bag_extensive :1182-1236 + mil_bag_classifier :1240-1256 + negatives)."""
+        if self.bbox_roi_extractor.rotated:
+            raise NotImplementedError("the list-based MIL methods are the HBB surface (4-d boxes); the rotated head runs "
+                                      "through refine.phase2_refine / mil_stage_packed (5-d boxes, rotated bags)")
         dev = x[0].device
         R = {}
         U1 = int(proposals_list[0].shape[0] / num_gt_pre_image[0])
