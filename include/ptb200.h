@@ -71,6 +71,10 @@ int pt_bbox_overlaps(const float* a, int lda, const float* b, int ldb, long long
  *   out_mode 1: fp32 [K,C,7,7] (the extractor's public layout)
  *   out_mode 2: bf16 [K, ld_out] = [hi | lo | hi] segments of 49*C (fp32-emulation operand) */
 int pt_nchw_to_nhwc(const float* in, void* out, int B, int C, int H, int W, int out_bf16, void* stream);
+/* same, and (fp16 output only) adds to *sat_count (device int32, may be NULL) the number of values the saturating
+ * conversion changed (|v| > 65504): the fp32 reference has no such limit, so the host layer refuses / falls back. */
+int pt_nchw_to_nhwc_ex(const float* in, void* out, int B, int C, int H, int W, int out_bf16, int* sat_count,
+                       void* stream);
 int pt_roi_align_forward(const void* feat, int feat_bf16, const float* rois, void* out, long long ld_out,
                          int out_mode, int K, int B, int C, int H, int W, int pooled, float spatial_scale,
                          int sampling_ratio, int aligned, int rotated, int clockwise, const int* roi_level,
@@ -243,6 +247,14 @@ int pt_colsum_bf16(const void* dZ, long long ld, int M, int N, float* db, void* 
 int pt_nhwc_to_nchw_f32(const float* in, float* out, int B, int C, int H, int W, int accumulate, void* stream);
 int pt_roi_align_backward(const void* dA_bf16, long long ld, const float* rois, int K, int B, int C, int H, int W,
                           float spatial_scale, int sampling_ratio, int aligned, float* dfeat, void* stream);
+/* multi-level FPN twins (single_level_roi_extractor.py:98-104): RoIs whose roi_level[k] != level are skipped, so one
+ * call per level scatters each RoI's gradient into its own level's map.  roi_level may be NULL (= all RoIs). */
+int pt_roi_align_backward_ex(const void* dA_bf16, long long ld, const float* rois, int K, int B, int C, int H, int W,
+                             float spatial_scale, int sampling_ratio, int aligned, float* dfeat, const int* roi_level,
+                             int level, void* stream);
+int pt_roi_align_rotated_backward_ex(const void* dA_bf16, long long ld, const float* rois, int K, int B, int C, int H,
+                                     int W, float spatial_scale, int sampling_ratio, int aligned, int clockwise,
+                                     float* dfeat, const int* roi_level, int level, void* stream);
 
 /* ---- strong_augmentation ---------------------------------------------------------
  * Replaces HBB_TOD/mmdet/models/detectors/syn_images_generator_v2.py:24-132 and

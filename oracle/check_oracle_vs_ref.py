@@ -308,7 +308,96 @@ def check_losses():
     return ok
 
 
+def check_detector(rotated=False, step=2, seed=0, stages=1):
+    """The reference's OWN detector-level MIL callers (``forward_mil_head_burn_in_step1/2``, run unbound on a stand-in
+    ``self`` whose ``student.bbox_head`` is the reference's own head) against oracle/detector.py's literal drivers over
+    the oracle backend: refined boxes / points tol 0, losses 1e-6, and the gradients of the summed losses
+    (``_parse_losses``) w.r.t. every MIL parameter (and the feature maps for HBB) 1e-5."""
+    from oracle import detector as D
+    dn = ref_shim.install_detectors()
+    if rotated:
+        d = synth.obb_batch(seed=seed, batch=2, img_hw=(256, 256), gt_range=(6, 10), n_neg=20)
+        head = ref_shim.build_ref_obb_mil_head(dn.obb, num_stages=stages, seed=seed)
+        P = hbb.MilHeadParams(num_classes=9, num_stages=stages, seed=seed).requires_grad_(True)
+        fine, ext, topk = synth.OBB_FINE_CFG * stages, synth.OBB_EXT_CFG * stages, 3
+        cls = dn.RotatedFCOS_TS
+    else:
+        d = synth.hbb_batch(seed=seed, batch=2, img_hw=(256, 256), gt_range=(6, 10), n_neg=20, num_stages=stages)
+        head = ref_shim.build_ref_mil_head(dn.hbb, num_stages=stages, top_k=1, seed=seed)
+        P = hbb.MilHeadParams(num_stages=stages, seed=seed).requires_grad_(True)
+        fine, ext, topk = synth.HBB_FINE_CFG, synth.HBB_EXT_CFG, 1
+        cls = dn.TS_P2B_FCOS
+    fine = [dict(c, gen_num_neg=20) for c in fine]
+    syn_boxes, feat_syn = D.synthetic_boxes_like(d, seed, rotated)
+    n = len(d["pseudo_boxes"])
+    cap = 7                                   # fewer than the GTs of every image: the tail must come back untouched
+
+    def run(which):
+        fo = d["feat"].clone().requires_grad_(not rotated)
+        fs = feat_syn.clone().requires_grad_(not rotated)
+        if which == "ref":
+            det = D.make_detector(head, fine, ext, stages, cap1=cap, cap2=cap)
+            head.zero_grad()
+            torch.manual_seed(100 + seed)
+            if step == 2:
+                out = cls.forward_mil_head_burn_in_step2(det, n, d["pseudo_boxes"], d["pseudo_points"],
+                                                         d["pseudo_labels"], d["gt_boxes"], d["img_metas"], (fo,))
+            elif rotated:
+                out = cls.forward_mil_head_burn_in_step1(det, n, syn_boxes, d["pseudo_boxes"], d["pseudo_points"],
+                                                         d["pseudo_labels"], d["gt_boxes"], d["img_metas"], (fs,), (fo,))
+            else:
+                out = cls.forward_mil_head_burn_in_step1(det, n, syn_boxes, d["pseudo_boxes"], d["pseudo_points"],
+                                                         d["pseudo_labels"], d["gt_boxes"], d["img_metas"], (fs,), (fo,), None)
+            params = dict(head.named_parameters())
+        else:
+            for t in P.state_dict().values():
+                t.grad = None
+            det = D.make_detector(D.OracleHead(P, [d["stride"]], topk, rotated=rotated), fine, ext, stages, cap1=cap, cap2=cap)
+            fns = D.oracle_backend(rotated)
+            torch.manual_seed(100 + seed)
+            if step == 2:
+                out = D.forward_mil_head_burn_in_step2(det, fns, n, d["pseudo_boxes"], d["pseudo_points"],
+                                                       d["pseudo_labels"], d["gt_boxes"], d["img_metas"], (fo,))
+            else:
+                out = D.forward_mil_head_burn_in_step1(det, fns, n, syn_boxes, d["pseudo_boxes"], d["pseudo_points"],
+                                                       d["pseudo_labels"], d["gt_boxes"], d["img_metas"], (fs,), (fo,))
+            params = P.state_dict()
+        D.parse_losses(out[2]).backward()
+        grads = {k: (None if params[k].grad is None else params[k].grad.clone()) for k in P.state_dict()}
+        return out, grads, fo.grad, fs.grad
+
+    (rb, rp, rl), rg, rfo, rfs = run("ref")
+    (ob, op, ol), og, ofo, ofs = run("oracle")
+    tag = f"{'OBB' if rotated else 'HBB'} step{step}"
+    ok = True
+    for i in range(n):
+        ok &= _eq(ob[i], rb[i], f"{tag} boxes img{i}", 0.0)
+        ok &= _eq(op[i], rp[i], f"{tag} points img{i}", 0.0)
+        ok &= bool(torch.equal(rb[i][cap:], d["pseudo_boxes"][i][cap:]))
+    assert set(rl) == set(ol), (sorted(rl), sorted(ol))
+    for k in rl:
+        ok &= _eq(ol[k].detach(), rl[k].detach(), f"{tag} {k}", 1e-6)
+    for k in rg:
+        if rg[k] is None or og[k] is None:
+            ok &= rg[k] is None and og[k] is None
+            continue
+        ok &= _eq(og[k], rg[k], f"{tag} grad {k}", 1e-5)
+    if not rotated:
+        ok &= _eq(ofo, rfo, f"{tag} grad feat_ori", 1e-5)
+        if step == 1:
+            ok &= _eq(ofs, rfs, f"{tag} grad feat_syn", 1e-5)
+    return ok
+
+
 if __name__ == "__main__":
+    if "--detector" in sys.argv:
+        good = True
+        for rot in (False, True):
+            for st in (2, 1):
+                good &= check_detector(rot, st, seed=3)
+        good &= check_detector(False, 1, seed=4, stages=2)
+        print("ALL OK" if good else "MISMATCH")
+        sys.exit(0 if good else 1)
     if "--losses" in sys.argv:
         good = check_losses()
         print("ALL OK" if good else "MISMATCH")

@@ -204,8 +204,74 @@ def overlaps_case():
     print("wrote bbox_overlaps")
 
 
+DET_CAP, DET_NEG = 7, 20      # detector-level cases: cap below every image's GT count; 20 negatives per image
+
+
+def detector_inputs(rotated, seed, stages=1):
+    """Seeded inputs of the detector-level cases (shared by this generator and tests/test_gpu_dropin.py)."""
+    from oracle import detector as D
+    if rotated:
+        d = synth.obb_batch(seed=seed, **OBB_SMALL)
+        fine, ext = synth.OBB_FINE_CFG * stages, synth.OBB_EXT_CFG * stages
+    else:
+        d = synth.hbb_batch(seed=seed, num_stages=stages, **SMALL)
+        fine, ext = synth.HBB_FINE_CFG, synth.HBB_EXT_CFG
+    fine = [dict(c, gen_num_neg=DET_NEG) for c in fine]
+    syn_boxes, feat_syn = D.synthetic_boxes_like(d, seed, rotated)
+    return d, fine, ext, syn_boxes, feat_syn
+
+
+def grad_digest(t, n=256):
+    """Norm + a fixed pseudo-random sample of entries (the FC1 weight gradient alone is 51 MB)."""
+    flat = t.detach().reshape(-1).double()
+    g = torch.Generator().manual_seed(flat.numel() % 9973)
+    idx = torch.randperm(flat.numel(), generator=g)[:n].clone()
+    return dict(norm=float(flat.norm()), idx=idx, val=flat[idx].float().clone())
+
+
+def detector_case(rotated, step, seed, stages=1):
+    """The reference's OWN detector-level callers (fcos_p2b_teacher_student.py:365-466 /
+    rotated_fcos_teacher_student.py:435-535, run unbound on a stand-in ``self``) with the reference's own head, the
+    negatives drawn by the reference's own ``gen_negative_proposals`` from the seeded global CPU generator, then
+    ``_parse_losses(...).backward()``: refined boxes / points, every loss entry and gradient digests."""
+    from oracle import detector as D
+    dn = ref_shim.install_detectors()
+    d, fine, ext, syn_boxes, feat_syn = detector_inputs(rotated, seed, stages)
+    if rotated:
+        head, cls = ref_shim.build_ref_obb_mil_head(dn.obb, num_stages=stages, seed=seed), dn.RotatedFCOS_TS
+    else:
+        head, cls = ref_shim.build_ref_mil_head(dn.hbb, num_stages=stages, top_k=1, seed=seed), dn.TS_P2B_FCOS
+    det = D.make_detector(head, fine, ext, stages, cap1=DET_CAP, cap2=DET_CAP)
+    n = len(d["pseudo_boxes"])
+    fo = d["feat"].clone().requires_grad_(not rotated)
+    fs = feat_syn.clone().requires_grad_(not rotated)
+    torch.manual_seed(100 + seed)
+    args = (d["pseudo_boxes"], d["pseudo_points"], d["pseudo_labels"], d["gt_boxes"], d["img_metas"])
+    if step == 2:
+        b, p, l = cls.forward_mil_head_burn_in_step2(det, n, *args, (fo,))
+    elif rotated:
+        b, p, l = cls.forward_mil_head_burn_in_step1(det, n, syn_boxes, *args, (fs,), (fo,))
+    else:
+        b, p, l = cls.forward_mil_head_burn_in_step1(det, n, syn_boxes, *args, (fs,), (fo,), None)
+    D.parse_losses(l).backward()
+    grads = {k: grad_digest(v.grad) for k, v in head.named_parameters() if v.grad is not None}
+    out = dict(rotated=rotated, step=step, seed=seed, stages=stages, cap=DET_CAP, boxes=[t.detach().clone() for t in b],
+               points=[t.detach().clone() for t in p], losses={k: v.detach().clone() for k, v in l.items()}, grads=grads,
+               feat_grad=None if rotated else grad_digest(fo.grad),
+               feat_syn_grad=None if (rotated or step == 2) else grad_digest(fs.grad))
+    tag = f"detector_{'obb' if rotated else 'hbb'}_step{step}"
+    torch.save(out, os.path.join(OUT, tag + ".pt"))
+    print("wrote", tag, {k: round(float(v), 5) for k, v in out["losses"].items()})
+
+
 if __name__ == "__main__":
     os.makedirs(OUT, exist_ok=True)
+    import sys
+    if "--detector" in sys.argv:
+        for rot in (False, True):
+            for st in (1, 2):
+                detector_case(rot, st, seed=3)
+        sys.exit(0)
     hbb_case(0, 1, 1, "s1_top1")
     hbb_case(1, 2, 3, "s2_top3")
     overlaps_case()

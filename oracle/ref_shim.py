@@ -316,6 +316,44 @@ def build_ref_mil_head(ns, num_classes=8, num_stages=1, top_k=1, beta=0.25, hype
     return head
 
 
+_DET = None
+
+
+def install_detectors():
+    """The reference's own teacher-student detector modules (only the class objects: their MIL caller methods
+    ``forward_mil_head_burn_in_step1/2`` are run unbound on a stand-in ``self``, see oracle/detector.py)."""
+    global _DET
+    if _DET is not None:
+        return _DET
+    ns = install()
+    _mk("mmdet.models.detectors.single_stage", SingleStageDetector=nn.Module)
+    _mk("mmdet.models.detectors.base", BaseDetector=nn.Module)
+    mb = sys.modules["mmdet.models.builder"]
+    for n in ("build_backbone", "build_neck", "build_detector"):
+        setattr(mb, n, lambda cfg, **k: None)
+    sys.modules["mmdet.core"].bbox2result = None
+    hbb_det = _imp("mmdet.models.detectors.fcos_p2b_teacher_student")
+    o = install_obb()
+    _mk("mmrotate.models.detectors.single_stage", RotatedSingleStageDetector=nn.Module)
+    _mk("mmrotate.models.detectors.base", BaseDetector=nn.Module)
+    rb = sys.modules["mmrotate.models.builder"]
+    rb.ROTATED_DETECTORS = sys.modules["mmdet.models.builder"].MODELS
+    rb.build_detector = lambda cfg, **k: None
+    sys.modules["mmcv"].ConfigDict = dict
+    core = sys.modules["mmrotate.core"]
+    for n in ("rbbox2result", "build_assigner", "build_sampler", "obb2xyxy"):
+        if not hasattr(core, n):
+            setattr(core, n, None)
+    obb_det = None
+    try:
+        obb_det = _imp("mmrotate.models.detectors.rotated_fcos_teacher_student")
+    except Exception as e:  # pragma: no cover - reported by the caller
+        print("OBB detector module did not import under the shim:", repr(e))
+    _DET = types.SimpleNamespace(hbb=ns, obb=o, TS_P2B_FCOS=hbb_det.TS_P2B_FCOS,
+                                 RotatedFCOS_TS=getattr(obb_det, "RotatedFCOS_TS", None))
+    return _DET
+
+
 _OBB = None
 
 

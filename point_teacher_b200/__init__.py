@@ -7,3 +7,13 @@ __version__ = "0.1.0"
 
 def library_path():
     return _lib.SO_PATH
+
+
+def install():
+    """Register every B200 class into the reference's registries under the reference's own type names
+    (``SingleRoIExtractor``, ``RotatedSingleRoIExtractor``, ``TopkAssigner``, ``FUSETopkAssigner``, ``MaxIoUAssigner``,
+    ``BboxOverlaps2D``, ``BboxDistanceMetric``, ``TS_P2BFCOSHead``, ``TS_P2RBRotatedFCOSHead``) with ``force=True``.
+    Call it after ``import mmdet.models`` (and ``mmrotate.models``) and before the detector is built; see
+    INTEGRATION.md.  Returns {reference head type name: class now registered}."""
+    from . import assigners, losses, mil_head, registry, roi_extractors  # noqa: F401  (import = register)
+    return registry.install_reference_heads()

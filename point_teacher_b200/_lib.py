@@ -23,6 +23,7 @@ SIGNATURES = {
     "pt_bbox_overlaps": (c_int, [c_void_p, c_int, c_void_p, c_int, c_ll, c_ll, c_int, c_int, c_float, c_void_p,
                                  c_void_p]),
     "pt_nchw_to_nhwc": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p]),
+    "pt_nchw_to_nhwc_ex": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),
     "pt_roi_align_forward": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_ll, c_int, c_int, c_int, c_int, c_int,
                                      c_int, c_int, c_float, c_int, c_int, c_int, c_int, c_void_p, c_int, c_void_p]),
     "pt_map_roi_levels": (c_int, [c_void_p, c_int, c_int, c_float, c_int, c_void_p, c_void_p]),
@@ -86,6 +87,10 @@ SIGNATURES = {
     "pt_nhwc_to_nchw_f32": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p]),
     "pt_roi_align_backward": (c_int, [c_void_p, c_ll, c_void_p, c_int, c_int, c_int, c_int, c_int, c_float, c_int, c_int,
                                       c_void_p, c_void_p]),
+    "pt_roi_align_backward_ex": (c_int, [c_void_p, c_ll, c_void_p, c_int, c_int, c_int, c_int, c_int, c_float, c_int,
+                                         c_int, c_void_p, c_void_p, c_int, c_void_p]),
+    "pt_roi_align_rotated_backward_ex": (c_int, [c_void_p, c_ll, c_void_p, c_int, c_int, c_int, c_int, c_int, c_float,
+                                                 c_int, c_int, c_int, c_void_p, c_void_p, c_int, c_void_p]),
     "pt_augment_param_stride": (c_int, []),
     "pt_augment_image": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
     "pt_augment_coords": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p,

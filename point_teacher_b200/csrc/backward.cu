@@ -355,7 +355,8 @@ constexpr int RB_WARPS = 4;
 
 __global__ void __launch_bounds__(RB_WARPS * 32)
 roi_align_bwd_kernel(const __nv_bfloat16* __restrict__ dA, long long ld, const float* __restrict__ rois, int K, int B,
-                     int C, int H, int W, float scale, int sampling_ratio, int aligned, float* __restrict__ dfeat) {
+                     int C, int H, int W, float scale, int sampling_ratio, int aligned, float* __restrict__ dfeat,
+                     const int* __restrict__ roi_level, int level) {
   extern __shared__ float tabs[];     // per warp: wx[(W+4)*8] , wy[(H+4)*8]
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   float* wx = tabs + (size_t)warp * ((W + 4) + (H + 4)) * 8;
@@ -365,6 +366,7 @@ roi_align_bwd_kernel(const __nv_bfloat16* __restrict__ dA, long long ld, const f
     const float* r = rois + (size_t)roi * 5;
     const int b = (int)r[0];
     if (b < 0 || b >= B) continue;
+    if (roi_level != nullptr && roi_level[roi] != level) continue;     // multi-level FPN: another level's RoI
     const float x1 = fsub(fmul(r[1], scale), off), y1 = fsub(fmul(r[2], scale), off);
     const float x2 = fsub(fmul(r[3], scale), off), y2 = fsub(fmul(r[4], scale), off);
     float rw = fsub(x2, x1), rh = fsub(y2, y1);
@@ -480,7 +482,7 @@ roi_align_bwd_kernel(const __nv_bfloat16* __restrict__ dA, long long ld, const f
 __global__ void __launch_bounds__(RB_WARPS * 32)
 roi_align_rotated_bwd_kernel(const __nv_bfloat16* __restrict__ dA, long long ld, const float* __restrict__ rois, int K,
                              int B, int C, int H, int W, float scale, int sampling_ratio, int aligned, int clockwise,
-                             float* __restrict__ dfeat) {
+                             float* __restrict__ dfeat, const int* __restrict__ roi_level, int level) {
   __shared__ __align__(16) float wmat_all[RB_WARPS][49 * 16];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   float* wmat = wmat_all[warp];
@@ -489,6 +491,7 @@ roi_align_rotated_bwd_kernel(const __nv_bfloat16* __restrict__ dA, long long ld,
     const float* r = rois + (size_t)roi * 6;
     const int b = (int)__ldg(r);
     if (b < 0 || b >= B) continue;
+    if (roi_level != nullptr && roi_level[roi] != level) continue;
     const float cx = fsub(fmul(__ldg(r + 1), scale), off), cy = fsub(fmul(__ldg(r + 2), scale), off);
     float rw = fmul(__ldg(r + 3), scale), rh = fmul(__ldg(r + 4), scale);
     float theta = __ldg(r + 5);
@@ -720,9 +723,9 @@ extern "C" int pt_nhwc_to_nchw_f32(const float* in, float* out, int B, int C, in
 }
 
 // dfeat NHWC fp32 [B,H,W,C] must be zeroed by the caller; dA bf16 [K, ld] bin-major.
-extern "C" int pt_roi_align_backward(const void* dA_bf16, long long ld, const float* rois, int K, int B, int C, int H,
-                                     int W, float spatial_scale, int sampling_ratio, int aligned, float* dfeat,
-                                     void* stream) {
+extern "C" int pt_roi_align_backward_ex(const void* dA_bf16, long long ld, const float* rois, int K, int B, int C,
+                                        int H, int W, float spatial_scale, int sampling_ratio, int aligned,
+                                        float* dfeat, const int* roi_level, int level, void* stream) {
   if (K <= 0) return PT_OK;
   if (C % 8 != 0) { set_error("pt_roi_align_backward: C must be a multiple of 8"); return PT_ERR_ARG; }
   const size_t smem = (size_t)RB_WARPS * ((W + 4) + (H + 4)) * 8 * sizeof(float);
@@ -732,19 +735,32 @@ extern "C" int pt_roi_align_backward(const void* dA_bf16, long long ld, const fl
   const int blocks = (K + RB_WARPS - 1) / RB_WARPS;
   roi_align_bwd_kernel<<<blocks < 148 * 8 ? blocks : 148 * 8, RB_WARPS * 32, smem, (cudaStream_t)stream>>>(
       reinterpret_cast<const __nv_bfloat16*>(dA_bf16), ld, rois, K, B, C, H, W, spatial_scale, sampling_ratio, aligned,
-      dfeat);
+      dfeat, roi_level, level);
   return check_launch("roi_align_bwd_kernel");
+}
+extern "C" int pt_roi_align_backward(const void* dA_bf16, long long ld, const float* rois, int K, int B, int C, int H,
+                                     int W, float spatial_scale, int sampling_ratio, int aligned, float* dfeat,
+                                     void* stream) {
+  return pt_roi_align_backward_ex(dA_bf16, ld, rois, K, B, C, H, W, spatial_scale, sampling_ratio, aligned, dfeat,
+                                  nullptr, 0, stream);
 }
 
 // RoIAlignRotated backward (mmcv roi_align_rotated, fixed or adaptive sampling grid): rois [K,6] (b,cx,cy,w,h,theta).
-extern "C" int pt_roi_align_rotated_backward(const void* dA_bf16, long long ld, const float* rois, int K, int B, int C,
-                                             int H, int W, float spatial_scale, int sampling_ratio, int aligned,
-                                             int clockwise, float* dfeat, void* stream) {
+extern "C" int pt_roi_align_rotated_backward_ex(const void* dA_bf16, long long ld, const float* rois, int K, int B,
+                                                int C, int H, int W, float spatial_scale, int sampling_ratio,
+                                                int aligned, int clockwise, float* dfeat, const int* roi_level,
+                                                int level, void* stream) {
   if (K <= 0) return PT_OK;
   if (C % 8 != 0) { set_error("pt_roi_align_rotated_backward: C must be a multiple of 8"); return PT_ERR_ARG; }
   const int blocks = (K + RB_WARPS - 1) / RB_WARPS;
   roi_align_rotated_bwd_kernel<<<blocks < 148 * 8 ? blocks : 148 * 8, RB_WARPS * 32, 0, (cudaStream_t)stream>>>(
       reinterpret_cast<const __nv_bfloat16*>(dA_bf16), ld, rois, K, B, C, H, W, spatial_scale, sampling_ratio, aligned,
-      clockwise, dfeat);
+      clockwise, dfeat, roi_level, level);
   return check_launch("roi_align_rotated_bwd_kernel");
+}
+extern "C" int pt_roi_align_rotated_backward(const void* dA_bf16, long long ld, const float* rois, int K, int B, int C,
+                                             int H, int W, float spatial_scale, int sampling_ratio, int aligned,
+                                             int clockwise, float* dfeat, void* stream) {
+  return pt_roi_align_rotated_backward_ex(dA_bf16, ld, rois, K, B, C, H, W, spatial_scale, sampling_ratio, aligned,
+                                          clockwise, dfeat, nullptr, 0, stream);
 }

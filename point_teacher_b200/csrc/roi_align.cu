@@ -45,8 +45,10 @@ template <> __device__ __forceinline__ __half cvt_out<__half>(float v) {
 }
 template <typename TOut>
 __global__ void __launch_bounds__(256)
-nchw_to_nhwc_kernel(const float* __restrict__ in, TOut* __restrict__ out, int C, int HW) {
+nchw_to_nhwc_kernel(const float* __restrict__ in, TOut* __restrict__ out, int C, int HW, int* __restrict__ sat_count) {
   __shared__ float tile[64][65];
+  int n_sat = 0;   // fp16 only: values the saturating conversion changes (|v| > 65504, inf) -- a deviation from the
+                   // fp32 reference that the host must hear about (roi_extractors._NHWCCache)
   const int b = blockIdx.z;
   const int c0 = blockIdx.y * 64, p0 = blockIdx.x * 64;
   const float* src = in + (size_t)b * C * HW;
@@ -77,6 +79,10 @@ nchw_to_nhwc_kernel(const float* __restrict__ in, TOut* __restrict__ out, int C,
       float v[4];
 #pragma unroll
       for (int j = 0; j < 4; j++) v[j] = tile[tx * 4 + j][ty + 16 * i];
+      if (IS_HALF<TOut>::value) {
+#pragma unroll
+        for (int j = 0; j < 4; j++) n_sat += (c + j < C && fabsf(v[j]) > 65504.f) ? 1 : 0;
+      }
       TOut* o = dst + (size_t)p * C + c;
       if ((C & 3) == 0) {
         if (sizeof(TOut) == 4) *reinterpret_cast<float4*>(o) = make_float4(v[0], v[1], v[2], v[3]);
@@ -87,6 +93,10 @@ nchw_to_nhwc_kernel(const float* __restrict__ in, TOut* __restrict__ out, int C,
         for (int j = 0; j < 4; j++) if (c + j < C) o[j] = cvt_out<TOut>(v[j]);
       }
     }
+  }
+  if (IS_HALF<TOut>::value && sat_count != nullptr && __any_sync(0xffffffffu, n_sat != 0)) {
+    n_sat = __reduce_add_sync(0xffffffffu, n_sat);
+    if ((threadIdx.x & 31) == 0) atomicAdd(sat_count, n_sat);
   }
 }
 
@@ -612,17 +622,21 @@ static int launch_fwd(bool rotated, const void* feat, const float* rois, void* o
 
 using namespace ptb;
 
-extern "C" int pt_nchw_to_nhwc(const float* in, void* out, int B, int C, int H, int W, int out_bf16, void* stream) {
+extern "C" int pt_nchw_to_nhwc_ex(const float* in, void* out, int B, int C, int H, int W, int out_bf16,
+                                  int* sat_count, void* stream) {
   if (B <= 0 || C <= 0 || H <= 0 || W <= 0) return PT_OK;
   const int HW = H * W;
   dim3 grid((HW + 63) / 64, (C + 63) / 64, B), block(256);
   if (out_bf16 == 2)
-    nchw_to_nhwc_kernel<__half><<<grid, block, 0, (cudaStream_t)stream>>>(in, (__half*)out, C, HW);
+    nchw_to_nhwc_kernel<__half><<<grid, block, 0, (cudaStream_t)stream>>>(in, (__half*)out, C, HW, sat_count);
   else if (out_bf16)
-    nchw_to_nhwc_kernel<__nv_bfloat16><<<grid, block, 0, (cudaStream_t)stream>>>(in, (__nv_bfloat16*)out, C, HW);
+    nchw_to_nhwc_kernel<__nv_bfloat16><<<grid, block, 0, (cudaStream_t)stream>>>(in, (__nv_bfloat16*)out, C, HW, nullptr);
   else
-    nchw_to_nhwc_kernel<float><<<grid, block, 0, (cudaStream_t)stream>>>(in, (float*)out, C, HW);
+    nchw_to_nhwc_kernel<float><<<grid, block, 0, (cudaStream_t)stream>>>(in, (float*)out, C, HW, nullptr);
   return check_launch("nchw_to_nhwc_kernel");
+}
+extern "C" int pt_nchw_to_nhwc(const float* in, void* out, int B, int C, int H, int W, int out_bf16, void* stream) {
+  return pt_nchw_to_nhwc_ex(in, out, B, C, H, W, out_bf16, nullptr, stream);
 }
 
 // feat: NHWC [B,H,W,C] fp32 (feat_bf16=0), bf16 (=1) or fp16 (=2).  rois: [K,5] (b,x1,y1,x2,y2) or, rotated, [K,6]

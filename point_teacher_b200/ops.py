@@ -152,13 +152,16 @@ def bbox_overlaps(b1, b2, mode="iou", is_aligned=False, eps=1e-6):
 
 
 # ------------------------------------------------------------------------------ RoIAlign
-def nchw_to_nhwc(x, out_dtype=_f32):
+def nchw_to_nhwc(x, out_dtype=_f32, sat_count=None):
+    """``sat_count``: optional (1,) int32 device counter; an fp16 output adds the number of saturated values."""
     _chk(x, "feat", _f32, 4)
     B, C, H, W = x.shape
     out = torch.empty((B, H, W, C), dtype=out_dtype, device=x.device)
     if out_dtype not in _FEAT_CODE:
         raise ValueError("NHWC feature map must be fp32, bf16 or fp16")
-    _lib.call("pt_nchw_to_nhwc", _p(x), _p(out), B, C, H, W, _FEAT_CODE[out_dtype], _stream())
+    if sat_count is not None:
+        _chk(sat_count, "sat_count", _i32, 1)
+    _lib.call("pt_nchw_to_nhwc_ex", _p(x), _p(out), B, C, H, W, _FEAT_CODE[out_dtype], _p(sat_count), _stream())
     return out
 
 
@@ -630,7 +633,7 @@ def nhwc_to_nchw_f32(x, out=None, accumulate=False):
 
 
 def roi_align_backward(dA, rois, feat_shape_nhwc, spatial_scale, sampling_ratio=0, aligned=True, dfeat=None, K=None,
-                       rotated=False, clockwise=True):
+                       rotated=False, clockwise=True, roi_level=None, level=0):
     """dA bf16 [K, 49*C] bin-major -> dfeat NHWC fp32 (accumulated into ``dfeat`` when given, else zero-initialised).
     ``rotated``: rois (K,6) [b,cx,cy,w,h,theta], RoIAlignRotated semantics."""
     _chk(dA, "dA", _bf16, 2)
@@ -640,11 +643,11 @@ def roi_align_backward(dA, rois, feat_shape_nhwc, spatial_scale, sampling_ratio=
         dfeat = torch.zeros((B, H, W, C), dtype=_f32, device=dA.device)
     K = rois.shape[0] if K is None else K
     if rotated:
-        _lib.call("pt_roi_align_rotated_backward", _p(dA), dA.shape[1], _p(rois), K, B, C, H, W, float(spatial_scale),
-                  int(sampling_ratio), int(aligned), int(clockwise), _p(dfeat), _stream())
+        _lib.call("pt_roi_align_rotated_backward_ex", _p(dA), dA.shape[1], _p(rois), K, B, C, H, W, float(spatial_scale),
+                  int(sampling_ratio), int(aligned), int(clockwise), _p(dfeat), _p(roi_level), int(level), _stream())
         return dfeat
-    _lib.call("pt_roi_align_backward", _p(dA), dA.shape[1], _p(rois), K, B, C, H, W, float(spatial_scale),
-              int(sampling_ratio), int(aligned), _p(dfeat), _stream())
+    _lib.call("pt_roi_align_backward_ex", _p(dA), dA.shape[1], _p(rois), K, B, C, H, W, float(spatial_scale),
+              int(sampling_ratio), int(aligned), _p(dfeat), _p(roi_level), int(level), _stream())
     return dfeat
 
 

@@ -34,19 +34,18 @@ def img_wh_tensor(img_meta, device):
                         torch.float32, device)
 
 
-def boxes_to_rois(box_list):
-    """``bbox2roi`` (core/bbox/transforms.py:58-78): list of (n_i, >=4) -> (sum n_i, 5)."""
+def boxes_to_rois(box_list, dim=None):
+    """``bbox2roi`` (core/bbox/transforms.py:58-78): list of (n_i, >=4) xyxy -> (sum n_i, 5); ``rbbox2roi``
+    (OBB_TOD/mmrotate/core/bbox/transforms.py:73-92) for 5-column (cx,cy,w,h,theta) boxes -> (sum n_i, 6).
+    ``dim`` forces the number of box columns copied (default: 5 when the boxes have exactly 5 columns, else 4)."""
     n = sum(b.size(0) for b in box_list)
     ref = box_list[0]
-    out = ref.new_empty((n, 5))
-    o = 0
-    for i, b in enumerate(box_list):
-        k = b.size(0)
-        if k:
-            out[o:o + k, 0] = float(i)
-            out[o:o + k, 1:5] = b[:, :4]
-        o += k
-    return out
+    d = dim if dim is not None else (5 if ref.size(-1) == 5 else 4)
+    if n == 0:
+        return ref.new_empty((0, d + 1))
+    idx = const_tensor([i for i, b in enumerate(box_list) for _ in range(int(b.size(0)))], torch.int32, ref.device)
+    boxes = torch.cat([b[:, :d] for b in box_list]).float().contiguous()
+    return ops.make_rois(boxes, idx)
 
 
 def _split(t, sizes):

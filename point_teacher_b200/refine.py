@@ -15,13 +15,17 @@ from .proposals import (MIL_gen_proposals_from_cfg, const_tensor, gen_negative_p
 
 def phase2_refine(head, x_ori, img_metas, pseudo_bboxes, pseudo_points, pseudo_labels, gt_bboxes,
                   fine_proposal_cfg, fine_proposal_extensive_cfg, num_stages=1, num_training_burninstep2=100,
-                  alpha=(0.01, 0.25), neg_boxes=None, train=False):
+                  alpha=(0.01, 0.25), neg_boxes=None, train=False, x_synthetic=None, synthetic_bboxes=None):
     """Returns (refined_pseudo_bboxes, refined_pseudo_points, losses) like the reference method.
     ``neg_boxes[stage][img]`` optionally injects the negative boxes the reference samples on the CPU.
 
     Everything between the input lists and the output lists runs on packed tensors: one ``torch.cat`` per
     input list, per-image bookkeeping as cached constant index tensors, ~20 kernel launches per stage and
-    no host synchronisation, so the whole call is CUDA-graph capturable (``CapturedPhase2``)."""
+    no host synchronisation, so the whole call is CUDA-graph capturable (``CapturedPhase2``).
+
+    ``train``: False -> forward only; True -> the MIL losses carry a ``grad_fn`` (train.mil_stage_train);
+    'manual' -> forward only with the intermediates kept for an explicit backward (train.Phase2Trainer).
+    ``x_synthetic`` + ``synthetic_bboxes``: the phase-1 variant (:func:`phase1_refine`)."""
     cap = num_training_burninstep2
     dev = pseudo_bboxes[0].device
     rot = head.bbox_roi_extractor.rotated       # OBB twin: rotated_fcos_teacher_student.py:494-535
@@ -31,11 +35,29 @@ def phase2_refine(head, x_ori, img_metas, pseudo_bboxes, pseudo_points, pseudo_l
     labels = torch.cat([l[:cap] for l in pseudo_labels]).long().contiguous()
     img_idx = const_tensor([i for i, c in enumerate(counts) for _ in range(c)], torch.int32, dev)
     img_wh = img_wh_tensor(img_metas, dev)
+    phase1 = synthetic_bboxes is not None
+    if phase1:
+        s_counts = [min(int(b.shape[0]), cap) for b in synthetic_bboxes]
+        sb = torch.cat([b[:cap, :] for b in synthetic_bboxes]).float().contiguous()
+        s_idx = const_tensor([i for i, c in enumerate(s_counts) for _ in range(c)], torch.int32, dev)
     forks = []
     with ops.fork() as f:                       # logged scalars run beside the data path
         losses = {"coarse_bboxes_iou": ops.aligned_iou_mean(pb, gb, rot)}
     forks.append(f)
     pts = None
+
+    def run_stage(x, *args, **kw):
+        if train == "manual":     # forward only, intermediates kept for an explicit backward (train.Phase2Trainer)
+            keep = {}
+            head._weights().clear()
+            out = head.mil_stage_packed(x, *args, keep=keep, **kw)
+            head._train_keeps = getattr(head, "_train_keeps", []) + [keep]
+            return out
+        if train:                 # the two MIL losses carry a grad_fn (feature map + head parameters), see train.py
+            from .train import mil_stage_train
+            return mil_stage_train(head, x, *args, **kw)
+        return head.mil_stage_packed(x, *args, **kw)
+
     for stage in range(num_stages):
         cfg = fine_proposal_cfg[stage]
         base_rois, _ = ops.bag_gen(ops.make_rois(pb, img_idx), img_wh, cfg["base_ratios"], cfg["shake_ratio"],
@@ -52,22 +74,17 @@ def phase2_refine(head, x_ori, img_metas, pseudo_bboxes, pseudo_points, pseudo_l
             for c in counts:
                 o.append(o[-1] + c * U1)
             offs = const_tensor(o, torch.int32, dev)
-        if train == "manual":     # forward only, intermediates kept for an explicit backward (train.Phase2Trainer)
-            keep = {}
-            head._wcache.clear()
-            pb_new, pts, mil_loss = head.mil_stage_packed(x_ori, img_metas, img_wh, base_rois, U1, pb, gb, negs, neg_idx,
-                                                          offs, labels, pb, fine_proposal_extensive_cfg[stage], stage,
-                                                          loss_scales=alpha, keep=keep)
-            head._train_keeps = getattr(head, "_train_keeps", []) + [keep]
-        elif train:    # the two MIL losses carry a grad_fn (feature map + head parameters), see train.py
-            from .train import mil_stage_train
-            pb_new, pts, mil_loss = mil_stage_train(head, x_ori, img_metas, img_wh, base_rois, U1, pb, gb, negs, neg_idx,
-                                                    offs, labels, pb, fine_proposal_extensive_cfg[stage], stage,
-                                                    loss_scales=alpha)
-        else:
-            pb_new, pts, mil_loss = head.mil_stage_packed(x_ori, img_metas, img_wh, base_rois, U1, pb, gb, negs, neg_idx,
-                                                          offs, labels, pb, fine_proposal_extensive_cfg[stage], stage,
-                                                          loss_scales=alpha)
+        syn_loss = None
+        if phase1:   # regression loss from the synthetic image's bags (fcos_p2b_teacher_student.py:395-397, head :1300-1304)
+            s_rois, _ = ops.bag_gen(ops.make_rois(sb, s_idx), img_wh, cfg["base_ratios"], cfg["shake_ratio"],
+                                    cfg["min_scale"], rot)
+            _, _, syn_loss = run_stage(x_synthetic, img_metas, img_wh, s_rois, U1, sb, sb, None, None, None, None, None,
+                                       fine_proposal_extensive_cfg[stage], stage, loss_scales=alpha, mode="reg_only")
+        pb_new, pts, mil_loss = run_stage(x_ori, img_metas, img_wh, base_rois, U1, pb, gb, negs, neg_idx, offs, labels, pb,
+                                          fine_proposal_extensive_cfg[stage], stage, loss_scales=alpha)
+        if syn_loss is not None:
+            mil_loss = dict(mil_loss)
+            mil_loss[f"stage{stage}_loss_mil_bbox"] = syn_loss[f"stage{stage}_loss_mil_bbox"]
         pb = pb_new
         with ops.fork() as f:
             losses[f"stage{stage}_refine_bboxes_iou"] = ops.aligned_iou_mean(pb, gb, rot)
@@ -85,6 +102,23 @@ def phase2_refine(head, x_ori, img_metas, pseudo_bboxes, pseudo_points, pseudo_l
     for f in forks:
         f.join()
     return refined_b, refined_p, losses
+
+
+def phase1_refine(head, x_synthetic, x_ori, img_metas, synthetic_bboxes, pseudo_bboxes, pseudo_points, pseudo_labels,
+                  gt_bboxes, fine_proposal_cfg, fine_proposal_extensive_cfg, num_stages=1, num_training_burninstep1=100,
+                  alpha=(0.01, 0.25), neg_boxes=None, train=False):
+    """Phase-1 (burn-in) MIL training step at the detector level: ``forward_mil_head_burn_in_step1``
+    (HBB_TOD/mmdet/models/detectors/fcos_p2b_teacher_student.py:365-424; OBB rotated_fcos_teacher_student.py:435-492).
+    The regression loss is taken on the bags around the SYNTHETIC boxes pooled from the synthetic image's features,
+    the bag loss / logs / selection on the real image.  Returns the same triple as the reference; when an image has
+    no synthetic box the reference returns empty lists and ``None`` (:369-373) -- so does this."""
+    if any(int(b.shape[0]) == 0 for b in synthetic_bboxes):
+        d = 5 if head.bbox_roi_extractor.rotated else 4
+        e = pseudo_bboxes[0]
+        return [e.new_empty((0, d)) for _ in pseudo_bboxes], [e.new_empty((0, 2)) for _ in pseudo_bboxes], None
+    return phase2_refine(head, x_ori, img_metas, pseudo_bboxes, pseudo_points, pseudo_labels, gt_bboxes,
+                         fine_proposal_cfg, fine_proposal_extensive_cfg, num_stages, num_training_burninstep1, alpha,
+                         neg_boxes, train, x_synthetic=x_synthetic, synthetic_bboxes=synthetic_bboxes)
 
 
 def phase2_refine_lists(head, x_ori, img_metas, pseudo_bboxes, pseudo_points, pseudo_labels, gt_bboxes,
@@ -120,13 +154,26 @@ def phase2_refine_lists(head, x_ori, img_metas, pseudo_bboxes, pseudo_points, ps
 
 
 class P2BRefineMixin:
-    """Drop-in for the detector method (same name and argument list)."""
+    """Drop-ins for the detector methods (same names and argument lists; HBB ``TS_P2B_FCOS`` and, without the trailing
+    ``img`` argument, OBB ``RotatedFCOS_TS``).  Differentiable whenever autograd is on and something requires a
+    gradient, like the reference's own methods."""
+
+    def _mil_train_flag(self, x):
+        return self.student.bbox_head._grad_wanted(x)
 
     def forward_mil_head_burn_in_step2(self, num_img, pseudo_bboxes, pseudo_points, pseudo_labels, gt_bboxes,
                                        img_metas, x_ori):
         return phase2_refine(self.student.bbox_head, x_ori, img_metas, pseudo_bboxes, pseudo_points,
                              pseudo_labels, gt_bboxes, self.fine_proposal_cfg, self.fine_proposal_extensive_cfg,
-                             self.num_stages, self.num_training_burninstep2, self.alpha)
+                             self.num_stages, self.num_training_burninstep2, self.alpha,
+                             train=self._mil_train_flag(x_ori))
+
+    def forward_mil_head_burn_in_step1(self, num_img, synthetic_bboxes, pseudo_bboxes, pseudo_points, pseudo_labels,
+                                       gt_bboxes, img_metas, x_synthetic, x_ori, img=None):
+        return phase1_refine(self.student.bbox_head, x_synthetic, x_ori, img_metas, synthetic_bboxes, pseudo_bboxes,
+                             pseudo_points, pseudo_labels, gt_bboxes, self.fine_proposal_cfg,
+                             self.fine_proposal_extensive_cfg, self.num_stages, self.num_training_burninstep1,
+                             self.alpha, train=self._mil_train_flag(x_ori) or self._mil_train_flag(x_synthetic))
 
 
 class CapturedPhase2:
@@ -160,7 +207,7 @@ class CapturedPhase2:
     def _step(self):
         i = self.inputs
         if self.refresh_weights:
-            self.head._wcache.clear()
+            self.head._weights().clear()
         # the NHWC feature-map cache is keyed on (pointer, version): inside a captured step it must MISS, otherwise
         # the capture would bake in the tensor transposed during warm-up and replays would read stale features
         for layer in self.head.bbox_roi_extractor.roi_layers:
@@ -169,6 +216,9 @@ class CapturedPhase2:
                              i["pseudo_labels"], i["gt_boxes"], neg_boxes=i.get("neg_boxes"), **self.kw)
 
     def replay(self):
+        # fp16 feature-map range guard: the word written by EARLIER replays (no synchronisation here)
+        for layer in self.head.bbox_roi_extractor.roi_layers:
+            layer._cache.check(captured=True)
         self.graph.replay()
         return self.outputs
 

@@ -46,8 +46,9 @@ def build_from_cfg(cfg, registry, default_args=None):
 
 
 def _try_import_registries():
+    """Covered by tests/test_registry_shim.py, which runs this under oracle/ref_shim's mmcv / mmdet shells."""
     regs = {}
-    try:  # pragma: no cover - OpenMMLab is not installed in the build image
+    try:
         from mmdet.models.builder import HEADS, ROI_EXTRACTORS, LOSSES
         from mmdet.core.bbox.builder import BBOX_ASSIGNERS, BBOX_CODERS
         from mmdet.core.bbox.iou_calculators.builder import IOU_CALCULATORS
@@ -103,3 +104,39 @@ def build_match_cost(cfg, default_args=None):
 
 def build_head(cfg):
     return HEADS.build(cfg)
+
+
+# reference type name -> (registry, mix-in class name in mil_head, standalone class name in mil_head)
+_REFERENCE_HEADS = {"TS_P2BFCOSHead": ("HEADS", "MILHeadMixin", "MILHead"),
+                    "TS_P2RBRotatedFCOSHead": ("ROTATED_HEADS", "RotatedMILHeadMixin", "RotatedMILHead")}
+
+
+def install_reference_heads(registries=None):
+    """Put the B200 MIL path behind the reference's own head type names, so that the teacher-student detectors'
+    configs (``bbox_head=dict(type='TS_P2BFCOSHead', ...)`` / ``'TS_P2RBRotatedFCOSHead'``, built at
+    HBB_TOD/mmdet/models/detectors/fcos_p2b_teacher_student.py:40-47 through HBB_TOD/mmdet/models/builder.py:47-59)
+    pick it up unchanged:
+
+      * the reference class is in the registry (mmdet / mmrotate imported): it is re-registered (``force=True``) as a
+        subclass ``type(name, (MILHeadMixin, ReferenceClass), {})`` -- the FCOS tower, losses and target code stay the
+        reference's, every MIL method resolves to the mix-in first in the MRO; parameter names are the reference's own;
+      * otherwise the standalone ``MILHead`` / ``RotatedMILHead`` (MIL part only) is registered under that name.
+
+    Call again after ``import mmdet.models`` if this package was imported first.  Returns {name: class}."""
+    from . import mil_head
+    regs = registries or {"HEADS": HEADS, "ROTATED_HEADS": ROTATED_HEADS}
+    out = {}
+    for name, (reg_name, mixin_name, standalone_name) in _REFERENCE_HEADS.items():
+        reg = regs.get(reg_name) or regs.get("HEADS")
+        mixin, standalone = getattr(mil_head, mixin_name), getattr(mil_head, standalone_name)
+        cur = reg.get(name)
+        if cur is None or cur is standalone:
+            cls = standalone
+        elif issubclass(cur, mil_head.MILHeadMixin):
+            cls = cur                                   # already wrapped
+        else:
+            cls = type(name, (mixin, cur), {"__module__": cur.__module__, "__doc__": cur.__doc__,
+                                            "_b200_wrapped_reference": cur})
+        reg.register_module(name=name, force=True, module=cls)
+        out[name] = cls
+    return out

@@ -9,6 +9,8 @@ Reference interfaces mirrored (paths under /root/reference):
     rotate_single_level_roi_extractor.py:13-167
 Forward is a hand-written sm_100a kernel (csrc/roi_align.cu); there is no CPU path.
 """
+import weakref
+
 import torch
 import torch.nn as nn
 
@@ -20,22 +22,132 @@ def _pair(v):
     return (int(v), int(v)) if isinstance(v, int) else tuple(int(t) for t in v)
 
 
+class FeatureRangeError(RuntimeError):
+    """The fp16 NHWC feature map saturated (|value| > 65504): the fp32 reference has no such limit."""
+
+
 class _NHWCCache:
-    """The feature map is transposed to NHWC once per (tensor, version) and reused by every
-    RoIAlign call of the step (three per MIL stage in the reference)."""
+    """The feature map is transposed to NHWC once per step and reused by every RoIAlign call of the step (three per
+    MIL stage in the reference).
+
+    The hit test is TENSOR IDENTITY (a weak reference to the source tensor + its version counter), never the data
+    pointer: a training loop produces a fresh backbone output every step, and the caching allocator usually hands
+    the same address back, so a pointer key would silently pool step N+1 from step N's features.
+
+    fp16 maps (the tensor-core RoIAlign operand) saturate at +-65504.  Every fp16 transpose counts the values it
+    clipped into a device counter whose value reaches a pinned host word asynchronously; the NEXT call looks at it
+    (no synchronisation on the hot path) and, if anything was clipped, switches this layer to bf16 maps for good
+    with a warning -- or raises ``FeatureRangeError`` when ``on_saturation == 'raise'`` (captured steps, which cannot
+    switch dtype, always raise from ``CapturedPhase2.replay``)."""
+
+    on_saturation = "fallback"          # 'fallback' (bf16 maps from now on, warn once) | 'raise'
 
     def __init__(self):
-        self._key, self._val = None, None
+        self._ref, self._key, self._val = None, None, None
+        self._sat = self._sat_host = self._sat_ev = None
+        self.force_bf16 = False
+        self.saturated_total = 0
+
+    def _poll(self, captured=False):
+        """Non-blocking look at the saturation word of EARLIER transposes."""
+        if self._sat_host is None:
+            return
+        if self._sat_ev is not None and not self._sat_ev.query():
+            return
+        n = int(self._sat_host[0])
+        if n > self.saturated_total:
+            new, self.saturated_total = n - self.saturated_total, n
+            msg = (f"{new} feature values exceeded the fp16 range (+-65504) and were clipped in the NHWC map that "
+                   "feeds the tensor-core RoIAlign; the fp32 reference does not clip")
+            if self.on_saturation == "raise" or captured or torch.cuda.is_current_stream_capturing():
+                raise FeatureRangeError(msg + "; build the head with feat_dtype=torch.bfloat16 (or precision='fp32')")
+            import warnings
+            warnings.warn(msg + "; switching this RoI layer to bf16 feature maps", RuntimeWarning, stacklevel=3)
+            self.force_bf16 = True
+
+    def check(self, sync=False, captured=False):
+        """Explicit check (``sync=True`` waits for the outstanding transposes first; ``captured``: the caller replays a
+        CUDA graph whose dtype is frozen, so a clipped value always raises)."""
+        if sync:
+            if self._sat_ev is not None:
+                self._sat_ev.synchronize()
+            else:
+                torch.cuda.current_stream().synchronize()
+        self._poll(captured)
+        return self.saturated_total
 
     def get(self, x, dtype):
-        key = (x.data_ptr(), x._version, tuple(x.shape), dtype, x.device)
-        if key != self._key:
-            self._val = ops.nchw_to_nhwc(x.contiguous(), dtype)
-            self._key = key
+        if dtype == torch.float16:
+            self._poll()
+            if self.force_bf16:
+                dtype = torch.bfloat16
+        key = (x._version, tuple(x.shape), dtype, x.device)
+        if self._ref is None or self._ref() is not x or key != self._key:
+            sat = None
+            if dtype == torch.float16:
+                if self._sat is None or self._sat.device != x.device:
+                    self._sat = torch.zeros((1,), dtype=torch.int32, device=x.device)
+                    self._sat_host = torch.zeros((1,), dtype=torch.int32).pin_memory()
+                sat = self._sat
+            self._val = ops.nchw_to_nhwc(x.contiguous(), dtype, sat_count=sat)
+            if sat is not None:
+                self._sat_host.copy_(sat, non_blocking=True)
+                if not torch.cuda.is_current_stream_capturing():
+                    self._sat_ev = torch.cuda.Event()
+                    self._sat_ev.record()
+                else:
+                    self._sat_ev = None            # a replayed graph refreshes the word; replay() polls it
+            self._ref, self._key = weakref.ref(x), key
         return self._val
 
     def clear(self):
-        self._key, self._val = None, None
+        self._ref, self._key, self._val = None, None, None
+
+
+class _RoIAlignFn(torch.autograd.Function):
+    """Autograd for the public (K,C,7,7) fp32 extractor output, so that the ``force=True`` replacement of
+    ``SingleRoIExtractor`` stays usable by every other differentiable user of the registry.  The backward reuses
+    the MIL path's scatter kernel, which consumes the output gradient as bf16 in bin-major order: the incoming fp32
+    gradient is rounded to bf16 once (relative 2^-9) -- stated here because mmcv's backward is fp32 throughout."""
+
+    @staticmethod
+    def forward(ctx, input, rois, layer, roi_level, level, out):
+        feat = layer.nhwc(input)
+        rot = layer.rotated
+        res = ops.roi_align_forward(feat, rois, ops.OUT_F32_NCHW, layer.spatial_scale, layer.sampling_ratio,
+                                    layer.aligned, rotated=rot, clockwise=getattr(layer, "clockwise", True), out=out,
+                                    roi_level=roi_level, level=level)
+        ctx.layer, ctx.level, ctx.shape = layer, level, tuple(input.shape)
+        ctx.save_for_backward(rois, roi_level if roi_level is not None else rois.new_empty(0))
+        ctx.has_lvl = roi_level is not None
+        if out is not None:
+            ctx.mark_dirty(out)
+        return res
+
+    @staticmethod
+    def backward(ctx, g):
+        rois, lvl = ctx.saved_tensors
+        layer = ctx.layer
+        B, C, H, W = ctx.shape
+        K = rois.shape[0]
+        dA = g.reshape(K, C, -1).permute(0, 2, 1).to(torch.bfloat16).reshape(K, -1).contiguous()   # bin-major bf16
+        dn = ops.roi_align_backward(dA, rois, (B, H, W, C), layer.spatial_scale, layer.sampling_ratio, layer.aligned,
+                                    rotated=layer.rotated, clockwise=getattr(layer, "clockwise", True),
+                                    roi_level=lvl if ctx.has_lvl else None, level=ctx.level)
+        return ops.nhwc_to_nchw_f32(dn), None, None, None, None, None
+
+
+def _roi_layer_forward(layer, input, rois, roi_level, level):
+    if torch.is_grad_enabled() and input.requires_grad:
+        out = None
+        if roi_level is not None:      # rows of other levels are not written by the kernel: start from zeros
+            out = torch.zeros((rois.shape[0], input.shape[1], *layer.output_size), dtype=torch.float32,
+                              device=rois.device)
+        return _RoIAlignFn.apply(input, rois, layer, roi_level, level, out)
+    feat = layer.nhwc(input)
+    return ops.roi_align_forward(feat, rois, ops.OUT_F32_NCHW, layer.spatial_scale, layer.sampling_ratio,
+                                 layer.aligned, rotated=layer.rotated, clockwise=getattr(layer, "clockwise", True),
+                                 roi_level=roi_level, level=level)
 
 
 class RoIAlign(nn.Module):
@@ -64,9 +176,7 @@ class RoIAlign(nn.Module):
     def forward(self, input, rois, roi_level=None, level=0):
         if rois.dim() != 2 or rois.size(1) != 5:
             raise ValueError("RoI must be (idx, x1, y1, x2, y2)!")
-        feat = self.nhwc(input)
-        return ops.roi_align_forward(feat, rois.contiguous().float(), ops.OUT_F32_NCHW, self.spatial_scale,
-                                     self.sampling_ratio, self.aligned, roi_level=roi_level, level=level)
+        return _roi_layer_forward(self, input, rois.contiguous().float(), roi_level, level)
 
     def __repr__(self):
         return (f"{self.__class__.__name__}(output_size={self.output_size}, spatial_scale={self.spatial_scale}, "
@@ -104,10 +214,7 @@ class RoIAlignRotated(nn.Module):
     def forward(self, input, rois, roi_level=None, level=0):
         if rois.dim() != 2 or rois.size(1) != 6:
             raise ValueError("RoI must be (idx, cx, cy, w, h, theta)!")
-        feat = self.nhwc(input)
-        return ops.roi_align_forward(feat, rois.contiguous().float(), ops.OUT_F32_NCHW, self.spatial_scale,
-                                     self.sampling_ratio, self.aligned, rotated=True, clockwise=self.clockwise,
-                                     roi_level=roi_level, level=level)
+        return _roi_layer_forward(self, input, rois.contiguous().float(), roi_level, level)
 
 
 _LAYERS = {"RoIAlign": RoIAlign, "RoIAlignRotated": RoIAlignRotated}
@@ -157,6 +264,9 @@ class BaseRoIExtractor(nn.Module):
         lvls = ops.map_roi_levels(rois, num_levels, self.finest_scale, rotated=self.rotated)
         if roi_scale_factor is not None:
             rois = self.roi_rescale(rois, roi_scale_factor)
+        if torch.is_grad_enabled() and any(f.requires_grad for f in feats[:num_levels]):
+            # differentiable (rare) path: one zero-initialised output per level, summed (every RoI lives in one level)
+            return sum(self.roi_layers[i](feats[i], rois, roi_level=lvls, level=i) for i in range(num_levels))
         out = torch.empty((rois.size(0), self.out_channels, *out_size), dtype=torch.float32, device=rois.device)
         for i in range(num_levels):
             layer = self.roi_layers[i]

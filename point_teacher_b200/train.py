@@ -45,78 +45,109 @@ def _fc_branch_backward(head, k, dZ2, need_dA):
 
 def mil_stage_backward(head, keep, x, g_bbox, g_bags, need_feat_grad=True):
     """Gradients of (g_bbox * loss_mil_bbox + g_bags * loss_mil_bags) for one stage.  g_* are 1-element fp32 CUDA
-    tensors (no host read).  Returns (dfeat NCHW fp32 | None, [14 parameter gradients in ``stage_params`` order])."""
-    stage, dev = keep["stage"], keep["cls"].device
+    tensors (no host read); ``None`` skips that branch altogether (phase 1: the synthetic pass has no bag loss and the
+    real pass no regression loss, fcos_head_p2b_ts.py:1279-1316).  ``x``: the feature map or the tuple of maps the
+    forward pooled from.  Returns (dfeat NCHW fp32 | None -- a list when ``x`` is a tuple --, [14 parameter gradients in
+    ``stage_params`` order, ``None`` for the skipped branch])."""
+    feats = list(x) if isinstance(x, (tuple, list)) else [x]
+    feats = feats[:head.bbox_roi_extractor.num_inputs]
+    stage, dev = keep["stage"], keep["ebags"].device
     K, G, U1, U2, n_neg = keep["K"], keep["G"], keep["U1"], keep["U2"], keep["n_neg"]
     s_bbox, s_bags = keep["loss_scales"]
     fr, fc, fi = head.fc_reg[stage], head.fc_cls[stage], head.fc_ins[stage]
     C = fc.weight.shape[0]
-    layer = head.bbox_roi_extractor.roi_layers[0]
+    ext = head.bbox_roi_extractor
+    rot = ext.rotated
+    do_reg = g_bbox is not None
+    do_bag = g_bags is not None and keep["cls"] is not None
+    r = b = None
+    dWreg = dbreg = dWci = dbci = None
     # ---- regression branch: DN-DIoU -> delta2bbox -> fc_reg -> FC2 -> FC1 -> RoIAlign
-    rot = head.bbox_roi_extractor.rotated
-    g4 = ops.reg_loss_grad(keep["deltas"], keep["ebags"], keep["evalid"], keep["ref"], U1 * U2, keep["max_wh"],
-                           keep["sums"], g_bbox, s_bbox, hyper=head.loss_bbox_denosing_hyper, rotated=rot)
-    dWreg, dbreg = torch.zeros_like(fr.weight), torch.zeros_like(fr.bias)
-    dZ2 = ops.head_bwd(g4, keep["reg"]["H2"], fr.weight.detach(), dWreg, dbreg, M=K)
-    r = _fc_branch_backward(head, keep["reg"], dZ2, need_feat_grad)
+    if do_reg:
+        g4 = ops.reg_loss_grad(keep["deltas"], keep["ebags"], keep["evalid"], keep["ref"], U1 * U2, keep["max_wh"],
+                               keep["sums"], g_bbox, s_bbox, hyper=head._dn_hyper(), rotated=rot)
+        dWreg, dbreg = torch.zeros_like(fr.weight), torch.zeros_like(fr.bias)
+        dZ2 = ops.head_bwd(g4, keep["reg"]["H2"], fr.weight.detach(), dWreg, dbreg, M=K)
+        r = _fc_branch_backward(head, keep["reg"], dZ2, need_feat_grad)
     # ---- bag branch: gfocal -> bag score -> (sigmoid, softmax x valid x L1) -> fc_cls / fc_ins -> FC2 -> FC1
-    g16 = ops.bag_loss_grad(keep["cls"], keep["ins"], keep["evalid"], keep["labels"], G, U1, U2, keep["neg_w"], n_neg,
-                            keep["sums"], g_bags, s_bags * head.bag_loss_pos_scale, s_bags * head.bag_loss_neg_scale)
-    Wci = torch.cat([fc.weight.detach(), fi.weight.detach()], 0).contiguous()
-    dWci, dbci = torch.zeros_like(Wci), torch.zeros((2 * C,), dtype=torch.float32, device=dev)
-    dZ2b = ops.head_bwd(g16, keep["bag"]["H2"], Wci, dWci, dbci, M=K + n_neg)
-    b = _fc_branch_backward(head, keep["bag"], dZ2b, need_feat_grad)
+    if do_bag:
+        g16 = ops.bag_loss_grad(keep["cls"], keep["ins"], keep["evalid"], keep["labels"], G, U1, U2, keep["neg_w"], n_neg,
+                                keep["sums"], g_bags, s_bags * head.bag_loss_pos_scale, s_bags * head.bag_loss_neg_scale)
+        Wci = torch.cat([fc.weight.detach(), fi.weight.detach()], 0).contiguous()
+        dWci, dbci = torch.zeros_like(Wci), torch.zeros((2 * C,), dtype=torch.float32, device=dev)
+        dZ2b = ops.head_bwd(g16, keep["bag"]["H2"], Wci, dWci, dbci, M=K + n_neg)
+        b = _fc_branch_backward(head, keep["bag"], dZ2b, need_feat_grad)
     dfeat = None
     if need_feat_grad:
-        Bn, _, H, W = x.shape
-        shape = (Bn, H, W, x.shape[1])
-        rk = dict(rotated=rot, clockwise=getattr(layer, "clockwise", True))
-        dn = ops.roi_align_backward(r[4], keep["ebags"], shape, layer.spatial_scale, layer.sampling_ratio, layer.aligned,
-                                    K=K, **rk)
-        ops.roi_align_backward(b[4], keep["rois2"], shape, layer.spatial_scale, layer.sampling_ratio, layer.aligned,
-                               dfeat=dn, K=K + n_neg, **rk)
-        dfeat = ops.nhwc_to_nchw_f32(dn)
-    grads = [r[0], r[1], r[2], r[3], b[0], b[1], b[2], b[3], dWreg, dbreg, dWci[:C], dbci[:C], dWci[C:], dbci[C:]]
+        dfeat = []
+        for lvl, f in enumerate(feats):
+            layer = ext.roi_layers[lvl]
+            Bn, Cf, H, W = f.shape
+            shape = (Bn, H, W, Cf)
+            rk = dict(rotated=rot, clockwise=getattr(layer, "clockwise", True), level=lvl)
+            dn = None
+            if do_reg:
+                dn = ops.roi_align_backward(r[4], keep["ebags"], shape, layer.spatial_scale, layer.sampling_ratio,
+                                            layer.aligned, K=K, roi_level=keep["reg"].get("lvls"), **rk)
+            if do_bag:
+                dn = ops.roi_align_backward(b[4], keep["rois2"], shape, layer.spatial_scale, layer.sampling_ratio,
+                                            layer.aligned, dfeat=dn, K=K + n_neg, roi_level=keep["bag"].get("lvls"), **rk)
+            dfeat.append(None if dn is None else ops.nhwc_to_nchw_f32(dn))
+        if not isinstance(x, (tuple, list)):
+            dfeat = dfeat[0]
+    r4 = list(r[:4]) if do_reg else [None] * 4
+    b4 = list(b[:4]) if do_bag else [None] * 4
+    grads = r4 + b4 + [dWreg, dbreg] + ([dWci[:C], dbci[:C], dWci[C:], dbci[C:]] if do_bag else [None] * 4)
     return dfeat, grads
 
 
 class _MILStageFn(torch.autograd.Function):
+    """forward(head, args, kwargs, n_feat, *feats, *stage_params) -> (loss_mil_bbox, loss_mil_bags, merged, pts)."""
+
     @staticmethod
-    def forward(ctx, feat, head, args, *params):
+    def forward(ctx, head, args, kwargs, n_feat, *tensors):
+        feats = tuple(tensors[:n_feat])
         keep = {}
         with torch.no_grad():
-            merged, pts, losses = head.mil_stage_packed((feat,), *args, keep=keep)
-        ctx.head, ctx.keep, ctx.feat_needs = head, keep, feat.requires_grad
-        ctx.save_for_backward(feat)
+            merged, pts, losses = head.mil_stage_packed(feats, *args, keep=keep, **kwargs)
+        ctx.head, ctx.keep, ctx.n_feat = head, keep, n_feat
+        ctx.feat_needs = any(f.requires_grad for f in feats)
+        ctx.n_params = len(tensors) - n_feat
+        ctx.save_for_backward(*feats)
+        ctx.set_materialize_grads(False)          # an unused loss arrives as None and its branch is skipped
         s = keep["stage"]
+        dev = feats[0].device
+        if merged is None:                        # 'reg_only': nothing is selected
+            merged, pts = torch.empty((0,), device=dev), torch.empty((0,), device=dev)
         ctx.mark_non_differentiable(merged, pts)
         return losses[f"stage{s}_loss_mil_bbox"].reshape(()), losses[f"stage{s}_loss_mil_bags"].reshape(()), merged, pts
 
     @staticmethod
     def backward(ctx, g_bbox, g_bags, _gm, _gp):
-        (feat,) = ctx.saved_tensors
-        dev = feat.device
-        one = lambda g: (torch.zeros((1,), dtype=torch.float32, device=dev) if g is None  # noqa: E731
-                         else g.detach().float().reshape(1).contiguous())
-        dfeat, grads = mil_stage_backward(ctx.head, ctx.keep, feat, one(g_bbox), one(g_bags), ctx.feat_needs)
+        feats = ctx.saved_tensors
+        one = lambda g: None if g is None else g.detach().float().reshape(1).contiguous()  # noqa: E731
+        dfeat, grads = mil_stage_backward(ctx.head, ctx.keep, tuple(feats), one(g_bbox), one(g_bags), ctx.feat_needs)
         ctx.keep = None
-        return (dfeat, None, None, *grads)
+        dfeat = dfeat if dfeat is not None else [None] * ctx.n_feat
+        return (None, None, None, None, *dfeat, *grads)
 
 
 def mil_stage_train(head, x, img_metas, img_wh, base_rois, U1, ref, real, neg_boxes, neg_img_idx, bag_offsets, labels,
-                    pseudo, cfg, stage, loss_scales=(1.0, 1.0)):
+                    pseudo, cfg, stage, loss_scales=(1.0, 1.0), neg_w=None, mode="full"):
     """Differentiable twin of ``mil_stage_packed``: same arguments and return value, but the two loss entries carry a
-    ``grad_fn`` (feature map + the stage's parameters)."""
+    ``grad_fn`` (feature maps + the stage's parameters)."""
     if getattr(head, "precision", "bf16") != "bf16":
-        raise NotImplementedError("the backward runs in bf16 precision")
-    if len(x[:head.bbox_roi_extractor.num_inputs]) != 1:
-        raise NotImplementedError("single feature level (both shipped configs)")
-    head._wcache.clear()                               # parameters change every iteration
-    args = (img_metas, img_wh, base_rois, U1, ref, real, neg_boxes, neg_img_idx, bag_offsets, labels, pseudo, cfg, stage,
-            loss_scales)
-    lb, lg, merged, pts = _MILStageFn.apply(x[0], head, args, *stage_params(head, stage))
+        raise NotImplementedError("the backward runs in bf16 precision (precision='fp32' is forward-only: wrap the "
+                                  "call in torch.no_grad())")
+    head._weights().clear()                            # parameters change every iteration
+    args = (img_metas, img_wh, base_rois, U1, ref, real, neg_boxes, neg_img_idx, bag_offsets, labels, pseudo, cfg, stage)
+    kwargs = dict(loss_scales=loss_scales, neg_w=neg_w, mode=mode)
+    feats = tuple(x[:head.bbox_roi_extractor.num_inputs])
+    lb, lg, merged, pts = _MILStageFn.apply(head, args, kwargs, len(feats), *feats, *stage_params(head, stage))
     losses = dict(head.last_losses)                    # detached logs (bag IoUs) + the two differentiable losses
     losses[f"stage{stage}_loss_mil_bbox"], losses[f"stage{stage}_loss_mil_bags"] = lb, lg
+    if mode != "full":
+        merged = pts = None
     return merged, pts, losses
 
 

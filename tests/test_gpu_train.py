@@ -322,3 +322,68 @@ def test_obb_training_step_gradients_vs_oracle(cuda, seed, alpha):
     close(x.grad, feat.grad, "feature map")
     for a, b in zip(gb, ob):
         assert a.shape[1] == 5 and _rel(a.detach(), b.detach()) < 2e-2
+
+
+def _multilevel_batch(seed, n_gt=12):
+    """A 512x512 batch whose boxes span three FPN levels under finest_scale = 56 (sqrt(wh) < 112 / < 224 / above)."""
+    g = torch.Generator().manual_seed(900 + seed)
+    d = synth.hbb_batch(seed=seed, batch=2, img_hw=(512, 512), gt_range=(n_gt, n_gt), n_neg=20)
+    gts = [synth.make_boxes(g, n_gt, (512, 512), median=110.0, sigma=0.8, lo=8.0, hi=420.0) for _ in range(2)]
+    d["gt_boxes"] = gts
+    d["pseudo_boxes"] = [synth.jitter_boxes(g, b, ctr_sigma=3.0, log_sigma=0.15) for b in gts]
+    d["pseudo_points"] = [torch.stack([(b[:, 0] + b[:, 2]) / 2, (b[:, 1] + b[:, 3]) / 2], 1) for b in d["pseudo_boxes"]]
+    feats = [d["feat"], torch.randn(2, 256, 32, 32, generator=g), torch.randn(2, 256, 16, 16, generator=g)]
+    return d, feats
+
+
+@pytest.mark.parametrize("precision,tol", [("fp32", 1e-3), ("bf16", 2e-2)])
+def test_multilevel_fused_mil_path_vs_oracle(cuda, precision, tol):
+    """north_star: "multi-level FPN RoIAlign over the bags" (single_level_roi_extractor.py:35-54, 98-104) on the FUSED
+    path: every RoI pooled from its mapped level straight into the FC1 operand; forward in both precisions and, in
+    bf16, the gradients w.r.t. all three feature maps and the parameters against torch autograd through the oracle."""
+    from point_teacher_b200.mil_head import MILHead
+    from point_teacher_b200.refine import phase2_refine
+    strides = [8, 16, 32]
+    d, feats = _multilevel_batch(3)
+    P = hbb.MilHeadParams(num_stages=1, seed=3).requires_grad_(precision == "bf16")
+    fo = [f.clone().requires_grad_(precision == "bf16") for f in feats]
+    ctx = torch.enable_grad() if precision == "bf16" else torch.no_grad()
+    with ctx:
+        ob, op, ol, aux = hbb.phase2_refine(P, tuple(fo), strides, d["img_metas"], d["pseudo_boxes"], d["pseudo_points"],
+                                            d["pseudo_labels"], d["gt_boxes"], synth.HBB_FINE_CFG, synth.HBB_EXT_CFG,
+                                            num_stages=1, alpha=(1.0, 1.0), topk=1, injected_negs=d["neg_boxes"])
+    lv = hbb.map_roi_levels(hbb.bbox2roi(aux[-1]["coarse_extensive_bags"]), 3)
+    assert all(int((lv == i).sum()) > 10 for i in range(3)), "the batch must exercise every level"
+    head = MILHead(num_classes=8, num_stages=1, top_k=1, precision=precision,
+                   bbox_roi_extractor=dict(type="SingleRoIExtractor", roi_layer=dict(type="RoIAlign", output_size=7),
+                                           out_channels=256, featmap_strides=strides)).to(cuda)
+    head.load_state_dict({k: v.detach() for k, v in P.state_dict().items()}, strict=False)
+    to = lambda l: [t.to(cuda) for t in l]  # noqa: E731
+    x = tuple(f.to(cuda).requires_grad_(precision == "bf16") for f in feats)
+    with ctx:
+        gb, gp, gl = phase2_refine(head, x, d["img_metas"], to(d["pseudo_boxes"]), to(d["pseudo_points"]),
+                                   to(d["pseudo_labels"]), to(d["gt_boxes"]), synth.HBB_FINE_CFG, synth.HBB_EXT_CFG,
+                                   num_stages=1, alpha=(1.0, 1.0), neg_boxes=[to(d["neg_boxes"][0])],
+                                   train=precision == "bf16")
+    R, ref = head.last_results, aux[-1]
+    assert _rel(R["cls_score"], ref["cls_score"].detach()) < tol
+    assert _rel(R["ins_score"], ref["ins_score"].detach()) < tol
+    assert _rel(torch.cat(R["extensive_bags"]), torch.cat(ref["extensive_bags"])) < tol
+    for k in ol:
+        assert abs(float(gl[k]) - float(ol[k])) <= tol * max(abs(float(ol[k])), 1e-3), k
+    for a, b in zip(gb, ob):
+        assert _rel(a.detach(), b.detach()) < tol
+    if precision != "bf16":
+        return
+    (ol["stage0_loss_mil_bbox"] + ol["stage0_loss_mil_bags"]).backward()
+    (gl["stage0_loss_mil_bbox"] + gl["stage0_loss_mil_bags"]).backward()
+    for i in range(3):
+        a, b = x[i].grad.double().cpu().flatten(), fo[i].grad.double().flatten()
+        cos = F.cosine_similarity(a, b, 0).item()
+        assert cos >= 0.995 and ((a - b).norm() / b.norm()).item() <= 0.1, (i, cos)
+    got = dict(head.named_parameters())
+    for k, v in P.state_dict().items():
+        a, b = got[k].grad.double().cpu().flatten(), v.grad.double().flatten()
+        if b.abs().max() < 1e-9:
+            continue
+        assert F.cosine_similarity(a, b, 0).item() >= 0.995, k
