@@ -59,7 +59,7 @@ class _NHWCCache:
             new, self.saturated_total = n - self.saturated_total, n
             msg = (f"{new} feature values exceeded the fp16 range (+-65504) and were clipped in the NHWC map that "
                    "feeds the tensor-core RoIAlign; the fp32 reference does not clip")
-            if self.on_saturation == "raise" or captured or torch.cuda.is_current_stream_capturing():
+            if self.on_saturation == "raise" or captured:
                 raise FeatureRangeError(msg + "; build the head with feat_dtype=torch.bfloat16 (or precision='fp32')")
             import warnings
             warnings.warn(msg + "; switching this RoI layer to bf16 feature maps", RuntimeWarning, stacklevel=3)
@@ -78,7 +78,8 @@ class _NHWCCache:
 
     def get(self, x, dtype):
         if dtype == torch.float16:
-            self._poll()
+            if not torch.cuda.is_current_stream_capturing():   # cudaEventQuery is illegal while a capture is open
+                self._poll()
             if self.force_bf16:
                 dtype = torch.bfloat16
         key = (x._version, tuple(x.shape), dtype, x.device)

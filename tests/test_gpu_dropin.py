@@ -106,7 +106,7 @@ def test_reference_driver_over_b200_classes(cuda, golden_dir, rotated, step):
     for k in (f"stage0_loss_mil_bbox", f"stage0_loss_mil_bags"):
         assert l16[k].grad_fn is not None, k
     for k, v in g["losses"].items():
-        assert abs(float(l16[k]) - float(v)) <= 2e-2 * max(abs(float(v)), 1e-3), (k, float(l16[k]), float(v))
+        assert abs(float(l16[k].detach()) - float(v)) <= 2e-2 * max(abs(float(v)), 1e-3), (k, float(l16[k].detach()), float(v))
     D.parse_losses(l16).backward()
     torch.cuda.synchronize()
 
@@ -122,7 +122,7 @@ def test_reference_driver_over_b200_classes(cuda, golden_dir, rotated, step):
     finally:
         obb.DIFFERENTIABLE_ROI = False
     for k in ol:
-        assert abs(float(l16[k]) - float(ol[k])) <= 2e-2 * max(abs(float(ol[k])), 1e-3), k
+        assert abs(float(l16[k].detach()) - float(ol[k].detach())) <= 2e-2 * max(abs(float(ol[k].detach())), 1e-3), k
     sd = Pg.state_dict()
     named = dict(head.named_parameters())
     checked = 0
@@ -133,6 +133,10 @@ def test_reference_driver_over_b200_classes(cuda, golden_dir, rotated, step):
         if ref is None:
             continue
         got = got.float().cpu()
+        checked += 1
+        if ref.abs().max() < 1e-9:        # mathematically zero (softmax shift invariance of fc_ins.bias)
+            assert got.abs().max() < 1e-6, k
+            continue
         cos = torch.nn.functional.cosine_similarity(got.reshape(1, -1).double(), ref.reshape(1, -1).double()).item()
         assert cos >= 0.995, (k, cos)
         assert (got - ref).norm() <= 0.1 * ref.norm() + 1e-12, (k, float((got - ref).norm() / ref.norm()))
@@ -141,7 +145,6 @@ def test_reference_driver_over_b200_classes(cuda, golden_dir, rotated, step):
         assert abs(float(got.double().norm()) - dg["norm"]) <= 0.1 * dg["norm"] + 1e-12, k
         samp = got.reshape(-1)[dg["idx"]]
         assert (samp - dg["val"]).norm() <= 0.15 * dg["val"].norm() + 1e-3 * dg["norm"], k
-        checked += 1
     assert checked == 14
     # every used parameter received a gradient; the constructed-but-unused reference modules did not
     for n_, p_ in head.named_parameters():
