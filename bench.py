@@ -103,24 +103,56 @@ def make_inputs(seed):
     return synth.hbb_batch(seed=seed)
 
 
+def hbb_config(n_img=2):
+    """The ``config`` object of the headline workload -- identical in the product arm and the reference arm."""
+    return {"workload": WORKLOAD, "images_per_gpu": n_img, "sharding": "per-image, no data-path collective",
+            "l2": "GPU arm: L2 flushed between steps (256 MiB write, untimed), per-step CUDA events; e2e: inputs arrive "
+                  "from pinned host memory every step and the per-step working set (~0.4 GB of operands) exceeds the "
+                  "126 MB L2.  CPU reference arm: host caches as they come",
+            "weights": "GPU arm: fp32->bf16 + FC1 column permutation redone inside every step (as after an optimizer "
+                       "update); CPU arm: fp32 parameters used directly"}
+
+
 def run_reference(args):
-    """CPU arm: the oracle port on all host threads.  One step = the same batch as the GPU arm."""
+    """CPU arm, honouring --steps / --warmup: one step = the same batch as the GPU arm.  Where /root/reference is
+    mounted (the dev container) the reference's OWN files are timed under the import shim (``kind: reference-shim``:
+    the reference's syn_images_generator_v2 functions + TS_P2BFCOSHead.MIL_head_burn_in_step2 with torchvision's
+    roi_align standing in for the un-vendored mmcv kernel); elsewhere (the GPU box) the oracle port, which is pinned
+    bit-for-bit against those files (``kind: port``).  All host threads."""
     import torch
-    from oracle import hbb
+    from oracle import hbb, ref_shim
     from point_teacher_b200 import synth
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     torch.set_num_threads(os.cpu_count() or 1)
     d = make_inputs(0)
-    P = hbb.MilHeadParams(num_stages=1, seed=0)
+    cap = 100
+    if ref_shim.available():
+        kind = "reference-shim"
+        ns = ref_shim.install()
+        head = ref_shim.build_ref_mil_head(ns, num_stages=1, top_k=1, seed=0)
+        pb = [b[:cap].clone() for b in d["pseudo_boxes"]]
+        gb = [b[:cap].clone() for b in d["gt_boxes"]]
+        pp = [b[:cap].clone() for b in d["pseudo_points"]]
+        pl = [b[:cap].clone() for b in d["pseudo_labels"]]
 
-    def step():
-        with torch.no_grad():
-            return hbb.phase2_refine(P, (d["feat"],), [d["stride"]], d["img_metas"], d["pseudo_boxes"],
-                                     d["pseudo_points"], d["pseudo_labels"], d["gt_boxes"], synth.HBB_FINE_CFG,
-                                     synth.HBB_EXT_CFG, num_stages=1, cap=100, injected_negs=d["neg_boxes"])
-    steps, warm = min(args.steps, 5), min(args.warmup, 1)
+        def step():
+            with torch.no_grad():
+                props, valids, refs, reals = ns.syn.MIL_gen_proposals_from_cfg(pp, pb, synth.HBB_FINE_CFG[0], gb, d["img_metas"])
+                negs, nw = ns.syn.gen_negative_proposals(pp, synth.HBB_FINE_CFG[0], props, d["img_metas"])
+                return head.MIL_head_burn_in_step2((d["feat"],), d["img_metas"], props, valids, refs, reals, negs, nw, pb,
+                                                   pl, synth.HBB_EXT_CFG[0], 0)
+    else:
+        kind = "port"
+        P = hbb.MilHeadParams(num_stages=1, seed=0)
+
+        def step():
+            with torch.no_grad():
+                return hbb.phase2_refine(P, (d["feat"],), [d["stride"]], d["img_metas"], d["pseudo_boxes"],
+                                         d["pseudo_points"], d["pseudo_labels"], d["gt_boxes"], synth.HBB_FINE_CFG,
+                                         synth.HBB_EXT_CFG, num_stages=1, cap=cap, injected_negs=d["neg_boxes"])
+    steps, warm = max(args.steps, 1), max(args.warmup, 0)
     for _ in range(warm):
         step()
     t0 = time.perf_counter()
@@ -128,12 +160,14 @@ def run_reference(args):
         step()
     dt = (time.perf_counter() - t0) / steps
     val = 2.0 / dt
-    sample = f"{steps} full steps of the workload (2 images each), {warm} warm-up"
+    sample = (f"{steps} full steps of the workload (2 images each) after {warm} warm-up steps; "
+              + ("the reference's own files under oracle/ref_shim.py" if kind == "reference-shim" else
+                 "oracle/hbb.py (PyTorch fp32 + torchvision roi_align), pinned bit-for-bit against the reference's files"))
     print(json.dumps({
         "impl": "reference", "metric": METRIC, "value": val, "unit": "imgs/s", "n_gpus": args.gpus, "steps": steps,
         "warmup": warm, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": "f32", "data": "synthetic", "config": {"workload": WORKLOAD},
-        "cpu_baseline": {"value": val, "unit": "imgs/s", "cores": torch.get_num_threads(), "kind": "port",
+        "dtype": "f32", "data": "synthetic", "config": hbb_config(),
+        "cpu_baseline": {"value": val, "unit": "imgs/s", "cores": torch.get_num_threads(), "kind": kind,
                          "sample": sample},
         "e2e": {"value": val, "unit": "imgs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
 
@@ -418,13 +452,8 @@ def run_ours(args):
             "scaling": "weak", "vs_baseline": None,
             "dtype": "bf16 (fp32 accumulate; fp32 box/score math)" if args.precision == "bf16" else "bf16x3 (fp32 emulation)",
             "data": "synthetic",
-            "config": {"workload": WORKLOAD, "images_per_gpu": n_img, "sharding": "per-image, no data-path collective",
-                       "launch": "eager" if args.no_graph else "cuda_graph",
-                       "l2": "value: flushed between steps (256 MiB write, untimed), per-step CUDA events; "
-                             "e2e: inputs arrive from pinned host memory every step and the per-step working set "
-                             "(~0.4 GB of operands) exceeds the 126 MB L2",
-                       "weights": "fp32->bf16 + FC1 column permutation redone inside every step",
-                       "roi_feature_map": f"NHWC {feat_dt}"},
+            "config": hbb_config(n_img),
+            "impl_details": {"launch": "eager" if args.no_graph else "cuda_graph", "roi_feature_map": f"NHWC {feat_dt}"},
             "e2e": {"value": total_imgs / (e2e_ms * 1e-3), "unit": "imgs/s", "h2d_bytes_per_step": h2d_bytes,
                     "d2h_bytes_per_step": d2h_bytes, "ms_per_step": e2e_ms,
                     "api": "point_teacher_b200.refine.Phase2Pipeline.submit/result (double-buffered H2D)",

@@ -285,6 +285,30 @@ unpermute_dw1_kernel(const float* __restrict__ dwp, int C, int bins, float* __re
   }
 }
 
+// Whole-row variant (C * bins * 4 B <= 64 KB, i.e. the shipped 256 x 49 = 50 KB): the bin-major row is one contiguous
+// 16-byte-vector read, lands in shared memory at its parameter position (stride `bins` between consecutive channels:
+// odd -> bank-conflict-free scalar stores) and leaves as one contiguous 16-byte-vector write.  4 CTAs / SM.
+__global__ void __launch_bounds__(256)
+unpermute_dw1_row_kernel(const float* __restrict__ dwp, int C, int bins, float* __restrict__ grad, int accumulate) {
+  extern __shared__ __align__(16) float row[];          // [C * bins] in parameter order
+  const int n = blockIdx.x, L = C * bins;
+  const float4* src = reinterpret_cast<const float4*>(dwp + (size_t)n * L);
+  for (int i = threadIdx.x; i < L / 4; i += blockDim.x) {
+    const float4 v = __ldcs(src + i);                   // streamed: read exactly once
+    const int j = i * 4, b = j / C, c = j - b * C;      // C % 4 == 0: the four values share the bin
+    row[(c + 0) * bins + b] = v.x; row[(c + 1) * bins + b] = v.y;
+    row[(c + 2) * bins + b] = v.z; row[(c + 3) * bins + b] = v.w;
+  }
+  __syncthreads();
+  float4* dst = reinterpret_cast<float4*>(grad + (size_t)n * L);
+  const float4* r4 = reinterpret_cast<const float4*>(row);
+  for (int i = threadIdx.x; i < L / 4; i += blockDim.x) {
+    float4 v = r4[i];
+    if (accumulate) { const float4 o = dst[i]; v.x += o.x; v.y += o.y; v.z += o.z; v.w += o.w; }
+    dst[i] = v;
+  }
+}
+
 // db[n] (+)= sum_m dZ[m][n], dZ bf16 [M, ld].  Block = 32 column groups (8 columns = one 16-byte load each) x 8 row
 // lanes; a block covers 256 columns and a contiguous slab of rows; partials meet in shared memory, one atomic per column.
 __global__ void __launch_bounds__(256)
@@ -693,9 +717,23 @@ extern "C" int pt_transpose_pad_bf16(const void* in, long long ldin, int R, int 
   return check_launch("transpose_pad_bf16_kernel");
 }
 
+static int unpermute_row(const float* dw_binmajor, int N, int C, int bins, float* grad, int accumulate, cudaStream_t st) {
+  const size_t smem = (size_t)C * bins * sizeof(float);
+  static bool attr_done = false;
+  if (!attr_done) {
+    cudaError_t e = cudaFuncSetAttribute(ptb::unpermute_dw1_row_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
+    if (e != cudaSuccess) { ptb::set_error("cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return PT_ERR_CUDA; }
+    attr_done = true;
+  }
+  ptb::unpermute_dw1_row_kernel<<<N, 256, smem, st>>>(dw_binmajor, C, bins, grad, accumulate);
+  return ptb::check_launch("unpermute_dw1_row_kernel");
+}
+
 extern "C" int pt_unpermute_dw1(const float* dw_binmajor, int N, int C, int bins, float* grad, int accumulate,
                                 void* stream) {
   if (N <= 0) return PT_OK;
+  if (C % 4 == 0 && (size_t)C * bins * sizeof(float) <= 64 * 1024 && (((uintptr_t)dw_binmajor | (uintptr_t)grad) & 15) == 0)
+    return unpermute_row(dw_binmajor, N, C, bins, grad, accumulate, (cudaStream_t)stream);
   const size_t smem = (size_t)(UNP_CH + 1) * bins * sizeof(float);
   if (smem > 48 * 1024) { set_error("pt_unpermute_dw1: %d bins exceed shared memory", bins); return PT_ERR_UNSUPPORTED; }
   dim3 grid(N, (C + UNP_CH - 1) / UNP_CH);

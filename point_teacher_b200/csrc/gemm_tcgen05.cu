@@ -607,9 +607,35 @@ extern "C" int pt_fc_gemm_bf16_mn(const void* A, long long lda, int a_mn, const 
   }
   const size_t sm = Cfg<false>::SMEM_BYTES;
   cudaStream_t st = (cudaStream_t)stream;
-  if (a_mn && b_mn) fc_gemm_kernel<false, true, true><<<grid_u, NUM_THREADS, sm, st>>>(ma, mb, p);
-  else if (a_mn) fc_gemm_kernel<false, true, false><<<grid_u, NUM_THREADS, sm, st>>>(ma, mb, p);
-  else if (b_mn) fc_gemm_kernel<false, false, true><<<grid_u, NUM_THREADS, sm, st>>>(ma, mb, p);
-  else fc_gemm_kernel<false><<<grid_u, NUM_THREADS, sm, st>>>(ma, mb, p);
+  // The split-K tail meets at a counter, so every CTA of the grid must be resident at the same time.  That is a
+  // CHECKED launch precondition, not an assumption: (1) the occupancy query must allow grid_u CTAs on num_sms SMs,
+  // else the launch falls back to the unsplit schedule; (2) split launches carry the cooperative attribute, with
+  // which the driver refuses a grid that cannot be co-resident (cudaErrorCooperativeLaunchTooLarge) and the
+  // hardware schedules the grid all-or-nothing even when other kernels (weight casts on the side stream, NCCL's
+  // all-reduce under the backward) hold part of the GPU.
+  static int occ_per_sm = -1;
+  if (occ_per_sm < 0) {
+    int o = 0;
+    cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o, fc_gemm_kernel<false>, NUM_THREADS, sm);
+    if (e != cudaSuccess) { set_error("cudaOccupancyMaxActiveBlocksPerMultiprocessor: %s", cudaGetErrorString(e)); return PT_ERR_CUDA; }
+    occ_per_sm = o;
+  }
+  if (p.split > 0 && (long long)grid_u > (long long)occ_per_sm * num_sms) { p.split = 0; p.ws = nullptr; p.counters = nullptr; }
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(grid_u); cfg.blockDim = dim3(NUM_THREADS);
+  cfg.dynamicSmemBytes = sm; cfg.stream = st;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeCooperative;
+  at[0].val.cooperative = 1;
+  cfg.attrs = at; cfg.numAttrs = p.split > 0 ? 1 : 0;
+  cudaError_t le;
+  if (a_mn && b_mn) le = cudaLaunchKernelEx(&cfg, fc_gemm_kernel<false, true, true>, ma, mb, p);
+  else if (a_mn) le = cudaLaunchKernelEx(&cfg, fc_gemm_kernel<false, true, false>, ma, mb, p);
+  else if (b_mn) le = cudaLaunchKernelEx(&cfg, fc_gemm_kernel<false, false, true>, ma, mb, p);
+  else le = cudaLaunchKernelEx(&cfg, fc_gemm_kernel<false>, ma, mb, p);
+  if (le != cudaSuccess) {
+    set_error("fc_gemm_kernel: launch failed (split %d, grid %d): %s", p.split, grid_u, cudaGetErrorString(le));
+    return PT_ERR_CUDA;
+  }
   return check_launch("fc_gemm_kernel");
 }

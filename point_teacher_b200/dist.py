@@ -43,31 +43,126 @@ def reduce_mean_losses(losses, group=None):
     return {k: vec[i] for i, k in enumerate(keys)}
 
 
+def _all_reduce_avg_(t, group=None, async_op=False):
+    """In-place mean over ranks.  NCCL averages inside the collective (ncclAvg); gloo (CPU tests) has no AVG."""
+    if dist.get_backend(group) == "nccl":
+        return dist.all_reduce(t, op=dist.ReduceOp.AVG, group=group, async_op=async_op)
+    t /= world()
+    return dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group, async_op=async_op)
+
+
 class MILGradBucket:
-    """One flat fp32 bucket over the gradients of the MIL-head parameters the path uses (27.8 M parameters = 111 MB
-    for one stage); ``all_reduce_()`` averages it across ranks with a single collective and scatters the result
-    back into ``param.grad``."""
+    """The gradients of the MIL-head parameters the path uses, laid out so that the backward kernels write them IN
+    PLACE and each branch can be reduced the moment its last kernel is enqueued.
+
+    ``flat`` (fp32, 27.8 M values = 111 MB per stage) is cut into one contiguous group per (stage, branch):
+
+        reg: [fc_reg.W | fc_reg.b | reg.0.b | reg.1.b | pad]  [reg.1.W]  [reg.0.W]
+        bag: [fc_cls.W fc_ins.W | fc_cls.b fc_ins.b | bag.0.b | bag.1.b | pad]  [bag.1.W]  [bag.0.W]
+             '---- "small" region: accumulated with atomics, zeroed per step ----'  '-- written whole by the wgrad GEMMs --'
+
+    * direct mode (``train.Phase2Trainer``, the hand-written backward): ``targets(stage)`` hands these views to the
+      kernels -- the FC1 weight gradient lands in the operand's bin-major column order straight from the GEMM
+      epilogue, ``reduce_group_(stage, branch)`` launches that group's all-reduce (average; asynchronous on NCCL's
+      stream, so it runs under the other branch's GEMMs / the RoIAlign backward) and ``finish_()`` waits, un-permutes
+      the two FC1 gradients into the parameters' ``c*49 + bin`` order and publishes ``param.grad`` (views of ``flat``
+      for everything else).  No pack / unpack copies, no separate 1/world pass.
+    * legacy mode (``pack_`` / ``all_reduce_`` / ``unpack_``): gradients that autograd left in ``param.grad`` are
+      copied in (parameter order for every entry), reduced with one collective and copied back (``loss.backward()``
+      flows, gloo tests)."""
 
     def __init__(self, head, prefixes=USED_PREFIXES):
-        self.named = [(n, p) for n, p in head.named_parameters() if n.startswith(prefixes) and p.requires_grad]
+        params = dict(head.named_parameters())
+        stages = sorted({int(n.split(".")[1]) for n in params if n.startswith("fc_reg.")})
+        self.groups, order = [], []            # groups: dict(stage, branch, names, lo, hi, small_hi)
+        off = 0
+
+        def pad4(x):
+            return (x + 3) // 4 * 4
+        self.offsets = {}
+        for s in stages:
+            for branch, heads in (("reg", [f"fc_reg.{s}"]), ("bag", [f"fc_cls.{s}", f"fc_ins.{s}"])):
+                fcs = f"shared_fcs_{branch}.{s}"
+                names = [h + ".weight" for h in heads] + [h + ".bias" for h in heads] + \
+                        [f"{fcs}.0.bias", f"{fcs}.1.bias", f"{fcs}.1.weight", f"{fcs}.0.weight"]
+                names = [n for n in names if n in params and n.startswith(prefixes) and params[n].requires_grad]
+                lo = off
+                for n in names:
+                    if n.endswith((".1.weight", ".0.weight")) and n.startswith("shared_fcs"):
+                        off = pad4(off)
+                    if n == f"{fcs}.1.weight":
+                        small_hi = off
+                    self.offsets[n] = off
+                    off += params[n].numel()
+                off = pad4(off)
+                self.groups.append(dict(stage=s, branch=branch, names=names, lo=lo, hi=off, small_hi=small_hi))
+                order += names
+        self.named = [(n, params[n]) for n in order]
         if not self.named:
             raise ValueError("no MIL-head parameters found")
         self.numel = sum(p.numel() for _, p in self.named)
         dev = self.named[0][1].device
-        self.flat = torch.zeros((self.numel,), dtype=torch.float32, device=dev)
-        self.views, off = [], 0
-        for _, p in self.named:
-            self.views.append(self.flat[off:off + p.numel()].view_as(p))
-            off += p.numel()
+        self.flat = torch.zeros((off,), dtype=torch.float32, device=dev)
+        self.views = [self.flat[self.offsets[n]:self.offsets[n] + p.numel()].view_as(p) for n, p in self.named]
+        self._view = {n: v for (n, _), v in zip(self.named, self.views)}
+        self._w1_grad = {}                     # persistent parameter-order gradient of the two FC1 weights per stage
+        self._works = []
+        self.head = head
 
     def names(self):
         return [n for n, _ in self.named]
 
+    # ---------------------------------------------------------------- direct mode
+    def targets(self, stage):
+        """Views the backward kernels of ``stage`` write into: {'reg'|'bag': dict(Wh, bh, b1, b2, W2, W1p)}."""
+        out = {}
+        v = self._view
+        for branch, heads in (("reg", [f"fc_reg.{stage}"]), ("bag", [f"fc_cls.{stage}", f"fc_ins.{stage}"])):
+            fcs = f"shared_fcs_{branch}.{stage}"
+            o0 = self.offsets[heads[0] + ".weight"]
+            rows = sum(v[h + ".weight"].shape[0] for h in heads)
+            D = v[heads[0] + ".weight"].shape[1]
+            ob = self.offsets[heads[0] + ".bias"]
+            out[branch] = dict(Wh=self.flat[o0:o0 + rows * D].view(rows, D), bh=self.flat[ob:ob + rows],
+                               b1=v[f"{fcs}.0.bias"], b2=v[f"{fcs}.1.bias"], W2=v[f"{fcs}.1.weight"],
+                               W1p=v[f"{fcs}.0.weight"])
+        return out
+
+    def zero_small_(self):
+        for g in self.groups:
+            self.flat[g["lo"]:g["small_hi"]].zero_()
+
+    def reduce_group_(self, stage, branch, group=None):
+        """Average this (stage, branch) slice over the ranks; asynchronous (joined by ``finish_``)."""
+        if world() == 1:
+            return
+        g = next(x for x in self.groups if x["stage"] == stage and x["branch"] == branch)
+        self._works.append(_all_reduce_avg_(self.flat[g["lo"]:g["hi"]], group=group, async_op=True))
+
+    def finish_(self):
+        """Join the outstanding reductions, put the FC1 weight gradients into parameter order, publish ``.grad``."""
+        from . import ops
+        for w in self._works:
+            w.wait()
+        self._works = []
+        head = self.head
+        for (n, p), v in zip(self.named, self.views):
+            if n.startswith("shared_fcs") and n.endswith(".0.weight"):
+                g = self._w1_grad.get(n)
+                if g is None:
+                    g = self._w1_grad[n] = torch.empty_like(p)
+                ops.unpermute_dw1(v, head.in_channels, head.roi_feat_area, g, accumulate=False)
+                p.grad = g
+            else:
+                p.grad = v
+        return self
+
+    # ---------------------------------------------------------------- legacy mode
     def pack_(self):
         for (_, p), v in zip(self.named, self.views):
             if p.grad is None:
                 v.zero_()
-            else:
+            elif p.grad.data_ptr() != v.data_ptr():
                 v.copy_(p.grad)
         return self.flat
 
@@ -75,8 +170,7 @@ class MILGradBucket:
         self.pack_()
         if world() == 1:
             return self.unpack_()
-        self.flat /= world()
-        work = dist.all_reduce(self.flat, op=dist.ReduceOp.SUM, group=group, async_op=async_op)
+        work = _all_reduce_avg_(self.flat, group=group, async_op=async_op)
         if async_op:
             return work
         return self.unpack_()
@@ -85,6 +179,6 @@ class MILGradBucket:
         for (_, p), v in zip(self.named, self.views):
             if p.grad is None:
                 p.grad = v.clone()
-            else:
+            elif p.grad.data_ptr() != v.data_ptr():
                 p.grad.copy_(v)
         return self

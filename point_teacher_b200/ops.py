@@ -229,9 +229,22 @@ PROFILE = {"on": False, "events": []}
 
 
 def gemm_workspace(device):
-    key = (device.index if device.index is not None else torch.cuda.current_device())
-    if key not in _WS:
+    """Split-K workspace (partial slots + counters that must be zero between launches).  Two GEMMs running
+    concurrently on different streams must not share it, so eager launches get one workspace per (device, stream);
+    launches recorded into CUDA graphs share one capture workspace per device (graph replays are stream-ordered by
+    their callers), allocated ahead of the capture so that no allocation / memset is recorded into a graph."""
+    dev = device.index if device.index is not None else torch.cuda.current_device()
+    n = None
+    cap_key = (dev, "capture")
+    if cap_key not in _WS and not torch.cuda.is_current_stream_capturing():
         n = _lib.load().pt_fc_gemm_workspace_bytes(num_sms())
+        _WS[cap_key] = torch.zeros((n,), dtype=_u8, device=device)
+    if torch.cuda.is_current_stream_capturing():
+        key = cap_key
+    else:
+        key = (dev, torch.cuda.current_stream(device).cuda_stream)
+    if key not in _WS:
+        n = n or _lib.load().pt_fc_gemm_workspace_bytes(num_sms())
         _WS[key] = torch.zeros((n,), dtype=_u8, device=device)  # zeroed once; the kernel leaves it zeroed
     return _WS[key]
 
@@ -534,7 +547,7 @@ def fc_gemm_masked(A, B, mask, out_dtype=_bf16, M=None, allow_split=True):
     return out
 
 
-def fc_gemm_mn(A, B, a_mn=False, b_mn=False, mask=None, out_dtype=_bf16, M=None, K=None, allow_split=True):
+def fc_gemm_mn(A, B, a_mn=False, b_mn=False, mask=None, out_dtype=_bf16, M=None, K=None, allow_split=True, out=None):
     """C[M,N] = A' @ B'^T with operands as they are stored: ``a_mn`` -> A is [K, M] (else [M, K]); ``b_mn`` -> B is
     [K, N] (else [N, K]).  ``M`` / ``K`` restrict to the leading rows of padded buffers.  Optional ReLU-backward
     ``mask`` [>=M, N] bf16.  nn.Linear autograd (dW = dY^T X, dX = dY W) with no transposed copies."""
@@ -555,10 +568,15 @@ def fc_gemm_mn(A, B, a_mn=False, b_mn=False, mask=None, out_dtype=_bf16, M=None,
         _chk(mask, "mask", _bf16, 2)
         if mask.shape[1] != N or mask.shape[0] < M:
             raise ValueError("fc_gemm_mn: mask shape mismatch")
-    out = torch.empty((rows_out, N), dtype=out_dtype, device=A.device)
+    if out is None:
+        out = torch.empty((rows_out, N), dtype=out_dtype, device=A.device)
+    else:
+        if out.dim() != 2 or out.shape[0] < rows_out or out.shape[1] != N or out.stride(1) != 1 or \
+                out.dtype not in (_bf16, _f32) or (out.data_ptr() & 15) or (out.stride(0) * out.element_size()) & 15:
+            raise ValueError("fc_gemm_mn: out must be a 16-byte aligned row-major [>=M, N] bf16 / fp32 tensor")
     ws = gemm_workspace(A.device)
     _lib.call("pt_fc_gemm_bf16_mn", _p(A), A.shape[1], int(a_mn), _p(B), B.shape[1], int(b_mn), _p(None), _p(out),
-              out.shape[1], M, N, K, 0, int(out.dtype == _f32), _p(mask), 0 if mask is None else mask.shape[1], _p(ws),
+              out.stride(0), M, N, K, 0, int(out.dtype == _f32), _p(mask), 0 if mask is None else mask.shape[1], _p(ws),
               ws.numel(), num_sms(), int(allow_split), _stream())
     return out
 

@@ -23,32 +23,44 @@ def stage_params(head, stage):
     return [t for m in mods for t in (m.weight, m.bias)]
 
 
-def _fc_branch_backward(head, k, dZ2, need_dA):
+def _fc_branch_backward(head, k, dZ2, need_dA, out=None):
     """k: what ``_fc_stack`` kept (A, H1, H2, W1 (bin-major bf16), W2 (bf16), M).  dZ2 bf16 [rows, 1024] = gradient
-    at the pre-activation of the second FC (already ReLU-masked).  Returns (dW1 in the parameter's column order, db1,
-    dW2, db2, dA | None)."""
+    at the pre-activation of the second FC (already ReLU-masked).  Returns (dW1, db1, dW2, db2, dA | None).
+    ``out`` (``dist.MILGradBucket.targets``): the kernels write into the bucket's views; dW1 then STAYS in the
+    operand's bin-major column order (``MILGradBucket.finish_`` un-permutes it after the all-reduce); without
+    ``out`` fresh tensors are returned and dW1 is in the parameter's column order."""
     M, dev = k["M"], dZ2.device
     N1 = k["W1"].shape[0]
+    o = out or {}
     # every operand is consumed in the layout the forward left it in (MN-major tcgen05 tiles): no transposed copies
     dZ1 = ops.fc_gemm_mn(dZ2, k["W2"], b_mn=True, mask=k["H1"], M=M)                                # (dZ2 @ W2) * (H1 > 0)
-    dW2 = ops.fc_gemm_mn(dZ2, k["H1"], a_mn=True, b_mn=True, out_dtype=torch.float32, K=M)          # dZ2^T @ H1
-    db2 = ops.colsum_bf16(dZ2, torch.zeros((dZ2.shape[1],), dtype=torch.float32, device=dev), M=M)
-    dW1p = ops.fc_gemm_mn(dZ1, k["A"], a_mn=True, b_mn=True, out_dtype=torch.float32, K=M)          # [N1, 49*C] bin-major
-    dW1 = torch.empty_like(dW1p)
-    ops.unpermute_dw1(dW1p, head.in_channels, head.roi_feat_area, dW1, accumulate=False)
-    db1 = ops.colsum_bf16(dZ1, torch.zeros((N1,), dtype=torch.float32, device=dev), M=M)
+    dW2 = ops.fc_gemm_mn(dZ2, k["H1"], a_mn=True, b_mn=True, out_dtype=torch.float32, K=M, out=o.get("W2"))   # dZ2^T @ H1
+    db2 = o["b2"] if out else torch.zeros((dZ2.shape[1],), dtype=torch.float32, device=dev)
+    ops.colsum_bf16(dZ2, db2, M=M)
+    dW1p = ops.fc_gemm_mn(dZ1, k["A"], a_mn=True, b_mn=True, out_dtype=torch.float32, K=M, out=o.get("W1p"))  # bin-major
+    if out:
+        dW1 = dW1p
+    else:
+        dW1 = torch.empty_like(dW1p)
+        ops.unpermute_dw1(dW1p, head.in_channels, head.roi_feat_area, dW1, accumulate=False)
+    db1 = o["b1"] if out else torch.zeros((N1,), dtype=torch.float32, device=dev)
+    ops.colsum_bf16(dZ1, db1, M=M)
     dA = None
     if need_dA:
         dA = ops.fc_gemm_mn(dZ1, k["W1"], b_mn=True, out_dtype=torch.bfloat16, M=M)                 # dZ1 @ W1
     return dW1, db1, dW2, db2, dA
 
 
-def mil_stage_backward(head, keep, x, g_bbox, g_bags, need_feat_grad=True):
+def mil_stage_backward(head, keep, x, g_bbox, g_bags, need_feat_grad=True, targets=None, branch_done=None):
     """Gradients of (g_bbox * loss_mil_bbox + g_bags * loss_mil_bags) for one stage.  g_* are 1-element fp32 CUDA
     tensors (no host read); ``None`` skips that branch altogether (phase 1: the synthetic pass has no bag loss and the
     real pass no regression loss, fcos_head_p2b_ts.py:1279-1316).  ``x``: the feature map or the tuple of maps the
     forward pooled from.  Returns (dfeat NCHW fp32 | None -- a list when ``x`` is a tuple --, [14 parameter gradients in
-    ``stage_params`` order, ``None`` for the skipped branch])."""
+    ``stage_params`` order, ``None`` for the skipped branch]).
+    ``targets`` (``MILGradBucket.targets(stage)``): parameter gradients are written in place into the bucket (FC1 weight
+    gradients bin-major, small-head / bias slots must have been zeroed); ``branch_done(stage, 'reg'|'bag')`` is
+    called the moment a branch's last parameter-gradient kernel is enqueued (the trainer launches that group's
+    all-reduce there, so that it runs under the rest of the backward)."""
     feats = list(x) if isinstance(x, (tuple, list)) else [x]
     feats = feats[:head.bbox_roi_extractor.num_inputs]
     stage, dev = keep["stage"], keep["ebags"].device
@@ -66,17 +78,24 @@ def mil_stage_backward(head, keep, x, g_bbox, g_bags, need_feat_grad=True):
     if do_reg:
         g4 = ops.reg_loss_grad(keep["deltas"], keep["ebags"], keep["evalid"], keep["ref"], U1 * U2, keep["max_wh"],
                                keep["sums"], g_bbox, s_bbox, hyper=head._dn_hyper(), rotated=rot)
-        dWreg, dbreg = torch.zeros_like(fr.weight), torch.zeros_like(fr.bias)
+        tg = targets["reg"] if targets else None
+        dWreg, dbreg = (tg["Wh"], tg["bh"]) if tg else (torch.zeros_like(fr.weight), torch.zeros_like(fr.bias))
         dZ2 = ops.head_bwd(g4, keep["reg"]["H2"], fr.weight.detach(), dWreg, dbreg, M=K)
-        r = _fc_branch_backward(head, keep["reg"], dZ2, need_feat_grad)
+        r = _fc_branch_backward(head, keep["reg"], dZ2, need_feat_grad, tg)
+        if branch_done is not None:
+            branch_done(stage, "reg")
     # ---- bag branch: gfocal -> bag score -> (sigmoid, softmax x valid x L1) -> fc_cls / fc_ins -> FC2 -> FC1
     if do_bag:
         g16 = ops.bag_loss_grad(keep["cls"], keep["ins"], keep["evalid"], keep["labels"], G, U1, U2, keep["neg_w"], n_neg,
                                 keep["sums"], g_bags, s_bags * head.bag_loss_pos_scale, s_bags * head.bag_loss_neg_scale)
         Wci = torch.cat([fc.weight.detach(), fi.weight.detach()], 0).contiguous()
-        dWci, dbci = torch.zeros_like(Wci), torch.zeros((2 * C,), dtype=torch.float32, device=dev)
+        tg = targets["bag"] if targets else None
+        dWci, dbci = (tg["Wh"], tg["bh"]) if tg else \
+            (torch.zeros_like(Wci), torch.zeros((2 * C,), dtype=torch.float32, device=dev))
         dZ2b = ops.head_bwd(g16, keep["bag"]["H2"], Wci, dWci, dbci, M=K + n_neg)
-        b = _fc_branch_backward(head, keep["bag"], dZ2b, need_feat_grad)
+        b = _fc_branch_backward(head, keep["bag"], dZ2b, need_feat_grad, tg)
+        if branch_done is not None:
+            branch_done(stage, "bag")
     dfeat = None
     if need_feat_grad:
         dfeat = []
@@ -191,15 +210,18 @@ class Phase2Trainer:
                 one = torch.ones((1,), dtype=torch.float32, device=x[0].device)
                 need_x = x[0].requires_grad
                 dx = None
+                self.bucket.zero_small_()
                 for keep in head._train_keeps:
-                    dfeat, grads = mil_stage_backward(head, keep, x[0], one, one, need_x)
-                    for p, g in zip(stage_params(head, keep["stage"]), grads):
-                        p.grad = g if p.grad is None else p.grad + g
+                    dfeat, _ = mil_stage_backward(head, keep, x[0], one, one, need_x,
+                                                  targets=self.bucket.targets(keep["stage"]),
+                                                  branch_done=self.bucket.reduce_group_)
                     if need_x:
                         dx = dfeat if dx is None else dx + dfeat
                 head._train_keeps = []
                 if need_x:
                     x[0].grad = dx if x[0].grad is None else x[0].grad + dx
+                self.bucket.finish_()
+            return boxes, pts, (reduce_mean_losses(losses) if reduce_logs else losses)
         self.bucket.all_reduce_()
         return boxes, pts, (reduce_mean_losses(losses) if reduce_logs else losses)
 
@@ -236,5 +258,7 @@ class CapturedTrainStep:
                                  i["gt_boxes"], neg_boxes=i.get("neg_boxes"), reduce_logs=False)
 
     def replay(self):
+        for layer in self.trainer.head.bbox_roi_extractor.roi_layers:
+            layer._cache.check(captured=True)          # fp16 feature-map range guard (word of earlier replays)
         self.graph.replay()
         return self.outputs
