@@ -627,7 +627,9 @@ extern "C" int pt_fc_gemm_bf16_mn(const void* A, long long lda, int a_mn, const 
   cudaLaunchAttribute at[1];
   at[0].id = cudaLaunchAttributeCooperative;
   at[0].val.cooperative = 1;
-  cfg.attrs = at; cfg.numAttrs = p.split > 0 ? 1 : 0;
+  static int no_coop = -1;       // PTB200_GEMM_NO_COOP=1: measurement switch only (drops the co-scheduling guarantee)
+  if (no_coop < 0) { const char* e = getenv("PTB200_GEMM_NO_COOP"); no_coop = (e != nullptr && e[0] == '1') ? 1 : 0; }
+  cfg.attrs = at; cfg.numAttrs = (p.split > 0 && !no_coop) ? 1 : 0;
   cudaError_t le;
   if (a_mn && b_mn) le = cudaLaunchKernelEx(&cfg, fc_gemm_kernel<false, true, true>, ma, mb, p);
   else if (a_mn) le = cudaLaunchKernelEx(&cfg, fc_gemm_kernel<false, true, false>, ma, mb, p);

@@ -159,8 +159,9 @@ def nchw_to_nhwc(x, out_dtype=_f32, sat_count=None):
     out = torch.empty((B, H, W, C), dtype=out_dtype, device=x.device)
     if out_dtype not in _FEAT_CODE:
         raise ValueError("NHWC feature map must be fp32, bf16 or fp16")
-    if sat_count is not None:
-        _chk(sat_count, "sat_count", _i32, 1)
+    if sat_count is not None:      # device int32, or PINNED host int32 (reached through the unified address space)
+        if sat_count.dtype != _i32 or sat_count.numel() != 1 or not (sat_count.is_cuda or sat_count.is_pinned()):
+            raise ValueError("sat_count: expected one int32 in device or pinned host memory")
     _lib.call("pt_nchw_to_nhwc_ex", _p(x), _p(out), B, C, H, W, _FEAT_CODE[out_dtype], _p(sat_count), _stream())
     return out
 

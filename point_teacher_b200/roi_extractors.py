@@ -34,9 +34,9 @@ class _NHWCCache:
     pointer: a training loop produces a fresh backbone output every step, and the caching allocator usually hands
     the same address back, so a pointer key would silently pool step N+1 from step N's features.
 
-    fp16 maps (the tensor-core RoIAlign operand) saturate at +-65504.  Every fp16 transpose counts the values it
-    clipped into a device counter whose value reaches a pinned host word asynchronously; the NEXT call looks at it
-    (no synchronisation on the hot path) and, if anything was clipped, switches this layer to bf16 maps for good
+    fp16 maps (the tensor-core RoIAlign operand) saturate at +-65504.  Every fp16 transpose adds the number of values
+    it clipped to a word in pinned host memory (written by the kernel itself, only when something clipped); the NEXT
+    call looks at it (no synchronisation on the hot path) and, if anything was clipped, switches this layer to bf16 maps for good
     with a warning -- or raises ``FeatureRangeError`` when ``on_saturation == 'raise'`` (captured steps, which cannot
     switch dtype, always raise from ``CapturedPhase2.replay``)."""
 
@@ -44,15 +44,13 @@ class _NHWCCache:
 
     def __init__(self):
         self._ref, self._key, self._val = None, None, None
-        self._sat = self._sat_host = self._sat_ev = None
+        self._sat_host = None
         self.force_bf16 = False
         self.saturated_total = 0
 
     def _poll(self, captured=False):
-        """Non-blocking look at the saturation word of EARLIER transposes."""
+        """Non-blocking look at the saturation word (it may lag the device by the transposes still in flight)."""
         if self._sat_host is None:
-            return
-        if self._sat_ev is not None and not self._sat_ev.query():
             return
         n = int(self._sat_host[0])
         if n > self.saturated_total:
@@ -66,38 +64,29 @@ class _NHWCCache:
             self.force_bf16 = True
 
     def check(self, sync=False, captured=False):
-        """Explicit check (``sync=True`` waits for the outstanding transposes first; ``captured``: the caller replays a
-        CUDA graph whose dtype is frozen, so a clipped value always raises)."""
+        """Explicit check (``sync=True`` waits for the device first; ``captured``: the caller replays a CUDA graph
+        whose dtype is frozen, so a clipped value always raises)."""
         if sync:
-            if self._sat_ev is not None:
-                self._sat_ev.synchronize()
-            else:
-                torch.cuda.current_stream().synchronize()
+            torch.cuda.synchronize()
         self._poll(captured)
         return self.saturated_total
 
     def get(self, x, dtype):
         if dtype == torch.float16:
-            if not torch.cuda.is_current_stream_capturing():   # cudaEventQuery is illegal while a capture is open
-                self._poll()
+            self._poll()
             if self.force_bf16:
                 dtype = torch.bfloat16
         key = (x._version, tuple(x.shape), dtype, x.device)
         if self._ref is None or self._ref() is not x or key != self._key:
             sat = None
             if dtype == torch.float16:
-                if self._sat is None or self._sat.device != x.device:
-                    self._sat = torch.zeros((1,), dtype=torch.int32, device=x.device)
+                if self._sat_host is None:
+                    # one int32 in PINNED HOST memory, incremented by the kernel itself through the unified address
+                    # space -- and only when a value actually saturates, so the normal step pays nothing: no
+                    # device-to-host copy, no event, nothing extra inside a captured graph
                     self._sat_host = torch.zeros((1,), dtype=torch.int32).pin_memory()
-                sat = self._sat
+                sat = self._sat_host
             self._val = ops.nchw_to_nhwc(x.contiguous(), dtype, sat_count=sat)
-            if sat is not None:
-                self._sat_host.copy_(sat, non_blocking=True)
-                if not torch.cuda.is_current_stream_capturing():
-                    self._sat_ev = torch.cuda.Event()
-                    self._sat_ev.record()
-                else:
-                    self._sat_ev = None            # a replayed graph refreshes the word; replay() polls it
             self._ref, self._key = weakref.ref(x), key
         return self._val
 
