@@ -186,7 +186,7 @@ class CapturedPhase2:
     the captured step, which is what a training loop (weights change every iteration) needs."""
 
     def __init__(self, head, inputs, img_metas, fine_cfg, ext_cfg, num_stages=1, cap=100, alpha=(0.01, 0.25),
-                 refresh_weights=True, warmup=3):
+                 refresh_weights=True, warmup=3, gather_outputs=False):
         self.head, self.inputs, self.img_metas = head, inputs, img_metas
         self.kw = dict(fine_proposal_cfg=fine_cfg, fine_proposal_extensive_cfg=ext_cfg, num_stages=num_stages,
                        num_training_burninstep2=cap, alpha=alpha)
@@ -203,6 +203,11 @@ class CapturedPhase2:
             self.outputs = self._step()
             self.loss_keys = sorted(self.outputs[2])
             self.loss_vec = torch.stack([self.outputs[2][k].reshape(()).float() for k in self.loss_keys])
+            self.out_arena = None
+            if gather_outputs:      # the step's results gathered into ONE device buffer by the graph's last nodes
+                tree = dict(boxes=list(self.outputs[0]), points=list(self.outputs[1]), losses=self.loss_vec)
+                self.out_arena = _Arena(tree, self.loss_vec.device)
+                self.out_arena.fill(tree)
 
     def _step(self):
         i = self.inputs
@@ -223,69 +228,126 @@ class CapturedPhase2:
         return self.outputs
 
 
-class Phase2Pipeline:
-    """Host-facing throughput API: phase-2 refinement of a stream of batches whose inputs live in (pinned) HOST
-    memory.  ``depth`` captured steps (``CapturedPhase2``) are used round-robin; the H2D copy of batch i+1 runs on
-    a copy stream while batch i computes, and every result (refined boxes, points, losses) is copied back into
-    pinned host buffers.  ``submit(host_inputs)`` never blocks the host; ``result(ticket)`` waits for that batch.
+class _Arena:
+    """ONE contiguous byte buffer (device, or pinned host) carrying a nested structure of tensors as 256-byte aligned
+    typed views, so that the whole structure crosses PCIe as a single ``cudaMemcpyAsync``."""
 
-    host_inputs / example_inputs: dict(feat (B,C,H,W) fp32, pseudo_boxes, pseudo_points, pseudo_labels, gt_boxes:
-    lists of per-image tensors, neg_boxes: [per-stage][per-image] injected negatives or None)."""
+    def __init__(self, example, device=None):
+        self.spec, off = [], 0
 
-    def __init__(self, head, example_inputs, img_metas, fine_cfg, ext_cfg, num_stages=1, cap=100,
-                 alpha=(0.01, 0.25), depth=2, refresh_weights=True):
-        def clone(v):
+        def walk(v):
+            nonlocal off
+            if v is None:
+                return None
+            if isinstance(v, dict):
+                return {k: walk(v[k]) for k in sorted(v)}
             if isinstance(v, (list, tuple)):
-                return [clone(t) for t in v]
-            return None if v is None else v.clone()
-        self.depth = depth
-        self.slots = [CapturedPhase2(head, {k: clone(v) for k, v in example_inputs.items()}, img_metas, fine_cfg,
-                                     ext_cfg, num_stages, cap, alpha, refresh_weights) for _ in range(depth)]
-        self.copy_stream = torch.cuda.Stream()
-        self.h2d_done = [torch.cuda.Event() for _ in range(depth)]
-        self.done = [torch.cuda.Event() for _ in range(depth)]
-        self.host_out = []
-        for s in self.slots:
-            boxes, pts, losses = s.outputs
-            self.host_out.append(dict(
-                boxes=[torch.empty(b.shape, dtype=b.dtype).pin_memory() for b in boxes],
-                points=[torch.empty(p.shape, dtype=p.dtype).pin_memory() for p in pts],
-                losses=torch.empty((len(losses),), dtype=torch.float32).pin_memory()))
-        self.loss_keys = self.slots[0].loss_keys
-        self.n = 0
-        self.h2d_bytes = sum(t.numel() * t.element_size() for t in self._flat(example_inputs))
-        self.d2h_bytes = sum(t.numel() * t.element_size()
-                             for t in self.host_out[0]["boxes"] + self.host_out[0]["points"]) + 4 * len(self.loss_keys)
+                return [walk(x) for x in v]
+            off = (off + 255) // 256 * 256
+            rec = (off, tuple(v.shape), v.dtype)
+            off += v.numel() * v.element_size()
+            self.spec.append(rec)
+            return rec
+        tree = walk(example)
+        self.nbytes = (off + 255) // 256 * 256
+        if device is None:
+            self.buf = torch.empty((self.nbytes,), dtype=torch.uint8)
+            if torch.cuda.is_available():
+                self.buf = self.buf.pin_memory()
+        else:
+            self.buf = torch.empty((self.nbytes,), dtype=torch.uint8, device=device)
+        self.payload = sum(int(torch.tensor([], dtype=d).element_size()) * int(torch.Size(sh).numel()) for _, sh, d in self.spec)
+
+        def build(t):
+            if t is None:
+                return None
+            if isinstance(t, dict):
+                return {k: build(x) for k, x in t.items()}
+            if isinstance(t, list):
+                return [build(x) for x in t]
+            o, shape, dtype = t
+            n = int(torch.Size(shape).numel()) * torch.tensor([], dtype=dtype).element_size()
+            return self.buf[o:o + n].view(dtype).view(shape)
+        self.views = build(tree)
 
     @staticmethod
-    def _flat(v):
+    def flat(v):
         if v is None:
             return []
         if isinstance(v, dict):
-            return [t for k in sorted(v) for t in Phase2Pipeline._flat(v[k])]
+            return [t for k in sorted(v) for t in _Arena.flat(v[k])]
         if isinstance(v, (list, tuple)):
-            return [t for x in v for t in Phase2Pipeline._flat(x)]
+            return [t for x in v for t in _Arena.flat(x)]
         return [v]
 
-    def submit(self, host_inputs):
+    def fill(self, values):
+        for dst, src in zip(self.flat(self.views), self.flat(values)):
+            dst.copy_(src)
+
+
+class Phase2Pipeline:
+    """Host-facing throughput API: phase-2 refinement of a stream of batches whose inputs live in HOST memory.
+
+    ``depth`` captured steps (``CapturedPhase2``) are used round-robin.  Every slot owns ONE pinned host staging
+    buffer and ONE device buffer for its inputs (and one pair for its results) with identical layouts
+    (``_Arena``): a step is exactly one ``cudaMemcpyAsync`` host -> device on a copy stream (overlapping the previous
+    step's compute), one graph replay (whose last nodes gather boxes / points / losses into the result buffer) and
+    one ``cudaMemcpyAsync`` device -> host.  The producer writes the next batch straight into
+    ``host_inputs(slot)`` (views of the pinned staging buffer); ``submit(values)`` with loose host tensors is also
+    accepted and first copies them into the staging buffer on the host.
+    ``submit`` never blocks the host; ``result(ticket)`` waits for that batch.
+
+    example_inputs: dict(feat (B,C,H,W) fp32, pseudo_boxes, pseudo_points, pseudo_labels, gt_boxes: lists of
+    per-image tensors, neg_boxes: [per-stage][per-image] injected negatives or None) on the device."""
+
+    def __init__(self, head, example_inputs, img_metas, fine_cfg, ext_cfg, num_stages=1, cap=100,
+                 alpha=(0.01, 0.25), depth=3, refresh_weights=True):
+        dev = example_inputs["feat"].device
+        self.depth = depth
+        self.dev_in = [_Arena(example_inputs, dev) for _ in range(depth)]
+        self.host_in = [_Arena(example_inputs) for _ in range(depth)]
+        for a in self.dev_in:
+            a.fill(example_inputs)
+        for a in self.host_in:
+            a.fill(example_inputs)
+        self.slots, self.dev_out, self.host_out = [], [], []
+        for s in range(depth):
+            c = CapturedPhase2(head, self.dev_in[s].views, img_metas, fine_cfg, ext_cfg, num_stages, cap, alpha,
+                               refresh_weights, gather_outputs=True)
+            self.slots.append(c)
+            self.dev_out.append(c.out_arena)
+            self.host_out.append(_Arena(c.out_arena.views))
+        self.copy_stream = torch.cuda.Stream()
+        self.h2d_done = [torch.cuda.Event() for _ in range(depth)]
+        self.done = [torch.cuda.Event() for _ in range(depth)]
+        self.loss_keys = self.slots[0].loss_keys
+        self.n = 0
+        self.h2d_bytes = self.host_in[0].payload          # what the step consumes (the copy moves nbytes incl. padding)
+        self.d2h_bytes = self.host_out[0].payload
+        self.h2d_copies_per_step = self.d2h_copies_per_step = 1
+
+    def host_inputs(self, slot=None):
+        """Pinned staging views of the slot the NEXT ``submit()`` will use: fill them, then ``submit()``."""
+        return self.host_in[self.n % self.depth if slot is None else slot].views
+
+    def submit(self, host_inputs=None):
         s = self.n % self.depth
         slot, cur = self.slots[s], torch.cuda.current_stream()
+        if host_inputs is not None:
+            self.done[s].synchronize()                         # the staging buffer's previous H2D has long finished
+            self.host_in[s].fill(host_inputs)
         self.copy_stream.wait_event(self.done[s])              # slot inputs are free once its last step finished
         with torch.cuda.stream(self.copy_stream):
-            for dst, src in zip(self._flat(slot.inputs), self._flat(host_inputs)):
-                dst.copy_(src, non_blocking=True)
+            self.dev_in[s].buf.copy_(self.host_in[s].buf, non_blocking=True)       # the ONE H2D of this step
             self.h2d_done[s].record(self.copy_stream)
         cur.wait_event(self.h2d_done[s])
-        boxes, pts, losses = slot.replay()
-        ho = self.host_out[s]
-        for dst, src in zip(ho["boxes"] + ho["points"], list(boxes) + list(pts)):
-            dst.copy_(src, non_blocking=True)
-        ho["losses"].copy_(slot.loss_vec, non_blocking=True)
+        slot.replay()
+        self.host_out[s].buf.copy_(self.dev_out[s].buf, non_blocking=True)         # the ONE D2H of this step
         self.done[s].record(cur)
         self.n += 1
         return s
 
     def result(self, ticket):
         self.done[ticket].synchronize()
-        ho = self.host_out[ticket]
+        ho = self.host_out[ticket].views
         return ho["boxes"], ho["points"], dict(zip(self.loss_keys, ho["losses"].tolist()))
