@@ -84,6 +84,21 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     }
   }
 }
+// Same wait for warps whose partner is a slower producer warp ON THE SAME SM (RoIAlign's MMA warps waiting for the
+// builder warps): back off between polls so that the spin does not take issue slots from the producer.
+__device__ __forceinline__ void mbar_wait_backoff(uint64_t* bar, uint32_t parity, uint32_t ns) {
+  if (mbar_try_wait(bar, parity)) return;
+  long long t0 = 0;
+  for (uint32_t spins = 1;; spins++) {
+    __nanosleep(ns);
+    if (mbar_try_wait(bar, parity)) return;
+    if ((spins & 255u) == 0) {
+      const long long now = clock64();
+      if (t0 == 0) t0 = now;
+      else if (now - t0 > 4000000000LL) __trap();
+    }
+  }
+}
 __device__ __forceinline__ void fence_barrier_init() {
   asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
 }

@@ -46,7 +46,8 @@ constexpr int THREADS = (MMA_WARPS + BUILDERS) * 32;
 // builder warps (12 stages, ~208 KB of shared memory) instead of two CTAs with 2 builders each.  The ncu source view
 // of the 2-builder variant showed the 8 MMA warps spinning on the full barriers 80 % of the time.  (8 builders with
 // single-buffered output staging measured the same step time: beyond 6 the builders are no longer the limiter.)
-constexpr int ROT_BUILDERS = 6;
+constexpr int ROT_BUILDERS = 8, ROT_DEPTH = 13;    // rotated: builder warps, stages of the shared ring
+constexpr int ROT_AHEAD = 4;                        // chunks whose TMA loads a builder fires ahead of its weight build
 constexpr int QUARTER_BYTES = 16 * 128;           // 16 pixels x 64 channels bf16
 constexpr int PATCH_BYTES = 4 * QUARTER_BYTES;    // 8 KB
 constexpr int AFRAG_BYTES = 4 * 32 * 16;          // 4 m-tiles x 32 lanes x uint4
@@ -140,15 +141,18 @@ __device__ __forceinline__ bool axis_setup(float v, int size, int& lo, int& hi, 
 
 // F16: the feature map (and therefore the interpolation weights) are fp16 instead of bf16 -- 3 more mantissa
 // bits on both mma operands, so the interpolation itself adds no visible error on top of the bf16 output.
-template <bool F16, bool ROT>
-__global__ void __launch_bounds__((MMA_WARPS + (ROT ? ROT_BUILDERS : BUILDERS)) * 32, ROT ? 1 : 2)
+template <bool F16, bool ROT, int NB, int DP>      // NB builder warps, each owning a DP-deep stage ring
+__global__ void __launch_bounds__((MMA_WARPS + NB) * 32, ROT ? 1 : 2)
 roi_align_mma_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ CUtensorMap omap,
                      const float* __restrict__ rois, int K, int B, int C, int H, int W,
                      float scale, int sampling_ratio, int aligned, const int* __restrict__ roi_level, int level,
                      int stg_bufs, int clockwise) {
   extern __shared__ uint8_t smem_raw[];
-  constexpr int NB = ROT ? ROT_BUILDERS : BUILDERS;     // builder warps
-  constexpr int NSTAGES = NB * DEPTH;
+  // horizontal: every builder warp owns a DP-deep ring (RoIs of 1..2 chunks).  rotated: ONE ring of DP stages shared by
+  // all builders and consumed strictly in order -- a RoI's chunks occupy consecutive stages starting at the prefix sum
+  // of the chunk counts of all earlier RoIs of this CTA (published builder to builder through a sequence word), so a
+  // many-chunk RoI can use the whole ring and eight builders fit beside it in shared memory.
+  constexpr int NSTAGES = ROT ? DP : NB * DP;
   // shared-window byte addresses (explicit .shared accesses below; generic pointers would cost LD/ST.E)
   const uint32_t sbase = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t s_patch = sbase;                                    // [STAGES][PATCH_BYTES], 1 KB aligned
@@ -162,12 +166,16 @@ roi_align_mma_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_cons
   uint8_t* gen = smem_raw + (sbase - smem_u32(smem_raw));            // generic view of the same window
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(gen + (s_full - sbase));
   uint64_t* empty_bar = reinterpret_cast<uint64_t*>(gen + (s_empty - sbase));
+  volatile int* seq_g = reinterpret_cast<volatile int*>(gen + (s_meta + NSTAGES * 8 - sbase));   // {RoIs published, stages}
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (threadIdx.x == 0) {
     tma_prefetch_desc(&tmap);
     tma_prefetch_desc(&omap);
-    for (int i = 0; i < NSTAGES; i++) { mbar_init(full_bar + i, 1); mbar_init(empty_bar + i, MMA_WARPS); }
+    // rotated: a stage is full after TWO arrivals -- the TMA issue (expect_tx, as soon as the stage is acquired) and
+    // the fragment write (later): the patch flies while the builder still computes the chunk's weights
+    for (int i = 0; i < NSTAGES; i++) { mbar_init(full_bar + i, ROT ? 2 : 1); mbar_init(empty_bar + i, MMA_WARPS); }
+    seq_g[0] = 0; seq_g[1] = 0; seq_g[2] = 0;
     fence_barrier_init();
   }
   __syncthreads();
@@ -189,7 +197,6 @@ roi_align_mma_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_cons
       const uint32_t tx_bytes = (uint32_t)(C / 64) * QUARTER_BYTES;
       const int gs = sampling_ratio, cnt = gs * gs;        // host guarantees 1 <= sampling_ratio <= 2
       const float inv_count = 1.0f / (float)cnt;
-      int slot = 0; uint32_t phase = 0;
       float rnext = 0.f;
       if (bw_id < n_iter && lane < 6) rnext = __ldg(rois + (size_t)(blockIdx.x + bw_id * gridDim.x) * 6 + lane);
       for (int it = bw_id; it < n_iter; it += NB) {
@@ -288,92 +295,136 @@ roi_align_mma_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_cons
           for (int o = 16; o > 0; o >>= 1) pc += __shfl_xor_sync(0xffffffffu, pc, o);
           total = pc;
         }
-        int done = 0;
-        for (int w = 0; w < nwords; w++) {
-          uint32_t bits = use_map ? map_g[w] : 0xffffffffu;
-          while (bits != 0u) {
-            const int chn = w * 32 + __ffs((int)bits) - 1;
-            bits &= bits - 1u;
-            if (chn >= nch) break;
-            const int cy = chn / ncx, cx = chn - cy * ncx;
-            done++;
-            int flags = (done == total ? F_LAST : 0);
-            if (empty) {
-              flags |= skip ? F_SKIP : F_ZERO;
-            } else {
-              const int x0 = xlo + cx * 4, y0 = ylo + cy * 4;
-              __syncwarp();   // the previous chunk's fragment gather is done reading W
-#pragma unroll
-              for (int j = 0; j < 2; j++) {
-                const int bin = lane + 32 * j;
-                if (bin < NBIN) {
-                  float wv[16];
-#pragma unroll
-                  for (int i = 0; i < 16; i++) wv[i] = 0.f;
-#pragma unroll
-                  for (int sub = 0; sub < ROT_SAMPLES; sub++) {
-                    const uint4 r = rec[j * ROT_SAMPLES + sub];
-                    const int dxl = (int)(r.x & 0xffffu) - x0, dxh = (int)(r.x >> 16) - x0;
-                    const int dyl = (int)(r.y & 0xffffu) - y0, dyh = (int)(r.y >> 16) - y0;
-                    const float lx = __uint_as_float(r.z), ly = __uint_as_float(r.w);
-                    const float hx = fsub(1.0f, lx), hy = fsub(1.0f, ly);
-                    float cw[4], rwt[4];
-#pragma unroll
-                    for (int c = 0; c < 4; c++) {
-                      cw[c] = (dxl == c ? hx : 0.f) + (dxh == c ? lx : 0.f);
-                      rwt[c] = (dyl == c ? hy : 0.f) + (dyh == c ? ly : 0.f);
-                    }
-#pragma unroll
-                    for (int rr = 0; rr < 4; rr++)
-#pragma unroll
-                      for (int c = 0; c < 4; c++) wv[rr * 4 + c] += rwt[rr] * cw[c];
-                  }
-                  const uint32_t wrow = s_w + (uint32_t)bin * (ROT_W_STRIDE * 4);
-#pragma unroll
-                  for (int i = 0; i < 4; i++)
-                    sts128(wrow + i * 16, make_uint4(__float_as_uint(wv[4 * i] * inv_count), __float_as_uint(wv[4 * i + 1] * inv_count),
-                                                     __float_as_uint(wv[4 * i + 2] * inv_count), __float_as_uint(wv[4 * i + 3] * inv_count)));
-                }
-              }
-              __syncwarp();
+        // Two cursors walk the RoI's chunk list: the ISSUE cursor acquires a stage and fires the chunk's TMA load at
+        // once (the box coordinates are all it needs), up to DP chunks ahead of the BUILD cursor, which computes the
+        // chunk's weights and writes its fragments into the already acquired stage.  The MMA warps consume RoIs in
+        // order, so what they used to wait for on every chunk -- fragment build, then TMA issue, then the load's L2
+        // latency -- is now off their path for every RoI of up to DP chunks.
+        auto word = [&](int w) -> uint32_t { return use_map ? map_g[w] : 0xffffffffu; };
+        auto next = [&](int& w, uint32_t& bits) -> int {
+          for (;;) {
+            if (w >= nwords) return -1;
+            if (bits != 0u) {
+              const int chn = w * 32 + __ffs((int)bits) - 1;
+              bits &= bits - 1u;
+              if (chn >= nch) { w = nwords; return -1; }
+              return chn;
             }
-            const int stage = bw_id * DEPTH + slot;
-            mbar_wait(empty_bar + stage, phase ^ 1);
-            if (!empty) {
-              // fragment order: rows g / g + 8 of m-tile mt, pixels k = 2t, 2t+1 (chunk row t>>1) and 2t+8, 2t+9 (row +2)
-              const uint32_t dst = s_afrag + stage * AFRAG_BYTES + lane * 16;
-              const uint32_t pix = (uint32_t)(((t >> 1) * 4 + 2 * (t & 1)) * 4);
-#pragma unroll
-              for (int mt = 0; mt < 4; mt++) {
-                uint32_t a[4];
-#pragma unroll
-                for (int hl = 0; hl < 2; hl++) {
-                  const int bin = mt * 16 + g + hl * 8;
-                  float2 lo = make_float2(0.f, 0.f), hi = make_float2(0.f, 0.f);
-                  if (bin < NBIN) {
-                    const uint2 u0 = lds64(s_w + (uint32_t)bin * (ROT_W_STRIDE * 4) + pix);
-                    const uint2 u1 = lds64(s_w + (uint32_t)bin * (ROT_W_STRIDE * 4) + pix + 32);
-                    lo = make_float2(__uint_as_float(u0.x), __uint_as_float(u0.y));
-                    hi = make_float2(__uint_as_float(u1.x), __uint_as_float(u1.y));
-                  }
-                  a[hl] = F16 ? pack_f16(lo.x, lo.y) : pack_bf16(lo.x, lo.y);
-                  a[2 + hl] = F16 ? pack_f16(hi.x, hi.y) : pack_bf16(hi.x, hi.y);
-                }
-                sts128(dst + mt * 512, make_uint4(a[0], a[1], a[2], a[3]));
-              }
-            }
-            if (lane == 0) asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(s_meta + stage * 8), "r"(roi), "r"(flags) : "memory");
-            __syncwarp();
-            if (lane == 0) {
-              if (empty) {
-                mbar_arrive(full_bar + stage);
-              } else {
-                mbar_expect_tx(full_bar + stage, tx_bytes);
-                tma_load_5d(s_patch + stage * PATCH_BYTES, &tmap, s_full + stage * 8, 0, xlo + cx * 4, ylo + cy * 4, b, 0);
-              }
-            }
-            if (++slot == DEPTH) { slot = 0; phase ^= 1; }
+            if (++w < nwords) bits = word(w);
           }
+        };
+        // this RoI's first stage in the shared ring = stages used by all earlier RoIs of the CTA
+        int base_j = 0;
+        if (lane == 0) {
+          while (seq_g[0] != it) __nanosleep(32);
+          base_j = seq_g[1];
+          seq_g[1] = base_j + total;
+          __threadfence_block();
+          seq_g[0] = it + 1;
+        }
+        base_j = __shfl_sync(0xffffffffu, base_j, 0);
+        // mbarrier waits only see a phase PARITY: a builder two laps ahead of the consumers would take the parity of
+        // lap k-3 for lap k-1.  Builders of many-chunk RoIs can get that far ahead, so the acquire first waits until MMA
+        // warp 0 has consumed stage j - DP (a plain shared word), which pins the barrier to lap k-1 or k.
+        auto acquire = [&](int j) {
+          const int stage = j % DP;
+          if (j >= DP) {
+            if (lane == 0) { while (seq_g[2] < j - DP + 1) __nanosleep(64); }
+            __syncwarp();
+          }
+          mbar_wait(empty_bar + stage, (uint32_t)(((j / DP) & 1) ^ 1));
+          return stage;
+        };
+        if (empty) {
+          const int stage = acquire(base_j);
+          if (lane == 0) {
+            asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(s_meta + stage * 8), "r"(roi), "r"(F_LAST | (skip ? F_SKIP : F_ZERO)) : "memory");
+            mbar_arrive(full_bar + stage);
+            mbar_arrive(full_bar + stage);
+          }
+          continue;
+        }
+        int wi = 0, wb = 0;
+        uint32_t bits_i = word(0), bits_b = bits_i;
+        int issued = 0, built = 0;
+        auto issue = [&]() {
+          const int chn = next(wi, bits_i);
+          const int cy = chn / ncx, cx = chn - cy * ncx;
+          const int stage = acquire(base_j + issued);
+          if (lane == 0) {
+            mbar_expect_tx(full_bar + stage, tx_bytes);
+            tma_load_5d(s_patch + stage * PATCH_BYTES, &tmap, s_full + stage * 8, 0, xlo + cx * 4, ylo + cy * 4, b, 0);
+          }
+          issued++;
+        };
+        while (issued < total && issued < ROT_AHEAD) issue();
+        while (built < total) {
+          const int chn = next(wb, bits_b);
+          const int cy = chn / ncx, cx = chn - cy * ncx;
+          const int x0 = xlo + cx * 4, y0 = ylo + cy * 4;
+          __syncwarp();   // the previous chunk's fragment gather is done reading W
+#pragma unroll
+          for (int j = 0; j < 2; j++) {
+            const int bin = lane + 32 * j;
+            if (bin < NBIN) {
+              float wv[16];
+#pragma unroll
+              for (int i = 0; i < 16; i++) wv[i] = 0.f;
+#pragma unroll
+              for (int sub = 0; sub < ROT_SAMPLES; sub++) {
+                const uint4 r = rec[j * ROT_SAMPLES + sub];
+                const int dxl = (int)(r.x & 0xffffu) - x0, dxh = (int)(r.x >> 16) - x0;
+                const int dyl = (int)(r.y & 0xffffu) - y0, dyh = (int)(r.y >> 16) - y0;
+                const float lx = __uint_as_float(r.z), ly = __uint_as_float(r.w);
+                const float hx = fsub(1.0f, lx), hy = fsub(1.0f, ly);
+                float cw[4], rwt[4];
+#pragma unroll
+                for (int c = 0; c < 4; c++) {
+                  cw[c] = (dxl == c ? hx : 0.f) + (dxh == c ? lx : 0.f);
+                  rwt[c] = (dyl == c ? hy : 0.f) + (dyh == c ? ly : 0.f);
+                }
+#pragma unroll
+                for (int rr = 0; rr < 4; rr++)
+#pragma unroll
+                  for (int c = 0; c < 4; c++) wv[rr * 4 + c] += rwt[rr] * cw[c];
+              }
+              const uint32_t wrow = s_w + (uint32_t)bin * (ROT_W_STRIDE * 4);
+#pragma unroll
+              for (int i = 0; i < 4; i++)
+                sts128(wrow + i * 16, make_uint4(__float_as_uint(wv[4 * i] * inv_count), __float_as_uint(wv[4 * i + 1] * inv_count),
+                                                 __float_as_uint(wv[4 * i + 2] * inv_count), __float_as_uint(wv[4 * i + 3] * inv_count)));
+            }
+          }
+          __syncwarp();
+          const int stage = (base_j + built) % DP;
+          {
+            // fragment order: rows g / g + 8 of m-tile mt, pixels k = 2t, 2t+1 (chunk row t>>1) and 2t+8, 2t+9 (row +2)
+            const uint32_t dst = s_afrag + stage * AFRAG_BYTES + lane * 16;
+            const uint32_t pix = (uint32_t)(((t >> 1) * 4 + 2 * (t & 1)) * 4);
+#pragma unroll
+            for (int mt = 0; mt < 4; mt++) {
+              uint32_t a[4];
+#pragma unroll
+              for (int hl = 0; hl < 2; hl++) {
+                const int bin = mt * 16 + g + hl * 8;
+                float2 lo = make_float2(0.f, 0.f), hi = make_float2(0.f, 0.f);
+                if (bin < NBIN) {
+                  const uint2 u0 = lds64(s_w + (uint32_t)bin * (ROT_W_STRIDE * 4) + pix);
+                  const uint2 u1 = lds64(s_w + (uint32_t)bin * (ROT_W_STRIDE * 4) + pix + 32);
+                  lo = make_float2(__uint_as_float(u0.x), __uint_as_float(u0.y));
+                  hi = make_float2(__uint_as_float(u1.x), __uint_as_float(u1.y));
+                }
+                a[hl] = F16 ? pack_f16(lo.x, lo.y) : pack_bf16(lo.x, lo.y);
+                a[2 + hl] = F16 ? pack_f16(hi.x, hi.y) : pack_bf16(hi.x, hi.y);
+              }
+              sts128(dst + mt * 512, make_uint4(a[0], a[1], a[2], a[3]));
+            }
+          }
+          built++;
+          if (lane == 0) asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(s_meta + stage * 8), "r"(roi), "r"(built == total ? (int)F_LAST : 0) : "memory");
+          __syncwarp();
+          if (lane == 0) mbar_arrive(full_bar + stage);        // second arrival: fragments + meta are in place
+          if (issued < total) issue();
         }
       }
       return;
@@ -394,11 +445,11 @@ roi_align_mma_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_cons
     // software prefetch of the RoI record one iteration ahead (lanes 0..4 hold the 5 floats)
     float rnext = 0.f;
     if (bw_id < n_iter && lane < 5) rnext = __ldg(rois + (size_t)(blockIdx.x + bw_id * gridDim.x) * 5 + lane);
-    for (int it = bw_id; it < n_iter; it += BUILDERS) {
+    for (int it = bw_id; it < n_iter; it += NB) {
       const int roi = blockIdx.x + it * gridDim.x;
       const float rcur = rnext;
-      if (it + BUILDERS < n_iter && lane < 5)
-        rnext = __ldg(rois + (size_t)(blockIdx.x + (it + BUILDERS) * gridDim.x) * 5 + lane);
+      if (it + NB < n_iter && lane < 5)
+        rnext = __ldg(rois + (size_t)(blockIdx.x + (it + NB) * gridDim.x) * 5 + lane);
       const bool skip = roi_level != nullptr && roi_level[roi] != level;   // another FPN level owns this RoI
       const int b = (int)__shfl_sync(0xffffffffu, rcur, 0);
       const float x1 = fsub(fmul(__shfl_sync(0xffffffffu, rcur, 1), scale), off);
@@ -466,7 +517,7 @@ roi_align_mma_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_cons
       const int ncx = empty ? 1 : (xmax - xmin) / 4 + 1, ncy = empty ? 1 : (ymax - ymin) / 4 + 1;
       for (int cy = 0; cy < ncy; cy++) {
         for (int cx = 0; cx < ncx; cx++) {
-          const int stage = bw_id * DEPTH + slot;
+          const int stage = bw_id * DP + slot;
           mbar_wait(empty_bar + stage, phase ^ 1);
           int flags = (cy == ncy - 1 && cx == ncx - 1 ? F_LAST : 0);
           if (empty) {
@@ -503,7 +554,7 @@ roi_align_mma_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_cons
               tma_load_5d(s_patch + stage * PATCH_BYTES, &tmap, s_full + stage * 8, 0, xmin + cx * 4, ymin + cy * 4, b, 0);
             }
           }
-          if (++slot == DEPTH) { slot = 0; phase ^= 1; }
+          if (++slot == DP) { slot = 0; phase ^= 1; }
         }
       }
     }
@@ -531,15 +582,17 @@ roi_align_mma_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_cons
   int sbuf = 0;
   float acc[4][4][4];
 
-  uint32_t slotbits = 0, phasebits = 0;          // per-builder ring position / parity (bit = builder id)
+  uint32_t slotpk = 0, phasebits = 0;            // per-builder ring position (4 bits each) / parity (bit = builder id)
+  int jring = 0;                                 // rotated: position in the shared ring
   for (int it = 0; it < n_iter; it++) {
     const int bw_id = it % NB;
     int roi, flags;
     bool first = true;
     do {
-      const int slot = (slotbits >> bw_id) & 1;
-      const int stage = bw_id * DEPTH + slot;
-      mbar_wait(full_bar + stage, (phasebits >> bw_id) & 1);
+      const int slot = ROT ? 0 : (int)((slotpk >> (4 * bw_id)) & 15u);
+      const int stage = ROT ? jring % DP : bw_id * DP + slot;
+      if (ROT) mbar_wait_backoff(full_bar + stage, (uint32_t)((jring / DP) & 1), 64);   // builders need the issue slots
+      else mbar_wait(full_bar + stage, (phasebits >> bw_id) & 1);
       {
         const uint2 m = lds64(s_meta + stage * 8);
         roi = (int)m.x; flags = (int)m.y;
@@ -587,8 +640,14 @@ roi_align_mma_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_cons
       first = false;
       __syncwarp();
       if (lane == 0) mbar_arrive(empty_bar + stage);
-      if (slot == DEPTH - 1) phasebits ^= 1u << bw_id;
-      slotbits ^= 1u << bw_id;
+      if (ROT) {
+        jring++;
+        if (warp == 0 && lane == 0) seq_g[2] = jring;     // after this warp's arrive on the stage's empty barrier
+      } else {
+        const int nslot = slot + 1 == DP ? 0 : slot + 1;
+        if (nslot == 0) phasebits ^= 1u << bw_id;
+        slotpk = (slotpk & ~(15u << (4 * bw_id))) | ((uint32_t)nslot << (4 * bw_id));
+      }
     } while (!(flags & F_LAST));
     if ((flags & F_SKIP) || !active) continue;
 
@@ -646,11 +705,21 @@ static EncodeTiledFn get_encode() {
 constexpr size_t SMEM_LIMIT = 113 * 1024;       // two CTAs per SM
 constexpr size_t SMEM_LIMIT_ROT = 226 * 1024;   // rotated: one CTA per SM
 
+// rotated pipeline shape: builder warps, stages of the shared ring (PTB200_ROT_CFG=<nb*100+stages> picks another
+// instantiated shape for measurements: 813, 810, 614, 610, 415, 410)
+static void rot_cfg(int& nb, int& dp) {
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("PTB200_ROT_CFG"); v = (e != nullptr && e[0] && e[1]) ? atoi(e) : ROT_BUILDERS * 100 + ROT_DEPTH; }
+  nb = v / 100; dp = v % 100;
+}
+
 size_t smem_bytes(int H, int W, int stg_bufs, bool rot) {
   const size_t tab = rot ? (size_t)ROT_TAB_FLOATS : (size_t)(W + 4) * 8 + (size_t)(H + 4) * 8;
-  const size_t nb = rot ? ROT_BUILDERS : BUILDERS, stages = nb * DEPTH;
+  int rnb = 0, rdp = 0;
+  rot_cfg(rnb, rdp);
+  const size_t nb = rot ? rnb : BUILDERS, stages = rot ? (size_t)rdp : nb * DEPTH;
   return 1024 + stages * (PATCH_BYTES + AFRAG_BYTES) + MMA_WARPS * stg_bufs * (size_t)STG_BYTES +
-         nb * tab * sizeof(float) + 3 * stages * 8 + 64;
+         nb * tab * sizeof(float) + 3 * stages * 8 + 64 + 32;
 }
 
 // rotated: fixed sampling grids of 1 or 2 samples per axis (the shipped sampling_ratio = 2); the adaptive grid
@@ -691,8 +760,21 @@ int launch(const void* feat_bf16_nhwc, int feat_f16, const float* rois, void* ou
   }
   const int stg_bufs = smem_bytes(H, W, 2, rot) <= (rot ? SMEM_LIMIT_ROT : SMEM_LIMIT) ? 2 : 1;   // large maps: single-buffered staging
   const size_t smem = smem_bytes(H, W, stg_bufs, rot);
-  auto kern = feat_f16 ? (rot ? roi_align_mma_kernel<true, true> : roi_align_mma_kernel<true, false>)
-                       : (rot ? roi_align_mma_kernel<false, true> : roi_align_mma_kernel<false, false>);
+  int rnb = 0, rdp = 0;
+  rot_cfg(rnb, rdp);
+  using KernT = void (*)(const CUtensorMap, const CUtensorMap, const float*, int, int, int, int, int, float, int, int,
+                         const int*, int, int, int);
+  KernT kern = nullptr;
+  int nbld = BUILDERS;
+  if (!rot) {
+    kern = feat_f16 ? roi_align_mma_kernel<true, false, BUILDERS, DEPTH> : roi_align_mma_kernel<false, false, BUILDERS, DEPTH>;
+  } else {
+    nbld = rnb;
+#define PT_ROT(NBV, DPV) if (rnb == NBV && rdp == DPV) kern = feat_f16 ? roi_align_mma_kernel<true, true, NBV, DPV> : roi_align_mma_kernel<false, true, NBV, DPV>
+    PT_ROT(8, 13); PT_ROT(8, 10); PT_ROT(6, 14); PT_ROT(6, 10); PT_ROT(4, 15); PT_ROT(4, 10);
+#undef PT_ROT
+    if (kern == nullptr) { set_error("roi_align_mma: PTB200_ROT_CFG=%d%d is not an instantiated pipeline shape", rnb, rdp); return PT_ERR_ARG; }
+  }
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) { set_error("cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return PT_ERR_CUDA; }
   int dev = 0, sms = 148;
@@ -700,7 +782,7 @@ int launch(const void* feat_bf16_nhwc, int feat_f16, const float* rois, void* ou
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   const int per_sm = rot ? 1 : 2;
   const int grid = K < per_sm * sms ? K : per_sm * sms;
-  kern<<<grid, (MMA_WARPS + (rot ? ROT_BUILDERS : BUILDERS)) * 32, smem, stream>>>(map, omap, rois, K, B, C, H, W, scale, sampling_ratio, aligned, roi_level, level,
+  kern<<<grid, (MMA_WARPS + nbld) * 32, smem, stream>>>(map, omap, rois, K, B, C, H, W, scale, sampling_ratio, aligned, roi_level, level,
                                         stg_bufs, clockwise);
   return check_launch("roi_align_mma_kernel");
 }

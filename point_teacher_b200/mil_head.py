@@ -111,7 +111,7 @@ class MILHeadMixin:
             hit = cache[key]
         return hit[1]
 
-    def _side_work(self, stage, between=None, stacks=(0, 1)):
+    def _side_work(self, stage, between=None, stacks=(0, 1), after=None):
         """Fork/join: work that the data path does not need immediately runs on a side stream -- the fp32 -> bf16
         rebuild of both FC stacks' operands when they are stale (training: every step; 2 x 77 MB weight streams that
         overlap bag generation and the first RoIAlign instead of sitting in front of the GEMMs) and ``between()``
@@ -132,6 +132,8 @@ class MILHeadMixin:
                 if i in stacks:
                     self._weight(fcs[0], True)
                     self._weight(fcs[1], False)
+                if i == 1 and after is not None:
+                    after()
                 ev = torch.cuda.Event()
                 ev.record(side)
                 evs.append(ev)
@@ -151,30 +153,27 @@ class MILHeadMixin:
         h1 = ops.fc_gemm(A, w1, b1, relu=True, out_dtype=torch.float32, M=M)
         return ops.fc_gemm(ops.split_bf16x3(h1), w2, b2, relu=True, out_dtype=torch.float32, M=M)
 
-    def _roi_operand(self, x, rois, keep=None):
-        """RoIAlign straight into the FC1 operand layout (bf16, bin-major columns).  Several feature levels
-        (single_level_roi_extractor.py:35-54, 98-104): each RoI is pooled from its mapped level -- one launch per
-        level, every launch skipping the other levels' RoIs and writing into the shared operand (no ``nonzero()``
-        synchronisation, no gather / scatter copies)."""
+    def _nhwc_maps(self, x):
+        """NHWC maps of the pooled levels (transposed once per step, cached on tensor identity)."""
         ext = self.bbox_roi_extractor
-        feats = x[:ext.num_inputs]
-        mode = ops.OUT_BF16X3_BINMAJOR if self._x3() else ops.OUT_BF16_BINMAJOR
         fd = self._feat_dtype()
-        if len(feats) == 1:
-            layer = ext.roi_layers[0]
-            return ops.roi_align_forward(layer.nhwc(feats[0], fd), rois, mode, layer.spatial_scale,
-                                         layer.sampling_ratio, layer.aligned, rotated=ext.rotated,
-                                         clockwise=getattr(layer, "clockwise", True))
-        lvls = ops.map_roi_levels(rois, len(feats), ext.finest_scale, rotated=ext.rotated)
-        out = None
-        for i, f in enumerate(feats):
+        return [ext.roi_layers[i].nhwc(f, fd) for i, f in enumerate(x[:ext.num_inputs])]
+
+    def _roi_operand(self, x, rois, out=None):
+        """RoIAlign straight into the FC1 operand layout (bf16, bin-major columns); ``out``: rows of a preallocated
+        operand.  Several feature levels (single_level_roi_extractor.py:35-54, 98-104): each RoI is pooled from its
+        mapped level -- one launch per level, every launch skipping the other levels' RoIs and writing into the
+        shared operand (no ``nonzero()`` synchronisation, no gather / scatter copies).  Returns (operand, levels)."""
+        ext = self.bbox_roi_extractor
+        maps = self._nhwc_maps(x)
+        mode = ops.OUT_BF16X3_BINMAJOR if self._x3() else ops.OUT_BF16_BINMAJOR
+        lvls = ops.map_roi_levels(rois, len(maps), ext.finest_scale, rotated=ext.rotated) if len(maps) > 1 else None
+        for i, m in enumerate(maps):
             layer = ext.roi_layers[i]
-            out = ops.roi_align_forward(layer.nhwc(f, fd), rois, mode, layer.spatial_scale, layer.sampling_ratio,
-                                        layer.aligned, rotated=ext.rotated, clockwise=getattr(layer, "clockwise", True),
-                                        out=out, roi_level=lvls, level=i)
-        if keep is not None:
-            keep["lvls"] = lvls
-        return out
+            out = ops.roi_align_forward(m, rois, mode, layer.spatial_scale, layer.sampling_ratio, layer.aligned,
+                                        rotated=ext.rotated, clockwise=getattr(layer, "clockwise", True), out=out,
+                                        roi_level=lvls, level=i)
+        return out, lvls
 
     def _grad_wanted(self, x):
         if not torch.is_grad_enabled():
@@ -382,13 +381,23 @@ class MILHeadMixin:
         K = base_rois.shape[0] * U2
         G = base_rois.shape[0] // max(U1, 1)
         rois2 = torch.empty((K + n_neg, rs), dtype=torch.float32, device=dev)
-        side = {"neg_w": neg_w}
+        side = {"neg_w": neg_w, "lv": None}
+        self._nhwc_maps(x)                           # transposed on the main stream before the side stream forks
+        A2 = None
+        if mode != "reg_only":
+            cols = self.in_channels * self.roi_feat_area * (3 if self._x3() else 1)
+            A2 = torch.empty((K + n_neg, cols), dtype=torch.bfloat16, device=dev)
 
         def negatives():
             if n_neg:
                 ops.make_rois(neg_boxes, neg_img_idx, out=rois2[K:])
                 if neg_w is None:
                     side["neg_w"] = ops.neg_weight(rois2[K:], base_rois, bag_offsets, rot)
+
+        # (Measured and NOT kept: pooling the negatives' rows of the classification operand on the side stream, under
+        # the first FC stack -- they do not depend on the regression pass.  The RoIAlign CTAs (113 / 220 KB of shared
+        # memory) cannot share an SM with the persistent GEMM's 200 KB CTAs, so the GEMM lost SMs for its first wave:
+        # HBB step 0.460 -> 0.468 ms, OBB 0.586 -> 0.604 ms.)
         ev_reg, ev_all = self._side_work(stage, negatives, stacks=(0,) if mode == "reg_only" else (0, 1))
         neg_w = side["neg_w"]
         ebags, evalid = ops.bag_gen(base_rois, img_wh, cfg["base_ratios"], cfg["shake_ratio"], cfg["min_scale"], rot)
@@ -396,7 +405,9 @@ class MILHeadMixin:
         sums = torch.zeros((8,), dtype=torch.float32, device=dev)
         kreg = {} if keep is not None else None
         kbag = {} if keep is not None else None
-        A = self._roi_operand(x, ebags, kreg)
+        A, lv = self._roi_operand(x, ebags)
+        if kreg is not None and lv is not None:
+            kreg["lvls"] = lv
         torch.cuda.current_stream().wait_event(ev_reg)
         H = self._fc_stack(A, self.shared_fcs_reg[stage], K, kreg)
         h0, w0, _ = img_metas[0]["img_shape"]            # decode clips to image 0 (reference quirk, :1211)
@@ -405,14 +416,18 @@ class MILHeadMixin:
                                           (w0, h0), sums, K=K, hyper=self._dn_hyper(), out_rois=rois2,
                                           rotated=rot, want_deltas=keep is not None)
         del A, H
-        torch.cuda.current_stream().wait_event(ev_all)      # negatives' RoIs + the bag stack's operands
         cls = ins = merged = pts = idx = sc = None
         if mode != "reg_only":
-            A2 = self._roi_operand(x, rois2, kbag)
+            torch.cuda.current_stream().wait_event(ev_all)      # the negatives' RoIs + the bag stack's operands
+            _, lv = self._roi_operand(x, rois2, out=A2)
+            if kbag is not None and lv is not None:
+                kbag["lvls"] = lv
             H2 = self._fc_stack(A2, self.shared_fcs_bag[stage], K + n_neg, kbag)
             fc, fi = self.fc_cls[stage], self.fc_ins[stage]
             cls, ins = ops.cls_ins_heads(H2, fc.weight.detach(), fc.bias.detach(), fi.weight.detach(),
                                          fi.bias.detach(), M=K + n_neg)
+        else:
+            torch.cuda.current_stream().wait_event(ev_all)
         if mode == "full":
             if n_neg:
                 with ops.fork() as fneg:                      # beside score_select (both reduce into ``sums``)
