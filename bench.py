@@ -115,7 +115,7 @@ def hbb_config(n_img=2):
 
 def run_reference(args):
     """CPU arm, honouring --steps / --warmup: one step = the same batch as the GPU arm.  Where /root/reference is
-    mounted (the dev container) the reference's OWN files are timed under the import shim (``kind: reference-shim``:
+    mounted (the dev container) the reference's OWN files are timed under the import shim (``kind: reference``:
     the reference's syn_images_generator_v2 functions + TS_P2BFCOSHead.MIL_head_burn_in_step2 with torchvision's
     roi_align standing in for the un-vendored mmcv kernel); elsewhere (the GPU box) the oracle port, which is pinned
     bit-for-bit against those files (``kind: port``).  All host threads."""
@@ -129,7 +129,7 @@ def run_reference(args):
     d = make_inputs(0)
     cap = 100
     if ref_shim.available():
-        kind = "reference-shim"
+        kind = "reference"
         ns = ref_shim.install()
         head = ref_shim.build_ref_mil_head(ns, num_stages=1, top_k=1, seed=0)
         pb = [b[:cap].clone() for b in d["pseudo_boxes"]]
@@ -161,7 +161,7 @@ def run_reference(args):
     dt = (time.perf_counter() - t0) / steps
     val = 2.0 / dt
     sample = (f"{steps} full steps of the workload (2 images each) after {warm} warm-up steps; "
-              + ("the reference's own files under oracle/ref_shim.py" if kind == "reference-shim" else
+              + ("the reference's own files under oracle/ref_shim.py" if kind == "reference" else
                  "oracle/hbb.py (PyTorch fp32 + torchvision roi_align), pinned bit-for-bit against the reference's files"))
     print(json.dumps({
         "impl": "reference", "metric": METRIC, "value": val, "unit": "imgs/s", "n_gpus": args.gpus, "steps": steps,
@@ -330,16 +330,22 @@ def run_ours(args):
     #      (a leading device-side sleep lets the host enqueue the whole eager step first, so that each event pair
     #      brackets device time only and not the host's launch latency)
     ops.PROFILE["on"], ops.PROFILE["events"] = True, []
+    _lib.TRACE["on"], _lib.TRACE["events"] = True, []
+    n_prof = min(args.steps, 10)
     with torch.no_grad():
-        for _ in range(min(args.steps, 10)):
+        for _ in range(n_prof):
             flush.zero_()
             torch.cuda._sleep(int(6e-3 * 1.9e9))
             cap._step()
     torch.cuda.synchronize()
-    ops.PROFILE["on"] = False
+    ops.PROFILE["on"] = _lib.TRACE["on"] = False
+    breakdown = {}
+    for name, a, b in _lib.TRACE["events"]:
+        breakdown[name] = breakdown.get(name, 0.0) + a.elapsed_time(b) * 1e3 / n_prof
+    breakdown = {k: round(v, 2) for k, v in sorted(breakdown.items(), key=lambda kv: -kv[1])}
     hbm_peak, tf_peak, peak_src = _peaks()
     gemm = [(a.elapsed_time(b), fl) for tag, a, b, fl, shp in ops.PROFILE["events"] if tag == "fc_gemm" and shp[2] > 4096]
-    roi = [(a.elapsed_time(b), by) for tag, a, b, by, shp in ops.PROFILE["events"] if tag == "roi_align"]
+    roi = [(a.elapsed_time(b), by) for tag, a, b, by, shp in ops.PROFILE["events"] if tag == "roi_align" and shp[0] >= 1000]
     gemm_ms = sum(t for t, _ in gemm) / max(len(gemm), 1)
     gemm_tf = (sum(f for _, f in gemm) / max(len(gemm), 1)) / (gemm_ms * 1e-3) / 1e12 if gemm else 0.0
     roi_ms = sum(t for t, _ in roi) / max(len(roi), 1)
@@ -481,6 +487,10 @@ def run_ours(args):
                                     "no compute (slowest rank); e2e is host/PCIe-bound when the two are close",
                     "host_numa_node_rank0": numa},
             "gpu_launches": launches_per_step * args.steps,
+            "step_breakdown_us": {"per_c_abi_entry_point": breakdown,
+                                  "note": "device time per step summed per C-ABI entry point, eager replay of the same "
+                                          "step behind a device-side sleep, CUDA events on the launching stream "
+                                          "(side-stream work overlaps the main stream: the sum exceeds the step time)"},
             "clocks": clocks,
             "roofline": {"kernel": "fc_gemm_kernel (FC1, M=5000/5400 N=1024 K=12544)", "bound": "tensor",
                          "achieved": gemm_tf, "peak": tf_peak, "unit": "TFLOP/s", "frac": gemm_tf / tf_peak,

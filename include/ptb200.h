@@ -197,6 +197,11 @@ int pt_nms_rotated(const float* dets, int ld, const float* scores, int lds, int 
                    unsigned char* keep_sorted, void* workspace, long long workspace_bytes, void* stream);
 int pt_black_paper_select(const float* bb, int N, const int* order, const unsigned char* keep_sorted, float imgsize,
                           float* out_bb, int* out_sel, int* polys, int* count, void* stream);
+/* same with trig = [N,2] (sin, cos) of every candidate's angle computed on the HOST (the CPU libm sin / cos the reference's tensor ops
+ * reach on the strided angle column, as obb2xyxy / obb2poly_le90 of the reference do, syn_images_generator_v2.py:382-396,
+ * data_augument_bank.py:516-541): corners then truncate exactly like the reference's; NULL = device sincos. */
+int pt_black_paper_select_ex(const float* bb, int N, const int* order, const unsigned char* keep_sorted, float imgsize,
+                             float* out_bb, int* out_sel, int* polys, int* count, const float* trig, void* stream);
 int pt_fill_polys(const int* polys, const int* count, int max_polys, float* img, unsigned char* mask, int C, int H,
                   int W, float value, void* stream);
 

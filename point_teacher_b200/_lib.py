@@ -66,6 +66,8 @@ SIGNATURES = {
                                c_void_p]),
     "pt_black_paper_select": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_float, c_void_p, c_void_p, c_void_p,
                                       c_void_p, c_void_p]),
+    "pt_black_paper_select_ex": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_float, c_void_p, c_void_p, c_void_p,
+                                         c_void_p, c_void_p, c_void_p]),
     "pt_fill_polys": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_int, c_int, c_int, c_float, c_void_p]),
     "pt_fc_gemm_bf16_ex": (c_int, [c_void_p, c_ll, c_void_p, c_ll, c_void_p, c_void_p, c_ll, c_int, c_int, c_int, c_int,
                                    c_int, c_void_p, c_ll, c_void_p, c_ll, c_int, c_int, c_void_p]),
@@ -133,9 +135,22 @@ _NO_KERNEL = {"pt_last_error", "pt_abi_version", "pt_build_arch", "pt_fc_gemm_wo
               "pt_nms_rotated_workspace_bytes", "pt_augment_param_stride"}
 
 
+# optional per-call device timing (bench.py's in-step breakdown): CUDA events on the launching stream around every
+# C-ABI call; only meaningful while the host runs ahead of the device (the bench parks the device behind a sleep first)
+TRACE = {"on": False, "events": []}
+
+
 def call(name, *args):
     lib = load()
-    rc = getattr(lib, name)(*args)
+    if TRACE["on"] and name not in _NO_KERNEL:
+        import torch
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        rc = getattr(lib, name)(*args)
+        e1.record()
+        TRACE["events"].append((name, e0, e1))
+    else:
+        rc = getattr(lib, name)(*args)
     if name not in _NO_KERNEL:
         LAUNCHES["count"] += 1
     if rc != 0:

@@ -74,7 +74,8 @@ __device__ __forceinline__ void sincos_ref(float a, float& s, float& c) {
 __global__ void __launch_bounds__(1024)
 black_paper_select_kernel(const float* __restrict__ bb, int N, const int* __restrict__ order,
                           const unsigned char* __restrict__ keep_sorted, float imgsize, float* __restrict__ out_bb,
-                          int* __restrict__ out_sel, int* __restrict__ polys, int* __restrict__ count) {
+                          int* __restrict__ out_sel, int* __restrict__ polys, int* __restrict__ count,
+                          const float* __restrict__ trig) {
   __shared__ int warp_sums[32];
   __shared__ int base;
   if (threadIdx.x == 0) base = 0;
@@ -87,7 +88,10 @@ black_paper_select_kernel(const float* __restrict__ bb, int N, const int* __rest
     if (i < N && keep_sorted[i]) {
       b = bb + (size_t)order[i] * 7;
       if (b[5] < 1.0f) {
-        sincos_ref(b[4], s, c);
+        // trig != NULL: (sin, cos) of every candidate's angle as the HOST's torch.sin / torch.cos produced them -- the
+        // only way to truncate a corner that sits on an integer boundary exactly like the reference's CPU libm does
+        if (trig != nullptr) { s = trig[2 * (size_t)order[i]]; c = trig[2 * (size_t)order[i] + 1]; }
+        else sincos_ref(b[4], s, c);
         const float ca = fabsf(c), sa = fabsf(s);
         const float dw = fadd(fmul(ca, b[2]), fmul(sa, b[3])), dh = fadd(fmul(sa, b[2]), fmul(ca, b[3]));
         const float x1 = fsub(b[0], fdiv(dw, 2.f)), y1 = fsub(b[1], fdiv(dh, 2.f));
@@ -249,12 +253,17 @@ extern "C" int pt_nms_rotated(const float* dets, int ld, const float* scores, in
 
 // The filters + polygon construction of generate_black_paper (:668-683).  bb [N,7]; out_bb [N,7], out_sel [N],
 // polys [N,8] int32 are filled for the first *count rows (score order).
-extern "C" int pt_black_paper_select(const float* bb, int N, const int* order, const unsigned char* keep_sorted,
-                                     float imgsize, float* out_bb, int* out_sel, int* polys, int* count, void* stream) {
+extern "C" int pt_black_paper_select_ex(const float* bb, int N, const int* order, const unsigned char* keep_sorted,
+                                        float imgsize, float* out_bb, int* out_sel, int* polys, int* count,
+                                        const float* trig, void* stream) {
   cudaStream_t s = (cudaStream_t)stream;
   if (N <= 0) { cudaMemsetAsync(count, 0, sizeof(int), s); return PT_OK; }
-  black_paper_select_kernel<<<1, 1024, 0, s>>>(bb, N, order, keep_sorted, imgsize, out_bb, out_sel, polys, count);
+  black_paper_select_kernel<<<1, 1024, 0, s>>>(bb, N, order, keep_sorted, imgsize, out_bb, out_sel, polys, count, trig);
   return check_launch("black_paper_select_kernel");
+}
+extern "C" int pt_black_paper_select(const float* bb, int N, const int* order, const unsigned char* keep_sorted,
+                                     float imgsize, float* out_bb, int* out_sel, int* polys, int* count, void* stream) {
+  return pt_black_paper_select_ex(bb, N, order, keep_sorted, imgsize, out_bb, out_sel, polys, count, nullptr, stream);
 }
 
 // cv2.fillPoly of max_polys (or *count, when count != NULL) integer quadrilaterals: img [C,H,W] fp32 <- value,

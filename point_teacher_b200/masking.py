@@ -58,15 +58,35 @@ def sample_black_paper_candidates(bb_occupied, prior_size, dense_cls, imgsize):
     return torch.cat((occ, cand), 0)
 
 
-def black_paper_from_candidates(img_syn, bb_all, imgsize, return_debug=False):
-    """Device tail (:664-690).  img_syn (C,H,W) fp32 CUDA, modified in place; bb_all (N,7) CUDA.
+def host_trig(bb_all_cpu):
+    """(N,2) fp32 (sin, cos) of the angle column, evaluated the way the reference evaluates them: ``torch.sin`` /
+    ``torch.cos`` on the CPU over the STRIDED column view of a (.,7) box tensor (``obb2xyxy``,
+    syn_images_generator_v2.py:382-396; ``obb2poly_le90``, data_augument_bank.py:516-541).  ATen's CPU kernels take
+    the scalar libm loop for such a view, so the value of an element does not depend on where it sits in the tensor."""
+    a = bb_all_cpu.float().contiguous()[:, 4]
+    return torch.stack([torch.sin(a), torch.cos(a)], 1).contiguous()
+
+
+def black_paper_from_candidates(img_syn, bb_all, imgsize, return_debug=False, trig=None):
+    """Device tail (:664-690).  img_syn (C,H,W) fp32 CUDA, modified in place; bb_all (N,7).
     Returns (img_syn, kept boxes (M,7)); one host read of the survivor count (the reference returns a
-    dynamically sized tensor too)."""
+    dynamically sized tensor too).
+
+    Bit-exactness of the filled pixel set: the polygon corners (and the inside-image filter) go through sin / cos of
+    the box angle.  When ``bb_all`` arrives on the HOST -- as it does from ``generate_black_paper``, whose candidates
+    are drawn from the CPU generators -- the (N,2) trig table is computed there with the reference's own torch ops
+    (``host_trig``) and uploaded with the boxes: corners, filter decisions and pixels are then identical to the
+    reference's.  Device-resident candidates without ``trig`` use the device's sincos (rounded once from double):
+    a corner sitting on an integer boundary may truncate differently (<= 1 px on < 1 % of the corners)."""
     if not img_syn.is_cuda:
         raise ValueError("img_syn: expected a CUDA tensor (this path has no CPU fallback)")
+    if trig is None and not bb_all.is_cuda:
+        trig = host_trig(bb_all)
+    if trig is not None:
+        trig = trig.to(img_syn.device, non_blocking=True).float().contiguous()
     bb_all = bb_all.to(img_syn.device).float().contiguous()
     order, keep = ops.nms_rotated(bb_all, bb_all[:, 5], 0.05)
-    out, sel, polys, count = ops.black_paper_select(bb_all, order, keep, imgsize)
+    out, sel, polys, count = ops.black_paper_select(bb_all, order, keep, imgsize, trig)
     ops.fill_polys(polys, img=img_syn, value=255.0, count=count)
     m = int(count.item())
     if return_debug:

@@ -499,16 +499,21 @@ def nms_rotated(dets, scores, iou_threshold):
     return order, keep
 
 
-def black_paper_select(bb, order, keep_sorted, imgsize):
-    """-> (kept boxes (N,7) padded, sel (N,) int32 padded, polys (N,4,2) int32 padded, count (1,) int32)."""
+def black_paper_select(bb, order, keep_sorted, imgsize, trig=None):
+    """-> (kept boxes (N,7) padded, sel (N,) int32 padded, polys (N,4,2) int32 padded, count (1,) int32).
+    ``trig`` (N,2) fp32 = host-computed (sin, cos) of column 4 (bit-exact corners); None = device sincos."""
     _chk(bb, "bb", _f32, 2, 7)
+    if trig is not None:
+        _chk(trig, "trig", _f32, 2, 2)
+        if trig.shape[0] != bb.shape[0]:
+            raise ValueError("trig needs one (sin, cos) row per box")
     N, dev = bb.shape[0], bb.device
     out = torch.zeros((N, 7), dtype=_f32, device=dev)
     sel = torch.zeros((N,), dtype=_i32, device=dev)
     polys = torch.zeros((N, 4, 2), dtype=_i32, device=dev)
     count = torch.zeros((1,), dtype=_i32, device=dev)
-    _lib.call("pt_black_paper_select", _p(bb), N, _p(order), _p(keep_sorted), float(imgsize), _p(out), _p(sel),
-              _p(polys), _p(count), _stream())
+    _lib.call("pt_black_paper_select_ex", _p(bb), N, _p(order), _p(keep_sorted), float(imgsize), _p(out), _p(sel),
+              _p(polys), _p(count), _p(trig), _stream())
     return out, sel, polys, count
 
 

@@ -406,5 +406,23 @@ def test_obb_bag_gen_bit_exact_and_neg_weight(cuda):
     rw = torch.cat([obb.negative_weights(negs[i], ref[i]) for i in range(2)])
     nrois = obb.rbbox2roi(negs).to(cuda)
     offs = torch.tensor([0, ref[0].shape[0], ref[0].shape[0] + ref[1].shape[0]], dtype=torch.int32, device=cuda)
-    w = ops.neg_weight(nrois, out, offs, rotated=True)
-    assert (w.bool().cpu() != rw).float().mean().item() <= 0.01
+    w = ops.neg_weight(nrois, out, offs, rotated=True).bool().cpu()
+    # The decision is ``all(IoU < 0.3)``.  Rotated IoU is a polygon-clipping result whose last bits depend on the
+    # evaluation order (oracle/c/rotated.c vs rotated_iou.cuh agree to ~1e-6), so a decision may only differ where
+    # some IoU of that negative sits within 1e-4 of the threshold: enumerate that borderline set and demand EXACT
+    # equality everywhere else (no percentage allowance).
+    border = torch.zeros_like(rw)
+    o = 0
+    for i in range(2):
+        iou = obb.rbbox_overlaps(negs[i], ref[i])
+        border[o:o + negs[i].shape[0]] = ((iou - 0.3).abs() < 1e-4).any(1)
+        o += negs[i].shape[0]
+    assert torch.equal(w[~border], rw[~border]), (w != rw).nonzero().flatten().tolist()
+    assert int(border.sum()) <= 2, "the borderline set must stay a handful, otherwise the test says nothing"
+    # many more negatives: the same statement on 2 x 2000 boxes
+    negs2 = [obb.sample_negative_boxes(2000, (512, 512, 3), g) for _ in range(2)]
+    rw2 = torch.cat([obb.negative_weights(negs2[i], ref[i]) for i in range(2)])
+    w2 = ops.neg_weight(obb.rbbox2roi(negs2).to(cuda), out, offs, rotated=True).bool().cpu()
+    border2 = torch.cat([((obb.rbbox_overlaps(negs2[i], ref[i]) - 0.3).abs() < 1e-4).any(1) for i in range(2)])
+    assert torch.equal(w2[~border2], rw2[~border2])
+    assert int(border2.sum()) <= 40 and 0.02 < rw2.float().mean() < 0.98
