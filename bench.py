@@ -800,7 +800,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
-    ap.add_argument("--config", default="hbb", choices=["hbb", "obb", "assign", "mask"],
+    ap.add_argument("--config", default="hbb", choices=["hbb", "obb", "assign", "mask", "train"],
                     help="hbb = the headline workload; the others print one line for a secondary configuration")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="eager launches (for ncu passes)")
@@ -811,7 +811,11 @@ def main():
         run_reference(args)
     elif args.config != "hbb":
         if int(os.environ.get("RANK", "0")) == 0:
-            {"obb": run_config_obb, "assign": run_config_assign, "mask": run_config_mask}[args.config](args)
+            if args.config == "train":       # BASELINE config #2: the full teacher-student training step (bench_cfg2.py)
+                import bench_cfg2
+                print(json.dumps(bench_cfg2.run(args, ClockSampler, _peaks())))
+            else:
+                {"obb": run_config_obb, "assign": run_config_assign, "mask": run_config_mask}[args.config](args)
     else:
         run_ours(args)
 

@@ -58,6 +58,45 @@ def sample_black_paper_candidates(bb_occupied, prior_size, dense_cls, imgsize):
     return torch.cat((occ, cand), 0)
 
 
+def sample_black_paper_candidates_fast(bb_occupied, prior_size, dense_cls, imgsize, rng=None):
+    """Vectorised draw of the same candidate DISTRIBUTION as ``sample_black_paper_candidates`` (:596-663) from a numpy
+    ``Generator``: one bulk draw per quantity instead of ~15 scalar tensor ops per GT (the reference's loop costs tens
+    of milliseconds per image at AI-TOD GT counts).  It does NOT reproduce the reference's random stream -- use it
+    when throughput matters and the literal function when the stream does.  Returns (N,7) on the CPU."""
+    rng = rng if rng is not None else np.random.default_rng()
+    occ = bb_occupied.detach().cpu().float().numpy().copy()
+    prior = prior_size.detach().cpu().float().numpy()
+    G = occ.shape[0]
+    ci = occ[:, 6].astype(np.int64)
+    side = prior[ci, 0] * 0.7
+    occ[:, 2], occ[:, 3], occ[:, 4] = side, side, 0
+    if G == 0:
+        return torch.from_numpy(occ)
+    lo, hi = 50, imgsize - 50
+    scale = rng.random(G, dtype=np.float32) * 2.0 + 0.5
+    xy = rng.random((G, 2), dtype=np.float32) * (hi - lo) + lo
+    w = scale * np.exp(np.clip(rng.standard_normal(G).astype(np.float32) * 0.4, -1, 1) * prior[ci, 2])
+    h = w * np.exp(np.clip(rng.standard_normal(G).astype(np.float32) * 0.4, -1, 1) * prior[ci, 3])
+    w, h = w * prior[ci, 0], h * prior[ci, 1]
+    a = rng.random(G, dtype=np.float32) * np.float32(math.pi) - np.float32(math.pi / 2)
+    x = np.clip(xy[:, 0], 0.71 * w, imgsize - 1 - 0.71 * w)
+    y = np.clip(xy[:, 1], 0.71 * h, imgsize - 1 - 0.71 * h)
+    score = (w * h) / imgsize / imgsize + 0.1
+    rows = [np.stack([x, y, w, h, a, score, occ[:, 6]], 1)]
+    dense = set(int(c) for c in dense_cls)
+    for n in np.nonzero(rng.random(G) < 0.2)[0][:2]:                 # at most two neighbour runs (adjboost = 2)
+        if int(ci[n]) in dense:
+            itv, dev, last = rng.random() * 4 + 2, rng.random() * 8 - 4, 5
+        else:
+            itv, dev, last = rng.random() * 40 + 10, 0.0, 3
+        ofx = (h[n] + itv) * math.sin(-a[n]) + dev * math.cos(a[n])
+        ofy = (h[n] + itv) * math.cos(a[n]) + dev * math.sin(a[n])
+        k = np.arange(1, last + 1, dtype=np.float32)
+        rows.append(np.stack([x[n] + k * ofx, y[n] + k * ofy, np.full_like(k, w[n]), np.full_like(k, h[n]),
+                              np.full_like(k, a[n]), score[n] - 0.001 * k, np.full_like(k, occ[n, 6])], 1))
+    return torch.from_numpy(np.concatenate([occ] + rows, 0).astype(np.float32))
+
+
 def host_trig(bb_all_cpu):
     """(N,2) fp32 (sin, cos) of the angle column, evaluated the way the reference evaluates them: ``torch.sin`` /
     ``torch.cos`` on the CPU over the STRIDED column view of a (.,7) box tensor (``obb2xyxy``,

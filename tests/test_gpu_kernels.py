@@ -419,8 +419,15 @@ def test_obb_bag_gen_bit_exact_and_neg_weight(cuda):
         o += negs[i].shape[0]
     assert torch.equal(w[~border], rw[~border]), (w != rw).nonzero().flatten().tolist()
     assert int(border.sum()) <= 2, "the borderline set must stay a handful, otherwise the test says nothing"
-    # many more negatives: the same statement on 2 x 2000 boxes
-    negs2 = [obb.sample_negative_boxes(2000, (512, 512, 3), g) for _ in range(2)]
+    # many more negatives, this time AROUND the bags (perturbed copies of bag boxes) so that the IoUs cover the
+    # whole range and roughly half of the decisions are rejections: the same statement on 2 x 2000 boxes
+    negs2 = []
+    for i in range(2):
+        pick = ref[i][torch.randint(0, ref[i].shape[0], (2000,), generator=g)].clone()
+        pick[:, :2] += torch.randn(2000, 2, generator=g) * 4
+        pick[:, 2:4] *= (torch.randn(2000, 2, generator=g) * 0.4).exp()
+        pick[:, 4] += torch.randn(2000, generator=g) * 0.3
+        negs2.append(pick)
     rw2 = torch.cat([obb.negative_weights(negs2[i], ref[i]) for i in range(2)])
     w2 = ops.neg_weight(obb.rbbox2roi(negs2).to(cuda), out, offs, rotated=True).bool().cpu()
     border2 = torch.cat([((obb.rbbox_overlaps(negs2[i], ref[i]) - 0.3).abs() < 1e-4).any(1) for i in range(2)])
