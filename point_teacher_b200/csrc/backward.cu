@@ -456,6 +456,13 @@ roi_align_bwd_kernel(const __nv_bfloat16* __restrict__ dA, long long ld, const f
 #pragma unroll
             for (int pw = 0; pw < 7; pw++)
               u7[pw] = __ldg(reinterpret_cast<const uint4*>(drow + (size_t)(ph * 7 + pw) * C + c0));
+            // separable accumulation: T[px] = sum_pw wx[px][pw] * g[pw] (one output row), then acc[py][px] += wy[py] * T[px]
+            // -- ~180 FMAs per output row instead of 49 x (16 tests + 16 products + ~32 FMAs) in the per-pixel form
+            float T[4][8];
+#pragma unroll
+            for (int px = 0; px < 4; px++)
+#pragma unroll
+              for (int j = 0; j < 8; j++) T[px][j] = 0.f;
 #pragma unroll
             for (int pw = 0; pw < 7; pw++) {
               float wxv[4];
@@ -467,14 +474,19 @@ roi_align_bwd_kernel(const __nv_bfloat16* __restrict__ dA, long long ld, const f
 #pragma unroll
               for (int q = 0; q < 4; q++) { d[2 * q] = __uint_as_float(wv[q] << 16); d[2 * q + 1] = __uint_as_float(wv[q] & 0xffff0000u); }
 #pragma unroll
-              for (int py = 0; py < 4; py++)
+              for (int px = 0; px < 4; px++) {
+                if (wxv[px] == 0.f) continue;        // warp-uniform: a bin of a tiny RoI touches 2 of the 4 columns
 #pragma unroll
-                for (int px = 0; px < 4; px++) {
-                  const float wgt = wyv[py] * wxv[px];
-                  if (wgt == 0.f) continue;      // warp-uniform: a bin of a tiny RoI touches 2x2 of the 4x4 pixels
+                for (int j = 0; j < 8; j++) T[px][j] = fmaf(wxv[px], d[j], T[px][j]);
+              }
+            }
 #pragma unroll
-                  for (int j = 0; j < 8; j++) acc[py * 4 + px][j] = fmaf(wgt, d[j], acc[py * 4 + px][j]);
-                }
+            for (int py = 0; py < 4; py++) {
+              if (wyv[py] == 0.f) continue;
+#pragma unroll
+              for (int px = 0; px < 4; px++)
+#pragma unroll
+                for (int j = 0; j < 8; j++) acc[py * 4 + px][j] = fmaf(wyv[py], T[px][j], acc[py * 4 + px][j]);
             }
           }
 #pragma unroll

@@ -559,14 +559,29 @@ extern "C" int pt_fc_gemm_bf16_mn(const void* A, long long lda, int a_mn, const 
   p.tiles_total = tiles_m * p.tiles_n;
   const int units = two ? num_sms / 2 : num_sms;           // scheduling units: CTA pairs or CTAs
   int grid_u = p.tiles_total < units ? p.tiles_total : units;
-  p.full_rounds = p.tiles_total / grid_u;
-  const int tail = p.tiles_total - p.full_rounds * grid_u;
+  const int kb_total = (K + BK - 1) / BK;
   const int sub = two ? 2 : 1;                             // 128-row output sub-tiles per scheduling tile
   p.split = 0;
   p.ws = nullptr; p.counters = nullptr;
-  if (allow_split && tail > 0 && tail * sub * 8 <= 4096 && workspace != nullptr) {
+  int tail;
+  // Few tiles, long contraction (wgrad of the 1024 x 1024 layer: 32 tiles, K = 5000 RoIs): EVERY tile is split along K
+  // over units / tiles CTAs -- the whole launch is then one "tail wave" of the scheme below (full_rounds = 0).
+  int S_all = (allow_split && workspace != nullptr && p.tiles_total * 2 <= units && kb_total >= 64) ? units / p.tiles_total : 0;
+  if (S_all > kb_total / 8) S_all = kb_total / 8;
+  if (S_all >= 2 && p.tiles_total * sub * 8 <= 4096 &&
+      (long long)p.tiles_total * sub * S_all * BM * BN * 4 + 4096 <= workspace_bytes) {
+    grid_u = S_all * p.tiles_total;
+    p.full_rounds = 0;
+    tail = p.tiles_total;
+    p.split = S_all;
+    p.counters = reinterpret_cast<int*>(workspace);
+    p.ws = reinterpret_cast<float*>(reinterpret_cast<char*>(workspace) + 4096);
+  } else {
+    p.full_rounds = p.tiles_total / grid_u;
+    tail = p.tiles_total - p.full_rounds * grid_u;
+  }
+  if (p.split == 0 && allow_split && tail > 0 && tail * sub * 8 <= 4096 && workspace != nullptr) {
     int S = grid_u / tail;
-    const int kb_total = (K + BK - 1) / BK;
     // every split must keep >= 8 k-blocks of MMA work, otherwise the fp32 reduction costs more than it saves; short
     // contractions (K < 4096: FC2, measured 43 us split vs 27 us unsplit at 5000x1024x1024) are never split
     if (S > kb_total / 8) S = kb_total / 8;
