@@ -15,8 +15,10 @@ namespace ptb {
 constexpr int SH_KS = 8;        // K slices per row tile: D/8 = 128 hidden units = 4 fully unrolled 32-wide steps per warp
 constexpr int SH_WARPS = 2 * SH_KS;   // 2 row tiles x 8 K slices per CTA: one round of load latency per tile
 
+// Two CTAs per SM (<= 64 registers, 2 x 82 KB of shared memory): the bench's 169 row tiles then run as ONE wave of
+// the 296 slots; with one CTA per SM (69 registers) the last 21 tiles formed a second wave and doubled the kernel time.
 template <int NT>
-__global__ void __launch_bounds__(SH_WARPS * 32)
+__global__ void __launch_bounds__(SH_WARPS * 32, 2)
 small_head_mma_kernel(const __nv_bfloat16* __restrict__ H, long long ldh, int D, const float* __restrict__ W0, int n0,
                       const float* __restrict__ b0, const float* __restrict__ W1, int n1, const float* __restrict__ b1,
                       int M, float* __restrict__ out0, float* __restrict__ out1) {
@@ -125,7 +127,7 @@ static int launch_small_head(const void* H, long long ldh, int D, const float* W
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) { set_error("cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return PT_ERR_CUDA; }
   int grid = (M + 31) / 32;
-  if (grid > 148 * 4) grid = 148 * 4;
+  if (grid > 148 * 2) grid = 148 * 2;           // resident slots; beyond that the persistent row loop takes over
   kern<<<grid, SH_WARPS * 32, smem, s>>>(reinterpret_cast<const __nv_bfloat16*>(H), ldh, D, W0, n0, b0, W1, n1, b1, M, out0,
                                          out1);
   return check_launch("small_head_mma_kernel");
