@@ -1,14 +1,22 @@
 #!/usr/bin/env python
-"""Turns the ncu artefacts of the last gpurun (gpurun_out/) into the tracked summaries under profiles/:
-  profiles/r01_launches.md     per-kernel share of one step (ncu --metrics gpu__time_duration.sum launch list)
-  profiles/r01_kernels.md      ncu --set full counters of the dominant kernels (in-step and at the stress shape)
-  profiles/traffic.json        per-launch DRAM bytes (read + write) that bench.py reports as roofline.traffic
-Usage: python tools/make_profiles.py"""
+"""Turns the artefacts of the last measurement run (tools_gpu_profiles_r02.sh -> gpurun_out/) into the tracked summaries
+under profiles/ (TAG = r02):
+  profiles/TAG_launches*.md   per-kernel share of one step (ncu --metrics gpu__time_duration.sum launch lists)
+  profiles/TAG_kernels.md     ncu --set full counters of the dominant kernels (in-step and at the stress shape)
+  profiles/TAG_sass.txt       per-kernel counts of the tcgen05 / TMEM / TMA SASS mnemonics (cuobjdump of the shipped .so)
+  profiles/traffic.json       per-launch DRAM bytes (read + write) that bench.py reports as roofline.traffic
+  + the bench lines, the GPU test log, the micro-benchmark log and the bf16 parity record, copied as they are
+Usage: python tools/make_profiles.py [TAG]"""
 import collections
 import csv
 import json
 import os
+import re
+import shutil
 import subprocess
+import sys
+
+TAG = sys.argv[1] if len(sys.argv) > 1 else "r02"
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 G = os.path.join(ROOT, "gpurun_out")
@@ -42,7 +50,7 @@ def to_bytes(v, unit):
     return f * {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}.get(unit, 1)
 
 
-def launches_md(src="launches.csv", dst="r01_launches.md", title="phase-2 step (current kernels)",
+def launches_md(src="launches.csv", dst=TAG + "_launches.md", title="phase-2 step (current kernels)",
                 cmd="python bench.py --steps 2 --warmup 1 --no-graph --no-cpu-baseline --no-stress --no-train"):
     if not os.path.exists(os.path.join(G, src)):
         return
@@ -59,8 +67,8 @@ def launches_md(src="launches.csv", dst="r01_launches.md", title="phase-2 step (
         a[0] += 1
         a[1] += v
     tot = sum(a[1] for a in agg.values())
-    lines = [f"# Round 1 - ncu launch list of the {title}", "",
-             f"Command: `ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv {cmd}` (cold-cache, "
+    lines = [f"# {TAG} - ncu launch list of the {title}", "",
+             f"Command: `ncu --metrics gpu__time_duration.sum --clock-control none -c 500 --csv {cmd}` (cold-cache, "
              "serialised launches: compare SHARES, not absolutes; the capture spans several eager steps).", "",
              "| kernel | launches | total ns | avg ns | share |", "|---|---:|---:|---:|---:|"]
     for k, a in sorted(agg.items(), key=lambda kv: -kv[1][1]):
@@ -70,13 +78,14 @@ def launches_md(src="launches.csv", dst="r01_launches.md", title="phase-2 step (
 
 def kernels_md():
     traffic = {}
-    lines = ["# Round 1 - ncu --set full counters of the dominant kernels", "",
+    lines = [f"# {TAG} - ncu --set full counters of the dominant kernels", "",
              "`--clock-control none --import-source on`; per-launch values.  In-step captures come from "
              "`bench.py --no-graph` (K = 5000 / 5400 RoIs), the stress capture from `tools/prof_roi.py` "
              "(96 000 RoIs = config #4, one image).", ""]
     for title, rep, keys in [("In-step kernels (bench workload)", "prof_step.ncu-rep", None),
                              ("RoIAlign at the stress shape (96 000 RoIs, 2.4 GB bf16 out)", "prof_roi_stress.ncu-rep", None),
-                             ("RoIAlignRotated on the TMA + mma path (OBB config #3, 5000 / 5400 RoIs)", "prof_obb_roi.ncu-rep", None)]:
+                             ("RoIAlignRotated on the TMA + mma path (OBB config #3, 5000 / 5400 RoIs)", "prof_obb_roi.ncu-rep", None),
+                             ("RoIAlign backward (training step, 5000 RoIs)", "prof_roi_bwd.ncu-rep", None)]:
         path = os.path.join(G, rep)
         if not os.path.exists(path):
             continue
@@ -97,15 +106,53 @@ def kernels_md():
                 traffic.setdefault("roi_align_mma_kernel_rot@5000", rd + wr)
             elif "roi_align_mma" in nm:
                 traffic.setdefault("roi_align_mma_kernel@96000" if "stress" in rep else "roi_align_mma_kernel@5000", rd + wr)
-    open(os.path.join(P, "r01_kernels.md"), "w").write("\n".join(lines) + "\n")
+    open(os.path.join(P, TAG + "_kernels.md"), "w").write("\n".join(lines) + "\n")
     json.dump(traffic, open(os.path.join(P, "traffic.json"), "w"), indent=1)
     return traffic
+
+
+def sass_txt():
+    """Per-kernel counts of the SASS mnemonics that prove tcgen05 / TMEM / TMA (B200_PROFILING.md)."""
+    so = os.path.join(ROOT, "point_teacher_b200", "_C", "libptb200.so")
+    out = subprocess.run(["cuobjdump", "-sass", so], capture_output=True, text=True).stdout
+    pats = ["UTCHMMA", "UTCHMMA.2CTA", "LDTM", "UTMALDG", "UTMASTG", "UTCBAR", "UTCATOMSWS", "HMMA.16816", "SYNCS", "REDG", "RED.E"]
+    cur, table = None, collections.OrderedDict()
+    for line in out.splitlines():
+        m = re.search(r"Function : (\S+)", line)
+        if m:
+            cur = subprocess.run(["c++filt", m.group(1)], capture_output=True, text=True).stdout.strip()[:110]
+            table[cur] = collections.Counter()
+            continue
+        if cur is None:
+            continue
+        for p in pats:
+            if re.search(r"\b" + re.escape(p) + r"(\.|\b)", line):
+                if p == "UTCHMMA" and "UTCHMMA.2CTA" in line:
+                    continue
+                table[cur][p] += 1
+    lines = [f"# {TAG} - SASS mnemonic counts per kernel (cuobjdump -sass point_teacher_b200/_C/libptb200.so, sm_100a)",
+             "# UTCHMMA = tcgen05.mma, LDTM = tcgen05.ld (TMEM), UTMALDG / UTMASTG = TMA tensor load / store, UTCBAR = tcgen05.commit,",
+             "# UTCATOMSWS = TMEM allocation, HMMA.16816 = mma.sync.m16n8k16 (RoIAlign interpolation, small heads)", ""]
+    for k, c in table.items():
+        if sum(c.values()):
+            lines.append(f"{k}\n    " + "  ".join(f"{p}={c[p]}" for p in pats if c[p]))
+    open(os.path.join(P, TAG + "_sass.txt"), "w").write("\n".join(lines) + "\n")
+
+
+def copy_logs():
+    for f in os.listdir(G):
+        if f.startswith(TAG + "_") and f.endswith((".json", ".log")):
+            shutil.copy(os.path.join(G, f), os.path.join(P, f))
+    if os.path.exists(os.path.join(G, "parity_r02.json")):
+        shutil.copy(os.path.join(G, "parity_r02.json"), os.path.join(P, TAG + "_parity.json"))
 
 
 if __name__ == "__main__":
     os.makedirs(P, exist_ok=True)
     launches_md()
-    launches_md("obb_launches.csv", "r01_launches_obb.md", "OBB (config #3) phase-2 step", "python tools/prof_obb.py 3")
-    launches_md("train_launches.csv", "r01_launches_train.md", "HBB training step (forward + backward)",
+    launches_md("obb_launches.csv", TAG + "_launches_obb.md", "OBB (config #3) phase-2 step", "python tools/prof_obb.py 3")
+    launches_md("train_launches.csv", TAG + "_launches_train.md", "HBB training step (forward + backward)",
                 "python tools/prof_train.py 3")
+    sass_txt()
+    copy_logs()
     print(kernels_md())
