@@ -397,7 +397,9 @@ class MILHeadMixin:
         # (Measured and NOT kept: pooling the negatives' rows of the classification operand on the side stream, under
         # the first FC stack -- they do not depend on the regression pass.  The RoIAlign CTAs (113 / 220 KB of shared
         # memory) cannot share an SM with the persistent GEMM's 200 KB CTAs, so the GEMM lost SMs for its first wave:
-        # HBB step 0.460 -> 0.468 ms, OBB 0.586 -> 0.604 ms.)
+        # HBB step 0.460 -> 0.468 ms, OBB 0.586 -> 0.604 ms.  Second attempt: only the rotated negatives' large-RoI GATHER
+        # pass -- no shared memory -- on the side stream: its three 224-thread CTAs per SM hold the registers the
+        # cooperative FC1 launch needs for co-residency, the GEMM waits for them: OBB 0.576 -> 0.598 ms.)
         ev_reg, ev_all = self._side_work(stage, negatives, stacks=(0,) if mode == "reg_only" else (0, 1))
         neg_w = side["neg_w"]
         ebags, evalid = ops.bag_gen(base_rois, img_wh, cfg["base_ratios"], cfg["shake_ratio"], cfg["min_scale"], rot)
