@@ -87,6 +87,39 @@ __global__ void prep_fc1_weight_kernel(const float* __restrict__ w, __nv_bfloat1
   }
 }
 
+// bf16 (non-x3) fast path, whole row in shared memory in PARAMETER order: the global read is one contiguous
+// 16-byte-vector stream and lands with conflict-free 16-byte shared stores; the permuted read k' = bin*C + c ->
+// c*bins + bin walks shared memory at stride `bins` (49: odd, bank-conflict-free scalar loads); 16-byte global stores.
+__global__ void __launch_bounds__(256)
+prep_fc1_weight_row_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ out, int C, int bins, long long ld) {
+  extern __shared__ __align__(16) float prow[];
+  const int n = blockIdx.x, K = C * bins;
+  const float4* src4 = reinterpret_cast<const float4*>(w + (size_t)n * K);
+  float4* p4 = reinterpret_cast<float4*>(prow);
+  for (int i = threadIdx.x; i < K / 4; i += blockDim.x) p4[i] = __ldcs(src4 + i);     // streamed: read exactly once
+  __syncthreads();
+  __nv_bfloat16* dst = out + (size_t)n * ld;
+  for (int kp = threadIdx.x * 8; kp < K; kp += blockDim.x * 8) {
+    const int bin = kp / C, c = kp - bin * C;
+    float v[8];
+#pragma unroll
+    for (int j = 0; j < 8; j++) v[j] = prow[(c + j) * bins + bin];
+    *reinterpret_cast<uint4*>(dst + kp) =
+        make_uint4(pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]), pack_bf16(v[4], v[5]), pack_bf16(v[6], v[7]));
+  }
+}
+
+// bf16 (non-x3) cast with 16-byte loads / 8-byte stores, no per-element division (K % 4 == 0, ld % 4 == 0)
+__global__ void __launch_bounds__(256)
+cast_weight_vec_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ out, int N, int K4, long long ld) {
+  const long long total = (long long)N * K4;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int n = (int)(i / K4), k4 = (int)(i - (long long)n * K4);
+    const float4 v = __ldcs(reinterpret_cast<const float4*>(w) + i);
+    *reinterpret_cast<uint2*>(out + (size_t)n * ld + 4 * k4) = make_uint2(pack_bf16(v.x, v.y), pack_bf16(v.z, v.w));
+  }
+}
+
 __global__ void cast_weight_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ out, int N, int K,
                                    long long ld, int x3) {
   const long long total = (long long)N * K;
@@ -495,6 +528,12 @@ extern "C" int pt_prep_fc1_weight(const float* w, void* out_bf16, int N, int C, 
   if (C % 8 != 0 || ld % 8 != 0) { set_error("pt_prep_fc1_weight: C and ld must be multiples of 8"); return PT_ERR_ARG; }
   const size_t smem = (size_t)(C + 4) * bins * sizeof(float);
   if (smem > 200 * 1024) { set_error("pt_prep_fc1_weight: row of %lld floats does not fit shared memory", K); return PT_ERR_UNSUPPORTED; }
+  if (!x3 && (K & 3) == 0 && (size_t)K * sizeof(float) <= 64 * 1024 && (((uintptr_t)w | (uintptr_t)out_bf16) & 15) == 0) {
+    static bool done = false;
+    if (!done) { cudaFuncSetAttribute(prep_fc1_weight_row_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024); done = true; }
+    prep_fc1_weight_row_kernel<<<N, 256, (size_t)K * sizeof(float), (cudaStream_t)stream>>>(w, (__nv_bfloat16*)out_bf16, C, bins, ld);
+    return check_launch("prep_fc1_weight_row_kernel");
+  }
   cudaFuncSetAttribute(prep_fc1_weight_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   prep_fc1_weight_kernel<<<N, 512, smem, (cudaStream_t)stream>>>(w, (__nv_bfloat16*)out_bf16, C, bins, ld, x3);
   return check_launch("prep_fc1_weight_kernel");
@@ -502,6 +541,10 @@ extern "C" int pt_prep_fc1_weight(const float* w, void* out_bf16, int N, int C, 
 
 extern "C" int pt_cast_weight_bf16(const float* w, void* out_bf16, int N, int K, long long ld, int x3, void* stream) {
   if (ld < (x3 ? 3LL : 1LL) * K) { set_error("pt_cast_weight_bf16: ld too small"); return PT_ERR_ARG; }
+  if (!x3 && (K & 3) == 0 && (ld & 3) == 0 && (((uintptr_t)w & 15) | ((uintptr_t)out_bf16 & 7)) == 0) {
+    cast_weight_vec_kernel<<<148 * 4, 256, 0, (cudaStream_t)stream>>>(w, (__nv_bfloat16*)out_bf16, N, K / 4, ld);
+    return check_launch("cast_weight_vec_kernel");
+  }
   cast_weight_kernel<<<148 * 8, 256, 0, (cudaStream_t)stream>>>(w, (__nv_bfloat16*)out_bf16, N, K, ld, x3);
   return check_launch("cast_weight_kernel");
 }

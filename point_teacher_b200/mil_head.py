@@ -116,7 +116,11 @@ class MILHeadMixin:
         rebuild of both FC stacks' operands when they are stale (training: every step; 2 x 77 MB weight streams that
         overlap bag generation and the first RoIAlign instead of sitting in front of the GEMMs) and ``between()``
         (the negatives' RoIs and weights).  Returns the events (first stack's weights ready, everything done); the
-        caller joins with ``wait_event``.  Works the same inside a CUDA-graph capture (the side stream is forked
+        caller joins with ``wait_event``.  (Measured and NOT kept: starting the first stack's preparation even earlier,
+        at the top of ``phase2_refine`` -- the weight stream then competes with the first RoIAlign's stores for HBM:
+        0.453 -> 0.460 ms.  The preparation costs ~35 us of the step however it is scheduled -- 0.420 ms with frozen
+        operands, ``bench.py --frozen-weights`` -- because the step's first 60 us are HBM-bound either way.)
+        Works the same inside a CUDA-graph capture (the side stream is forked
         from, and joined back into, the capturing stream).  (Measured: moving the NCHW -> NHWC transpose here as
         well gains nothing -- it then competes with the weight stream for HBM in front of the first RoIAlign.)"""
         main = torch.cuda.current_stream()
@@ -382,7 +386,6 @@ class MILHeadMixin:
         G = base_rois.shape[0] // max(U1, 1)
         rois2 = torch.empty((K + n_neg, rs), dtype=torch.float32, device=dev)
         side = {"neg_w": neg_w, "lv": None}
-        self._nhwc_maps(x)                           # transposed on the main stream before the side stream forks
         A2 = None
         if mode != "reg_only":
             cols = self.in_channels * self.roi_feat_area * (3 if self._x3() else 1)

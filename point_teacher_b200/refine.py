@@ -29,6 +29,8 @@ def phase2_refine(head, x_ori, img_metas, pseudo_bboxes, pseudo_points, pseudo_l
     cap = num_training_burninstep2
     dev = pseudo_bboxes[0].device
     rot = head.bbox_roi_extractor.rotated       # OBB twin: rotated_fcos_teacher_student.py:494-535
+    if train == "manual" or train:
+        head._weights().clear()                 # parameters change every iteration
     counts = [min(int(b.shape[0]), cap) for b in pseudo_bboxes]
     pb = torch.cat([b[:cap, :] for b in pseudo_bboxes]).float().contiguous()
     gb = torch.cat([b[:cap, :] for b in gt_bboxes]).float().contiguous()
@@ -49,13 +51,12 @@ def phase2_refine(head, x_ori, img_metas, pseudo_bboxes, pseudo_points, pseudo_l
     def run_stage(x, *args, **kw):
         if train == "manual":     # forward only, intermediates kept for an explicit backward (train.Phase2Trainer)
             keep = {}
-            head._weights().clear()
             out = head.mil_stage_packed(x, *args, keep=keep, **kw)
             head._train_keeps = getattr(head, "_train_keeps", []) + [keep]
             return out
         if train:                 # the two MIL losses carry a grad_fn (feature map + head parameters), see train.py
             from .train import mil_stage_train
-            return mil_stage_train(head, x, *args, **kw)
+            return mil_stage_train(head, x, *args, clear_weights=False, **kw)
         return head.mil_stage_packed(x, *args, **kw)
 
     for stage in range(num_stages):

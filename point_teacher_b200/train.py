@@ -152,13 +152,14 @@ class _MILStageFn(torch.autograd.Function):
 
 
 def mil_stage_train(head, x, img_metas, img_wh, base_rois, U1, ref, real, neg_boxes, neg_img_idx, bag_offsets, labels,
-                    pseudo, cfg, stage, loss_scales=(1.0, 1.0), neg_w=None, mode="full"):
+                    pseudo, cfg, stage, loss_scales=(1.0, 1.0), neg_w=None, mode="full", clear_weights=True):
     """Differentiable twin of ``mil_stage_packed``: same arguments and return value, but the two loss entries carry a
     ``grad_fn`` (feature maps + the stage's parameters)."""
     if getattr(head, "precision", "bf16") != "bf16":
         raise NotImplementedError("the backward runs in bf16 precision (precision='fp32' is forward-only: wrap the "
                                   "call in torch.no_grad())")
-    head._weights().clear()                            # parameters change every iteration
+    if clear_weights:
+        head._weights().clear()                        # parameters change every iteration
     args = (img_metas, img_wh, base_rois, U1, ref, real, neg_boxes, neg_img_idx, bag_offsets, labels, pseudo, cfg, stage)
     kwargs = dict(loss_scales=loss_scales, neg_w=neg_w, mode=mode)
     feats = tuple(x[:head.bbox_roi_extractor.num_inputs])
