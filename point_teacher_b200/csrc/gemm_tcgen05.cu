@@ -52,6 +52,8 @@ struct Params {
   int tiles_n, tiles_total, split;  // split = S (>=2) when the tail wave is K-split, else 0
   int full_rounds;
   int a_mn, b_mn;                   // operand stored [K, M] / [K, N] (MN-major): wgrad / dgrad without a transposed copy
+  int diag;                         // measurement only (PTB200_GEMM_DIAG): 1 = no TMA loads after the first ring fill
+                                    // (MMA + shared-memory operand reads alone), 2 = no MMAs (TMA feed alone)
 };
 
 struct Unit {
@@ -247,6 +249,11 @@ fc_gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
         for (int kb = u.kb0; kb < u.kb1; kb++) {
           mbar_wait(empty_bar + stage, phase ^ 1);
           uint8_t* sa = smem + stage * STAGE_BYTES;
+          if (p.diag == 1 && (it > 0 || kb - u.kb0 >= STAGES)) {      // diagnostic: stale operands, timing only
+            mbar_arrive(full_bar + stage);
+            if (++stage == STAGES) { stage = 0; phase ^= 1; }
+            continue;
+          }
           if (TWO) {
             // CTA 0's barrier collects the bytes of both CTAs' loads (its own arrive arms 2 x STAGE_BYTES)
             if (rank == 0) mbar_expect_tx(full_bar + stage, 2 * STAGE_BYTES);
@@ -297,6 +304,7 @@ fc_gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
             constexpr uint32_t idesc = IDESC | (amn ? (1u << 15) : 0u) | (bmn ? (1u << 16) : 0u);
 #pragma unroll
             for (int k = 0; k < BK / UMMA_K; k++) {
+              if (p.diag == 2 && !(kb == u.kb0 && k == 0)) continue;   // diagnostic: one MMA per tile, timing only
               if (TWO) tc_mma_bf16_pair(tmem_d, adesc + 2 * k, bdesc + 2 * k, IDESC_PAIR, (kb > u.kb0 || k > 0) ? 1u : 0u);
               else tc_mma_bf16(tmem_d, adesc + astep * k, bdesc + bstep * k, idesc, (kb > u.kb0 || k > 0) ? 1u : 0u);
             }
@@ -552,6 +560,11 @@ extern "C" int pt_fc_gemm_bf16_mn(const void* A, long long lda, int a_mn, const 
   Params p;
   p.mask = reinterpret_cast<const __nv_bfloat16*>(mask); p.ldmask = (int)ldmask;
   p.a_mn = a_mn ? 1 : 0; p.b_mn = b_mn ? 1 : 0;
+  {
+    static int diag = -1;
+    if (diag < 0) { const char* e = getenv("PTB200_GEMM_DIAG"); diag = e != nullptr ? atoi(e) : 0; }
+    p.diag = diag;
+  }
   p.bias = bias; p.C = C; p.M = M; p.N = N; p.K = K; p.ldc = (int)ldc; p.relu = relu; p.out_f32 = out_f32;
   p.tiles_n = N / BN;
   const int tile_rows = two ? 2 * BM : BM;                 // rows of one scheduling tile
