@@ -201,43 +201,52 @@ __global__ void neg_loss_grad_kernel(const float* __restrict__ neg_cls, const ui
 // dW [NOUT, D] += g^T H; db [NOUT] += sum_m g.  Block = 256 threads, thread owns 4 consecutive hidden units of a
 // 1024-wide column tile; a block walks a contiguous range of rows.
 template <int NOUT>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 2)
 head_bwd_kernel(const float* __restrict__ g, const __nv_bfloat16* __restrict__ H, long long ldh, int D,
                 const float* __restrict__ W, int M, __nv_bfloat16* __restrict__ dZ, long long ldz,
                 float* __restrict__ dW, float* __restrict__ db) {
+  // thread = 2 consecutive hidden units of a 512-wide column slab (blockIdx.y), block = a contiguous range of rows;
+  // two rows per iteration so that two independent H loads are in flight.  (Round 1 owned 4 units per thread:
+  // 167 registers, one CTA per SM, 296 CTAs = two serial waves of latency-bound row walks: 34 us at 5400 x 16.)
   const int rows_per = (M + gridDim.x - 1) / gridDim.x;
   const int r0 = blockIdx.x * rows_per, r1 = min(M, r0 + rows_per);
   if (r0 >= r1) return;
-  for (int c0 = threadIdx.x * 4; c0 < D; c0 += 1024) {
-    float w[NOUT][4], acc[NOUT][4];
+  for (int c0 = blockIdx.y * 512 + threadIdx.x * 2; c0 < D; c0 += gridDim.y * 512) {
+    float w[NOUT][2], acc[NOUT][2];
 #pragma unroll
     for (int o = 0; o < NOUT; o++) {
-      const float4 t = *reinterpret_cast<const float4*>(W + (size_t)o * D + c0);
-      w[o][0] = t.x; w[o][1] = t.y; w[o][2] = t.z; w[o][3] = t.w;
-#pragma unroll
-      for (int j = 0; j < 4; j++) acc[o][j] = 0.f;
+      const float2 t = *reinterpret_cast<const float2*>(W + (size_t)o * D + c0);
+      w[o][0] = t.x; w[o][1] = t.y;
+      acc[o][0] = 0.f; acc[o][1] = 0.f;
     }
-    for (int r = r0; r < r1; r++) {
-      const uint2 hv = *reinterpret_cast<const uint2*>(H + (size_t)r * ldh + c0);
-      const float h[4] = {__uint_as_float(hv.x << 16), __uint_as_float(hv.x & 0xffff0000u),
-                          __uint_as_float(hv.y << 16), __uint_as_float(hv.y & 0xffff0000u)};
-      float dz[4] = {0.f, 0.f, 0.f, 0.f};
+    for (int r = r0; r < r1; r += 2) {
+      const bool two = r + 1 < r1;
+      const uint32_t hv0 = *reinterpret_cast<const uint32_t*>(H + (size_t)r * ldh + c0);
+      const uint32_t hv1 = two ? *reinterpret_cast<const uint32_t*>(H + (size_t)(r + 1) * ldh + c0) : 0u;
+      const float h0[2] = {__uint_as_float(hv0 << 16), __uint_as_float(hv0 & 0xffff0000u)};
+      const float h1[2] = {__uint_as_float(hv1 << 16), __uint_as_float(hv1 & 0xffff0000u)};
+      float dz0[2] = {0.f, 0.f}, dz1[2] = {0.f, 0.f};
 #pragma unroll
       for (int o = 0; o < NOUT; o++) {
-        const float gv = __ldg(g + (size_t)r * NOUT + o);
+        const float g0 = __ldg(g + (size_t)r * NOUT + o);
+        const float g1 = two ? __ldg(g + (size_t)(r + 1) * NOUT + o) : 0.f;
 #pragma unroll
-        for (int j = 0; j < 4; j++) { dz[j] += gv * w[o][j]; acc[o][j] += gv * h[j]; }
+        for (int j = 0; j < 2; j++) {
+          dz0[j] += g0 * w[o][j]; dz1[j] += g1 * w[o][j];
+          acc[o][j] += g0 * h0[j] + g1 * h1[j];
+        }
       }
-#pragma unroll
-      for (int j = 0; j < 4; j++) dz[j] = h[j] > 0.f ? dz[j] : 0.f;
-      *reinterpret_cast<uint2*>(dZ + (size_t)r * ldz + c0) = make_uint2(pack_bf16(dz[0], dz[1]), pack_bf16(dz[2], dz[3]));
+      *reinterpret_cast<uint32_t*>(dZ + (size_t)r * ldz + c0) = pack_bf16(h0[0] > 0.f ? dz0[0] : 0.f, h0[1] > 0.f ? dz0[1] : 0.f);
+      if (two)
+        *reinterpret_cast<uint32_t*>(dZ + (size_t)(r + 1) * ldz + c0) =
+            pack_bf16(h1[0] > 0.f ? dz1[0] : 0.f, h1[1] > 0.f ? dz1[1] : 0.f);
     }
 #pragma unroll
-    for (int o = 0; o < NOUT; o++)     // one 16-byte reduction per output row instead of four scalar atomics
-      asm volatile("red.relaxed.gpu.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dW + (size_t)o * D + c0),
-                   "f"(acc[o][0]), "f"(acc[o][1]), "f"(acc[o][2]), "f"(acc[o][3]) : "memory");
+    for (int o = 0; o < NOUT; o++)
+      asm volatile("red.relaxed.gpu.global.add.v2.f32 [%0], {%1, %2};" ::"l"(dW + (size_t)o * D + c0), "f"(acc[o][0]),
+                   "f"(acc[o][1]) : "memory");
   }
-  if (threadIdx.x < NOUT) {
+  if (blockIdx.y == 0 && threadIdx.x < NOUT) {
     float s = 0.f;
     for (int r = r0; r < r1; r++) s += g[(size_t)r * NOUT + threadIdx.x];
     atomicAdd(db + threadIdx.x, s);
@@ -705,9 +714,9 @@ extern "C" int pt_bag_loss_grad(const float* cls, const float* ins, const unsign
 extern "C" int pt_head_bwd(const float* g, int nout, const void* H_bf16, long long ldh, int D, const float* W, int M,
                            void* dZ_bf16, long long ldz, float* dW, float* db, void* stream) {
   if (M <= 0) return PT_OK;
-  if (D % 4 != 0 || (ldh % 4) || (ldz % 4)) { set_error("pt_head_bwd: D / leading dimensions must be multiples of 4"); return PT_ERR_ARG; }
+  if (D % 512 != 0 || (ldh % 4) || (ldz % 4)) { set_error("pt_head_bwd: D must be a multiple of 512, leading dimensions of 4"); return PT_ERR_ARG; }
   cudaStream_t s = (cudaStream_t)stream;
-  const int grid = M < 296 ? M : 296;     // 2 CTAs per SM: the dW reductions (grid x nout x D / 4) stay cheap
+  const dim3 grid(M < 296 ? M : 296, D >= 1024 ? 2 : 1);   // 592 CTAs, 2 resident per SM; dW: grid.x x nout x D / 2 reds
   const __nv_bfloat16* H = reinterpret_cast<const __nv_bfloat16*>(H_bf16);
   __nv_bfloat16* dZ = reinterpret_cast<__nv_bfloat16*>(dZ_bf16);
   switch (nout) {
