@@ -20,6 +20,12 @@
 
 namespace ptb {
 
+namespace ramma {   // roi_align_mma.cu: tensor-core RoIAlign backward
+bool bwd_supported(int C, int H, int W, long long ld);
+int launch_bwd(const void* dA_bf16, long long ld, const float* rois, int K, int B, int C, int H, int W, float scale,
+               int sampling_ratio, int aligned, float* dfeat, const int* roi_level, int level, cudaStream_t stream);
+}  // namespace ramma
+
 // ---------------------------------------------------------------------------------------- dual numbers (4 seeds)
 struct D4 {
   float v, d[4];
@@ -787,6 +793,11 @@ extern "C" int pt_roi_align_backward_ex(const void* dA_bf16, long long ld, const
                                         float* dfeat, const int* roi_level, int level, void* stream) {
   if (K <= 0) return PT_OK;
   if (C % 8 != 0) { set_error("pt_roi_align_backward: C must be a multiple of 8"); return PT_ERR_ARG; }
+  // tensor-core path (roi_align_mma.cu); PTB200_RA_BWD_MMA=0 keeps the register formulation below for A/B measurements
+  static const bool use_mma = [] { const char* e = getenv("PTB200_RA_BWD_MMA"); return e == nullptr || e[0] != '0'; }();
+  if (use_mma && ramma::bwd_supported(C, H, W, ld))
+    return ramma::launch_bwd(dA_bf16, ld, rois, K, B, C, H, W, spatial_scale, sampling_ratio, aligned, dfeat, roi_level,
+                             level, (cudaStream_t)stream);
   const size_t smem = (size_t)RB_WARPS * ((W + 4) + (H + 4)) * 8 * sizeof(float);
   if (smem > 200 * 1024) { set_error("pt_roi_align_backward: feature map too large for the shared weight tables"); return PT_ERR_UNSUPPORTED; }
   cudaError_t e = cudaFuncSetAttribute(roi_align_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);

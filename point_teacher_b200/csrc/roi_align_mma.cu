@@ -686,6 +686,287 @@ roi_align_mma_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_cons
   if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // smem must outlive the reads
 }
 
+// ------------------------------------------------------------------------------------------------ backward
+// mmcv RoIAlign backward (HBB_TOD/mmdet/models/roi_heads/roi_extractors/single_level_roi_extractor.py:56-114 under
+// autograd) with the forward's machinery turned around: per 4x4-pixel chunk
+//     dP[pix, c] = sum_bin Wmat[bin, pix] * dA[bin, c]                  (16 x 49) * (49 x 256)
+// is ONE m16n8k16 row of tiles per warp (M = the chunk's 16 pixels, K = 49 bins padded to 64, N = the warp's 32
+// channels) instead of ~3 000 FFMAs per lane in backward.cu's register formulation.  dA of a RoI is fetched once per
+// MMA warp by TMA (the forward's output box: 49 bins x 32 channels, SWIZZLE_64B) and held as B fragments for all
+// chunks of the RoI; the builder warps produce Wmat in A-fragment order, split into a bf16 head and a bf16 remainder
+// (two mma passes), so the weights carry ~16 mantissa bits and the result matches the fp32-weight kernel to the
+// rounding of the fp32 accumulation.  The chunk's gradient goes to the NHWC fp32 map with red.global.add.v4.f32.
+constexpr int BW_BUILDERS = 2, BW_DEPTH = 2, BW_STAGES = BW_BUILDERS * BW_DEPTH;
+constexpr int BW_STG_BYTES = 64 * STG_ROW_BYTES;     // 64 bin rows (49 loaded by TMA, 15 kept zero) x 32 channels
+constexpr int BW_META_BYTES = 32;                    // {roi, flags, x0, y0, image, xmax, ymax, -}
+
+__device__ __forceinline__ void tma_load_3d(uint32_t dst, const void* desc, uint32_t bar, int c0, int c1, int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+      ::"r"(dst), "l"(desc), "r"(bar), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
+__device__ __forceinline__ void red_add_v4(float* p, float a, float b, float c, float d) {
+  asm volatile("red.relaxed.gpu.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(a), "f"(b), "f"(c), "f"(d)
+               : "memory");
+}
+// bf16 head / remainder of a weight pair
+__device__ __forceinline__ void split_bf16(float a, float b, uint32_t& hi, uint32_t& lo) {
+  const __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+  const float2 hf = __bfloat1622float2(h);
+  hi = *reinterpret_cast<const uint32_t*>(&h);
+  lo = pack_bf16(a - hf.x, b - hf.y);
+}
+
+__global__ void __launch_bounds__((MMA_WARPS + BW_BUILDERS) * 32, 2)
+roi_align_bwd_mma_kernel(const __grid_constant__ CUtensorMap gmap, const float* __restrict__ rois, int K, int B, int C,
+                         int H, int W, float scale, int sampling_ratio, int aligned, float* __restrict__ dfeat,
+                         const int* __restrict__ roi_level, int level) {
+  extern __shared__ uint8_t smem_raw[];
+  constexpr int NB = BW_BUILDERS, DP = BW_DEPTH, NSTAGES = BW_STAGES;
+  const uint32_t sbase = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t s_stg = sbase;                                           // [MMA_WARPS][2][BW_STG_BYTES], 512 B aligned
+  const uint32_t s_afrag = s_stg + MMA_WARPS * 2 * BW_STG_BYTES;          // [STAGES][hi, lo][AFRAG_BYTES]
+  const uint32_t s_tab = s_afrag + NSTAGES * 2 * AFRAG_BYTES;             // [BUILDERS] wx | wy
+  const int tab_floats = (W + 4) * 8 + (H + 4) * 8;
+  const uint32_t s_full = s_tab + NB * tab_floats * 4;
+  const uint32_t s_empty = s_full + NSTAGES * 8;
+  const uint32_t s_gbar = s_empty + NSTAGES * 8;                          // [MMA_WARPS][2]: a warp's dA slice has landed
+  const uint32_t s_meta = s_gbar + MMA_WARPS * 2 * 8;                     // [STAGES][BW_META_BYTES]
+  uint8_t* gen = smem_raw + (sbase - smem_u32(smem_raw));
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(gen + (s_full - sbase));
+  uint64_t* empty_bar = reinterpret_cast<uint64_t*>(gen + (s_empty - sbase));
+  uint64_t* g_bar = reinterpret_cast<uint64_t*>(gen + (s_gbar - sbase));
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) {
+    tma_prefetch_desc(&gmap);
+    for (int i = 0; i < NSTAGES; i++) { mbar_init(full_bar + i, 1); mbar_init(empty_bar + i, MMA_WARPS); }
+    for (int i = 0; i < MMA_WARPS * 2; i++) mbar_init(g_bar + i, 1);
+    fence_barrier_init();
+  }
+  // bin rows 49..63 of every staging buffer: read by the last k-step, never written by TMA
+  for (int i = threadIdx.x; i < MMA_WARPS * 2 * (64 - NBIN) * (STG_ROW_BYTES / 16); i += blockDim.x) {
+    const int bufi = i / ((64 - NBIN) * (STG_ROW_BYTES / 16)), r = i % ((64 - NBIN) * (STG_ROW_BYTES / 16));
+    sts128(s_stg + bufi * BW_STG_BYTES + NBIN * STG_ROW_BYTES + r * 16, make_uint4(0u, 0u, 0u, 0u));
+  }
+  __syncthreads();
+  const int n_iter = blockIdx.x < K ? (K - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+  const int g = lane >> 2, t = lane & 3;
+
+  if (warp >= MMA_WARPS) {
+    // ---------------------------------------------------------------------------------- builder warps
+    const int bw_id = warp - MMA_WARPS;
+    float* wx = reinterpret_cast<float*>(gen + (s_tab - sbase)) + bw_id * tab_floats;   // wx[col - xmin][pw]
+    float* wy = wx + (W + 4) * 8;                                                        // wy[row - ymin][ph]
+    const float off = aligned ? 0.5f : 0.f;
+    int slot = 0; uint32_t phase = 0;
+    // A fragment of Wmat^T: rows = pixels g (rows 0..1 of the chunk) and g + 8 (rows 2..3), k = bins
+    // 16 ks + 2t + {0, 1, 8, 9}
+    int phs[16], pws[16];
+#pragma unroll
+    for (int i = 0; i < 16; i++) {
+      const int bq = (i >> 2) * 16 + 2 * t + (i & 1) + ((i >> 1) & 1) * 8;
+      phs[i] = bq < NBIN ? bq / P7 : -1;
+      pws[i] = bq < NBIN ? bq % P7 : 0;
+    }
+    float rnext = 0.f;
+    if (bw_id < n_iter && lane < 5) rnext = __ldg(rois + (size_t)(blockIdx.x + bw_id * gridDim.x) * 5 + lane);
+    for (int it = bw_id; it < n_iter; it += NB) {
+      const int roi = blockIdx.x + it * gridDim.x;
+      const float rcur = rnext;
+      if (it + NB < n_iter && lane < 5)
+        rnext = __ldg(rois + (size_t)(blockIdx.x + (it + NB) * gridDim.x) * 5 + lane);
+      const bool skip = roi_level != nullptr && roi_level[roi] != level;
+      const int b = (int)__shfl_sync(0xffffffffu, rcur, 0);
+      const float x1 = fsub(fmul(__shfl_sync(0xffffffffu, rcur, 1), scale), off);
+      const float y1 = fsub(fmul(__shfl_sync(0xffffffffu, rcur, 2), scale), off);
+      const float x2 = fsub(fmul(__shfl_sync(0xffffffffu, rcur, 3), scale), off);
+      const float y2 = fsub(fmul(__shfl_sync(0xffffffffu, rcur, 4), scale), off);
+      float rw = fsub(x2, x1), rh = fsub(y2, y1);
+      if (!aligned) { rw = fmaxf(rw, 1.f); rh = fmaxf(rh, 1.f); }
+      const bool isx = (lane & 8) == 0;
+      const int bi = lane & 7;
+      const float bin = fdiv(isx ? rw : rh, (float)P7);
+      const float bin_o = __shfl_xor_sync(0xffffffffu, bin, 8);
+      const int gs = sampling_ratio > 0 ? sampling_ratio : (int)ceilf(bin);
+      const int gs_o = sampling_ratio > 0 ? sampling_ratio : (int)ceilf(bin_o);
+      const int cnt = gs * gs_o > 1 ? gs * gs_o : 1;
+      const float inv_count = 1.0f / (float)cnt;
+      const bool b_ok = b >= 0 && b < B && !skip;
+      const float start = isx ? x1 : y1;
+      const int size = isx ? W : H;
+      float* tab = isx ? wx : wy;
+      const float base = fadd(start, fmul((float)bi, bin));
+      int lo = 1 << 30, hi = -1;
+      const bool owner = lane < 16 && bi < P7;
+      if (owner && b_ok) {
+        for (int i = 0; i < gs; i++) {
+          const float v = fadd(base, fdiv(fmul((float)i + .5f, bin), (float)gs));
+          int l, h; float fl, fh;
+          if (axis_setup(v, size, l, h, fl, fh)) { lo = min(lo, l); hi = max(hi, h); }
+        }
+      }
+      int glo = lo, ghi = hi;
+#pragma unroll
+      for (int o = 4; o > 0; o >>= 1) {
+        glo = min(glo, __shfl_xor_sync(0xffffffffu, glo, o));
+        ghi = max(ghi, __shfl_xor_sync(0xffffffffu, ghi, o));
+      }
+      if (ghi < 0) { glo = 0; ghi = -1; }
+      __syncwarp();   // the previous RoI's fragment builds are done reading the tables
+      if (owner) {
+        const int npad = (ghi - glo + 4) & ~3;
+        for (int c = 0; c < npad; c++) tab[c * 8 + bi] = 0.f;
+        if (b_ok) {
+          for (int i = 0; i < gs; i++) {
+            const float v = fadd(base, fdiv(fmul((float)i + .5f, bin), (float)gs));
+            int l, h; float fl, fh;
+            if (axis_setup(v, size, l, h, fl, fh)) { tab[(l - glo) * 8 + bi] += fh; tab[(h - glo) * 8 + bi] += fl; }
+          }
+        }
+      }
+      __syncwarp();
+      const int xmin = __shfl_sync(0xffffffffu, glo, 0), xmax = __shfl_sync(0xffffffffu, ghi, 0);
+      const int ymin = __shfl_sync(0xffffffffu, glo, 8), ymax = __shfl_sync(0xffffffffu, ghi, 8);
+      const bool empty = !b_ok || xmax < xmin || ymax < ymin;
+      const int ncx = empty ? 1 : (xmax - xmin) / 4 + 1, ncy = empty ? 1 : (ymax - ymin) / 4 + 1;
+      for (int cy = 0; cy < ncy; cy++) {
+        for (int cx = 0; cx < ncx; cx++) {
+          const int stage = bw_id * DP + slot;
+          mbar_wait(empty_bar + stage, phase ^ 1);
+          int flags = (cy == ncy - 1 && cx == ncx - 1 ? F_LAST : 0);
+          if (empty) {
+            flags |= F_SKIP;
+          } else {
+            const int rA = cy * 4 + (g >> 2), cc = cx * 4 + (g & 3);
+            const uint32_t dst = s_afrag + stage * 2 * AFRAG_BYTES + lane * 16;
+#pragma unroll
+            for (int ks = 0; ks < 4; ks++) {
+              uint32_t ah[4], al[4];
+#pragma unroll
+              for (int hb = 0; hb < 2; hb++) {          // bins 2t, 2t+1 (hb = 0) and 2t+8, 2t+9 (hb = 1) of this k-step
+                float vA[2] = {0.f, 0.f}, vB[2] = {0.f, 0.f};
+#pragma unroll
+                for (int e = 0; e < 2; e++) {
+                  const int i = ks * 4 + hb * 2 + e;
+                  if (phs[i] >= 0) {
+                    const float wxv = wx[cc * 8 + pws[i]];
+                    vA[e] = wy[rA * 8 + phs[i]] * inv_count * wxv;
+                    vB[e] = wy[(rA + 2) * 8 + phs[i]] * inv_count * wxv;
+                  }
+                }
+                split_bf16(vA[0], vA[1], ah[hb * 2], al[hb * 2]);              // a0 / a2: pixel row g
+                split_bf16(vB[0], vB[1], ah[hb * 2 + 1], al[hb * 2 + 1]);      // a1 / a3: pixel row g + 8
+              }
+              sts128(dst + ks * 512, make_uint4(ah[0], ah[1], ah[2], ah[3]));
+              sts128(dst + AFRAG_BYTES + ks * 512, make_uint4(al[0], al[1], al[2], al[3]));
+            }
+          }
+          if (lane == 0) {
+            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(s_meta + stage * BW_META_BYTES), "r"(roi), "r"(flags),
+                         "r"(xmin + cx * 4), "r"(ymin + cy * 4) : "memory");
+            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(s_meta + stage * BW_META_BYTES + 16), "r"(b), "r"(xmax),
+                         "r"(ymax), "r"(0) : "memory");
+          }
+          __syncwarp();
+          if (lane == 0) mbar_arrive(full_bar + stage);
+          if (++slot == DP) { slot = 0; phase ^= 1; }
+        }
+      }
+    }
+    return;
+  }
+
+  // ------------------------------------------------------------------------------------ MMA warps
+  const int cb = warp * 32;
+  const bool active = cb < C;
+  const uint32_t sg0 = s_stg + warp * 2 * BW_STG_BYTES;
+  const uint32_t gb0 = s_gbar + warp * 16;
+  // ldmatrix.x4.trans row address inside the warp's [bin][32 ch] staging (SWIZZLE_64B: chunk ^= (row >> 1) & 3):
+  // matrix i = lane >> 3: bins (i & 1) * 8 + (lane & 7) of the k-step, channels 8 * (2 np + (i >> 1))
+  uint32_t boff[2];
+  {
+    const int i = lane >> 3, rr = lane & 7;
+    const int p = (i & 1) * 8 + rr;                         // + 16 ks: (p >> 1) & 3 is unchanged by multiples of 8
+#pragma unroll
+    for (int np = 0; np < 2; np++) {
+      const int jj = np * 2 + (i >> 1);
+      boff[np] = (uint32_t)(p * STG_ROW_BYTES + ((jj ^ ((p >> 1) & 3)) << 4));
+    }
+  }
+  const uint32_t tx_bytes = NBIN * STG_ROW_BYTES;
+  if (active && lane == 0 && n_iter > 0) {
+    mbar_expect_tx(g_bar + warp * 2, tx_bytes);
+    tma_load_3d(sg0, &gmap, gb0, cb, 0, blockIdx.x);
+  }
+  uint32_t slotpk = 0, phasebits = 0;
+  for (int it = 0; it < n_iter; it++) {
+    const int bw_id = it % NB;
+    const int buf = it & 1;
+    uint32_t bf[4][2][4];
+    if (active) {
+      // the other buffer was last read (ldmatrix, values long consumed) two RoIs ago: refill it for the next RoI
+      if (lane == 0 && it + 1 < n_iter) {
+        mbar_expect_tx(g_bar + warp * 2 + (buf ^ 1), tx_bytes);
+        tma_load_3d(sg0 + (buf ^ 1) * BW_STG_BYTES, &gmap, gb0 + (buf ^ 1) * 8, cb, 0, blockIdx.x + (it + 1) * gridDim.x);
+      }
+      mbar_wait(g_bar + warp * 2 + buf, (uint32_t)((it >> 1) & 1));
+      const uint32_t sg = sg0 + buf * BW_STG_BYTES;
+#pragma unroll
+      for (int ks = 0; ks < 4; ks++) {
+        ldsm_x4_trans(sg + ks * 16 * STG_ROW_BYTES + boff[0], bf[ks][0]);
+        ldsm_x4_trans(sg + ks * 16 * STG_ROW_BYTES + boff[1], bf[ks][1]);
+      }
+    }
+    int flags;
+    do {
+      const int slot = (int)((slotpk >> (4 * bw_id)) & 15u);
+      const int stage = bw_id * DP + slot;
+      mbar_wait(full_bar + stage, (phasebits >> bw_id) & 1);
+      const uint4 m0 = lds128(s_meta + stage * BW_META_BYTES);
+      flags = (int)m0.y;
+      if (!(flags & F_SKIP) && active) {
+        const uint4 m1 = lds128(s_meta + stage * BW_META_BYTES + 16);
+        const uint32_t af = s_afrag + stage * 2 * AFRAG_BYTES + lane * 16;
+        float acc[4][4];
+#pragma unroll
+        for (int ks = 0; ks < 4; ks++) {
+          const uint4 ah = lds128(af + ks * 512);
+          const uint4 al = lds128(af + AFRAG_BYTES + ks * 512);
+#pragma unroll
+          for (int nt = 0; nt < 4; nt++) {
+            const uint32_t b0 = bf[ks][nt >> 1][(nt & 1) * 2], b1 = bf[ks][nt >> 1][(nt & 1) * 2 + 1];
+            if (ks == 0) mma_bf16_z(acc[nt], ah, b0, b1);
+            else mma_bf16(acc[nt], ah, b0, b1);
+            mma_bf16(acc[nt], al, b0, b1);
+          }
+        }
+        // lane (g, t) holds pixel g (acc[.][0..1]) and pixel g + 8 (acc[.][2..3]), channels 8 nt + 2t, +1: the lane pair
+        // (t, t ^ 1) trades halves so that the even lane owns 4 consecutive channels of pixel g, the odd lane of g + 8
+        const int x = (int)m0.z + (g & 3);
+        const int y = (int)m0.w + (g >> 2) + ((t & 1) ? 2 : 0);
+        const bool ok = x <= (int)m1.y && y <= (int)m1.z;
+        float* dst = dfeat + (((size_t)(int)m1.x * H + y) * W + x) * C + cb + 2 * (t & ~1);
+#pragma unroll
+        for (int nt = 0; nt < 4; nt++) {
+          const float s0 = (t & 1) ? acc[nt][0] : acc[nt][2], s1 = (t & 1) ? acc[nt][1] : acc[nt][3];
+          const float r0 = __shfl_xor_sync(0xffffffffu, s0, 1), r1 = __shfl_xor_sync(0xffffffffu, s1, 1);
+          if (ok) {
+            if (t & 1) red_add_v4(dst + nt * 8, r0, r1, acc[nt][2], acc[nt][3]);
+            else red_add_v4(dst + nt * 8, acc[nt][0], acc[nt][1], r0, r1);
+          }
+        }
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(empty_bar + stage);
+      const int nslot = slot + 1 == DP ? 0 : slot + 1;
+      if (nslot == 0) phasebits ^= 1u << bw_id;
+      slotpk = (slotpk & ~(15u << (4 * bw_id))) | ((uint32_t)nslot << (4 * bw_id));
+    } while (!(flags & F_LAST));
+  }
+}
+
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -785,6 +1066,43 @@ int launch(const void* feat_bf16_nhwc, int feat_f16, const float* rois, void* ou
   kern<<<grid, (MMA_WARPS + nbld) * 32, smem, stream>>>(map, omap, rois, K, B, C, H, W, scale, sampling_ratio, aligned, roi_level, level,
                                         stg_bufs, clockwise);
   return check_launch("roi_align_mma_kernel");
+}
+
+size_t bwd_smem_bytes(int H, int W) {
+  return 1024 + MMA_WARPS * 2 * (size_t)BW_STG_BYTES + BW_STAGES * 2 * (size_t)AFRAG_BYTES +
+         BW_BUILDERS * ((size_t)(W + 4) * 8 + (size_t)(H + 4) * 8) * sizeof(float) + 2 * BW_STAGES * 8 +
+         MMA_WARPS * 2 * 8 + BW_STAGES * BW_META_BYTES + 64;
+}
+
+bool bwd_supported(int C, int H, int W, long long ld) {
+  return C % 32 == 0 && C >= 32 && C <= 256 && ld % 8 == 0 && bwd_smem_bytes(H, W) <= SMEM_LIMIT;
+}
+
+// dfeat (B, H, W, C) fp32, zeroed by the caller, += the RoIAlign gradient of dA (K rows of pitch ld, bf16 bin-major)
+int launch_bwd(const void* dA_bf16, long long ld, const float* rois, int K, int B, int C, int H, int W, float scale,
+               int sampling_ratio, int aligned, float* dfeat, const int* roi_level, int level, cudaStream_t stream) {
+  EncodeTiledFn enc = get_encode();
+  if (enc == nullptr) { set_error("cuTensorMapEncodeTiled entry point not found"); return PT_ERR_DRIVER; }
+  if ((uintptr_t)dA_bf16 & 15) { set_error("roi_align_bwd_mma: dA must be 16-byte aligned"); return PT_ERR_ARG; }
+  CUtensorMap gmap;
+  cuuint64_t gd[3] = {(cuuint64_t)C, (cuuint64_t)NBIN, (cuuint64_t)K};
+  cuuint64_t gs[2] = {(cuuint64_t)C * 2, (cuuint64_t)ld * 2};
+  cuuint32_t gb[3] = {32, (cuuint32_t)NBIN, 1};
+  cuuint32_t ge[3] = {1, 1, 1};
+  CUresult r = enc(&gmap, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(dA_bf16), gd, gs, gb, ge,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) { set_error("roi_align_bwd_mma: cuTensorMapEncodeTiled failed: CUresult %d", (int)r); return PT_ERR_DRIVER; }
+  const size_t smem = bwd_smem_bytes(H, W);
+  cudaError_t e = cudaFuncSetAttribute(roi_align_bwd_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) { set_error("cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return PT_ERR_CUDA; }
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const int grid = K < 2 * sms ? K : 2 * sms;
+  roi_align_bwd_mma_kernel<<<grid, (MMA_WARPS + BW_BUILDERS) * 32, smem, stream>>>(
+      gmap, rois, K, B, C, H, W, scale, sampling_ratio, aligned, dfeat, roi_level, level);
+  return check_launch("roi_align_bwd_mma_kernel");
 }
 
 }  // namespace ramma
