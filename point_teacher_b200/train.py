@@ -23,12 +23,14 @@ def stage_params(head, stage):
     return [t for m in mods for t in (m.weight, m.bias)]
 
 
-def _fc_branch_backward(head, k, dZ2, need_dA, out=None):
+def _fc_branch_backward(head, k, dZ2, need_dA, out=None, after_wgrad=None):
     """k: what ``_fc_stack`` kept (A, H1, H2, W1 (bin-major bf16), W2 (bf16), M).  dZ2 bf16 [rows, 1024] = gradient
     at the pre-activation of the second FC (already ReLU-masked).  Returns (dW1, db1, dW2, db2, dA | None).
     ``out`` (``dist.MILGradBucket.targets``): the kernels write into the bucket's views; dW1 then STAYS in the
     operand's bin-major column order (``MILGradBucket.finish_`` un-permutes it after the all-reduce); without
-    ``out`` fresh tensors are returned and dW1 is in the parameter's column order."""
+    ``out`` fresh tensors are returned and dW1 is in the parameter's column order.  ``after_wgrad()`` is called once the
+    branch's last PARAMETER-gradient kernel is enqueued, i.e. before the FC1 dgrad (which only feeds the feature map):
+    the gradient all-reduce of the branch starts there and the dgrad runs under it."""
     M, dev = k["M"], dZ2.device
     N1 = k["W1"].shape[0]
     o = out or {}
@@ -45,6 +47,8 @@ def _fc_branch_backward(head, k, dZ2, need_dA, out=None):
         ops.unpermute_dw1(dW1p, head.in_channels, head.roi_feat_area, dW1, accumulate=False)
     db1 = o["b1"] if out else torch.zeros((N1,), dtype=torch.float32, device=dev)
     ops.colsum_bf16(dZ1, db1, M=M)
+    if after_wgrad is not None:
+        after_wgrad()
     dA = None
     if need_dA:
         dA = ops.fc_gemm_mn(dZ1, k["W1"], b_mn=True, out_dtype=torch.bfloat16, M=M)                 # dZ1 @ W1
@@ -81,9 +85,8 @@ def mil_stage_backward(head, keep, x, g_bbox, g_bags, need_feat_grad=True, targe
         tg = targets["reg"] if targets else None
         dWreg, dbreg = (tg["Wh"], tg["bh"]) if tg else (torch.zeros_like(fr.weight), torch.zeros_like(fr.bias))
         dZ2 = ops.head_bwd(g4, keep["reg"]["H2"], fr.weight.detach(), dWreg, dbreg, M=K)
-        r = _fc_branch_backward(head, keep["reg"], dZ2, need_feat_grad, tg)
-        if branch_done is not None:
-            branch_done(stage, "reg")
+        r = _fc_branch_backward(head, keep["reg"], dZ2, need_feat_grad, tg,
+                                None if branch_done is None else (lambda: branch_done(stage, "reg")))
     # ---- bag branch: gfocal -> bag score -> (sigmoid, softmax x valid x L1) -> fc_cls / fc_ins -> FC2 -> FC1
     if do_bag:
         g16 = ops.bag_loss_grad(keep["cls"], keep["ins"], keep["evalid"], keep["labels"], G, U1, U2, keep["neg_w"], n_neg,
@@ -93,9 +96,8 @@ def mil_stage_backward(head, keep, x, g_bbox, g_bags, need_feat_grad=True, targe
         dWci, dbci = (tg["Wh"], tg["bh"]) if tg else \
             (torch.zeros_like(Wci), torch.zeros((2 * C,), dtype=torch.float32, device=dev))
         dZ2b = ops.head_bwd(g16, keep["bag"]["H2"], Wci, dWci, dbci, M=K + n_neg)
-        b = _fc_branch_backward(head, keep["bag"], dZ2b, need_feat_grad, tg)
-        if branch_done is not None:
-            branch_done(stage, "bag")
+        b = _fc_branch_backward(head, keep["bag"], dZ2b, need_feat_grad, tg,
+                                None if branch_done is None else (lambda: branch_done(stage, "bag")))
     dfeat = None
     if need_feat_grad:
         dfeat = []
