@@ -9,6 +9,8 @@ image's feature map).  The only exchange steps are
     constructed-but-unused ``shared_fcs``, ``shared_fcs_refine`` and ``fc_iou`` never receive a gradient.
 Per-rank loss denominators (``avg_factor = K_local``, ``num_sample_local``) are kept per process exactly like the
 reference under DDP.  Backend: NCCL over NVLink on the GPUs, gloo on CPU (tests)."""
+import os
+
 import torch
 import torch.distributed as dist
 
@@ -108,6 +110,11 @@ class MILGradBucket:
         self._w1_grad = {}                     # persistent parameter-order gradient of the two FC1 weights per stage
         self._works = []
         self.head = head
+        # SMs the persistent GEMMs leave to NCCL while a reduction of this bucket is in flight (0 = none);
+        # PTB200_NCCL_SM_RESERVE overrides it for measurements (tools/mb_train_dist.py)
+        # measured (training step, max over ranks): N = 8 1.61-1.64 ms with 0, 1.55 / 1.56 / 1.58 / 1.52 ms with
+        # 16 / 24 / 32 / 40; N = 2 1.43 ms with 0-16, 1.45-1.46 ms with 24-40
+        self.sm_reserve = int(os.environ.get("PTB200_NCCL_SM_RESERVE", "16" if world() >= 4 else "0"))
 
     def names(self):
         return [n for n, _ in self.named]
@@ -138,6 +145,9 @@ class MILGradBucket:
             return
         g = next(x for x in self.groups if x["stage"] == stage and x["branch"] == branch)
         self._works.append(_all_reduce_avg_(self.flat[g["lo"]:g["hi"]], group=group, async_op=True))
+        if self.sm_reserve and self.flat.is_cuda:
+            from . import ops
+            ops.set_gemm_sm_reserve(self.sm_reserve)        # until finish_(): the GEMMs leave NCCL's SMs alone
 
     def finish_(self):
         """Join the outstanding reductions, put the FC1 weight gradients into parameter order, publish ``.grad``."""
@@ -145,6 +155,8 @@ class MILGradBucket:
         for w in self._works:
             w.wait()
         self._works = []
+        if self.sm_reserve and self.flat.is_cuda:
+            ops.set_gemm_sm_reserve(0)
         head = self.head
         for (n, p), v in zip(self.named, self.views):
             if n.startswith("shared_fcs") and n.endswith(".0.weight"):

@@ -74,6 +74,20 @@ def num_sms():
     return torch.cuda.get_device_properties(torch.cuda.current_device()).multi_processor_count
 
 
+# SMs the persistent GEMM leaves free (its grid is num_sms() - reserve CTAs).  The trainer sets it while a gradient
+# all-reduce is in flight on NCCL's stream: the GEMM assigns tiles to CTAs statically, so CTAs that cannot become
+# resident beside NCCL's would otherwise hold their tiles until the collective has finished.
+_SM_RESERVE = {"n": 0}
+
+
+def set_gemm_sm_reserve(n):
+    _SM_RESERVE["n"] = max(0, int(n))
+
+
+def gemm_sms():
+    return max(8, num_sms() - _SM_RESERVE["n"])
+
+
 # ------------------------------------------------------------------------------ bags
 def bag_gen(in_rois, img_wh, base_ratios, shake_ratio, min_scale, rotated=False):
     """in_rois (G,5) -> (rois (G*U,5), valid (G*U,) uint8); rotated: 6-column RoIs (img,cx,cy,w,h,theta)."""
@@ -269,7 +283,7 @@ def fc_gemm(A, B, bias=None, relu=False, out_dtype=_bf16, M=None, out=None, allo
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
     _lib.call("pt_fc_gemm_bf16", _p(A), A.shape[1], _p(B), B.shape[1], _p(bias), _p(out), out.shape[1], M, N, K,
-              int(relu), int(out.dtype == _f32), _p(ws), ws.numel(), num_sms(), int(allow_split), _stream())
+              int(relu), int(out.dtype == _f32), _p(ws), ws.numel(), gemm_sms(), int(allow_split), _stream())
     if PROFILE["on"]:
         e1.record()
         PROFILE["events"].append(("fc_gemm", e0, e1, 2.0 * M * N * K, (M, N, K)))
@@ -549,7 +563,7 @@ def fc_gemm_masked(A, B, mask, out_dtype=_bf16, M=None, allow_split=True):
     out = torch.empty((A.shape[0], N), dtype=out_dtype, device=A.device)
     ws = gemm_workspace(A.device)
     _lib.call("pt_fc_gemm_bf16_ex", _p(A), A.shape[1], _p(B), B.shape[1], _p(None), _p(out), out.shape[1], M, N, K, 0,
-              int(out.dtype == _f32), _p(mask), mask.shape[1], _p(ws), ws.numel(), num_sms(), int(allow_split), _stream())
+              int(out.dtype == _f32), _p(mask), mask.shape[1], _p(ws), ws.numel(), gemm_sms(), int(allow_split), _stream())
     return out
 
 
@@ -583,7 +597,7 @@ def fc_gemm_mn(A, B, a_mn=False, b_mn=False, mask=None, out_dtype=_bf16, M=None,
     ws = gemm_workspace(A.device)
     _lib.call("pt_fc_gemm_bf16_mn", _p(A), A.shape[1], int(a_mn), _p(B), B.shape[1], int(b_mn), _p(None), _p(out),
               out.stride(0), M, N, K, 0, int(out.dtype == _f32), _p(mask), 0 if mask is None else mask.shape[1], _p(ws),
-              ws.numel(), num_sms(), int(allow_split), _stream())
+              ws.numel(), gemm_sms(), int(allow_split), _stream())
     return out
 
 
