@@ -33,8 +33,6 @@ def phase2_refine(head, x_ori, img_metas, pseudo_bboxes, pseudo_points, pseudo_l
         head._weights().clear()                 # parameters change every iteration
     counts = [min(int(b.shape[0]), cap) for b in pseudo_bboxes]
     pb = torch.cat([b[:cap, :] for b in pseudo_bboxes]).float().contiguous()
-    gb = torch.cat([b[:cap, :] for b in gt_bboxes]).float().contiguous()
-    labels = torch.cat([l[:cap] for l in pseudo_labels]).long().contiguous()
     img_idx = const_tensor([i for i, c in enumerate(counts) for _ in range(c)], torch.int32, dev)
     img_wh = img_wh_tensor(img_metas, dev)
     phase1 = synthetic_bboxes is not None
@@ -43,9 +41,16 @@ def phase2_refine(head, x_ori, img_metas, pseudo_bboxes, pseudo_points, pseudo_l
         sb = torch.cat([b[:cap, :] for b in synthetic_bboxes]).float().contiguous()
         s_idx = const_tensor([i for i, c in enumerate(s_counts) for _ in range(c)], torch.int32, dev)
     forks = []
-    with ops.fork() as f:                       # logged scalars run beside the data path
+    # the packing of everything the first bag generation does not read (GT boxes, labels, the first stage's negatives)
+    # and the logged scalars run beside the data path; joined right before the first stage needs them
+    nl0 = neg_boxes[0] if (neg_boxes is not None and fine_proposal_cfg[0]["gen_num_neg"]) else None
+    negs0 = None
+    with ops.fork() as f0:
+        gb = torch.cat([b[:cap, :] for b in gt_bboxes]).float().contiguous()
+        labels = torch.cat([l[:cap] for l in pseudo_labels]).long().contiguous()
+        if nl0 is not None:
+            negs0 = torch.cat(list(nl0)).float().contiguous()
         losses = {"coarse_bboxes_iou": ops.aligned_iou_mean(pb, gb, rot)}
-    forks.append(f)
     pts = None
 
     def run_stage(x, *args, **kw):
@@ -69,7 +74,7 @@ def phase2_refine(head, x_ori, img_metas, pseudo_bboxes, pseudo_points, pseudo_l
         if n_neg:
             nl = neg_boxes[stage] if neg_boxes is not None else \
                 [sample_negative_boxes(n_neg, m["img_shape"], rotated=rot).to(dev) for m in img_metas]
-            negs = torch.cat(list(nl)).float().contiguous()
+            negs = negs0 if (stage == 0 and negs0 is not None) else torch.cat(list(nl)).float().contiguous()
             neg_idx = const_tensor([i for i, t in enumerate(nl) for _ in range(int(t.shape[0]))], torch.int32, dev)
             o = [0]
             for c in counts:
@@ -81,6 +86,8 @@ def phase2_refine(head, x_ori, img_metas, pseudo_bboxes, pseudo_points, pseudo_l
                                     cfg["min_scale"], rot)
             _, _, syn_loss = run_stage(x_synthetic, img_metas, img_wh, s_rois, U1, sb, sb, None, None, None, None, None,
                                        fine_proposal_extensive_cfg[stage], stage, loss_scales=alpha, mode="reg_only")
+        if stage == 0:
+            f0.join()
         pb_new, pts, mil_loss = run_stage(x_ori, img_metas, img_wh, base_rois, U1, pb, gb, negs, neg_idx, offs, labels, pb,
                                           fine_proposal_extensive_cfg[stage], stage, loss_scales=alpha)
         if syn_loss is not None:
@@ -98,8 +105,10 @@ def phase2_refine(head, x_ori, img_metas, pseudo_bboxes, pseudo_points, pseudo_l
     for i in range(len(pseudo_bboxes)):
         box_parts += [mb[i].to(pseudo_bboxes[i].dtype), pseudo_bboxes[i][cap:, :]]
         pt_parts += [mp[i].to(pseudo_points[i].dtype), pseudo_points[i][cap:, :]]
+    with ops.fork() as f:
+        refined_p = list(torch.split(torch.cat(pt_parts), sizes))
+    forks.append(f)
     refined_b = list(torch.split(torch.cat(box_parts), sizes))
-    refined_p = list(torch.split(torch.cat(pt_parts), sizes))
     for f in forks:
         f.join()
     return refined_b, refined_p, losses

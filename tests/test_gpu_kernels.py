@@ -386,6 +386,21 @@ def test_box_iou_rotated_vs_oracle(cuda, mode):
         assert (ops.box_iou_rotated(a0.to(cuda), b0.to(cuda)).cpu() - ax).abs().max() < 1e-3
 
 
+def test_box_iou_rotated_known_answer_from_reference_tests(cuda):
+    """OBB_TOD/tests/test_utils/test_overlaps.py:7-15 (vanishing / astronomically large boxes -> IoU 0 at atol 1e-3),
+    through ``rbbox_overlaps``' clamp of w, h to >= 1e-3 (mmrotate/core/bbox/iou_calculators/rotate_iou2d_calculator.py):
+    without it a box whose four vertices collapse onto its centre in fp32 makes the published algorithm itself return
+    garbage, which is why the reference clamps."""
+    from oracle import obb
+    from point_teacher_b200 import ops
+    from test_oracle import REF_RBBOX_GT, REF_RBBOX_PREDICT      # same directory (rootdir-relative test modules)
+    a, b = torch.tensor(REF_RBBOX_PREDICT), torch.tensor(REF_RBBOX_GT)
+    got = ops.box_iou_rotated(a.to(cuda), b.to(cuda), clamp_wh=True).cpu()
+    assert got.shape == (3, 4)
+    assert torch.allclose(got, torch.zeros(3, 4), atol=1e-3), got
+    assert torch.allclose(got, obb.rbbox_overlaps(a, b), atol=1e-3)
+
+
 def test_obb_bag_gen_bit_exact_and_neg_weight(cuda):
     from oracle import obb
     from point_teacher_b200 import ops

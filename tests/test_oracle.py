@@ -145,6 +145,24 @@ def test_rotated_iou_theta0_equals_axis_aligned_and_cv2():
     assert torch.allclose(ident, torch.ones(50), atol=1e-4)
 
 
+# The one known-answer vector the reference itself holds for the rotated overlaps
+# (OBB_TOD/tests/test_utils/test_overlaps.py:7-15: vanishing and astronomically large predictions against four
+# ordinary boxes; expected IoU 0 everywhere at atol 1e-3).
+REF_RBBOX_PREDICT = [[903.34, 1034.4, 1.81e-7, 1e-7, -0.312], [903.34, 1034.4, 1e-7, 1e-3, -0.312],
+                     [903.34, 1034.4, 1.81e7, 1e7, -0.312]]
+REF_RBBOX_GT = [[2.1525e+02, 7.5750e+01, 3.3204e+01, 1.2649e+01, 3.2175e-01],
+                [3.0013e+02, 7.7144e+02, 4.9222e+02, 3.1368e+02, -1.3978e+00],
+                [8.4887e+02, 6.9989e+02, 4.6854e+02, 3.0743e+02, -1.4008e+00],
+                [8.5250e+02, 7.0250e+02, 7.6181e+02, 3.8200e+02, -1.3984e+00]]
+
+
+def test_rbbox_overlaps_known_answer_from_reference_tests():
+    from oracle import obb
+    ious = obb.rbbox_overlaps(torch.tensor(REF_RBBOX_PREDICT), torch.tensor(REF_RBBOX_GT))
+    assert ious.shape == (3, 4)
+    assert torch.allclose(ious, torch.zeros(3, 4), atol=1e-3), ious
+
+
 def test_rotated_nms_keeps_descending_score_order():
     dets = torch.tensor([[50., 50., 20., 20., 0.], [52., 50., 20., 20., 0.1], [150., 150., 20., 10., 0.7],
                          [50., 51., 20., 20., 0.]])
