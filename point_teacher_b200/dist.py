@@ -109,6 +109,8 @@ class MILGradBucket:
         self._view = {n: v for (n, _), v in zip(self.named, self.views)}
         self._w1_grad = {}                     # persistent parameter-order gradient of the two FC1 weights per stage
         self._works = []
+        self._forks = []
+        self._w1_done = set()
         self.head = head
         # SMs the persistent GEMMs leave to NCCL while a reduction of this bucket is in flight (0 = none);
         # PTB200_NCCL_SM_RESERVE overrides it for measurements (tools/mb_train_dist.py)
@@ -140,18 +142,38 @@ class MILGradBucket:
             self.flat[g["lo"]:g["small_hi"]].zero_()
 
     def reduce_group_(self, stage, branch, group=None):
-        """Average this (stage, branch) slice over the ranks; asynchronous (joined by ``finish_``)."""
+        """Called the moment the last parameter-gradient kernel of (stage, branch) is enqueued.  The FC1 weight
+        gradient (51 MB, bin-major in the bucket) is put into parameter order on the forked stream, under the rest of
+        the backward; with more than one rank that copy and the remainder of the group's slice are averaged over the
+        ranks by two asynchronous all-reduces (joined by ``finish_``)."""
+        from . import ops
+        g = next(x for x in self.groups if x["stage"] == stage and x["branch"] == branch)
+        w1 = f"shared_fcs_{branch}.{stage}.0.weight"
+        lo, hi = g["lo"], g["hi"]
+        if w1 in self.offsets and self.flat.is_cuda:
+            p = dict(self.named)[w1]
+            buf = self._w1_grad.get(w1)
+            if buf is None:
+                buf = self._w1_grad[w1] = torch.empty_like(p)
+            with ops.fork() as f:
+                ops.unpermute_dw1(self._view[w1], self.head.in_channels, self.head.roi_feat_area, buf, accumulate=False)
+                if world() > 1:     # issued from the forked stream: NCCL orders itself behind the un-permute
+                    self._works.append(_all_reduce_avg_(buf.view(-1), group=group, async_op=True))
+            self._forks.append(f)
+            self._w1_done.add(w1)
+            hi = self.offsets[w1]                           # FC1 W is the last entry of the group's slice
         if world() == 1:
             return
-        g = next(x for x in self.groups if x["stage"] == stage and x["branch"] == branch)
-        self._works.append(_all_reduce_avg_(self.flat[g["lo"]:g["hi"]], group=group, async_op=True))
+        self._works.append(_all_reduce_avg_(self.flat[lo:hi], group=group, async_op=True))
         if self.sm_reserve and self.flat.is_cuda:
-            from . import ops
             ops.set_gemm_sm_reserve(self.sm_reserve)        # until finish_(): the GEMMs leave NCCL's SMs alone
 
     def finish_(self):
-        """Join the outstanding reductions, put the FC1 weight gradients into parameter order, publish ``.grad``."""
+        """Join the forked un-permutes and the outstanding reductions, publish ``.grad``."""
         from . import ops
+        for f in self._forks:
+            f.join()
+        self._forks = []
         for w in self._works:
             w.wait()
         self._works = []
@@ -163,10 +185,12 @@ class MILGradBucket:
                 g = self._w1_grad.get(n)
                 if g is None:
                     g = self._w1_grad[n] = torch.empty_like(p)
-                ops.unpermute_dw1(v, head.in_channels, head.roi_feat_area, g, accumulate=False)
+                if n not in self._w1_done:      # a branch whose reduce_group_ was not called (direct callers)
+                    ops.unpermute_dw1(v, head.in_channels, head.roi_feat_area, g, accumulate=False)
                 p.grad = g
             else:
                 p.grad = v
+        self._w1_done = set()
         return self
 
     # ---------------------------------------------------------------- legacy mode

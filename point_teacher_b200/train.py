@@ -36,17 +36,19 @@ def _fc_branch_backward(head, k, dZ2, need_dA, out=None, after_wgrad=None):
     o = out or {}
     # every operand is consumed in the layout the forward left it in (MN-major tcgen05 tiles): no transposed copies
     dZ1 = ops.fc_gemm_mn(dZ2, k["W2"], b_mn=True, mask=k["H1"], M=M)                                # (dZ2 @ W2) * (H1 > 0)
-    dW2 = ops.fc_gemm_mn(dZ2, k["H1"], a_mn=True, b_mn=True, out_dtype=torch.float32, K=M, out=o.get("W2"))   # dZ2^T @ H1
     db2 = o["b2"] if out else torch.zeros((dZ2.shape[1],), dtype=torch.float32, device=dev)
-    ops.colsum_bf16(dZ2, db2, M=M)
+    db1 = o["b1"] if out else torch.zeros((N1,), dtype=torch.float32, device=dev)
+    with ops.fork() as f:             # the two bias gradients (10 MB column sums) run beside the wgrad GEMMs
+        ops.colsum_bf16(dZ2, db2, M=M)
+        ops.colsum_bf16(dZ1, db1, M=M)
+    dW2 = ops.fc_gemm_mn(dZ2, k["H1"], a_mn=True, b_mn=True, out_dtype=torch.float32, K=M, out=o.get("W2"))   # dZ2^T @ H1
     dW1p = ops.fc_gemm_mn(dZ1, k["A"], a_mn=True, b_mn=True, out_dtype=torch.float32, K=M, out=o.get("W1p"))  # bin-major
     if out:
         dW1 = dW1p
     else:
         dW1 = torch.empty_like(dW1p)
         ops.unpermute_dw1(dW1p, head.in_channels, head.roi_feat_area, dW1, accumulate=False)
-    db1 = o["b1"] if out else torch.zeros((N1,), dtype=torch.float32, device=dev)
-    ops.colsum_bf16(dZ1, db1, M=M)
+    f.join()
     if after_wgrad is not None:
         after_wgrad()
     dA = None
