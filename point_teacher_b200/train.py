@@ -12,6 +12,8 @@ refined boxes are detached exactly where the reference detaches them (``pred.clo
 The big contractions run on the tcgen05 GEMM: dgrad = GEMM against a transposed bf16 weight copy with the ReLU mask
 fused in the epilogue; wgrad = GEMM over transposed (row-padded) copies of the activation gradient and the layer
 input.  bf16 operands, fp32 accumulation, fp32 parameter gradients."""
+import contextlib
+
 import torch
 
 from . import ops
@@ -81,6 +83,19 @@ def mil_stage_backward(head, keep, x, g_bbox, g_bags, need_feat_grad=True, targe
     r = b = None
     dWreg = dbreg = dWci = dbci = None
     # ---- regression branch: DN-DIoU -> delta2bbox -> fc_reg -> FC2 -> FC1 -> RoIAlign
+    # The bag branch's front end (loss gradient -> fc_cls / fc_ins backward, ~50 us of small HBM-bound kernels) does not
+    # depend on the regression branch: it runs on the forked stream under the regression branch's GEMMs.
+    fb = None
+    if do_bag:
+        with (ops.fork() if do_reg else contextlib.nullcontext()) as fb:
+            g16 = ops.bag_loss_grad(keep["cls"], keep["ins"], keep["evalid"], keep["labels"], G, U1, U2, keep["neg_w"],
+                                    n_neg, keep["sums"], g_bags, s_bags * head.bag_loss_pos_scale,
+                                    s_bags * head.bag_loss_neg_scale)
+            Wci = torch.cat([fc.weight.detach(), fi.weight.detach()], 0).contiguous()
+            tgb = targets["bag"] if targets else None
+            dWci, dbci = (tgb["Wh"], tgb["bh"]) if tgb else \
+                (torch.zeros_like(Wci), torch.zeros((2 * C,), dtype=torch.float32, device=dev))
+            dZ2b = ops.head_bwd(g16, keep["bag"]["H2"], Wci, dWci, dbci, M=K + n_neg)
     if do_reg:
         g4 = ops.reg_loss_grad(keep["deltas"], keep["ebags"], keep["evalid"], keep["ref"], U1 * U2, keep["max_wh"],
                                keep["sums"], g_bbox, s_bbox, hyper=head._dn_hyper(), rotated=rot)
@@ -91,14 +106,9 @@ def mil_stage_backward(head, keep, x, g_bbox, g_bags, need_feat_grad=True, targe
                                 None if branch_done is None else (lambda: branch_done(stage, "reg")))
     # ---- bag branch: gfocal -> bag score -> (sigmoid, softmax x valid x L1) -> fc_cls / fc_ins -> FC2 -> FC1
     if do_bag:
-        g16 = ops.bag_loss_grad(keep["cls"], keep["ins"], keep["evalid"], keep["labels"], G, U1, U2, keep["neg_w"], n_neg,
-                                keep["sums"], g_bags, s_bags * head.bag_loss_pos_scale, s_bags * head.bag_loss_neg_scale)
-        Wci = torch.cat([fc.weight.detach(), fi.weight.detach()], 0).contiguous()
-        tg = targets["bag"] if targets else None
-        dWci, dbci = (tg["Wh"], tg["bh"]) if tg else \
-            (torch.zeros_like(Wci), torch.zeros((2 * C,), dtype=torch.float32, device=dev))
-        dZ2b = ops.head_bwd(g16, keep["bag"]["H2"], Wci, dWci, dbci, M=K + n_neg)
-        b = _fc_branch_backward(head, keep["bag"], dZ2b, need_feat_grad, tg,
+        if fb is not None:
+            fb.join()
+        b = _fc_branch_backward(head, keep["bag"], dZ2b, need_feat_grad, tgb,
                                 None if branch_done is None else (lambda: branch_done(stage, "bag")))
     dfeat = None
     if need_feat_grad:
