@@ -13,10 +13,14 @@ The big contractions run on the tcgen05 GEMM: dgrad = GEMM against a transposed 
 fused in the epilogue; wgrad = GEMM over transposed (row-padded) copies of the activation gradient and the layer
 input.  bf16 operands, fp32 accumulation, fp32 parameter gradients."""
 import contextlib
+import os
 
 import torch
 
 from . import ops
+
+
+EARLY_ROI_BWD = os.environ.get("PTB200_EARLY_ROI_BWD", "1") != "0"
 
 
 def stage_params(head, stage):
@@ -105,6 +109,16 @@ def mil_stage_backward(head, keep, x, g_bbox, g_bags, need_feat_grad=True, targe
         r = _fc_branch_backward(head, keep["reg"], dZ2, need_feat_grad, tg,
                                 None if branch_done is None else (lambda: branch_done(stage, "reg")))
     # ---- bag branch: gfocal -> bag score -> (sigmoid, softmax x valid x L1) -> fc_cls / fc_ins -> FC2 -> FC1
+    # the regression branch's RoIAlign backward only needs that branch's dA: forked under the bag branch's GEMMs
+    # (it fills the SMs their tail waves leave idle)
+    early = None
+    if do_reg and do_bag and need_feat_grad and len(feats) == 1 and EARLY_ROI_BWD:
+        layer = ext.roi_layers[0]
+        Bn, Cf, H, W = feats[0].shape
+        with ops.fork() as fe:
+            early = ops.roi_align_backward(r[4], keep["ebags"], (Bn, H, W, Cf), layer.spatial_scale, layer.sampling_ratio,
+                                           layer.aligned, K=K, roi_level=keep["reg"].get("lvls"), rotated=rot,
+                                           clockwise=getattr(layer, "clockwise", True), level=0)
     if do_bag:
         if fb is not None:
             fb.join()
@@ -119,7 +133,10 @@ def mil_stage_backward(head, keep, x, g_bbox, g_bags, need_feat_grad=True, targe
             shape = (Bn, H, W, Cf)
             rk = dict(rotated=rot, clockwise=getattr(layer, "clockwise", True), level=lvl)
             dn = None
-            if do_reg:
+            if early is not None:
+                fe.join()
+                dn = early
+            elif do_reg:
                 dn = ops.roi_align_backward(r[4], keep["ebags"], shape, layer.spatial_scale, layer.sampling_ratio,
                                             layer.aligned, K=K, roi_level=keep["reg"].get("lvls"), **rk)
             if do_bag:
