@@ -54,10 +54,13 @@ struct Params {
   int a_mn, b_mn;                   // operand stored [K, M] / [K, N] (MN-major): wgrad / dgrad without a transposed copy
   int diag;                         // measurement only (PTB200_GEMM_DIAG): 1 = no TMA loads after the first ring fill
                                     // (MMA + shared-memory operand reads alone), 2 = no MMAs (TMA feed alone)
+  int nsplit;                       // > 1: the tiles of the tail round are cut into nsplit column slices (short K)
+  int b_box;                        // rows of one K-major B TMA box (BN, or 64 when nsplit is active)
 };
 
 struct Unit {
   int m_blk, n_blk, kb0, kb1, tail_idx;  // tail_idx >= 0: split unit
+  int n_off, n_w;                        // column slice [n_off, n_off + n_w) of the tile (whole tile: 0, BN)
 };
 
 // G / c: number and index of the scheduling units (CTAs, or CTA pairs); rank: CTA inside the pair (0 when unpaired).
@@ -65,6 +68,7 @@ struct Unit {
 __device__ __forceinline__ bool get_unit(const Params& p, int it, Unit& u, int G, int c, int pair, int rank) {
   const int kb_total = (p.K + BK - 1) / BK;   // a ragged last k-block is zero-filled by TMA (out-of-bounds rows / columns)
   int tile;
+  u.n_off = 0; u.n_w = BN;
   if (it < p.full_rounds) {
     tile = it * G + c;
     u.kb0 = 0; u.kb1 = kb_total; u.tail_idx = -1;
@@ -78,6 +82,14 @@ __device__ __forceinline__ bool get_unit(const Params& p, int it, Unit& u, int G
       u.kb0 = (int)(((long long)s * kb_total) / p.split);
       u.kb1 = (int)(((long long)(s + 1) * kb_total) / p.split);
       u.tail_idx = t;
+    } else if (p.nsplit > 1) {
+      // short contraction: no K-split (the reduction would cost more than it saves); the tail tiles are cut into
+      // column slices instead -- no reduction at all, every CTA writes its own output columns
+      const int t = c / p.nsplit, q = c % p.nsplit;
+      if (t >= tail) return false;
+      tile = p.full_rounds * G + t;
+      u.n_w = BN / p.nsplit; u.n_off = q * u.n_w;
+      u.kb0 = 0; u.kb1 = kb_total; u.tail_idx = -1;
     } else {
       if (c >= tail) return false;
       tile = p.full_rounds * G + c;
@@ -260,7 +272,7 @@ fc_gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
             tma_load_2d_pair(sa, &tma_a, full_bar + stage, kb * BK, u.m_blk * BM);
             tma_load_2d_pair(sa + A_BYTES, &tma_b, full_bar + stage, kb * BK, u.n_blk * BN + rank * B_ROWS);
           } else {
-            mbar_expect_tx(full_bar + stage, STAGE_BYTES);
+            mbar_expect_tx(full_bar + stage, (uint32_t)(A_BYTES + u.n_w * BK * 2));
             if (AMN) {
 #pragma unroll
               for (int j = 0; j < BM / 64; j++)
@@ -268,12 +280,13 @@ fc_gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
             } else {
               tma_load_2d(sa, &tma_a, full_bar + stage, kb * BK, u.m_blk * BM);
             }
+            const int ncol0 = u.n_blk * BN + u.n_off;
             if (BMN) {
-#pragma unroll
-              for (int j = 0; j < BN / 64; j++)
-                tma_load_2d(sa + A_BYTES + j * (64 * BK * 2), &tma_b, full_bar + stage, u.n_blk * BN + j * 64, kb * BK);
+              for (int j = 0; j < u.n_w / 64; j++)
+                tma_load_2d(sa + A_BYTES + j * (64 * BK * 2), &tma_b, full_bar + stage, ncol0 + j * 64, kb * BK);
             } else {
-              tma_load_2d(sa + A_BYTES, &tma_b, full_bar + stage, kb * BK, u.n_blk * BN);
+              for (int j = 0; j < u.n_w / p.b_box; j++)      // one box for a whole tile unless the launch slices its tail
+                tma_load_2d(sa + A_BYTES + j * (p.b_box * BK * 2), &tma_b, full_bar + stage, kb * BK, ncol0 + j * p.b_box);
             }
           }
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
@@ -301,7 +314,9 @@ fc_gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
             // K-major: advance 16 bf16 = 32 B along K inside the 128 B swizzle row: +2 in 16 B units;
             // MN-major: 16 k-rows of 128 B = 2048 B: +128
             constexpr uint32_t astep = amn ? 128u : 2u, bstep = bmn ? 128u : 2u;
-            constexpr uint32_t idesc = IDESC | (amn ? (1u << 15) : 0u) | (bmn ? (1u << 16) : 0u);
+            // N of the instruction follows the unit's column slice (256, or 128 / 64 for a sliced tail tile)
+            const uint32_t idesc = ((IDESC & ~(0x3Fu << 17)) | ((uint32_t)(u.n_w >> 3) << 17)) |
+                                   (amn ? (1u << 15) : 0u) | (bmn ? (1u << 16) : 0u);
 #pragma unroll
             for (int k = 0; k < BK / UMMA_K; k++) {
               if (p.diag == 2 && !(kb == u.kb0 && k == 0)) continue;   // diagnostic: one MMA per tile, timing only
@@ -331,11 +346,11 @@ fc_gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * BN;
       if (u.tail_idx < 0) {
 #pragma unroll 1
-        for (int ch = 0; ch < BN / 32; ch++) {
+        for (int ch = 0; ch < u.n_w / 32; ch++) {
           uint32_t r[32];
           tmem_ld_32x32(taddr + ch * 32, r);
           tmem_ld_wait();
-          store_chunk(p, row, u.n_blk * BN + ch * 32, r, row_ok);
+          store_chunk(p, row, u.n_blk * BN + u.n_off + ch * 32, r, row_ok);
         }
         tc_fence_before();
         __syncwarp();
@@ -554,8 +569,6 @@ extern "C" int pt_fc_gemm_bf16_mn(const void* A, long long lda, int a_mn, const 
   CUtensorMap ma, mb;
   int rc = a_mn ? make_map_mn(&ma, A, K, M, lda) : make_map(&ma, A, M, K, lda, BM);
   if (rc != PT_OK) return rc;
-  rc = b_mn ? make_map_mn(&mb, B, K, N, ldb) : make_map(&mb, B, N, K, ldb, two ? BN / 2 : BN);
-  if (rc != PT_OK) return rc;
 
   Params p;
   p.mask = reinterpret_cast<const __nv_bfloat16*>(mask); p.ldmask = (int)ldmask;
@@ -607,6 +620,20 @@ extern "C" int pt_fc_gemm_bf16_mn(const void* A, long long lda, int a_mn, const 
       p.ws = reinterpret_cast<float*>(reinterpret_cast<char*>(workspace) + 4096);   // counters live in the first 4 KB
     }
   }
+  // Short contractions (FC2, the dgrads: K = 1024) are never K-split; their tail round (160 tiles on 148 CTAs: 12 tiles
+  // in the second round) is cut into 2 or 4 column slices per tile instead, one CTA each.  PTB200_GEMM_NSPLIT=0: off.
+  p.nsplit = 0; p.b_box = BN;
+  {
+    static int ns_on = -1;
+    if (ns_on < 0) { const char* e = getenv("PTB200_GEMM_NSPLIT"); ns_on = (e != nullptr && e[0] == '0') ? 0 : 1; }
+    if (ns_on && !two && p.split == 0 && tail > 0 && p.full_rounds > 0 && kb_total < 64) {
+      const int ns = grid_u / tail;
+      p.nsplit = ns >= 4 ? 4 : (ns >= 2 ? 2 : 0);
+      if (p.nsplit) p.b_box = 64;
+    }
+  }
+  rc = b_mn ? make_map_mn(&mb, B, K, N, ldb) : make_map(&mb, B, N, K, ldb, two ? BN / 2 : p.b_box);
+  if (rc != PT_OK) return rc;
   static bool attr_set = false;
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(fc_gemm_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<false>::SMEM_BYTES);

@@ -256,7 +256,9 @@ def test_multi_level_extractor_matches_oracle(cuda):
 @pytest.mark.parametrize("M,N,K,relu,f32,split", [
     (128, 256, 64, False, True, False), (300, 256, 128, True, False, False), (1000, 1024, 1024, True, False, True),
     (5400, 1024, 12544, True, False, True), (5400, 1024, 12544, True, False, False),
-    (4736, 1024, 1024, False, True, True), (77, 512, 3072, True, True, True)])
+    (4736, 1024, 1024, False, True, True), (77, 512, 3072, True, True, True),
+    # short contractions with a tail round: the tail tiles are cut into 4 / 4 / 2 column slices (no K-split)
+    (5000, 1024, 1024, True, False, True), (20000, 512, 512, False, True, True), (6600, 1024, 512, True, True, True)])
 def test_fc_gemm_vs_fp32_reference(cuda, M, N, K, relu, f32, split):
     from point_teacher_b200 import ops
     g = torch.Generator().manual_seed(M + N + K)
