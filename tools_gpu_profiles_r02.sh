@@ -9,7 +9,7 @@ python bench.py --steps 200 --warmup 5 > gpurun_out/r02_bench_n1.json 2> gpurun_
 python bench.py --impl reference --steps 10 --warmup 2 > gpurun_out/r02_bench_reference.json 2>> gpurun_out/r02_bench.err
 python bench.py --steps 50 --precision fp32 --no-cpu-baseline --no-stress > gpurun_out/r02_bench_n1_fp32.json 2>> gpurun_out/r02_bench.err
 for c in obb assign mask train; do timeout 400 python bench.py --config $c --steps 50 > gpurun_out/r02_bench_$c.json 2> gpurun_out/r02_bench_$c.err; echo "$c exit $?"; done
-for t in mb_roi_sweep.py "mb_roi_sweep.py rot" mb_gemm_waves.py mb_heads.py trace_train.py; do echo "== $t"; python tools/$t; done > gpurun_out/r02_microbench.log 2>&1
+for t in mb_roi_sweep.py "mb_roi_sweep.py rot" "mb_roi_bwd.py 5000" "mb_roi_bwd.py 96000" mb_gemm_waves.py mb_heads.py trace_train.py "mb_train_dist.py 0"; do echo "== $t"; python tools/$t; done > gpurun_out/r02_microbench.log 2>&1
 # launch lists (each only after the same command exited 0 without ncu)
 B="bench.py --steps 2 --warmup 1 --no-graph --no-cpu-baseline --no-stress --no-train"
 python $B > gpurun_out/plain.log 2>&1 &&
@@ -23,5 +23,5 @@ ncu --set full --clock-control none --import-source on -k regex:"fc_gemm_kernel|
     -o gpurun_out/prof_step -f python $B > gpurun_out/ncu_full.log 2>&1
 python tools/prof_roi.py > /dev/null 2>&1 && ncu --set full --clock-control none --import-source on -k regex:roi_align_mma -s 1 -c 1 -o gpurun_out/prof_roi_stress -f python tools/prof_roi.py > gpurun_out/ncu_roi_stress.log 2>&1
 ncu --set full --clock-control none --import-source on -k regex:"roi_align_mma_kernel" -s 2 -c 2 -o gpurun_out/prof_obb_roi -f python tools/prof_obb.py 2 > gpurun_out/ncu_obb_full.log 2>&1
-ncu --set full --clock-control none --import-source on -k regex:"roi_align_bwd_kernel" -s 2 -c 1 -o gpurun_out/prof_roi_bwd -f python tools/prof_train.py 2 > gpurun_out/ncu_bwd_full.log 2>&1
+ncu --set full --clock-control none --import-source on -k regex:"roi_align_bwd_mma_kernel" -s 2 -c 1 -o gpurun_out/prof_roi_bwd -f python tools/prof_train.py 2 > gpurun_out/ncu_bwd_full.log 2>&1
 ls gpurun_out | wc -l
