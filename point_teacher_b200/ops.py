@@ -50,9 +50,12 @@ class fork:
     ``f.join()`` makes the current stream wait for them.  Used for work that is off the critical path of the step
     (logged IoU means); graph-capture safe as long as every fork is joined before the capture ends."""
 
+    def __init__(self, lane=1):
+        self.lane = lane          # independent side streams: work forked on different lanes does not queue up
+
     def __enter__(self):
         main = torch.cuda.current_stream()
-        key = (main.device.index, 1)
+        key = (main.device.index, self.lane)
         if key not in _SIDE:
             _SIDE[key] = torch.cuda.Stream(device=main.device)
         self.side = _SIDE[key]

@@ -115,7 +115,7 @@ def mil_stage_backward(head, keep, x, g_bbox, g_bags, need_feat_grad=True, targe
     if do_reg and do_bag and need_feat_grad and len(feats) == 1 and EARLY_ROI_BWD:
         layer = ext.roi_layers[0]
         Bn, Cf, H, W = feats[0].shape
-        with ops.fork() as fe:
+        with ops.fork(lane=2) as fe:     # its own lane: the bag branch's column sums must not queue behind it
             early = ops.roi_align_backward(r[4], keep["ebags"], (Bn, H, W, Cf), layer.spatial_scale, layer.sampling_ratio,
                                            layer.aligned, K=K, roi_level=keep["reg"].get("lvls"), rotated=rot,
                                            clockwise=getattr(layer, "clockwise", True), level=0)
