@@ -150,7 +150,10 @@ class MILGradBucket:
         g = next(x for x in self.groups if x["stage"] == stage and x["branch"] == branch)
         w1 = f"shared_fcs_{branch}.{stage}.0.weight"
         lo, hi = g["lo"], g["hi"]
-        if w1 in self.offsets and self.flat.is_cuda:
+        # PTB200_REDUCE_SCHEME=split|group overrides: 'split' un-permutes on the forked stream and reduces that copy on
+        # its own; 'group' reduces the whole slice with one all-reduce and un-permutes in finish_()
+        scheme = os.environ.get("PTB200_REDUCE_SCHEME", "split" if world() == 1 else "group")
+        if scheme == "split" and w1 in self.offsets and self.flat.is_cuda:
             p = dict(self.named)[w1]
             buf = self._w1_grad.get(w1)
             if buf is None:

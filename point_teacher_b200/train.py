@@ -20,7 +20,13 @@ import torch
 from . import ops
 
 
-EARLY_ROI_BWD = os.environ.get("PTB200_EARLY_ROI_BWD", "1") != "0"
+def _early_roi_bwd():
+    """PTB200_EARLY_ROI_BWD=0|1 overrides; default: on for a single rank, off when a gradient all-reduce shares the SMs."""
+    e = os.environ.get("PTB200_EARLY_ROI_BWD")
+    if e is not None:
+        return e != "0"
+    from .dist import world
+    return world() == 1
 
 
 def stage_params(head, stage):
@@ -112,7 +118,7 @@ def mil_stage_backward(head, keep, x, g_bbox, g_bags, need_feat_grad=True, targe
     # the regression branch's RoIAlign backward only needs that branch's dA: forked under the bag branch's GEMMs
     # (it fills the SMs their tail waves leave idle)
     early = None
-    if do_reg and do_bag and need_feat_grad and len(feats) == 1 and EARLY_ROI_BWD:
+    if do_reg and do_bag and need_feat_grad and len(feats) == 1 and _early_roi_bwd():
         layer = ext.roi_layers[0]
         Bn, Cf, H, W = feats[0].shape
         with ops.fork(lane=2) as fe:     # its own lane: the bag branch's column sums must not queue behind it

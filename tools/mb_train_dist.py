@@ -27,8 +27,15 @@ tin = dict(feat=d["feat"].to(dev), pseudo_boxes=to(d["pseudo_boxes"]), pseudo_po
            pseudo_labels=to(d["pseudo_labels"]), gt_boxes=to(d["gt_boxes"]), neg_boxes=[to(d["neg_boxes"][0])])
 flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
 keep = []
-for r in [int(a) for a in sys.argv[1:]] or [0]:
+# arguments: <sm_reserve>[:<reduce scheme split|group>[:<early roi bwd 0|1>]] ...
+for arg in sys.argv[1:] or ["0"]:
+    parts = arg.split(":")
+    r = int(parts[0])
     os.environ["PTB200_NCCL_SM_RESERVE"] = str(r)
+    if len(parts) > 1:
+        os.environ["PTB200_REDUCE_SCHEME"] = parts[1]
+    if len(parts) > 2:
+        os.environ["PTB200_EARLY_ROI_BWD"] = parts[2]
     c = CapturedTrainStep(head, tin, d["img_metas"], synth.HBB_FINE_CFG, synth.HBB_EXT_CFG, num_stages=1, cap=100)
     keep.append(c)
     for _ in range(3):
@@ -48,7 +55,7 @@ for r in [int(a) for a in sys.argv[1:]] or [0]:
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     if rank == 0:
-        print("world %d  sm_reserve %3d  train step %.4f ms (max over ranks)" % (world, r, t.item()), flush=True)
+        print("world %d  cfg %-14s  train step %.4f ms (max over ranks)" % (world, arg, t.item()), flush=True)
 if world > 1:
     torch.cuda.synchronize()
     dist.barrier()
