@@ -48,6 +48,28 @@ def _worker(rank, world, port, out):
             err = max(err, float((p.grad - mean).abs().max()))
         res["grad_err"] = err
         res["untouched"] = all(p.grad is None for n, p in head.named_parameters() if not n.startswith(pd.USED_PREFIXES))
+        # direct mode: the backward kernels write into the flat buffer and each (stage, branch) group is reduced on its
+        # own, asynchronously, the moment its branch is done (the multi-rank 'group' scheme; the un-permute of
+        # finish_() is a CUDA kernel and is covered by tools/check_dist_grads.py on GPUs)
+        b2 = pd.MILGradBucket(head)
+        b2.flat.copy_(torch.randn(b2.flat.shape, generator=torch.Generator().manual_seed(7 + rank)))
+        local = b2.flat.clone()
+        b2.reduce_group_(0, "reg")
+        b2.reduce_group_(0, "bag")
+        for w in b2._works:
+            w.wait()
+        both = [None] * world
+        dist.all_gather_object(both, local)
+        res["direct_err"] = float((b2.flat - sum(both) / world).abs().max())
+        # layout invariants the kernels rely on: groups tile the buffer, 16-byte aligned weight slots, the FC1 weight
+        # (reduced / un-permuted separately on one rank) is the last entry of its group
+        gs = b2.groups
+        res["layout_ok"] = (gs[0]["lo"] == 0 and all(a["hi"] == b["lo"] for a, b in zip(gs, gs[1:])) and
+                            gs[-1]["hi"] == b2.flat.numel() and
+                            all(b2.offsets[n] % 4 == 0 for n in b2.names() if n.endswith((".0.weight", ".1.weight"))) and
+                            all(g["names"][-1].endswith(".0.weight") and
+                                b2.offsets[g["names"][-1]] + dict(b2.named)[g["names"][-1]].numel() <= g["hi"] and
+                                g["lo"] < g["small_hi"] <= b2.offsets[g["names"][-1]] for g in gs))
         out[rank] = res
     finally:
         dist.destroy_process_group()
@@ -66,6 +88,7 @@ def test_world_size_2_gloo():
         assert abs(r["losses"]["stage0_loss_mil_bbox"] - 0.75) < 1e-6
         assert abs(r["losses"]["coarse_bboxes_iou"] - 0.25) < 1e-6
         assert r["grad_err"] < 1e-6 and r["untouched"]
+        assert r["direct_err"] < 1e-6 and r["layout_ok"]
         assert all(n.split(".")[0] in ("shared_fcs_reg", "shared_fcs_bag", "fc_cls", "fc_ins", "fc_reg") for n in r["names"])
         # per stage: 2 x (Linear(8*49 -> 1024) + Linear(1024 -> 1024)) + fc_cls + fc_ins + fc_reg
         assert r["numel"] == 2 * (8 * 49 * 1024 + 1024 + 1024 * 1024 + 1024) + 2 * (1024 * 8 + 8) + 1024 * 4 + 4
